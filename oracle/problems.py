@@ -1,0 +1,127 @@
+"""NumPy problem zoo for the oracle, the golden generator and the CPU baseline.
+
+TEST INFRASTRUCTURE ONLY (see oracle/rk_oracle.py header).  Every builder returns a
+``Problem`` whose ``nl_func`` is the NumPy closure the reference would be given and whose
+``model``/``params`` name the fused CUDA nonlinearity that computes the same thing.
+
+Formulations (reference file:line):
+  KS ........ README.md:86-104, demos/ks.ipynb:126-131
+  KdV ....... rkstiff/models.py:113-145, tests/testing_util.py:42-56
+  Burgers ... rkstiff/models.py:153-194, tests/testing_util.py:28-39
+  NLS 1-D ... demos/nls.ipynb (L = -i k^2, N = i*gamma*F{|u|^2 u}, gamma = 2)
+  grids ..... rkstiff/grids.py:40-131
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Dict, Optional
+
+import numpy as np
+
+
+@dataclass
+class Problem:
+    name: str
+    lin_op: np.ndarray                 # (n_c,) float64 or complex128
+    nl_func: Callable[[np.ndarray], np.ndarray]
+    u0: np.ndarray                     # (n_c,) or (B, n_c) complex128 spectrum
+    model: str                         # fused-NL id: "ks" | "burgers" | "kdv" | "nls"
+    n: int                             # real-space grid points per trajectory
+    kx: np.ndarray                     # wavenumbers (rfft or fft layout)
+    params: Dict[str, float] = field(default_factory=dict)
+    x: Optional[np.ndarray] = None
+
+
+def x_kx_rfft(n: int, a: float, b: float):
+    """grids.py:40-85: x = arange(a, b, dx), kx = 2 pi rfftfreq(n, dx)."""
+    dx = (b - a) / n
+    return np.arange(a, b, dx), 2 * np.pi * np.fft.rfftfreq(n, d=dx)
+
+
+def x_kx_fft(n: int, a: float, b: float):
+    """grids.py:88-131."""
+    dx = (b - a) / n
+    return np.arange(a, b, dx), 2 * np.pi * np.fft.fftfreq(n, d=dx)
+
+
+def _uux_nl(kx: np.ndarray, c: float):
+    """N(u^) = -c * rfft(irfft(u^) * irfft(i kx u^)) along the last axis (models.py:140-143)."""
+    def nl(uf):
+        u = np.fft.irfft(uf, axis=-1)
+        ux = np.fft.irfft(1j * kx * uf, axis=-1)
+        if c == 1.0:
+            return -np.fft.rfft(u * ux, axis=-1)
+        return -c * np.fft.rfft(u * ux, axis=-1)
+    return nl
+
+
+def ks(n: int = 1024, batch: int = 0, seed: int = 0) -> Problem:
+    """Kuramoto-Sivashinsky on [0, 32 pi): L = k^2(1-k^2), N = -F{u u_x}."""
+    x, kx = x_kx_rfft(n, 0.0, 32.0 * np.pi)
+    lin = kx ** 2 * (1 - kx ** 2)
+    if batch:
+        phi = np.random.default_rng(seed).uniform(0.0, 2 * np.pi, size=(batch, 1))
+        u0 = np.cos(x[None, :] / 16 + phi) * (1.0 + np.sin(x[None, :] / 16))
+    else:
+        u0 = np.cos(x / 16) * (1.0 + np.sin(x / 16))
+    return Problem("ks", lin, _uux_nl(kx, 1.0), np.fft.rfft(u0, axis=-1), "ks", n, kx, {"c": 1.0}, x)
+
+
+def kdv_soliton_profile(x, ampl=0.5, x0=0.0, t=0.0):
+    """models.py:32: 0.5 a^2 sech^2(a (x - x0 - a^2 t)/2)."""
+    return 0.5 * ampl ** 2 / np.cosh(ampl * (x - x0 - ampl ** 2 * t) / 2) ** 2
+
+
+def kdv(n: int = 256, batch: int = 0, seed: int = 0) -> Problem:
+    """KdV soliton test problem of tests/testing_util.py:42-56: L = i k^3, N = -6 F{u u_x}."""
+    x, kx = x_kx_rfft(n, -30.0, 30.0)
+    lin = 1j * kx ** 3
+    if batch:
+        rng = np.random.default_rng(seed)
+        a = rng.uniform(0.8, 1.2, size=(batch, 1))
+        x0 = rng.uniform(-8.0, -2.0, size=(batch, 1))
+        u0 = kdv_soliton_profile(x[None, :], a, x0)
+    else:
+        u0 = kdv_soliton_profile(x, 1.0, -5.0)
+    return Problem("kdv", lin, _uux_nl(kx, 6.0), np.fft.rfft(u0, axis=-1), "kdv", n, kx, {"c": 6.0}, x)
+
+
+def burgers(n: int = 1024, mu: float = 0.0005, batch: int = 0, seed: int = 0) -> Problem:
+    """Viscous Burgers of tests/testing_util.py:28-39: L = -mu k^2, N = -F{u u_x}."""
+    x, kx = x_kx_rfft(n, -np.pi, np.pi)
+    lin = -mu * kx ** 2
+    if batch:
+        amp = np.random.default_rng(seed).uniform(0.5, 1.5, size=(batch, 1))
+        u0 = amp * np.exp(-10 * np.sin(x[None, :] / 2) ** 2)
+    else:
+        u0 = np.exp(-10 * np.sin(x / 2) ** 2)
+    return Problem("burgers", lin, _uux_nl(kx, 1.0), np.fft.rfft(u0, axis=-1), "burgers", n, kx,
+                   {"c": 1.0, "mu": mu}, x)
+
+
+def nls(n: int = 8192, batch: int = 0, seed: int = 2, gamma: float = 2.0,
+        half_width: float = 40.0 * np.pi) -> Problem:
+    """Focusing NLS u_t = i u_xx + i gamma |u|^2 u on [-W, W): L = -i k^2, N = i gamma F{|u|^2 u}.
+
+    Batch members are solitons eta sech(eta (x - x0)) exp(i c x) (cfg 2).
+    """
+    x, kx = x_kx_fft(n, -half_width, half_width)
+    lin = -1j * kx ** 2
+
+    def nl(uf):
+        f = np.fft.ifft(uf, axis=-1)
+        f2 = f.real ** 2 + f.imag ** 2
+        return 1j * gamma * np.fft.fft(f2 * f, axis=-1)
+
+    if batch:
+        rng = np.random.default_rng(seed)
+        eta = rng.uniform(0.5, 1.5, size=(batch, 1))
+        x0 = rng.uniform(-20.0, 20.0, size=(batch, 1))
+        c = rng.uniform(-0.5, 0.5, size=(batch, 1))
+        u0 = eta / np.cosh(eta * (x[None, :] - x0)) * np.exp(1j * c * x[None, :])
+    else:
+        u0 = 1.0 / np.cosh(x) * np.exp(0.25j * x)
+    return Problem("nls", lin, nl, np.fft.fft(u0, axis=-1), "nls", n, kx, {"gamma": gamma}, x)
+
+
+BUILDERS = {"ks": ks, "kdv": kdv, "burgers": burgers, "nls": nls}

@@ -1,0 +1,452 @@
+"""CPU oracle: a NumPy restatement of rkstiff's diagonal ETD/IF Runge-Kutta path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``rkstiff_b200/`` may import this
+module; only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` use it, and only as the checker or the
+timed CPU baseline -- never as the thing shipped.
+
+Parity status: PINNED.  ``oracle/make_golden.py`` runs the unmodified reference
+(imported from /root/reference through a ``rkstiff.__version__`` shim) on the
+same inputs and stores its outputs under ``tests/golden/``;
+``tests/test_oracle_golden.py`` checks this restatement against those vectors
+and against the reference's own published fingerprints.
+
+What is restated (reference file:line):
+  psi1/psi2/psi3 ....................... rkstiff/etd.py:134-182
+  ETD4  coefficients / stages .......... rkstiff/etd4.py:87-139 / 152-175
+  ETD34 coefficients / stages .......... rkstiff/etd34.py:84-149 / 162-191
+  ETD5  coefficients / stages .......... rkstiff/etd5.py:115-203 / 219-261
+  ETD35 coefficients / stages .......... rkstiff/etd35.py:157-288 / 301-345
+  IF4 / IF34 coefficients / stages ..... rkstiff/if4.py:72-122, if34.py:81-131
+  IF45DP coefficients / stages ......... rkstiff/if45dp.py:183-238 / 112-181
+  adaptive controller .................. rkstiff/solveras.py:336-554
+  adaptive / fixed evolve loops ........ rkstiff/solveras.py:556-650, solvercs.py:191-279
+
+The restatement is table driven (one coefficient builder per tableau family and
+one generic stage interpreter) instead of one class per method, but evaluates
+the same NumPy expressions in the same association order so that it agrees with
+the reference to rounding and costs the same CPU time per step.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+ADAPTIVE = ("IF34", "ETD34", "ETD35", "IF45DP")
+FIXED = ("IF4", "ETD4", "ETD5")
+METHODS = FIXED + ADAPTIVE
+
+MAX_LOOPS = 50   # solveras.py:255
+MAX_S = 4.0      # solveras.py:256
+MIN_S = 0.25     # solveras.py:257
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+class MaxLoopsExceeded(OracleError):
+    pass
+
+
+class MinimumStepReached(OracleError):
+    pass
+
+
+@dataclass
+class Config:
+    """SolverConfig + ETDConfig scalars (solveras.py:71-94, etd.py:81-131)."""
+    epsilon: float = 1e-4
+    incr_f: float = 1.25
+    decr_f: float = 0.85
+    safety_f: float = 0.8
+    adapt_cutoff: float = 0.01
+    minh: float = 1e-16
+    modecutoff: float = 0.01
+    contour_points: int = 32
+    contour_radius: float = 1.0
+    if45dp_r4_fix: bool = False   # False reproduces the 17/1920 weight of if45dp.py:234
+
+
+# ----------------------------------------------------------------------------
+# psi functions, etd.py:148,165,182  (psi_r = r! * phi_r)
+# ----------------------------------------------------------------------------
+def psi1(z):
+    return (np.exp(z) - 1) / z
+
+
+def psi2(z):
+    return 2 * (np.exp(z) - 1 - z) / z ** 2
+
+
+def psi3(z):
+    return 6 * (np.exp(z) - 1 - z - z ** 2 / 2) / z ** 3
+
+
+def _psi_table(z: np.ndarray, h: float, cfg: Config, wanted: Sequence[Tuple[Callable, str, float]]):
+    """Evaluate h*psi_k(c*z) for every (func, key, c) in ``wanted``.
+
+    Modes with |z| >= modecutoff use the closed forms; the others the mean over
+    the M contour nodes R*exp(2 pi i (j+1/2)/M) of psi_k(c*(z+r_j))
+    (etd35.py:185-288, etd4.py:91-139).
+    """
+    small = np.abs(z) < cfg.modecutoff
+    out = {key: np.zeros(z.shape, dtype=np.complex128) for _, key, _ in wanted}
+    big = ~small
+    if np.any(big):
+        zb = z[big]
+        for func, key, c in wanted:
+            if c == 1.0:
+                arg = zb
+            elif c == 0.75:
+                arg = 3 * zb / 4
+            else:
+                arg = zb * c          # exact scaling by 1/2, 1/4
+            out[key][big] = h * func(arg)
+    if np.any(small):
+        zs = z[small]
+        m = cfg.contour_points
+        nodes = cfg.contour_radius * np.exp(2j * np.pi * np.arange(0.5, m) / m)
+        zz = zs[:, None] + nodes[None, :]
+        for func, key, c in wanted:
+            if c == 1.0:
+                arg = zz
+            elif c == 0.75:
+                arg = 3 * zz / 4
+            else:
+                arg = zz * c
+            out[key][small] = h * np.sum(func(arg), axis=1) / m
+    return out
+
+
+def coefficients(method: str, lin_op: np.ndarray, h: float, cfg: Config) -> Dict[str, np.ndarray]:
+    """All per-mode arrays a trial step of ``method`` needs for step size ``h``."""
+    if method in ("ETD4", "ETD34"):
+        L = lin_op.astype(np.complex128, copy=False)
+        z = h * L
+        c = {"E": np.exp(z), "E2": np.exp(z / 2)}
+        p = _psi_table(z, h, cfg, [(psi1, "p1h", 0.5), (psi2, "p2h", 0.5),
+                                   (psi1, "p1", 1.0), (psi2, "p2", 1.0), (psi3, "p3", 1.0)])
+        c["a21"] = 0.5 * p["p1h"]
+        c["a31"] = 0.5 * (p["p1h"] - p["p2h"])
+        c["a32"] = 0.5 * p["p2h"]
+        c["a41"] = p["p1"] - p["p2"]
+        c["a43"] = p["p2"]
+        c["a51"] = p["p1"] - 3.0 / 2 * p["p2"] + 2.0 / 3 * p["p3"]
+        c["a52"] = p["p2"] - 2.0 / 3 * p["p3"]
+        c["a54"] = -(1.0 / 2) * p["p2"] + 2.0 / 3 * p["p3"]
+        return c
+    if method in ("ETD5", "ETD35"):
+        L = lin_op.astype(np.complex128, copy=False)
+        z = h * L
+        c = {"E14": np.exp(z / 4.0), "E12": np.exp(z / 2.0), "E34": np.exp(3.0 * z / 4.0), "E": np.exp(z)}
+        p = _psi_table(z, h, cfg, [(psi1, "p1q", 0.25), (psi2, "p2q", 0.25),
+                                   (psi1, "p1h", 0.5), (psi2, "p2h", 0.5),
+                                   (psi1, "p1t", 0.75), (psi2, "p2t", 0.75),
+                                   (psi1, "p1", 1.0), (psi2, "p2", 1.0), (psi3, "p3", 1.0)])
+        c["a21"] = p["p1q"] / 4.0
+        c["a31"] = (p["p1q"] - p["p2q"] / 2.0) / 4.0
+        c["a32"] = p["p2q"] / 8.0
+        c["a41"] = (p["p1h"] - p["p2h"]) / 2.0
+        c["a43"] = p["p2h"] / 2.0
+        c["a51"] = 3.0 * (p["p1t"] - 3.0 * p["p2t"] / 4.0) / 4.0
+        c["a52"] = -3 * p["p1t"] / 8.0
+        c["a54"] = 9 * p["p2t"] / 16.0
+        c["a61"] = (-77 * p["p1"] + 59 * p["p2"]) / 42.0
+        c["a62"] = 8 * p["p1"] / 7.0
+        c["a63"] = (111 * p["p1"] - 87 * p["p2"]) / 28.0
+        c["a65"] = (-47 * p["p1"] + 143 * p["p2"]) / 84.0
+        c["a71"] = 7 * (257 * p["p1"] - 497 * p["p2"] + 270 * p["p3"]) / 2700
+        c["a73"] = (1097 * p["p1"] - 467 * p["p2"] - 150 * p["p3"]) / 1350
+        c["a74"] = 2 * (-49 * p["p1"] + 199 * p["p2"] - 135 * p["p3"]) / 225
+        c["a75"] = (-313 * p["p1"] + 883 * p["p2"] - 90 * p["p3"]) / 1350
+        c["a76"] = (509 * p["p1"] - 2129 * p["p2"] + 1830 * p["p3"]) / 2700
+        return c
+    if method in ("IF4", "IF34"):
+        z = h * lin_op                    # no complex cast: real L stays real (if34.py:71)
+        return {"E": np.exp(z), "E2": np.exp(z / 2)}
+    if method == "IF45DP":
+        z = h * lin_op
+        E15, E310, E45, E89, E = (np.exp(z / 5), np.exp(3 * z / 10), np.exp(4 * z / 5),
+                                  np.exp(8 * z / 9), np.exp(z))
+        E710, E19 = np.exp(7 * z / 10), np.exp(z / 9)
+        c = {"E15": E15, "E310": E310, "E45": E45, "E89": E89, "E": E}
+        c["a21"] = h * E15 / 5.0
+        c["a31"] = 3 * h * E310 / 40.0
+        c["a32"] = 9 * h * np.exp(z / 10) / 40.0
+        c["a41"] = 44 * h * E45 / 45.0
+        c["a42"] = -56 * h * np.exp(3 * z / 5) / 15.0
+        c["a43"] = 32 * h * np.exp(z / 2) / 9.0
+        c["a51"] = 19372 * h * E89 / 6561.0
+        c["a52"] = -25360 * h * np.exp(31 * z / 45) / 2187.0
+        c["a53"] = 64448.0 * h * np.exp(53 * z / 90) / 6561.0
+        c["a54"] = -212 * h * np.exp(4 * z / 45) / 729.0
+        c["a61"] = 9017 * h * E / 3168.0
+        c["a62"] = -355 * h * E45 / 33.0
+        c["a63"] = 46732 * h * E710 / 5247.0
+        c["a64"] = 49 * h * E15 / 176.0
+        c["a65"] = -5103 * h * E19 / 18656.0
+        c["a71"] = 35 * h * E / 384.0
+        c["a73"] = 500 * h * E710 / 1113.0
+        c["a74"] = 125 * h * E15 / 192.0
+        c["a75"] = -2187 * h * E19 / 6784.0
+        c["a76"] = 11 * h / 84.0
+        c["r1"] = h * 71 * E / 57600.0
+        c["r3"] = -71 * h * E710 / 16695.0
+        r4_num = 71 if cfg.if45dp_r4_fix else 17          # if45dp.py:234 ships 17
+        c["r4"] = r4_num * h * E15 / 1920.0
+        c["r5"] = -17253 * h * E19 / 339200.0
+        c["r6"] = 22 * h / 525.0
+        c["r7"] = -h / 40.0
+        return c
+    raise ValueError(f"unknown method {method}")
+
+
+# ----------------------------------------------------------------------------
+# Stage passes.  Each returns (u_new, err_or_None) and updates the N-buffers.
+# ----------------------------------------------------------------------------
+def _stages_krogstad(c, nl, u, N):
+    """ETD4 / ETD34 tableau (etd4.py:167-173, etd34.py:182-188).  N[1] must hold N(u)."""
+    k = c["E2"] * u + c["a21"] * N[1]
+    N[2] = nl(k)
+    k = c["E2"] * u + c["a31"] * N[1] + c["a32"] * N[2]
+    N[3] = nl(k)
+    k = c["E"] * u + c["a41"] * N[1] + c["a43"] * N[3]
+    N[4] = nl(k)
+    k = c["E"] * u + c["a51"] * N[1] + c["a52"] * (N[2] + N[3]) + c["a54"] * N[4]
+    return k
+
+
+def _stages_etd5(c, nl, u, N):
+    """ETD5 / ETD35 tableau (etd5.py:236-258, etd35.py:320-343)."""
+    k = c["E14"] * u + c["a21"] * N[1]
+    N[2] = nl(k)
+    k = c["E14"] * u + c["a31"] * N[1] + c["a32"] * N[2]
+    N[3] = nl(k)
+    k = c["E12"] * u + c["a41"] * N[1] + c["a43"] * N[3]
+    N[4] = nl(k)
+    k = c["E34"] * u + c["a51"] * N[1] + c["a52"] * (N[2] - N[3]) + c["a54"] * N[4]
+    N[5] = nl(k)
+    k = (c["E"] * u + c["a61"] * N[1] + c["a62"] * (N[2] - 3 * N[4] / 2.0)
+         + c["a63"] * N[3] + c["a65"] * N[5])
+    N[6] = nl(k)
+    k = (c["E"] * u + c["a71"] * N[1] + c["a73"] * N[3] + c["a74"] * N[4]
+         + c["a75"] * N[5] + c["a76"] * N[6])
+    return k
+
+
+def _stages_if4(c, nl, u, N, h):
+    """RK4 in integrating-factor form (if4.py:112-120, if34.py:120-128)."""
+    E, E2 = c["E"], c["E2"]
+    k = E2 * u + h * E2 * N[1] / 2.0
+    N[2] = nl(k)
+    k = E2 * u + h * N[2] / 2.0
+    N[3] = nl(k)
+    k = E * u + h * E2 * N[3]
+    N[4] = nl(k)
+    k = E * u + h * (E * N[1] / 6.0 + E2 * N[2] / 3.0 + E2 * N[3] / 3.0 + N[4] / 6.0)
+    return k
+
+
+def _stages_dp(c, nl, u, N):
+    """Dormand-Prince in IF form (if45dp.py:140-171)."""
+    k = c["E15"] * u + c["a21"] * N[1]
+    N[2] = nl(k)
+    k = c["E310"] * u + c["a31"] * N[1] + c["a32"] * N[2]
+    N[3] = nl(k)
+    k = c["E45"] * u + c["a41"] * N[1] + c["a42"] * N[2] + c["a43"] * N[3]
+    N[4] = nl(k)
+    k = c["E89"] * u + c["a51"] * N[1] + c["a52"] * N[2] + c["a53"] * N[3] + c["a54"] * N[4]
+    N[5] = nl(k)
+    k = (c["E"] * u + c["a61"] * N[1] + c["a62"] * N[2] + c["a63"] * N[3]
+         + c["a64"] * N[4] + c["a65"] * N[5])
+    N[6] = nl(k)
+    k = (c["E"] * u + c["a71"] * N[1] + c["a73"] * N[3] + c["a74"] * N[4]
+         + c["a75"] * N[5] + c["a76"] * N[6])
+    return k
+
+
+_Q = {"IF34": 4, "ETD34": 4, "ETD35": 4, "IF45DP": 5}   # if34.py:336 etd34.py:611 etd35.py:880 if45dp.py:240
+
+
+@dataclass
+class TrialRecord:
+    h: float          # step size tried
+    s: float          # controller scale factor
+    accepted: bool
+    t_after: float    # time after the trial (unchanged if rejected); NaN when driven by step()
+
+
+@dataclass
+class OracleSolver:
+    """One solver instance: mirrors the reference's public evolve()/step() semantics."""
+    method: str
+    lin_op: np.ndarray
+    nl_func: Callable[[np.ndarray], np.ndarray]
+    cfg: Config = field(default_factory=Config)
+
+    def __post_init__(self):
+        if self.method not in METHODS:
+            raise ValueError(self.method)
+        self.adaptive = self.method in ADAPTIVE
+        self.t: List[float] = []
+        self.u: List[np.ndarray] = []
+        self.log: List[TrialRecord] = []
+        self.nl_calls = 0
+        self.coeff_updates = 0
+        self._reset()
+
+    # -- state ---------------------------------------------------------------
+    def _reset(self):
+        self._h_coeff = None
+        self._coef = None
+        self._n1_ready = False
+        self._accept = False
+        self._N: Dict[int, np.ndarray] = {}
+
+    def reset(self):
+        self.t, self.u, self.log = [], [], []
+        self.nl_calls = 0
+        self.coeff_updates = 0
+        self._reset()
+
+    def _nl(self, v):
+        self.nl_calls += 1
+        return self.nl_func(v)
+
+    def _update_coeffs(self, h):
+        if h == self._h_coeff:                      # exact float equality, etd35.py:851
+            return
+        self._h_coeff = h
+        self._coef = coefficients(self.method, self.lin_op, h, self.cfg)
+        self.coeff_updates += 1
+
+    # -- one pass over the stages -------------------------------------------
+    def trial(self, u, h):
+        """Stage pass for step size h. Returns u_new (fixed) or (u_new, err) (adaptive)."""
+        self._update_coeffs(h)
+        c, N, m = self._coef, self._N, self.method
+        if m in ("ETD4", "ETD5", "IF4"):
+            if not self._n1_ready:
+                N[1] = self._nl(u)
+                self._n1_ready = True
+            if m == "ETD4":
+                k = _stages_krogstad(c, self._nl, u, N)
+            elif m == "ETD5":
+                k = _stages_etd5(c, self._nl, u, N)
+            else:
+                k = _stages_if4(c, self._nl, u, N, h)
+            N[1] = self._nl(k)                      # etd4.py:174, etd5.py:260, if4.py:121
+            return k
+        if m == "ETD35":
+            if not self._n1_ready:
+                N[1] = self._nl(u)
+                self._n1_ready = True
+            if self._accept:                        # not FSAL: etd35.py:317-318
+                N[1] = self._nl(u)
+            k = _stages_etd5(c, self._nl, u, N)
+            err = c["a75"] * (-N[1] + 4 * N[3] - 6 * N[4] + 4 * N[5] - N[6])
+            return k, err
+        if m == "ETD34":
+            if not self._n1_ready:
+                N[1] = self._nl(u)
+                self._n1_ready = True
+            if self._accept:
+                N[1] = N[5].copy()                  # FSAL, etd34.py:179-180
+            k = _stages_krogstad(c, self._nl, u, N)
+            N[5] = self._nl(k)
+            return k, c["a54"] * (N[4] - N[5])
+        if m == "IF34":
+            if not self._n1_ready:
+                N[1] = self._nl(u)
+                self._n1_ready = True
+            if self._accept:
+                N[1] = N[5].copy()                  # if34.py:117-118
+            k = _stages_if4(c, self._nl, u, N, h)
+            N[5] = self._nl(k)
+            return k, h * (N[4] - N[5]) / 6.0
+        # IF45DP
+        if not self._n1_ready:
+            N[1] = self._nl(u)
+            self._n1_ready = True
+        elif self._accept:
+            N[1] = N[7].copy()                      # if45dp.py:137-138
+        k = _stages_dp(c, self._nl, u, N)
+        N[7] = self._nl(k)
+        err = (c["r1"] * N[1] + c["r3"] * N[3] + c["r4"] * N[4] + c["r5"] * N[5]
+               + c["r6"] * N[6] + c["r7"] * N[7])
+        return k, err
+
+    # -- controller, solveras.py:412-554 ------------------------------------
+    def compute_s(self, u, err):
+        mag = np.abs(u)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            idx = mag / mag.max() > self.cfg.adapt_cutoff
+            tol = self.cfg.epsilon * np.linalg.norm(u[idx])
+            return self.cfg.safety_f * np.power(tol / np.linalg.norm(err[idx]), 1.0 / _Q[self.method])
+
+    def step(self, u, h_suggest):
+        if not self.adaptive:
+            assert h_suggest >= 0.0
+            return self.trial(u, h_suggest)
+        h = h_suggest
+        assert h >= 0.0
+        loops = 0
+        while True:
+            unew, err = self.trial(u, h)
+            s = self.compute_s(unew, err)
+            if np.isinf(s) or np.isnan(s) or s < 1.0:
+                self._accept = False
+                self.log.append(TrialRecord(h, float(s), False, float("nan")))
+                if np.isinf(s) or np.isnan(s):
+                    h = MIN_S * h
+                else:
+                    sc = min(max(s, MIN_S), self.cfg.decr_f)
+                    h = sc * h
+            else:
+                self._accept = True
+                self.log.append(TrialRecord(h, float(s), True, float("nan")))
+                sc = min(s, MAX_S)
+                h_next = sc * h if sc > self.cfg.incr_f else h
+                return unew, h, h_next
+            loops += 1
+            if loops > MAX_LOOPS:
+                raise MaxLoopsExceeded("too many attempts")
+            if h < self.cfg.minh:
+                raise MinimumStepReached("minimum step size reached")
+
+    # -- drivers -------------------------------------------------------------
+    def evolve(self, u, t0, tf, h=None, store_data=True, store_freq=1):
+        self.reset()
+        tc = t0
+        if store_data:
+            self.t.append(t0)
+            self.u.append(u)
+        count = 0
+        if self.adaptive:
+            if h is None:
+                h = (tf - t0) / 100.0
+            if tc + h > tf:
+                h = tf - tc
+            while tc < tf:
+                u, h, h_next = self.step(u, h)
+                tc += h
+                self.log[-1].t_after = tc
+                count += 1
+                h = tf - tc if tc + h_next > tf else h_next
+                if store_data and count % store_freq == 0:
+                    self.t.append(tc)
+                    self.u.append(u)
+            return u
+        if tc + h > tf:
+            raise ValueError("Step size h must be <= (tf - t0)")
+        while tc < tf:                               # float-accumulated: solvercs.py:258-261
+            u = self.step(u, h)
+            tc += h
+            count += 1
+            if store_data and count % store_freq == 0:
+                self.t.append(tc)
+                self.u.append(u)
+        return u
