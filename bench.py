@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""Benchmark of the rkstiff_b200 stepping engine (contract: see the task statement / DESIGN.md 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3]
+
+Workloads (BASELINE.json configs):
+  cfg2 (default, the configuration the metric is quoted on): NLS 1-D, n = 8192 complex128, ETD35
+        adaptive (epsilon 1e-6), a batch of 4096 independent soliton trajectories PER GPU sharing
+        one dt.  A "step" is one trial step (accepted or rejected) of the whole batch.
+  cfg3: KS 1-D rfft n = 1024, ETD4 fixed step h = 0.05, 65536 trajectories per GPU.
+Metric: real-space grid points x RK (trial) steps per second, whole job over all GPUs.
+N > 1: one process per GPU under torchrun; the batch is sharded by rank (weak scaling, 4096 or
+65536 trajectories per GPU) and, for the adaptive workload, the three error-norm scalars are
+all-reduced (MAX, then SUM) over NCCL so that every rank takes the same accept/reject decision.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_NLS, B_NLS = 8192, 4096
+N_KS, B_KS = 1024, 65536
+METRIC = "rk_step_gridpoints_per_s"
+UNIT = "gridpoint*steps/s"
+
+# algorithmic bytes per complex element per trial (SURVEY.md 8d / DESIGN.md 4)
+BYTES_PER_ELEM = {"ETD35": 736, "ETD4": 400}
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic inputs (generated with torch on the device; the oracle gets a slice of the same)
+# ------------------------------------------------------------------------------------------
+def nls_inputs(torch, batch, device, seed=2):
+    n, w = N_NLS, 40.0 * math.pi
+    dx = 2 * w / n
+    x = torch.arange(n, dtype=torch.float64, device=device) * dx - w
+    kx = 2 * math.pi * torch.fft.fftfreq(n, d=dx, dtype=torch.float64, device=device)
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    eta = (0.5 + torch.rand(batch, 1, generator=g, dtype=torch.float64)).to(device)
+    x0 = (-20.0 + 40.0 * torch.rand(batch, 1, generator=g, dtype=torch.float64)).to(device)
+    c = (-0.5 + torch.rand(batch, 1, generator=g, dtype=torch.float64)).to(device)
+    u0 = eta / torch.cosh(eta * (x[None, :] - x0)) * torch.exp(1j * c * x[None, :])
+    return kx, torch.fft.fft(u0, dim=-1)
+
+
+def ks_inputs(torch, batch, device, seed=0):
+    n = N_KS
+    dx = 32.0 * math.pi / n
+    x = torch.arange(n, dtype=torch.float64, device=device) * dx
+    kx = 2 * math.pi * torch.fft.rfftfreq(n, d=dx, dtype=torch.float64, device=device)
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    phi = (2 * math.pi * torch.rand(batch, 1, generator=g, dtype=torch.float64)).to(device)
+    u0 = torch.cos(x[None, :] / 16 + phi) * (1.0 + torch.sin(x[None, :] / 16))
+    return kx, torch.fft.rfft(u0, dim=-1)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.tmp,
+                                         stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons)}
+        try:
+            os.unlink(self.tmp.name)
+        except OSError:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (NumPy port of the reference path), bounded sample
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    workload, rows, seed, steps, warmup = args
+    import numpy as np
+    from oracle import problems
+    from oracle.rk_oracle import Config, OracleSolver
+    if workload == "cfg2":
+        p = problems.nls(N_NLS, batch=rows, seed=seed)
+        sol = OracleSolver("ETD35", p.lin_op, p.nl_func, Config(epsilon=1e-6))
+        u, h = p.u0, 0.01
+        n = N_NLS
+        for _ in range(warmup):
+            u, _, h = sol.step(u, h)
+        sol.log.clear()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            u, _, h = sol.step(u, h)
+        dt = time.perf_counter() - t0
+        trials = len(sol.log)
+    else:
+        p = problems.ks(N_KS, batch=rows, seed=seed)
+        sol = OracleSolver("ETD4", p.lin_op, p.nl_func)
+        u, n = p.u0, N_KS
+        for _ in range(warmup):
+            u = sol.step(u, 0.05)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            u = sol.step(u, 0.05)
+        dt = time.perf_counter() - t0
+        trials = steps
+    assert np.isfinite(u).all()
+    return trials * rows * n, dt
+
+
+def cpu_baseline(workload, cores, steps, warmup, rows):
+    """gp*steps/s of the oracle on `cores` processes, each stepping its own `rows`-trajectory shard."""
+    import multiprocessing as mp
+    jobs = [(workload, rows, 100 + i, steps, warmup) for i in range(cores)]
+    if cores == 1:
+        res = [_cpu_worker(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(cores) as pool:
+            res = pool.map(_cpu_worker, jobs)
+    work = sum(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    return work / wall, wall
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port: the reference is
+    pure Python/NumPy and cannot travel to the GPU box) on all host cores, same metric and config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    cores = os.cpu_count() or 1
+    rows = 16 if args.workload == "cfg2" else 256
+    steps = max(1, min(args.steps, 12 if args.workload == "cfg2" else 40))
+    warm = max(1, min(args.warmup, 2))
+    value, wall = cpu_baseline(args.workload, cores, steps, warm, rows)
+    sample = (f"{cores} processes x {rows} trajectories x {steps} steps of the oracle "
+              f"({'NLS n=8192 ETD35 adaptive' if args.workload == 'cfg2' else 'KS n=1024 ETD4 h=0.05'})")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.workload, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(workload, gpus):
+    if workload == "cfg2":
+        return {"workload": "cfg2: NLS 1-D n=8192 complex128, ETD35 adaptive eps=1e-6, 4096 soliton trajectories "
+                            "per GPU, one shared dt", "method": "ETD35", "n": N_NLS, "batch_per_gpu": B_NLS,
+                "parallelism": f"batch-sharded x{gpus}", "l2": "working set 5.4 GB >> 126 MB L2 (no flush needed)"}
+    return {"workload": "cfg3: KS 1-D rfft n=1024, ETD4 fixed step h=0.05, 65536 trajectories per GPU",
+            "method": "ETD4", "n": N_KS, "batch_per_gpu": B_KS, "parallelism": f"batch-sharded x{gpus}",
+            "l2": "working set 3.2 GB >> 126 MB L2 (no flush needed)"}
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def time_kernel(torch, fn, reps):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / reps
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import rkstiff_b200 as rk
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: rkstiff_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+        group = dist.group.WORLD
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+
+    K, W = args.steps, max(3, args.warmup)
+    if args.workload == "cfg2":
+        method, n, batch, n_c = "ETD35", N_NLS, B_NLS, N_NLS
+        kx, u0 = nls_inputs(torch, batch, device, seed=2 + rank)
+        lin, nl = rk.models.nls_ops(kx, gamma=2.0)
+        sol = rk.ETD35(lin, nl, config=rk.SolverConfig(epsilon=1e-6), group=group)
+    else:
+        method, n, batch, n_c = "ETD4", N_KS, B_KS, N_KS // 2 + 1
+        kx, u0 = ks_inputs(torch, batch, device, seed=rank)
+        lin, nl = rk.models.ks_ops(kx)
+        sol = rk.ETD4(lin, nl, group=group)
+    eng = sol._get_engine(u0)
+
+    # ---- device-resident throughput: K steps, inputs already in HBM --------------------------
+    if args.workload == "cfg2":
+        eng.begin(0.0, 1e9, 0.01, 0, False)
+        eng.set_u(u0)
+        run = eng.run_trials
+    else:
+        eng.begin(0.0, 0.0, 0.05, 0, True)
+        eng.ensure_fixed_coeffs(0.05)
+        eng.set_u(u0)
+        run = eng.run_fixed
+    run(W)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = eng.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(K)
+    e1.record()
+    barrier()
+    secs = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    launches = eng.launches() - l0
+    clocks = sampler.stop() if sampler else None
+    if args.workload == "cfg2":
+        c = eng.read_ctrl()
+        assert c.status == 0 and c.trial_count == K + W, (c.status, c.trial_count)
+        accepted = int(c.step_count)
+    else:
+        accepted = K
+        assert torch.isfinite(eng.get_u().real).all()
+    value = world * batch * n * K / secs
+
+    # ---- per-kernel roofline (each kernel timed alone on the launching stream) ---------------
+    elems = batch * n_c
+    reps = 10
+    kern = {}
+    S = eng.stages
+    t_nl = time_kernel(torch, lambda: eng.nl(2), reps)
+    kern["nl (K4 fused spectral nonlinearity)"] = (t_nl, 2 * 16 * elems, S)
+    stage_bytes = {"ETD35": [3, 4, 4, 6, 7, 8], "ETD4": [3, 4, 4, 6]}[method]   # passes (reads + writes)
+    for s in range(1, S + 1):
+        if method == "ETD4" and s == S:
+            continue            # in place: timing it alone would overwrite u repeatedly (harmless, but skip)
+        t = time_kernel(torch, lambda s=s: eng.stage(s), reps)
+        kern[f"stage{s} (K1 combine)"] = (t, stage_bytes[s - 1] * 16 * elems, 1)
+    if method == "ETD35":
+        t = time_kernel(torch, lambda: rk._abi.check(rk._abi.lib.rks_error_sums(eng.plan, eng.st)), reps)
+        kern["norm (K3 masked norms)"] = (t, 2 * 16 * elems, 1)
+    shares = {k: v[0] * v[2] for k, v in kern.items()}
+    top = max(shares, key=shares.get)
+    t_top, b_top, _ = kern[top]
+    roofline = {"bound": "hbm", "kernel": top, "achieved": b_top / t_top / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                "frac": b_top / t_top / 1e9 / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "share_of_step": shares[top] / sum(shares.values()),
+                "whole_step": {"algorithmic_bytes_per_elem": BYTES_PER_ELEM[method],
+                               "achieved": BYTES_PER_ELEM[method] * elems * K / secs / 1e9,
+                               "frac": BYTES_PER_ELEM[method] * elems * K / secs / 1e9 / peak_gbs},
+                "kernels": {k: {"us": v[0] * 1e6, "GBps": v[1] / v[0] / 1e9, "frac": v[1] / v[0] / 1e9 / peak_gbs,
+                                "launches_per_step": v[2]} for k, v in kern.items()}}
+
+    # ---- end to end through the public API: host buffers in, host buffers out ----------------
+    u_host = torch.empty(u0.shape, dtype=u0.dtype, pin_memory=True)
+    u_host.copy_(u0)
+    out_host = torch.empty(u0.shape, dtype=u0.dtype, pin_memory=True)
+    state_bytes = u0.numel() * 16
+
+    def e2e_once():
+        ud = u_host.to(device, non_blocking=True)
+        if args.workload == "cfg2":
+            uf = sol.evolve(ud, 0.0, 1.0, store_data=False)
+            steps_done = len(sol.trial_log)
+        else:
+            uf = sol.evolve(ud, 0.0, 2.0, 0.05, store_data=False)
+            steps_done, tc = 0, 0.0
+            while tc < 2.0:                      # the reference's float-accumulated loop count
+                tc += 0.05
+                steps_done += 1
+        out_host.copy_(uf, non_blocking=True)
+        torch.cuda.synchronize()
+        return steps_done
+
+    e2e_once()
+    barrier()
+    t0 = time.perf_counter()
+    reps_e2e, steps_e2e = 2, 0
+    for _ in range(reps_e2e):
+        steps_e2e += e2e_once()
+    barrier()
+    e2e_secs = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": world * batch * n * steps_e2e / e2e_secs, "unit": UNIT,
+           "h2d_bytes_per_step": state_bytes * reps_e2e / steps_e2e, "d2h_bytes_per_step": state_bytes * reps_e2e / steps_e2e,
+           "call": ("ETD35.evolve(u0, 0, 1)" if args.workload == "cfg2" else "ETD4.evolve(u0, 0, 2, h=0.05)")
+                   + " with u0 copied from pinned host memory and the final state copied back, per call",
+           "steps_per_call": steps_e2e / reps_e2e, "h2d_bytes_per_call": state_bytes, "d2h_bytes_per_call": state_bytes}
+
+    # ---- CPU baseline on rank 0, N = 1 only ---------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rows, cs, cw = (16, 6, 1) if args.workload == "cfg2" else (256, 40, 2)
+        v, wall = cpu_baseline(args.workload, 1, cs, cw, rows)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"oracle (NumPy port of the reference path), 1 process, {rows} trajectories x {cs} steps, "
+                         f"{wall:.1f} s"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": 1e3 * secs / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": workload_config(args.workload, world),
+                "accepted_steps": accepted, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

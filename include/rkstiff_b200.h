@@ -1,0 +1,190 @@
+/*
+ * rkstiff_b200 -- C ABI of the B200 stepping engine for rkstiff's diagonal ETD/IF
+ * Runge-Kutta hot path.
+ *
+ * The reference (whalenpt/rkstiff) is a pure-Python class library with no FFI.  The seam
+ * this library replaces is the per-method "strategy" object every public solver class
+ * holds (`self._method`), whose interface is
+ *     update_coeffs(h)            rkstiff/etd35.py:157, etd34.py:84, etd4.py:87, etd5.py:115,
+ *                                 if34.py:81, if4.py:72, if45dp.py:183
+ *     n1_init(u) / stage_init(u)  rkstiff/etd4.py:141, if34.py:95, etd35.py:290
+ *     update_stages(u[,h][,acc])  rkstiff/etd4.py:152, etd5.py:219, etd34.py:162, etd35.py:301,
+ *                                 if4.py:96, if34.py:99, if45dp.py:112
+ * plus the controller the adaptive base class runs around it
+ *     _compute_s / _reject_step_size / _accept_step_size / step / evolve
+ *                                 rkstiff/solveras.py:412-455, 457-506, 508-554, 336-410, 556-650
+ * and the spectral nonlinear closures the demos/models pass as nl_func
+ *                                 rkstiff/models.py:140-143, 189-192; README.md:94-97; demos/nls.ipynb.
+ *
+ * Conventions
+ *  - plain C, no torch/C++ types; all array arguments are DEVICE pointers unless named *_host.
+ *  - every state array is complex128, row-major (batch, n_c); n_c = modes per trajectory.
+ *  - lin_op is float64 or complex128 with lin_elems == n_c (shared by the batch) or
+ *    lin_elems == batch*n_c ("shaped like u").
+ *  - every call returns 0 on success or a negative rks_status; rks_last_error() gives text.
+ *  - a plan is bound to one device and is not thread safe; all work is enqueued on the
+ *    cudaStream_t passed in (void* here so that the header needs no CUDA include).
+ *  - device-side failures of the adaptive loop are reported through rks_ctrl_host.status,
+ *    never through return codes (no host sync inside the stepping calls).
+ */
+#ifndef RKSTIFF_B200_H
+#define RKSTIFF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RKS_ABI_VERSION 1
+
+/* method ids (one per public reference class) */
+enum rks_method {
+    RKS_IF4 = 0,    /* rkstiff/if4.py    IF4    fixed step  */
+    RKS_ETD4 = 1,   /* rkstiff/etd4.py   ETD4   fixed step  */
+    RKS_ETD5 = 2,   /* rkstiff/etd5.py   ETD5   fixed step  */
+    RKS_IF34 = 3,   /* rkstiff/if34.py   IF34   adaptive    */
+    RKS_ETD34 = 4,  /* rkstiff/etd34.py  ETD34  adaptive    */
+    RKS_ETD35 = 5,  /* rkstiff/etd35.py  ETD35  adaptive    */
+    RKS_IF45DP = 6  /* rkstiff/if45dp.py IF45DP adaptive    */
+};
+
+/* fused spectral nonlinearities (K4) */
+enum rks_model {
+    RKS_MODEL_NONE = 0,
+    RKS_MODEL_UUX_RFFT = 1, /* N = -c * rfft(irfft(u^) * irfft(i kx u^)); KS/Burgers c=1, KdV c=6
+                               models.py:140-143,189-192, README.md:94-97. n_c = n/2+1, params[0]=c */
+    RKS_MODEL_NLS_FFT = 2   /* N = i*gamma * fft(|ifft u^|^2 ifft u^); demos/nls.ipynb. n_c = n, params[0]=gamma */
+};
+
+enum rks_status {
+    RKS_OK = 0,
+    RKS_ERR_ARG = -1,
+    RKS_ERR_CUDA = -2,
+    RKS_ERR_UNSUPPORTED = -3,
+    RKS_ERR_WORKSPACE = -4
+};
+
+/* values of rks_ctrl_host.status (device controller state) */
+enum rks_ctrl_status {
+    RKS_CTRL_RUNNING = 0,
+    RKS_CTRL_DONE = 1,       /* evolve: t >= tf reached; step mode: trial accepted */
+    RKS_CTRL_MAX_LOOPS = 2,  /* solveras.py:399-403 -> MaxLoopsExceeded      */
+    RKS_CTRL_MIN_STEP = 3    /* solveras.py:405-410 -> MinimumStepReached    */
+};
+
+/* SolverConfig (solveras.py:71-94) + ETDConfig (etd.py:81-131) scalars */
+typedef struct rks_config {
+    double epsilon, incr_f, decr_f, safety_f, adapt_cutoff, minh;
+    double modecutoff, contour_radius;
+    int32_t contour_points;
+    int32_t if45dp_r4_fix; /* 0 (default): r4 = 17h e^{z/5}/1920 as shipped (if45dp.py:234); 1: 71/1920 */
+} rks_config;
+
+/* host copy of the device control block */
+typedef struct rks_ctrl_host {
+    double h;          /* step size the next trial will use                                  */
+    double h_last;     /* step size of the last accepted trial (step(): "h" return value)     */
+    double h_coeff;    /* step size the coefficient arrays were built for                     */
+    double t, tf;
+    double s_last;     /* last controller scale factor                                        */
+    int64_t step_count;  /* accepted steps since rks_begin                                    */
+    int64_t trial_count; /* all trials since rks_begin                                        */
+    int64_t nl_evals;    /* fused NL evaluations actually executed (predicated ones excluded) */
+    int64_t coeff_updates;
+    int32_t status;    /* rks_ctrl_status */
+    int32_t accept;    /* last trial accepted                                                */
+    int32_t numloops;
+    int32_t u_sel;     /* which of the two state buffers holds the current u                  */
+    int32_t n_sel;     /* FSAL role swap of N1 / N_last                                       */
+    int32_t need_n1;
+    int32_t log_count;   /* trial records written since rks_begin (ring of RKS_LOG_CAP)       */
+    int32_t snap_count;  /* snapshots written since rks_begin                                 */
+} rks_ctrl_host;
+
+#define RKS_LOG_CAP 4096
+typedef struct rks_trial_rec {
+    double h;        /* step size tried */
+    double s;        /* scale factor    */
+    double t_after;  /* time after the trial */
+    int32_t accepted;
+    int32_t pad;
+} rks_trial_rec;
+
+typedef struct rks_plan rks_plan;
+
+int rks_abi_version(void);
+const char* rks_last_error(void);
+
+/* number of stage-combine kernels S and of N-buffers for a method */
+int rks_num_stages(int method);
+int rks_num_nl_buffers(int method);
+int rks_is_adaptive(int method);
+
+/* bytes of device workspace a plan needs (caller allocates; 256-byte aligned) */
+size_t rks_workspace_bytes(int method, int64_t batch, int64_t n_c, int64_t lin_elems, int lin_is_complex);
+
+/* Build a plan.  lin_op is copied into the workspace.  Replaces the strategy-object
+ * constructors (etd35.py:115-155 etc.). */
+int rks_plan_create(rks_plan** out, int method, int64_t batch, int64_t n_c, const void* lin_op,
+                    int lin_is_complex, int64_t lin_elems, const rks_config* cfg, void* workspace,
+                    size_t workspace_bytes, void* stream);
+void rks_plan_destroy(rks_plan* plan);
+
+/* SolverConfig/ETDConfig are read live by the reference on every trial (solveras.py:452-454) */
+int rks_set_config(rks_plan* plan, const rks_config* cfg, void* stream);
+
+/* Select the fused nonlinearity: n = real-space points per trajectory, kx = wavenumber array
+ * (n_c doubles, device; copied).  Afterwards rks_nl() and rks_run_*() are available. */
+int rks_set_model(rks_plan* plan, int model, int64_t n, const double* kx, const double* params_host,
+                  int nparams, void* stream);
+
+/* (re)start: clears FSAL state / cached h (BaseSolver*.reset + _reset, solveras.py:306-312,
+ * etd35.py:836-840) and arms the controller.  step_mode != 0: stop after the first accepted
+ * trial (step()); otherwise integrate until t >= tf (evolve(), solveras.py:605-650). */
+int rks_begin(rks_plan* plan, double t0, double tf, double h, int64_t store_freq, int step_mode,
+              int keep_fsal, void* stream);
+int rks_set_h(rks_plan* plan, double h, void* stream);
+
+/* state in/out (device-to-device copies of batch*n_c complex128) */
+int rks_set_u(rks_plan* plan, const void* u, void* stream);
+int rks_get_u(rks_plan* plan, void* u_out, void* stream);   /* current u (after accept: the new state) */
+
+/* K2: coefficient arrays for ctrl.h; no-op on device when ctrl.h == ctrl.h_coeff (etd35.py:851) */
+int rks_update_coeffs(rks_plan* plan, void* stream);
+/* K1: stage-combine kernel `stage` in 1..S; the last one also emits err (ETD35) and max|u+|^2 */
+int rks_stage(rks_plan* plan, int stage, void* stream);
+/* K4: N_j = N(input_j), j in 1..S+1 (see DESIGN.md for the input of each j); predicated on device */
+int rks_nl(rks_plan* plan, int j, void* stream);
+/* for caller-supplied nl_func: device pointers valid for the roles last read by rks_read_ctrl */
+void* rks_nl_input(rks_plan* plan, int j);
+void* rks_nl_output(rks_plan* plan, int j);
+/* K3: masked norms -> s -> accept/reject -> new h, t, roles, status, log record */
+int rks_error_control(rks_plan* plan, void* stream);
+/* K3 split for multi-GPU shared-dt ensembles: local partial results live in three doubles
+ * (max|u+|^2, sum|u+|^2, sum|err|^2) the caller all-reduces between the calls. */
+int rks_error_sums(rks_plan* plan, void* stream);
+int rks_controller(rks_plan* plan, void* stream);
+double* rks_reduction_scalars(rks_plan* plan);   /* device ptr to {umax2, sum_u2, sum_e2} */
+
+/* whole trials / steps with the fused nonlinearity, no host sync */
+int rks_run_trials(rks_plan* plan, int ntrials, void* snap_ring, double* snap_t, int snap_cap, void* stream);
+int rks_run_fixed(rks_plan* plan, int nsteps, void* stream);
+
+/* snapshot ring: copies the accepted state into ring[(snap_count-1) % cap] when the last
+ * controller call asked for one (solveras.py:643-645) */
+int rks_snapshot(rks_plan* plan, void* snap_ring, double* snap_t, int snap_cap, void* stream);
+
+/* the only syncing calls */
+int rks_read_ctrl(rks_plan* plan, rks_ctrl_host* out, void* stream);
+int rks_read_log(rks_plan* plan, rks_trial_rec* out_host, int first, int count, void* stream);
+
+/* introspection for tests: device pointer of a named array ("E", "a21", ..., "N1".., "K", "ERR", "U0", "U1") */
+void* rks_array(rks_plan* plan, const char* name);
+int64_t rks_kernel_launches(rks_plan* plan);   /* kernels launched through this plan so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RKSTIFF_B200_H */

@@ -1,0 +1,260 @@
+"""Host-side wrapper of one engine plan (include/rkstiff_b200.h) for one (method, lin_op, u-shape).
+
+PyTorch is used for device memory (the plan's workspace is one uint8 tensor), streams and,
+for multi-GPU shared-dt ensembles, ``torch.distributed``; every numeric operation of the
+stepping path runs in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_double, c_void_p
+from typing import Callable, List, Optional, Tuple
+
+import torch
+
+from . import _abi
+from ._abi import RksConfig, RksCtrl, RksTrialRec, check, lib
+
+
+def _stream(device) -> c_void_p:
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Engine:
+    """One plan: owns the workspace tensor and exposes the strategy-object operations
+    (update_coeffs / n1_init / update_stages of the reference) plus the device controller."""
+
+    def __init__(self, method: str, lin_op: torch.Tensor, u_shape: torch.Size, cfg: RksConfig,
+                 fused=None, group=None):
+        if not lin_op.is_cuda:
+            raise ValueError("lin_op must be a CUDA tensor: rkstiff_b200 has no CPU path")
+        if lin_op.dtype not in (torch.float64, torch.complex128):
+            raise TypeError("lin_op must be float64 or complex128")
+        nd = lin_op.dim()
+        if tuple(u_shape[len(u_shape) - nd:]) != tuple(lin_op.shape):
+            raise ValueError(f"lin_op shape {tuple(lin_op.shape)} must match the trailing dims of u {tuple(u_shape)}")
+        self.method = method
+        self.mid = _abi.METHOD_IDS[method]
+        self.device = lin_op.device
+        self.u_shape = torch.Size(u_shape)
+        self.n_c = lin_op.numel()
+        self.batch = 1
+        for d in u_shape[: len(u_shape) - nd]:
+            self.batch *= int(d)
+        self.adaptive = bool(lib.rks_is_adaptive(self.mid))
+        self.stages = lib.rks_num_stages(self.mid)
+        self.n_nl = lib.rks_num_nl_buffers(self.mid)
+        self.fsal = method in ("IF34", "ETD34", "IF45DP")
+        self.group = group
+        self.fused = fused
+        lin = lin_op.contiguous()
+        is_cx = lin.dtype == torch.complex128
+        self.lin_complex = is_cx      # coefficient arrays are real only for IF methods with a real lin_op
+        with torch.cuda.device(self.device):
+            nbytes = lib.rks_workspace_bytes(self.mid, self.batch, self.n_c, self.n_c, int(is_cx))
+            if nbytes == 0:
+                raise ValueError("invalid plan geometry")
+            self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.plan = c_void_p()
+            self._cfg = cfg
+            check(lib.rks_plan_create(byref(self.plan), self.mid, self.batch, self.n_c, c_void_p(lin.data_ptr()),
+                                      int(is_cx), self.n_c, byref(cfg), c_void_p(self.ws.data_ptr()), nbytes,
+                                      _stream(self.device)))
+            if fused is not None:
+                kx = fused.kx.to(device=self.device, dtype=torch.float64).contiguous() if fused.kx is not None else None
+                params = (c_double * 1)(float(fused.param))
+                check(lib.rks_set_model(self.plan, fused.model_id, fused.n,
+                                        c_void_p(kx.data_ptr()) if kx is not None else None, params, 1,
+                                        _stream(self.device)))
+        self.state_bytes = self.batch * self.n_c * 16
+        self.ctrl = RksCtrl()
+        self.ctrl.need_n1 = 1
+        self._h_host: Optional[float] = None          # fixed-step: h the coefficient arrays hold
+        self._h_set: Optional[float] = None
+        self._n1_ready = False
+        self._red = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "plan", None):
+                lib.rks_plan_destroy(self.plan)
+                self.plan = None
+        except Exception:
+            pass
+
+    # -- plumbing -------------------------------------------------------------------------
+    @property
+    def st(self) -> c_void_p:
+        return _stream(self.device)
+
+    def _view(self, ptr: int) -> torch.Tensor:
+        off = ptr - self.ws.data_ptr()
+        return self.ws[off: off + self.state_bytes].view(torch.complex128).view(self.u_shape)
+
+    def array(self, name: str) -> int:
+        p = lib.rks_array(self.plan, name.encode())
+        if not p:
+            raise KeyError(name)
+        return p
+
+    def state_view(self, name: str) -> torch.Tensor:
+        return self._view(self.array(name))
+
+    def coef_view(self, name: str) -> torch.Tensor:
+        real = self.method in ("IF4", "IF34", "IF45DP") and not self.lin_complex
+        off = self.array(name) - self.ws.data_ptr()
+        nb = self.n_c * (8 if real else 16)
+        return self.ws[off: off + nb].view(torch.float64 if real else torch.complex128)
+
+    def set_config(self, cfg: RksConfig) -> None:
+        self._cfg = cfg
+        check(lib.rks_set_config(self.plan, byref(cfg), self.st))
+        self._h_host = None
+
+    def launches(self) -> int:
+        return int(lib.rks_kernel_launches(self.plan))
+
+    # -- state ----------------------------------------------------------------------------
+    def begin(self, t0: float, tf: float, h: float, store_freq: int, step_mode: bool, keep_fsal: bool = False):
+        check(lib.rks_begin(self.plan, t0, tf, h, int(store_freq), int(step_mode), int(keep_fsal), self.st))
+        self._h_set = h
+        if not keep_fsal:
+            self._h_host = None
+            self._n1_ready = False
+            self.ctrl.need_n1 = 1
+            self.ctrl.n_sel = 0
+            self.ctrl.log_count = 0
+            self.ctrl.snap_count = 0
+
+    def set_h(self, h: float) -> None:
+        check(lib.rks_set_h(self.plan, h, self.st))
+        self._h_set = h
+
+    def _as_state(self, u: torch.Tensor) -> torch.Tensor:
+        if tuple(u.shape) != tuple(self.u_shape):
+            raise ValueError(f"u has shape {tuple(u.shape)}, plan was built for {tuple(self.u_shape)}")
+        if not u.is_cuda:
+            raise ValueError("u must be a CUDA tensor")
+        if u.dtype != torch.complex128:
+            u = u.to(torch.complex128)
+        return u.contiguous()
+
+    def set_u(self, u: torch.Tensor) -> None:
+        u = self._as_state(u)
+        check(lib.rks_set_u(self.plan, c_void_p(u.data_ptr()), self.st))
+
+    def get_u(self) -> torch.Tensor:
+        out = torch.empty(self.u_shape, dtype=torch.complex128, device=self.device)
+        check(lib.rks_get_u(self.plan, c_void_p(out.data_ptr()), self.st))
+        return out
+
+    # -- reference strategy operations ----------------------------------------------------
+    def update_coeffs(self) -> None:
+        check(lib.rks_update_coeffs(self.plan, self.st))
+
+    def stage(self, s: int) -> None:
+        check(lib.rks_stage(self.plan, s, self.st))
+
+    def nl(self, j: int) -> None:
+        check(lib.rks_nl(self.plan, j, self.st))
+
+    def nl_apply(self, j: int, nl_func: Callable) -> None:
+        """N_j = nl_func(input_j) for a caller-supplied torch callable (roles from the last read_ctrl)."""
+        src = self._view(lib.rks_nl_input(self.plan, j))
+        dst = self._view(lib.rks_nl_output(self.plan, j))
+        res = nl_func(src)
+        if not torch.is_tensor(res):
+            raise TypeError("nl_func must return a torch tensor")
+        dst.copy_(res.reshape(self.u_shape))
+
+    def _red_view(self) -> torch.Tensor:
+        if self._red is None:
+            off = lib.rks_reduction_scalars(self.plan) - self.ws.data_ptr()
+            self._red = self.ws[off: off + 24].view(torch.float64)
+        return self._red
+
+    def error_control(self) -> None:
+        if self.group is None:
+            check(lib.rks_error_control(self.plan, self.st))
+            return
+        # shared-dt ensemble sharded by batch: reference-exact global norms (solveras.py:451-454)
+        import torch.distributed as dist
+        red = self._red_view()
+        dist.all_reduce(red[0:1], op=dist.ReduceOp.MAX, group=self.group)
+        check(lib.rks_error_sums(self.plan, self.st))
+        dist.all_reduce(red[1:3], op=dist.ReduceOp.SUM, group=self.group)
+        check(lib.rks_controller(self.plan, self.st))
+
+    def read_ctrl(self) -> RksCtrl:
+        check(lib.rks_read_ctrl(self.plan, byref(self.ctrl), self.st))
+        return self.ctrl
+
+    def read_log(self, first: int, count: int) -> List[RksTrialRec]:
+        if count <= 0:
+            return []
+        buf = (RksTrialRec * count)()
+        check(lib.rks_read_log(self.plan, buf, first, count, self.st))
+        return list(buf)
+
+    # -- whole trials ---------------------------------------------------------------------
+    def enqueue_trial(self, nl_func: Optional[Callable], ring=None, ring_t=None) -> None:
+        """One adaptive trial.  nl_func None => fused NL kernels (device predicated, no sync needed);
+        otherwise the torch callable (roles/need_n1 taken from the last read_ctrl)."""
+        S = self.stages
+        self.update_coeffs()
+        if nl_func is None:
+            self.nl(1)
+        elif self.ctrl.need_n1:
+            self.nl_apply(1, nl_func)
+        for s in range(1, S + 1):
+            self.stage(s)
+            if s < S or self.fsal:
+                if nl_func is None:
+                    self.nl(s + 1)
+                else:
+                    self.nl_apply(s + 1, nl_func)
+        self.error_control()
+        if ring is not None:
+            check(lib.rks_snapshot(self.plan, c_void_p(ring.data_ptr()), c_void_p(ring_t.data_ptr()), ring.shape[0],
+                                   self.st))
+
+    def run_trials(self, k: int, ring=None, ring_t=None) -> None:
+        """k fused trials without host sync (kernels after the final accept are predicated off)."""
+        if self.group is None:
+            check(lib.rks_run_trials(self.plan, k, c_void_p(ring.data_ptr()) if ring is not None else None,
+                                     c_void_p(ring_t.data_ptr()) if ring is not None else None,
+                                     ring.shape[0] if ring is not None else 0, self.st))
+        else:
+            for _ in range(k):
+                self.enqueue_trial(None, ring, ring_t)
+
+    # -- fixed step -----------------------------------------------------------------------
+    def ensure_fixed_coeffs(self, h: float) -> None:
+        if self._h_set != h:
+            self.set_h(h)
+        if self._h_host != h:                      # exact float equality, etd4.py:392
+            self.update_coeffs()
+            self._h_host = h
+
+    def fixed_step(self, nl_func: Optional[Callable]) -> None:
+        S = self.stages
+        if not self._n1_ready:
+            if nl_func is None:
+                self.nl(1)
+            else:
+                self.nl_apply(1, nl_func)
+            self._n1_ready = True
+        if nl_func is None:
+            check(lib.rks_run_fixed(self.plan, 1, self.st))
+            return
+        for s in range(1, S + 1):
+            self.stage(s)
+            self.nl_apply(s + 1 if s < S else 1, nl_func)
+
+    def run_fixed(self, nsteps: int) -> None:
+        if nsteps <= 0:
+            return
+        if not self._n1_ready:
+            self.nl(1)
+            self._n1_ready = True
+        check(lib.rks_run_fixed(self.plan, nsteps, self.st))

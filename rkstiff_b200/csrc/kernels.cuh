@@ -1,0 +1,488 @@
+// Device kernels of the rkstiff_b200 engine (sm_100a).  See DESIGN.md for the byte model of each.
+#pragma once
+#include "common.cuh"
+#include "coeffs.cuh"
+#include "stages.cuh"
+#include "errctl.cuh"
+#include "fft.cuh"
+
+namespace rks {
+
+// 128-bit global accesses (LDG.E.128 / STG.E.128)
+RKS_D cplx ldg(const cplx* p) {
+    const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+    return mk(v.x, v.y);
+}
+RKS_D cplx ldcs(const cplx* p) {     // streaming load: state arrays are touched once per kernel
+    const double2 v = __ldcs(reinterpret_cast<const double2*>(p));
+    return mk(v.x, v.y);
+}
+RKS_D cplx ld_plain(const cplx* p) {
+    const double2 v = *reinterpret_cast<const double2*>(p);
+    return mk(v.x, v.y);
+}
+RKS_D void stg(cplx* p, cplx v) { *reinterpret_cast<double2*>(p) = make_double2(v.x, v.y); }
+RKS_D double ldcoef(const double* p) { return __ldg(p); }
+RKS_D cplx ldcoef(const cplx* p) { return ldg(p); }
+
+RKS_D unsigned long long nonneg_bits(double v) {
+    // bit pattern that orders like the value for v >= 0; NaN maps above +inf
+    if (v != v) return 0x7ff8000000000000ull;
+    return (unsigned long long)__double_as_longlong(v);
+}
+
+// ---------------------------------------------------------------------------------------
+// control-block helpers
+// ---------------------------------------------------------------------------------------
+struct BeginArgs {
+    double t0, tf, h;
+    long long store_freq;
+    int step_mode, keep_fsal, n1_refresh;
+};
+
+__global__ void begin_kernel(Ctrl* c, BeginArgs a) {
+    c->t = a.t0; c->tf = a.tf; c->h = a.h; c->h_last = a.h;
+    c->store_freq = a.store_freq;
+    c->step_mode = a.step_mode;
+    c->n1_refresh = a.n1_refresh;
+    c->status = ST_RUNNING;
+    c->numloops = 0;
+    c->red[0] = c->red[1] = c->red[2] = 0.0;
+    c->ticket = 0u;
+    c->snap_pending = 0;
+    if (!a.keep_fsal) {
+        c->h_coeff = __longlong_as_double(0x7ff8000000000000ll);   // NaN: never equal
+        c->accept = 0; c->need_n1 = 1; c->n_sel = 0;
+        c->step_count = 0; c->trial_count = 0; c->nl_evals = 0; c->coeff_updates = 0;
+        c->log_count = 0; c->snap_count = 0; c->s_last = 0.0;
+    }
+}
+
+__global__ void set_h_kernel(Ctrl* c, double h) {
+    c->h = h;
+    c->status = ST_RUNNING;
+    c->numloops = 0;
+}
+
+struct CfgArgs {
+    double epsilon, incr_f, decr_f, safety_f, adapt_cutoff, minh, inv_q, modecutoff, contour_radius;
+    int contour_points, r4_fix;
+};
+__global__ void set_config_kernel(Ctrl* c, CfgArgs a) {
+    c->epsilon = a.epsilon; c->incr_f = a.incr_f; c->decr_f = a.decr_f; c->safety_f = a.safety_f;
+    c->adapt_cutoff = a.adapt_cutoff; c->minh = a.minh; c->inv_q = a.inv_q;
+    c->modecutoff = a.modecutoff; c->contour_radius = a.contour_radius;
+    c->contour_points = a.contour_points; c->r4_fix = a.r4_fix;
+}
+
+__global__ void twiddle_kernel(cplx* tw, int n) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double s, c;
+    sincospi(-2.0 * (double)j / (double)n, &s, &c);
+    tw[j] = mk(c, s);
+}
+
+// ---------------------------------------------------------------------------------------
+// K2: coefficient kernel.  One lane per mode; modes below the cutoff are finished by the
+// whole warp, one contour node per lane (M = 32 nodes == one warp by default).
+// FAM: 0 = IF4/IF34 (E, E2), 1 = Krogstad ETD4/ETD34, 2 = ETD5/ETD35, 3 = IF45DP
+// ---------------------------------------------------------------------------------------
+template <typename T> RKS_D T load_lin(const void* lin, long long i);
+template <> RKS_D double load_lin<double>(const void* lin, long long i) { return __ldg((const double*)lin + i); }
+template <> RKS_D cplx load_lin<cplx>(const void* lin, long long i) { return ldg((const cplx*)lin + i); }
+
+RKS_D cplx warp_sum(cplx v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    }
+    return v;
+}
+
+template <int FAM, typename LT>
+__global__ void __launch_bounds__(128) coef_kernel(DevPlan p, int force) {
+    Ctrl* c = p.ctrl;
+    const double h = c->h;
+    if (!force) {
+        if (c->status != ST_RUNNING) return;
+        if (h == c->h_coeff) return;                      // etd35.py:851: exact float equality
+    }
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < p.lin_elems;
+    const long long stride = p.lin_elems;
+    if (i == 0) atomicAdd((unsigned long long*)&c->coeff_updates, 1ull);
+
+    if (FAM == 0) {
+        if (!valid) return;
+        LT* out = (LT*)p.coef;
+        const LT z = scale(h, load_lin<LT>(p.lin, i));
+        out[ifc::E * stride + i] = cexp_t(z);
+        out[ifc::E2 * stride + i] = cexp_t(z / 2.0);
+        return;
+    }
+    if (FAM == 3) {
+        if (!valid) return;
+        LT* out = (LT*)p.coef;
+        LT arr[dp::COUNT];
+        tableau_if45dp<LT>(scale(h, load_lin<LT>(p.lin, i)), h, c->r4_fix, arr);
+#pragma unroll
+        for (int s = 0; s < dp::COUNT; ++s) out[s * stride + i] = arr[s];
+        return;
+    }
+    if (FAM == 1 || FAM == 2) {
+        // ETD strategies cast lin_op to complex128 (etd35.py:124)
+        constexpr bool FIVE = (FAM == 2);
+        cplx* out = (cplx*)p.coef;
+        cplx z = mk(0.0, 0.0);
+        if (valid) {
+            if (p.lin_complex) z = scale(h, ldg((const cplx*)p.lin + i));
+            else z = mk(h * __ldg((const double*)p.lin + i), 0.0);
+        }
+        const bool small = valid && (hypot(z.x, z.y) < c->modecutoff);    // np.abs(z) < modecutoff
+        PsiSet ps = psi_zero();
+        if (valid && !small) {
+            psi_accumulate<FIVE>(ps, z);
+            psi_scale(ps, h, 1.0);
+        }
+        // contour mean for the small modes of this warp (etd35.py:239-269)
+        unsigned todo = __ballot_sync(0xffffffffu, small);
+        const int lane = threadIdx.x & 31;
+        const int m = c->contour_points;
+        const double radius = c->contour_radius;
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            cplx zs;
+            zs.x = __shfl_sync(0xffffffffu, z.x, src);
+            zs.y = __shfl_sync(0xffffffffu, z.y, src);
+            PsiSet acc = psi_zero();
+            for (int j = lane; j < m; j += 32) psi_accumulate<FIVE>(acc, zs + contour_node(radius, j, m));
+            acc.p1h = warp_sum(acc.p1h); acc.p2h = warp_sum(acc.p2h);
+            acc.p1 = warp_sum(acc.p1); acc.p2 = warp_sum(acc.p2); acc.p3 = warp_sum(acc.p3);
+            if (FIVE) {
+                acc.p1q = warp_sum(acc.p1q); acc.p2q = warp_sum(acc.p2q);
+                acc.p1t = warp_sum(acc.p1t); acc.p2t = warp_sum(acc.p2t);
+            }
+            if (lane == src) { ps = acc; psi_scale(ps, h, (double)m); }
+        }
+        if (!valid) return;
+        if (FIVE) {
+            cplx arr[e5::COUNT];
+            arr[e5::E14] = cexp(z / 4.0);
+            arr[e5::E12] = cexp(z / 2.0);
+            arr[e5::E34] = cexp((3.0 * z) / 4.0);
+            arr[e5::E] = cexp(z);
+            tableau_etd5(ps, arr);
+#pragma unroll
+            for (int s = 0; s < e5::COUNT; ++s) stg(out + s * stride + i, arr[s]);
+        } else {
+            cplx arr[kro::COUNT];
+            arr[kro::E] = cexp(z);
+            arr[kro::E2] = cexp(z / 2.0);
+            tableau_krogstad(ps, arr);
+#pragma unroll
+            for (int s = 0; s < kro::COUNT; ++s) stg(out + s * stride + i, arr[s]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K1: stage combine.  !FULL: block (32, 8), thread = one mode column x R batch rows, the
+// coefficients of the column are loaded once.  FULL (lin_op shaped like u): block of 256,
+// R elements per thread, coefficients per element.
+// ---------------------------------------------------------------------------------------
+constexpr int STAGE_R = 2;
+
+template <int M, int S, typename CT, bool FULL>
+__global__ void __launch_bounds__(256) stage_kernel(DevPlan p) {
+    constexpr int R = STAGE_R;
+    constexpr bool ADAPT = method_adaptive(M);
+    constexpr int SMAX = method_stages(M);
+    constexpr bool LAST = (S == SMAX);
+    constexpr unsigned NMASK = stage_nl_mask(M, S);
+    constexpr unsigned CMASK = stage_coef_mask(M, S);
+    constexpr int NC = method_ncoef(M);
+    const Ctrl* c = p.ctrl;
+    int u_sel = 0, n_sel = 0;
+    if (ADAPT) {
+        if (c->status != ST_RUNNING) return;
+        u_sel = c->u_sel; n_sel = c->n_sel;
+    }
+    const double h = c->h;
+    const cplx* u = p.U[u_sel];
+    cplx* out = LAST ? (ADAPT ? p.U[1 - u_sel] : p.U[0]) : p.K;
+    const CT* __restrict__ coef = (const CT*)p.coef;
+    const long long cstride = p.lin_elems;
+
+    long long didx[R], cidx[R];
+    bool ok[R];
+    if (FULL) {
+        const long long total = p.batch * p.n_c;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const long long e = ((long long)blockIdx.x * R + r) * 256 + threadIdx.y * 32 + threadIdx.x;
+            didx[r] = e; cidx[r] = e; ok[r] = e < total;
+        }
+    } else {
+        const long long col = (long long)blockIdx.x * 32 + threadIdx.x;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const long long row = ((long long)blockIdx.y * 8 + threadIdx.y) * R + r;
+            didx[r] = row * p.n_c + col; cidx[r] = col; ok[r] = (col < p.n_c) && (row < p.batch);
+        }
+    }
+
+    // ---- loads (all issued before any use)
+    CT cv[R][NC];
+    cplx uv[R], nv[R][8];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (!ok[r]) continue;
+        if (FULL || r == 0) {
+#pragma unroll
+            for (int s = 0; s < NC; ++s)
+                if (CMASK & (1u << s)) cv[r][s] = ldcoef(coef + s * cstride + cidx[r]);
+        }
+        uv[r] = (LAST && !ADAPT) ? ld_plain(u + didx[r]) : ldcs(u + didx[r]);   // fixed step: u+ overwrites u in place
+#pragma unroll
+        for (int j = 1; j <= 7; ++j)
+            if (NMASK & (1u << j)) nv[r][j] = ldcs(p.NL[nl_phys(M, j, n_sel)] + didx[r]);
+    }
+    // ---- combine + store
+    unsigned long long mx = 0ull;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (!ok[r]) continue;
+        const CT* cr = FULL ? cv[r] : cv[0];
+        const cplx k = stage_combine<M, S, CT>(uv[r], nv[r], cr, h);
+        stg(out + didx[r], k);
+        if (LAST && ADAPT) {
+            const unsigned long long b = nonneg_bits(abs2(k));
+            mx = b > mx ? b : mx;
+            if (M == M_ETD35) stg(p.ERR + didx[r], etd35_err<CT>(nv[r], cr));
+        }
+    }
+    if (LAST && ADAPT) {
+        // block max of |u+|^2 -> one atomicMax per block (solveras.py:451: magu.max())
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, mx, o);
+            mx = t > mx ? t : mx;
+        }
+        __shared__ unsigned long long smx[8];
+        const int w = threadIdx.y;
+        if (threadIdx.x == 0) smx[w] = mx;
+        __syncthreads();
+        if (w == 0 && threadIdx.x == 0) {
+            unsigned long long m = smx[0];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) m = smx[i] > m ? smx[i] : m;
+            if (m) atomicMax((unsigned long long*)&p.ctrl->red[0], m);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K4: fused spectral nonlinearity, one trajectory row per CTA slot, row resident in smem.
+// j selects input/output roles; predicated on device so that no host sync is needed.
+// ---------------------------------------------------------------------------------------
+struct NlRoles {
+    const cplx* in;
+    cplx* out;
+    bool run;
+};
+
+RKS_D NlRoles nl_roles(const DevPlan& p, int j, int force) {
+    const Ctrl* c = p.ctrl;
+    NlRoles r;
+    const int m = p.method;
+    const bool adapt = method_adaptive(m);
+    const int S = method_stages(m);
+    const int u_sel = adapt ? c->u_sel : 0;
+    const int n_sel = adapt ? c->n_sel : 0;
+    r.run = force || (c->status == ST_RUNNING && (j != 1 || c->need_n1));
+    if (j == 1) r.in = p.U[u_sel];
+    else if (j <= S) r.in = p.K;
+    else r.in = p.U[1 - u_sel];                      // FSAL: N(u+)
+    r.out = p.NL[nl_phys(m, j, n_sel)];
+    return r;
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(1024) nl_kernel(DevPlan p, int j, int force, int rows_per_cta) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* smem = reinterpret_cast<cplx*>(smem_raw);
+    const NlRoles roles = nl_roles(p, j, force);
+    if (!roles.run) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&p.ctrl->nl_evals, 1ull);
+
+    const int n = (int)p.n;
+    const int log2n = p.log2n;
+    const int tpr = blockDim.x / rows_per_cta;               // threads per row
+    const int lrow = threadIdx.x / tpr, tid = threadIdx.x - lrow * tpr;
+    const long long row = (long long)blockIdx.x * rows_per_cta + lrow;
+    const bool active = row < p.batch;
+    cplx* x = smem + (size_t)lrow * n;
+    const cplx* in = roles.in + row * p.n_c;
+    cplx* out = roles.out + row * p.n_c;
+
+    if (active) {
+        if (MODEL == 1) uux_load(x, in, p.kx, n, tid, tpr);
+        else nls_load(x, in, n, tid, tpr);
+    }
+    __syncthreads();
+    const int np = fft_num_passes(log2n);
+    for (int q = 0; q < np; ++q) {
+        if (active) ifft_dif_pass(x, log2n, q, p.tw, tid, tpr);
+        __syncthreads();
+    }
+    if (active) {
+        if (MODEL == 1) uux_pointwise(x, n, tid, tpr);
+        else nls_pointwise(x, n, tid, tpr);
+    }
+    __syncthreads();
+    for (int q = 0; q < np; ++q) {
+        if (active) fft_dit_pass(x, log2n, q, p.tw, tid, tpr);
+        __syncthreads();
+    }
+    if (active) {
+        if (MODEL == 1) uux_store(out, x, p.model_p0, n, tid, tpr);
+        else nls_store(out, x, p.model_p0, n, tid, tpr);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3: masked norms (solveras.py:451-454) + controller tail.
+// grid (gx, gy): columns grid-stride over x, rows grid-stride over y; 128 threads.
+// ---------------------------------------------------------------------------------------
+template <int BT>
+RKS_D double block_sum(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < BT / 32; ++i) t += sh[i];
+    }
+    return t;     // valid in thread 0
+}
+
+template <int M, typename CT, bool FULL>
+__global__ void __launch_bounds__(128) norm_kernel(DevPlan p, int fuse_controller) {
+    constexpr unsigned NMASK = err_nl_mask(M);
+    constexpr unsigned CMASK = err_coef_mask(M);
+    constexpr int NC = method_ncoef(M);
+    Ctrl* c = p.ctrl;
+    if (c->status != ST_RUNNING) return;
+    const int u_sel = c->u_sel, n_sel = c->n_sel;
+    const double h = c->h;
+    const double m = sqrt(c->red[0]);                       // max |u+|
+    const double cutoff = c->adapt_cutoff;
+    const cplx* __restrict__ un = p.U[1 - u_sel];
+    const CT* __restrict__ coef = (const CT*)p.coef;
+    const long long cstride = p.lin_elems;
+    const long long ncols = FULL ? p.batch * p.n_c : p.n_c;
+    const long long nrows = FULL ? 1 : p.batch;
+
+    double su = 0.0, se = 0.0;
+    for (long long col = (long long)blockIdx.x * 128 + threadIdx.x; col < ncols; col += (long long)gridDim.x * 128) {
+        CT cv[NC];
+#pragma unroll
+        for (int s = 0; s < NC; ++s)
+            if (CMASK & (1u << s)) cv[s] = ldcoef(coef + s * cstride + col);
+        for (long long row = blockIdx.y; row < nrows; row += gridDim.y) {
+            const long long d = row * ncols + col;
+            const cplx uv = ldcs(un + d);
+            cplx ev;
+            if (M == M_ETD35) {
+                ev = ldcs(p.ERR + d);
+            } else {
+                cplx nv[8];
+#pragma unroll
+                for (int j = 1; j <= 7; ++j)
+                    if (NMASK & (1u << j)) nv[j] = ldcs(p.NL[nl_phys(M, j, n_sel)] + d);
+                ev = embedded_err<M, CT>(nv, cv, h);
+            }
+            const double u2 = abs2(uv);
+            // idx = magu / magu.max() > adapt_cutoff   (solveras.py:452)
+            if (sqrt(u2) / m > cutoff) {
+                su += u2;
+                se += abs2(ev);
+            }
+        }
+    }
+    __shared__ double sh[4];
+    __shared__ bool is_last;
+    const double bu = block_sum<128>(su, sh);
+    const double be = block_sum<128>(se, sh);
+    const unsigned nblocks = gridDim.x * gridDim.y;
+    const unsigned bid = blockIdx.y * gridDim.x + blockIdx.x;
+    if (threadIdx.x == 0) {
+        p.partials[2 * bid] = bu;
+        p.partials[2 * bid + 1] = be;
+        __threadfence();
+        const unsigned t = atomicAdd(&c->ticket, 1u);
+        is_last = (t == nblocks - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // deterministic final reduction of the per-block partials
+    double fu = 0.0, fe = 0.0;
+    for (unsigned i = threadIdx.x; i < nblocks; i += 128) {
+        fu += __ldcg(p.partials + 2 * i);
+        fe += __ldcg(p.partials + 2 * i + 1);
+    }
+    const double tu = block_sum<128>(fu, sh);
+    const double te = block_sum<128>(fe, sh);
+    if (threadIdx.x == 0) {
+        c->red[1] = tu;
+        c->red[2] = te;
+        c->ticket = 0u;
+        if (fuse_controller) {
+            Ctrl local = *c;
+            controller_advance(local, p.log);
+            *c = local;
+        }
+    }
+}
+
+__global__ void controller_kernel(DevPlan p) {
+    Ctrl* c = p.ctrl;
+    if (c->status != ST_RUNNING) return;
+    Ctrl local = *c;
+    controller_advance(local, p.log);
+    *c = local;
+}
+
+// snapshot of the accepted state into the ring (solveras.py:643-645)
+__global__ void __launch_bounds__(256) snapshot_kernel(DevPlan p, cplx* ring, double* ring_t, int cap) {
+    const Ctrl* c = p.ctrl;
+    if (!c->snap_pending) return;
+    const long long total = p.batch * p.n_c;
+    const int slot = (c->snap_count - 1) % cap;
+    const cplx* src = p.U[c->u_sel];
+    cplx* dst = ring + (size_t)slot * total;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256)
+        stg(dst + e, ldcs(src + e));
+    if (blockIdx.x == 0 && threadIdx.x == 0) ring_t[slot] = c->t;
+}
+
+// copy a caller array into / out of the role-selected state buffer
+__global__ void __launch_bounds__(256) copy_u_kernel(DevPlan p, cplx* ext, int to_plan) {
+    const int u_sel = method_adaptive(p.method) ? p.ctrl->u_sel : 0;
+    cplx* mine = p.U[u_sel];
+    const long long total = p.batch * p.n_c;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        if (to_plan) stg(mine + e, ldcs(ext + e));
+        else stg(ext + e, ldcs(mine + e));
+    }
+}
+
+}  // namespace rks

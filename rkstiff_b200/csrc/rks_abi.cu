@@ -1,0 +1,588 @@
+// C ABI of the rkstiff_b200 engine: plan management, kernel dispatch, control-block I/O.
+// Declared in include/rkstiff_b200.h.  No C++ exception crosses this boundary.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+
+#include "../../include/rkstiff_b200.h"
+#include "kernels.cuh"
+
+using namespace rks;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, const char* detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+#define CUDA_TRY(expr)                                                              \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) return fail(RKS_ERR_CUDA, #expr ": %s", cudaGetErrorString(_e)); \
+    } while (0)
+
+static_assert(sizeof(rks_trial_rec) == sizeof(TrialRec), "log record layout");
+static_assert(RKS_LOG_CAP == LOG_CAP, "log capacity");
+
+// ---------------------------------------------------------------------------------------
+// workspace layout
+// ---------------------------------------------------------------------------------------
+constexpr size_t ALIGN = 256;
+constexpr int NORM_MAX_BLOCKS = 4096;
+constexpr long long MODEL_MAX_N = 16384;        // longest row the smem-resident FFT handles
+
+static size_t align_up(size_t v) { return (v + ALIGN - 1) / ALIGN * ALIGN; }
+
+struct Layout {
+    size_t ctrl, log, partials, tw, kx, lin, coef, U[2], K, ERR, NL[8], total;
+};
+
+static Layout make_layout(int method, long long batch, long long n_c, long long lin_elems, int lin_is_complex) {
+    Layout L;
+    memset(&L, 0, sizeof(L));
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+    const size_t state = (size_t)batch * (size_t)n_c * sizeof(cplx);
+    const bool is_if = method_is_if(method);
+    const size_t coef_elem = (is_if && !lin_is_complex) ? sizeof(double) : sizeof(cplx);
+    L.ctrl = take(sizeof(Ctrl));
+    L.log = take(sizeof(TrialRec) * LOG_CAP);
+    L.partials = take(sizeof(double) * 2 * NORM_MAX_BLOCKS);
+    const long long nmax = n_c <= MODEL_MAX_N ? 2 * n_c : 0;
+    L.tw = take(sizeof(cplx) * (size_t)nmax);
+    L.kx = take(sizeof(double) * (size_t)(n_c <= MODEL_MAX_N ? n_c : 0));
+    L.lin = take((lin_is_complex ? sizeof(cplx) : sizeof(double)) * (size_t)lin_elems);
+    L.coef = take(coef_elem * (size_t)lin_elems * method_ncoef(method));
+    L.U[0] = take(state);
+    L.U[1] = method_adaptive(method) ? take(state) : L.U[0];
+    L.K = take(state);
+    L.ERR = method == M_ETD35 ? take(state) : 0;
+    for (int j = 1; j <= method_nl_buffers(method); ++j) L.NL[j] = take(state);
+    L.total = off;
+    return L;
+}
+
+struct rks_plan {
+    DevPlan d;
+    Layout lay;
+    unsigned char* ws;
+    rks_config cfg;
+    int method, device;
+    int sm_count;
+    long long launches;
+    rks_ctrl_host* pinned_ctrl;     // pinned staging for rks_read_ctrl
+    Ctrl* pinned_raw;
+    TrialRec* pinned_log;
+    double h_coeff_host;            // fixed-step methods: host-side cache key (etd4.py:392)
+    bool have_h_coeff_host;
+    int roles_u_sel, roles_n_sel;   // host mirror refreshed by rks_read_ctrl
+    int nl_rows_per_cta, nl_threads;
+    size_t nl_smem;
+};
+
+extern "C" int rks_abi_version(void) { return RKS_ABI_VERSION; }
+extern "C" const char* rks_last_error(void) { return g_err; }
+
+static bool valid_method(int m) { return m >= 0 && m <= 6; }
+extern "C" int rks_num_stages(int method) { return valid_method(method) ? method_stages(method) : -1; }
+extern "C" int rks_num_nl_buffers(int method) { return valid_method(method) ? method_nl_buffers(method) : -1; }
+extern "C" int rks_is_adaptive(int method) { return valid_method(method) ? (int)method_adaptive(method) : -1; }
+
+extern "C" size_t rks_workspace_bytes(int method, int64_t batch, int64_t n_c, int64_t lin_elems, int lin_is_complex) {
+    if (!valid_method(method) || batch <= 0 || n_c <= 0) return 0;
+    if (lin_elems != n_c && lin_elems != batch * n_c) return 0;
+    return make_layout(method, batch, n_c, lin_elems, lin_is_complex).total;
+}
+
+static CfgArgs cfg_args(const rks_config& c, int method) {
+    CfgArgs a;
+    a.epsilon = c.epsilon; a.incr_f = c.incr_f; a.decr_f = c.decr_f; a.safety_f = c.safety_f;
+    a.adapt_cutoff = c.adapt_cutoff; a.minh = c.minh;
+    a.inv_q = 1.0 / (double)method_q(method);            // 1.0 / self._q(), solveras.py:454
+    a.modecutoff = c.modecutoff; a.contour_radius = c.contour_radius;
+    a.contour_points = c.contour_points; a.r4_fix = c.if45dp_r4_fix;
+    return a;
+}
+
+static int check_cfg(const rks_config* c) {
+    if (!c) return fail(RKS_ERR_ARG, "config is null");
+    if (!(c->epsilon > 0) || !(c->incr_f > 1.0) || !(c->decr_f < 1.0) || !(c->safety_f <= 1.0) ||
+        !(c->adapt_cutoff < 1.0) || !(c->minh > 0))
+        return fail(RKS_ERR_ARG, "SolverConfig value out of range (solveras.py:99-169)");
+    if (!(c->modecutoff > 0 && c->modecutoff <= 1.0) || c->contour_points <= 1 || !(c->contour_radius > 0))
+        return fail(RKS_ERR_ARG, "ETDConfig value out of range (etd.py:95-131)");
+    return RKS_OK;
+}
+
+extern "C" int rks_plan_create(rks_plan** out, int method, int64_t batch, int64_t n_c, const void* lin_op,
+                               int lin_is_complex, int64_t lin_elems, const rks_config* cfg, void* workspace,
+                               size_t workspace_bytes, void* stream_v) {
+    if (!out) return fail(RKS_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (!valid_method(method)) return fail(RKS_ERR_ARG, "unknown method id");
+    if (batch <= 0 || n_c <= 0) return fail(RKS_ERR_ARG, "batch and n_c must be positive");
+    if (lin_elems != n_c && lin_elems != batch * n_c)
+        return fail(RKS_ERR_ARG, "lin_op must have n_c or batch*n_c elements");
+    if (!lin_op || !workspace) return fail(RKS_ERR_ARG, "null device pointer");
+    if (((uintptr_t)workspace) % ALIGN) return fail(RKS_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+    if (int rc = check_cfg(cfg)) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    Layout L = make_layout(method, batch, n_c, lin_elems, lin_is_complex);
+    if (workspace_bytes < L.total) return fail(RKS_ERR_WORKSPACE, "workspace too small");
+
+    rks_plan* p = new (std::nothrow) rks_plan();
+    if (!p) return fail(RKS_ERR_ARG, "out of host memory");
+    memset(&p->d, 0, sizeof(DevPlan));
+    p->lay = L;
+    p->ws = (unsigned char*)workspace;
+    p->cfg = *cfg;
+    p->method = method;
+    p->launches = 0;
+    p->have_h_coeff_host = false;
+    p->roles_u_sel = p->roles_n_sel = 0;
+    CUDA_TRY(cudaGetDevice(&p->device));
+    CUDA_TRY(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device));
+    CUDA_TRY(cudaMallocHost((void**)&p->pinned_raw, sizeof(Ctrl)));
+    CUDA_TRY(cudaMallocHost((void**)&p->pinned_log, sizeof(TrialRec) * LOG_CAP));
+
+    DevPlan& d = p->d;
+    unsigned char* w = p->ws;
+    d.ctrl = (Ctrl*)(w + L.ctrl);
+    d.log = (TrialRec*)(w + L.log);
+    d.partials = (double*)(w + L.partials);
+    d.tw = (const cplx*)(w + L.tw);
+    d.kx = (const double*)(w + L.kx);
+    d.lin = w + L.lin;
+    d.coef = w + L.coef;
+    d.U[0] = (cplx*)(w + L.U[0]);
+    d.U[1] = (cplx*)(w + L.U[1]);
+    d.K = (cplx*)(w + L.K);
+    d.ERR = method == M_ETD35 ? (cplx*)(w + L.ERR) : nullptr;
+    for (int j = 1; j <= method_nl_buffers(method); ++j) d.NL[j] = (cplx*)(w + L.NL[j]);
+    d.batch = batch; d.n_c = n_c; d.lin_elems = lin_elems; d.n = 0;
+    d.method = method; d.lin_complex = lin_is_complex; d.lin_full = (lin_elems == batch * n_c) ? 1 : 0;   // also true for batch == 1: linear kernels
+    d.model = RKS_MODEL_NONE; d.log2n = 0; d.model_p0 = 0.0;
+
+    CUDA_TRY(cudaMemsetAsync(w + L.ctrl, 0, L.partials + sizeof(double) * 2 * NORM_MAX_BLOCKS - L.ctrl, stream));
+    CUDA_TRY(cudaMemcpyAsync(w + L.lin, lin_op, (lin_is_complex ? sizeof(cplx) : sizeof(double)) * (size_t)lin_elems,
+                             cudaMemcpyDeviceToDevice, stream));
+    set_config_kernel<<<1, 1, 0, stream>>>(d.ctrl, cfg_args(*cfg, method));
+    BeginArgs b;
+    b.t0 = 0.0; b.tf = 0.0; b.h = 0.0; b.store_freq = 0; b.step_mode = 1; b.keep_fsal = 0;
+    b.n1_refresh = method == M_ETD35;
+    begin_kernel<<<1, 1, 0, stream>>>(d.ctrl, b);
+    p->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    *out = p;
+    return RKS_OK;
+}
+
+extern "C" void rks_plan_destroy(rks_plan* p) {
+    if (!p) return;
+    cudaFreeHost(p->pinned_raw);
+    cudaFreeHost(p->pinned_log);
+    delete p;
+}
+
+extern "C" int rks_set_config(rks_plan* p, const rks_config* cfg, void* stream) {
+    if (!p) return fail(RKS_ERR_ARG, "plan is null");
+    if (int rc = check_cfg(cfg)) return rc;
+    const bool etd_changed = cfg->modecutoff != p->cfg.modecutoff || cfg->contour_points != p->cfg.contour_points ||
+                             cfg->contour_radius != p->cfg.contour_radius || cfg->if45dp_r4_fix != p->cfg.if45dp_r4_fix;
+    p->cfg = *cfg;
+    if (etd_changed) p->have_h_coeff_host = false;
+    set_config_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p->d.ctrl, cfg_args(*cfg, p->method));
+    p->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
+extern "C" int rks_set_model(rks_plan* p, int model, int64_t n, const double* kx, const double* params_host,
+                             int nparams, void* stream_v) {
+    if (!p) return fail(RKS_ERR_ARG, "plan is null");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    DevPlan& d = p->d;
+    if (model == RKS_MODEL_NONE) { d.model = 0; return RKS_OK; }
+    if (model != RKS_MODEL_UUX_RFFT && model != RKS_MODEL_NLS_FFT) return fail(RKS_ERR_ARG, "unknown model id");
+    if (d.lin_elems != d.n_c) return fail(RKS_ERR_UNSUPPORTED, "fused 1-D models need lin_op of n_c elements");
+    if (n < 16 || n > MODEL_MAX_N || (n & (n - 1))) return fail(RKS_ERR_UNSUPPORTED, "n must be a power of two in [16, 16384]");
+    const long long want_nc = model == RKS_MODEL_UUX_RFFT ? n / 2 + 1 : n;
+    if (want_nc != d.n_c) return fail(RKS_ERR_ARG, "n does not match n_c for this model");
+    if (nparams < 1 || !params_host) return fail(RKS_ERR_ARG, "model needs one parameter");
+    if (model == RKS_MODEL_UUX_RFFT && !kx) return fail(RKS_ERR_ARG, "kx is null");
+    int log2n = 0;
+    while ((1ll << log2n) < n) ++log2n;
+    d.n = n; d.log2n = log2n; d.model = model; d.model_p0 = params_host[0];
+    twiddle_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((cplx*)(p->ws + p->lay.tw), (int)n);
+    p->launches += 1;
+    if (kx) CUDA_TRY(cudaMemcpyAsync(p->ws + p->lay.kx, kx, sizeof(double) * (size_t)d.n_c, cudaMemcpyDeviceToDevice, stream));
+    // launch shape of the NL kernel: one row per CTA for long rows, several for short ones
+    const size_t row_bytes = (size_t)n * sizeof(cplx);
+    int tpr = (int)(n / 4);                       // one radix-4 butterfly per thread per pass
+    if (tpr > 512) tpr = 512;
+    if (tpr < 32) tpr = 32;
+    int rows = 256 / tpr;
+    if (rows < 1) rows = 1;
+    while (rows > 1 && (long long)rows > d.batch) rows >>= 1;
+    p->nl_rows_per_cta = rows;
+    p->nl_threads = rows * tpr;
+    p->nl_smem = row_bytes * rows;
+    if (p->nl_smem > 227 * 1024) return fail(RKS_ERR_UNSUPPORTED, "row does not fit in shared memory");
+    if (model == RKS_MODEL_UUX_RFFT)
+        CUDA_TRY(cudaFuncSetAttribute(nl_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->nl_smem));
+    else
+        CUDA_TRY(cudaFuncSetAttribute(nl_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->nl_smem));
+    CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
+extern "C" int rks_begin(rks_plan* p, double t0, double tf, double h, int64_t store_freq, int step_mode,
+                         int keep_fsal, void* stream) {
+    if (!p) return fail(RKS_ERR_ARG, "plan is null");
+    BeginArgs b;
+    b.t0 = t0; b.tf = tf; b.h = h; b.store_freq = store_freq; b.step_mode = step_mode; b.keep_fsal = keep_fsal;
+    b.n1_refresh = p->method == M_ETD35;
+    if (!keep_fsal) { p->have_h_coeff_host = false; p->roles_n_sel = 0; }
+    begin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p->d.ctrl, b);
+    p->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
+extern "C" int rks_set_h(rks_plan* p, double h, void* stream) {
+    if (!p) return fail(RKS_ERR_ARG, "plan is null");
+    set_h_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p->d.ctrl, h);
+    p->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
+static unsigned copy_grid(const rks_plan* p) {
+    const long long total = p->d.batch * p->d.n_c;
+    long long g = (total + 255) / 256;
+    const long long cap = (long long)p->sm_count * 16;
+    return (unsigned)(g < cap ? g : cap);
+}
+
+extern "C" int rks_set_u(rks_plan* p, const void* u, void* stream) {
+    if (!p || !u) return fail(RKS_ERR_ARG, "null argument");
+    copy_u_kernel<<<copy_grid(p), 256, 0, (cudaStream_t)stream>>>(p->d, (cplx*)u, 1);
+    p->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
+extern "C" int rks_get_u(rks_plan* p, void* u_out, void* stream) {
+    if (!p || !u_out) return fail(RKS_ERR_ARG, "null argument");
+    copy_u_kernel<<<copy_grid(p), 256, 0, (cudaStream_t)stream>>>(p->d, (cplx*)u_out, 0);
+    p->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// K2 dispatch
+// ---------------------------------------------------------------------------------------
+static int launch_coeffs(rks_plan* p, int force, cudaStream_t stream) {
+    const DevPlan& d = p->d;
+    const unsigned grid = (unsigned)((d.lin_elems + 127) / 128);
+    const int m = p->method;
+    const bool cx = d.lin_complex != 0;
+    if (m == M_IF4 || m == M_IF34) {
+        if (cx) coef_kernel<0, cplx><<<grid, 128, 0, stream>>>(d, force);
+        else coef_kernel<0, double><<<grid, 128, 0, stream>>>(d, force);
+    } else if (m == M_ETD4 || m == M_ETD34) {
+        coef_kernel<1, cplx><<<grid, 128, 0, stream>>>(d, force);
+    } else if (m == M_ETD5 || m == M_ETD35) {
+        coef_kernel<2, cplx><<<grid, 128, 0, stream>>>(d, force);
+    } else {
+        if (cx) coef_kernel<3, cplx><<<grid, 128, 0, stream>>>(d, force);
+        else coef_kernel<3, double><<<grid, 128, 0, stream>>>(d, force);
+    }
+    p->launches += 1;
+    return RKS_OK;
+}
+
+extern "C" int rks_update_coeffs(rks_plan* p, void* stream) {
+    if (!p) return fail(RKS_ERR_ARG, "plan is null");
+    // adaptive methods: the device compares ctrl.h with ctrl.h_coeff.  Fixed-step methods have no
+    // controller kernel, so the host keeps the cache key (the caller sets h through rks_set_h).
+    launch_coeffs(p, method_adaptive(p->method) ? 0 : 1, (cudaStream_t)stream);
+    CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// K1 dispatch
+// ---------------------------------------------------------------------------------------
+template <int M, int S, typename CT>
+static void launch_stage_t(rks_plan* p, cudaStream_t stream) {
+    const DevPlan& d = p->d;
+    const dim3 block(32, 8);
+    if (d.lin_full) {
+        const long long total = d.batch * d.n_c;
+        const unsigned gx = (unsigned)((total + 256 * STAGE_R - 1) / (256 * STAGE_R));
+        stage_kernel<M, S, CT, true><<<dim3(gx), block, 0, stream>>>(d);
+    } else {
+        const unsigned gx = (unsigned)((d.n_c + 31) / 32);
+        const unsigned gy = (unsigned)((d.batch + 8 * STAGE_R - 1) / (8 * STAGE_R));
+        stage_kernel<M, S, CT, false><<<dim3(gx, gy), block, 0, stream>>>(d);
+    }
+}
+
+template <int M, typename CT>
+static int launch_stage_m(rks_plan* p, int s, cudaStream_t stream) {
+    constexpr int SMAX = method_stages(M);
+    switch (s) {
+        case 1: launch_stage_t<M, 1, CT>(p, stream); break;
+        case 2: launch_stage_t<M, 2, CT>(p, stream); break;
+        case 3: launch_stage_t<M, 3, CT>(p, stream); break;
+        case 4: launch_stage_t<M, 4, CT>(p, stream); break;
+        case 5: if (SMAX >= 5) launch_stage_t<M, (SMAX >= 5 ? 5 : 1), CT>(p, stream); break;
+        case 6: if (SMAX >= 6) launch_stage_t<M, (SMAX >= 6 ? 6 : 1), CT>(p, stream); break;
+        default: break;
+    }
+    return RKS_OK;
+}
+
+extern "C" int rks_stage(rks_plan* p, int s, void* stream_v) {
+    if (!p) return fail(RKS_ERR_ARG, "plan is null");
+    if (s < 1 || s > method_stages(p->method)) return fail(RKS_ERR_ARG, "stage out of range");
+    if (p->d.batch > 65535ll * 8 * STAGE_R && !p->d.lin_full) return fail(RKS_ERR_UNSUPPORTED, "batch too large for one launch");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    const bool cx = p->d.lin_complex != 0;
+    switch (p->method) {
+        case M_IF4: cx ? launch_stage_m<M_IF4, cplx>(p, s, stream) : launch_stage_m<M_IF4, double>(p, s, stream); break;
+        case M_IF34: cx ? launch_stage_m<M_IF34, cplx>(p, s, stream) : launch_stage_m<M_IF34, double>(p, s, stream); break;
+        case M_IF45DP: cx ? launch_stage_m<M_IF45DP, cplx>(p, s, stream) : launch_stage_m<M_IF45DP, double>(p, s, stream); break;
+        case M_ETD4: launch_stage_m<M_ETD4, cplx>(p, s, stream); break;
+        case M_ETD34: launch_stage_m<M_ETD34, cplx>(p, s, stream); break;
+        case M_ETD5: launch_stage_m<M_ETD5, cplx>(p, s, stream); break;
+        case M_ETD35: launch_stage_m<M_ETD35, cplx>(p, s, stream); break;
+    }
+    p->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// K4 dispatch
+// ---------------------------------------------------------------------------------------
+static int launch_nl(rks_plan* p, int j, int force, cudaStream_t stream) {
+    const DevPlan& d = p->d;
+    const unsigned grid = (unsigned)((d.batch + p->nl_rows_per_cta - 1) / p->nl_rows_per_cta);
+    if (d.model == RKS_MODEL_UUX_RFFT)
+        nl_kernel<1><<<grid, p->nl_threads, p->nl_smem, stream>>>(d, j, force, p->nl_rows_per_cta);
+    else
+        nl_kernel<2><<<grid, p->nl_threads, p->nl_smem, stream>>>(d, j, force, p->nl_rows_per_cta);
+    p->launches += 1;
+    return RKS_OK;
+}
+
+extern "C" int rks_nl(rks_plan* p, int j, void* stream) {
+    if (!p) return fail(RKS_ERR_ARG, "plan is null");
+    if (p->d.model == RKS_MODEL_NONE) return fail(RKS_ERR_UNSUPPORTED, "no fused model set (rks_set_model)");
+    const int S = method_stages(p->method);
+    const int jmax = method_fsal(p->method) ? S + 1 : S;
+    if (j < 1 || j > jmax) return fail(RKS_ERR_ARG, "N index out of range");
+    // fixed-step methods have no device predicate: the caller decides when N1 is (re)computed
+    launch_nl(p, j, method_adaptive(p->method) ? 0 : 1, (cudaStream_t)stream);
+    CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
+extern "C" void* rks_nl_input(rks_plan* p, int j) {
+    if (!p) return nullptr;
+    const int S = method_stages(p->method);
+    const int u_sel = method_adaptive(p->method) ? p->roles_u_sel : 0;
+    if (j == 1) return p->d.U[u_sel];
+    if (j <= S) return p->d.K;
+    return p->d.U[1 - u_sel];
+}
+
+extern "C" void* rks_nl_output(rks_plan* p, int j) {
+    if (!p || j < 1 || j > method_nl_buffers(p->method)) return nullptr;
+    const int n_sel = method_adaptive(p->method) ? p->roles_n_sel : 0;
+    return p->d.NL[nl_phys(p->method, j, n_sel)];
+}
+
+// ---------------------------------------------------------------------------------------
+// K3 dispatch
+// ---------------------------------------------------------------------------------------
+template <int M, typename CT>
+static void launch_norm_t(rks_plan* p, int fuse, cudaStream_t stream) {
+    const DevPlan& d = p->d;
+    const long long ncols = d.lin_full ? d.batch * d.n_c : d.n_c;
+    const long long nrows = d.lin_full ? 1 : d.batch;
+    const long long target = (long long)p->sm_count * 8;          // resident 128-thread CTAs we aim for
+    long long gx = (ncols + 127) / 128;
+    if (gx > target) gx = target;
+    long long gy = target / gx;
+    if (gy < 1) gy = 1;
+    if (gy > nrows) gy = nrows;
+    while (gx * gy > NORM_MAX_BLOCKS) { if (gy > 1) --gy; else --gx; }
+    if (d.lin_full) norm_kernel<M, CT, true><<<dim3((unsigned)gx, (unsigned)gy), 128, 0, stream>>>(d, fuse);
+    else norm_kernel<M, CT, false><<<dim3((unsigned)gx, (unsigned)gy), 128, 0, stream>>>(d, fuse);
+}
+
+static int launch_norm(rks_plan* p, int fuse, cudaStream_t stream) {
+    const bool cx = p->d.lin_complex != 0;
+    switch (p->method) {
+        case M_IF34: cx ? launch_norm_t<M_IF34, cplx>(p, fuse, stream) : launch_norm_t<M_IF34, double>(p, fuse, stream); break;
+        case M_IF45DP: cx ? launch_norm_t<M_IF45DP, cplx>(p, fuse, stream) : launch_norm_t<M_IF45DP, double>(p, fuse, stream); break;
+        case M_ETD34: launch_norm_t<M_ETD34, cplx>(p, fuse, stream); break;
+        case M_ETD35: launch_norm_t<M_ETD35, cplx>(p, fuse, stream); break;
+        default: return fail(RKS_ERR_UNSUPPORTED, "fixed-step methods have no error control");
+    }
+    p->launches += 1;
+    return RKS_OK;
+}
+
+extern "C" int rks_error_control(rks_plan* p, void* stream) {
+    if (!p) return fail(RKS_ERR_ARG, "plan is null");
+    if (int rc = launch_norm(p, 1, (cudaStream_t)stream)) return rc;
+    CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
+extern "C" int rks_error_sums(rks_plan* p, void* stream) {
+    if (!p) return fail(RKS_ERR_ARG, "plan is null");
+    if (int rc = launch_norm(p, 0, (cudaStream_t)stream)) return rc;
+    CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
+extern "C" int rks_controller(rks_plan* p, void* stream) {
+    if (!p) return fail(RKS_ERR_ARG, "plan is null");
+    if (!method_adaptive(p->method)) return fail(RKS_ERR_UNSUPPORTED, "fixed-step methods have no controller");
+    controller_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p->d);
+    p->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
+extern "C" double* rks_reduction_scalars(rks_plan* p) { return p ? p->d.ctrl->red : nullptr; }
+
+// ---------------------------------------------------------------------------------------
+// snapshots, whole trials, whole fixed steps
+// ---------------------------------------------------------------------------------------
+extern "C" int rks_snapshot(rks_plan* p, void* ring, double* ring_t, int cap, void* stream) {
+    if (!p || !ring || !ring_t || cap < 1) return fail(RKS_ERR_ARG, "bad snapshot ring");
+    snapshot_kernel<<<copy_grid(p), 256, 0, (cudaStream_t)stream>>>(p->d, (cplx*)ring, ring_t, cap);
+    p->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
+static int enqueue_trial(rks_plan* p, void* ring, double* ring_t, int cap, void* stream) {
+    const int m = p->method, S = method_stages(m);
+    int rc;
+    if ((rc = rks_update_coeffs(p, stream))) return rc;
+    if ((rc = rks_nl(p, 1, stream))) return rc;                 // runs only when ctrl.need_n1
+    for (int s = 1; s <= S; ++s) {
+        if ((rc = rks_stage(p, s, stream))) return rc;
+        if (s < S || method_fsal(m)) {
+            if ((rc = rks_nl(p, s + 1, stream))) return rc;
+        }
+    }
+    if ((rc = rks_error_control(p, stream))) return rc;
+    if (ring) return rks_snapshot(p, ring, ring_t, cap, stream);
+    return RKS_OK;
+}
+
+extern "C" int rks_run_trials(rks_plan* p, int ntrials, void* ring, double* ring_t, int cap, void* stream) {
+    if (!p) return fail(RKS_ERR_ARG, "plan is null");
+    if (!method_adaptive(p->method)) return fail(RKS_ERR_UNSUPPORTED, "rks_run_trials needs an adaptive method");
+    if (p->d.model == RKS_MODEL_NONE) return fail(RKS_ERR_UNSUPPORTED, "no fused model set (rks_set_model)");
+    for (int i = 0; i < ntrials; ++i)
+        if (int rc = enqueue_trial(p, ring, ring_t, cap, stream)) return rc;
+    return RKS_OK;
+}
+
+extern "C" int rks_run_fixed(rks_plan* p, int nsteps, void* stream) {
+    if (!p) return fail(RKS_ERR_ARG, "plan is null");
+    if (method_adaptive(p->method)) return fail(RKS_ERR_UNSUPPORTED, "rks_run_fixed needs a fixed-step method");
+    if (p->d.model == RKS_MODEL_NONE) return fail(RKS_ERR_UNSUPPORTED, "no fused model set (rks_set_model)");
+    const int S = method_stages(p->method);
+    int rc;
+    for (int i = 0; i < nsteps; ++i) {
+        for (int s = 1; s <= S; ++s) {
+            if ((rc = rks_stage(p, s, stream))) return rc;
+            // after the last stage U holds u+ and N1 <- N(u+)  (etd4.py:174)
+            if ((rc = rks_nl(p, s < S ? s + 1 : 1, stream))) return rc;
+        }
+    }
+    return RKS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// syncing reads
+// ---------------------------------------------------------------------------------------
+extern "C" int rks_read_ctrl(rks_plan* p, rks_ctrl_host* out, void* stream_v) {
+    if (!p || !out) return fail(RKS_ERR_ARG, "null argument");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    CUDA_TRY(cudaMemcpyAsync(p->pinned_raw, p->d.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    const Ctrl& c = *p->pinned_raw;
+    out->h = c.h; out->h_last = c.h_last; out->h_coeff = c.h_coeff; out->t = c.t; out->tf = c.tf;
+    out->s_last = c.s_last;
+    out->step_count = c.step_count; out->trial_count = c.trial_count; out->nl_evals = c.nl_evals;
+    out->coeff_updates = c.coeff_updates;
+    out->status = c.status; out->accept = c.accept; out->numloops = c.numloops;
+    out->u_sel = c.u_sel; out->n_sel = c.n_sel; out->need_n1 = c.need_n1;
+    out->log_count = c.log_count; out->snap_count = c.snap_count;
+    p->roles_u_sel = c.u_sel;
+    p->roles_n_sel = c.n_sel;
+    return RKS_OK;
+}
+
+extern "C" int rks_read_log(rks_plan* p, rks_trial_rec* out, int first, int count, void* stream_v) {
+    if (!p || !out || first < 0 || count < 0 || count > LOG_CAP) return fail(RKS_ERR_ARG, "bad log range");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    CUDA_TRY(cudaMemcpyAsync(p->pinned_log, p->d.log, sizeof(TrialRec) * LOG_CAP, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    for (int i = 0; i < count; ++i) memcpy(&out[i], &p->pinned_log[(first + i) % LOG_CAP], sizeof(TrialRec));
+    return RKS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// introspection
+// ---------------------------------------------------------------------------------------
+static int coef_slot(int m, const std::string& s) {
+    static const char* kro_n[] = {"E", "E2", "a21", "a31", "a32", "a41", "a43", "a51", "a52", "a54"};
+    static const char* e5_n[] = {"E14", "E12", "E34", "E", "a21", "a31", "a32", "a41", "a43", "a51", "a52", "a54",
+                                 "a61", "a62", "a63", "a65", "a71", "a73", "a74", "a75", "a76"};
+    static const char* if_n[] = {"E", "E2"};
+    static const char* dp_n[] = {"E15", "E310", "E45", "E89", "E", "a21", "a31", "a32", "a41", "a42", "a43", "a51",
+                                 "a52", "a53", "a54", "a61", "a62", "a63", "a64", "a65", "a71", "a73", "a74", "a75",
+                                 "r1", "r3", "r4", "r5"};
+    const char** names = (m == M_IF4 || m == M_IF34) ? if_n : (m == M_ETD4 || m == M_ETD34) ? kro_n
+                       : (m == M_ETD5 || m == M_ETD35) ? e5_n : dp_n;
+    for (int i = 0; i < method_ncoef(m); ++i)
+        if (s == names[i]) return i;
+    return -1;
+}
+
+extern "C" void* rks_array(rks_plan* p, const char* name) {
+    if (!p || !name) return nullptr;
+    const std::string s(name);
+    const DevPlan& d = p->d;
+    if (s == "U0") return d.U[0];
+    if (s == "U1") return d.U[1];
+    if (s == "K") return d.K;
+    if (s == "ERR") return d.ERR;
+    if (s == "ctrl") return d.ctrl;
+    if (s == "tw") return (void*)d.tw;
+    if (s.size() == 2 && s[0] == 'N' && s[1] >= '1' && s[1] <= '7') {
+        const int j = s[1] - '0';
+        return j <= method_nl_buffers(p->method) ? d.NL[j] : nullptr;
+    }
+    const int slot = coef_slot(p->method, s);
+    if (slot < 0) return nullptr;
+    const bool real_coef = method_is_if(p->method) && !d.lin_complex;
+    const size_t elem = real_coef ? sizeof(double) : sizeof(cplx);
+    return (unsigned char*)d.coef + elem * (size_t)d.lin_elems * slot;
+}
+
+extern "C" int64_t rks_kernel_launches(rks_plan* p) { return p ? p->launches : 0; }

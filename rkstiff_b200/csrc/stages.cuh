@@ -1,0 +1,121 @@
+// K1 -- per-stage linear combinations, one fused pass per RK stage.
+// Restates the update_stages bodies of
+//   rkstiff/if4.py:112-121, if34.py:120-130, etd4.py:167-174, etd34.py:182-190,
+//   etd5.py:236-260, etd35.py:320-344, if45dp.py:140-179.
+// `nv[j]` is the value of N_j at this element, `cv[slot]` the coefficient of this mode.
+#pragma once
+#include "common.cuh"
+#include "coeffs.cuh"
+
+namespace rks {
+
+// which logical N buffers stage S of method M reads (bit j set => N_j)
+RKS_HD constexpr unsigned stage_nl_mask(int M, int S) {
+    if (M == M_IF4 || M == M_IF34)
+        return S == 1 ? 0x02u : S == 2 ? 0x04u : S == 3 ? 0x08u : 0x1Eu;
+    if (M == M_ETD4 || M == M_ETD34)
+        return S == 1 ? 0x02u : S == 2 ? 0x06u : S == 3 ? 0x0Au : 0x1Eu;
+    if (M == M_ETD5 || M == M_ETD35)
+        return S == 1 ? 0x02u : S == 2 ? 0x06u : S == 3 ? 0x0Au : S == 4 ? 0x1Eu : S == 5 ? 0x3Eu : 0x7Au;
+    // IF45DP
+    return S == 1 ? 0x02u : S == 2 ? 0x06u : S == 3 ? 0x0Eu : S == 4 ? 0x1Eu : S == 5 ? 0x3Eu : 0x7Au;
+}
+
+// which coefficient slots stage S of method M reads
+RKS_HD constexpr unsigned stage_coef_mask(int M, int S) {
+#define B(x) (1u << (x))
+    if (M == M_IF4 || M == M_IF34)
+        return S <= 2 ? B(ifc::E2) : (B(ifc::E) | B(ifc::E2));
+    if (M == M_ETD4 || M == M_ETD34)
+        return S == 1 ? (B(kro::E2) | B(kro::a21)) : S == 2 ? (B(kro::E2) | B(kro::a31) | B(kro::a32))
+             : S == 3 ? (B(kro::E) | B(kro::a41) | B(kro::a43))
+                      : (B(kro::E) | B(kro::a51) | B(kro::a52) | B(kro::a54));
+    if (M == M_ETD5 || M == M_ETD35)
+        return S == 1 ? (B(e5::E14) | B(e5::a21)) : S == 2 ? (B(e5::E14) | B(e5::a31) | B(e5::a32))
+             : S == 3 ? (B(e5::E12) | B(e5::a41) | B(e5::a43))
+             : S == 4 ? (B(e5::E34) | B(e5::a51) | B(e5::a52) | B(e5::a54))
+             : S == 5 ? (B(e5::E) | B(e5::a61) | B(e5::a62) | B(e5::a63) | B(e5::a65))
+                      : (B(e5::E) | B(e5::a71) | B(e5::a73) | B(e5::a74) | B(e5::a75) | B(e5::a76));
+    return S == 1 ? (B(dp::E15) | B(dp::a21)) : S == 2 ? (B(dp::E310) | B(dp::a31) | B(dp::a32))
+         : S == 3 ? (B(dp::E45) | B(dp::a41) | B(dp::a42) | B(dp::a43))
+         : S == 4 ? (B(dp::E89) | B(dp::a51) | B(dp::a52) | B(dp::a53) | B(dp::a54))
+         : S == 5 ? (B(dp::E) | B(dp::a61) | B(dp::a62) | B(dp::a63) | B(dp::a64) | B(dp::a65))
+                  : (B(dp::E) | B(dp::a71) | B(dp::a73) | B(dp::a74) | B(dp::a75));
+#undef B
+}
+
+// N buffers / coefficient slots the embedded error estimate reads when it is formed inside the
+// norm kernel (IF34, ETD34, IF45DP); ETD35 emits err from its last stage instead.
+RKS_HD constexpr unsigned err_nl_mask(int M) {
+    return (M == M_IF34 || M == M_ETD34) ? 0x30u : M == M_IF45DP ? 0xFAu : 0u;
+}
+RKS_HD constexpr unsigned err_coef_mask(int M) {
+    return M == M_ETD34 ? (1u << kro::a54)
+         : M == M_IF45DP ? ((1u << dp::r1) | (1u << dp::r3) | (1u << dp::r4) | (1u << dp::r5)) : 0u;
+}
+
+template <int M, int S, typename CT>
+RKS_HD cplx stage_combine(cplx u, const cplx* nv, const CT* cv, double h) {
+    if (M == M_IF4 || M == M_IF34) {
+        // if4.py:112-120: coefficients are formed on the fly from h, E, E2
+        if (S == 1) return cmul(cv[ifc::E2], u) + cmul(scale(h, cv[ifc::E2]), nv[1]) / 2.0;
+        if (S == 2) return cmul(cv[ifc::E2], u) + (h * nv[2]) / 2.0;
+        if (S == 3) return cmul(cv[ifc::E], u) + cmul(scale(h, cv[ifc::E2]), nv[3]);
+        return cmul(cv[ifc::E], u)
+             + h * (cmul(cv[ifc::E], nv[1]) / 6.0 + cmul(cv[ifc::E2], nv[2]) / 3.0
+                    + cmul(cv[ifc::E2], nv[3]) / 3.0 + nv[4] / 6.0);
+    }
+    if (M == M_ETD4 || M == M_ETD34) {
+        if (S == 1) return cmul(cv[kro::E2], u) + cmul(cv[kro::a21], nv[1]);
+        if (S == 2) return cmul(cv[kro::E2], u) + cmul(cv[kro::a31], nv[1]) + cmul(cv[kro::a32], nv[2]);
+        if (S == 3) return cmul(cv[kro::E], u) + cmul(cv[kro::a41], nv[1]) + cmul(cv[kro::a43], nv[3]);
+        return cmul(cv[kro::E], u) + cmul(cv[kro::a51], nv[1]) + cmul(cv[kro::a52], nv[2] + nv[3])
+             + cmul(cv[kro::a54], nv[4]);
+    }
+    if (M == M_ETD5 || M == M_ETD35) {
+        if (S == 1) return cmul(cv[e5::E14], u) + cmul(cv[e5::a21], nv[1]);
+        if (S == 2) return cmul(cv[e5::E14], u) + cmul(cv[e5::a31], nv[1]) + cmul(cv[e5::a32], nv[2]);
+        if (S == 3) return cmul(cv[e5::E12], u) + cmul(cv[e5::a41], nv[1]) + cmul(cv[e5::a43], nv[3]);
+        if (S == 4)
+            return cmul(cv[e5::E34], u) + cmul(cv[e5::a51], nv[1]) + cmul(cv[e5::a52], nv[2] - nv[3])
+                 + cmul(cv[e5::a54], nv[4]);
+        if (S == 5)
+            return cmul(cv[e5::E], u) + cmul(cv[e5::a61], nv[1])
+                 + cmul(cv[e5::a62], nv[2] - (3.0 * nv[4]) / 2.0) + cmul(cv[e5::a63], nv[3])
+                 + cmul(cv[e5::a65], nv[5]);
+        return cmul(cv[e5::E], u) + cmul(cv[e5::a71], nv[1]) + cmul(cv[e5::a73], nv[3])
+             + cmul(cv[e5::a74], nv[4]) + cmul(cv[e5::a75], nv[5]) + cmul(cv[e5::a76], nv[6]);
+    }
+    // IF45DP
+    if (S == 1) return cmul(cv[dp::E15], u) + cmul(cv[dp::a21], nv[1]);
+    if (S == 2) return cmul(cv[dp::E310], u) + cmul(cv[dp::a31], nv[1]) + cmul(cv[dp::a32], nv[2]);
+    if (S == 3)
+        return cmul(cv[dp::E45], u) + cmul(cv[dp::a41], nv[1]) + cmul(cv[dp::a42], nv[2])
+             + cmul(cv[dp::a43], nv[3]);
+    if (S == 4)
+        return cmul(cv[dp::E89], u) + cmul(cv[dp::a51], nv[1]) + cmul(cv[dp::a52], nv[2])
+             + cmul(cv[dp::a53], nv[3]) + cmul(cv[dp::a54], nv[4]);
+    if (S == 5)
+        return cmul(cv[dp::E], u) + cmul(cv[dp::a61], nv[1]) + cmul(cv[dp::a62], nv[2])
+             + cmul(cv[dp::a63], nv[3]) + cmul(cv[dp::a64], nv[4]) + cmul(cv[dp::a65], nv[5]);
+    return cmul(cv[dp::E], u) + cmul(cv[dp::a71], nv[1]) + cmul(cv[dp::a73], nv[3])
+         + cmul(cv[dp::a74], nv[4]) + cmul(cv[dp::a75], nv[5]) + dp_a76(h) * nv[6];
+}
+
+// ETD35 error estimate, formed in the last stage kernel (etd35.py:344)
+template <typename CT>
+RKS_HD cplx etd35_err(const cplx* nv, const CT* cv) {
+    return cmul(cv[e5::a75], -nv[1] + 4.0 * nv[3] - 6.0 * nv[4] + 4.0 * nv[5] - nv[6]);
+}
+
+// error estimates that need N(u+) and are therefore formed in the norm kernel
+// (if34.py:130, etd34.py:190, if45dp.py:172-179)
+template <int M, typename CT>
+RKS_HD cplx embedded_err(const cplx* nv, const CT* cv, double h) {
+    if (M == M_IF34) return (h * (nv[4] - nv[5])) / 6.0;
+    if (M == M_ETD34) return cmul(cv[kro::a54], nv[4] - nv[5]);
+    return cmul(cv[dp::r1], nv[1]) + cmul(cv[dp::r3], nv[3]) + cmul(cv[dp::r4], nv[4])
+         + cmul(cv[dp::r5], nv[5]) + dp_r6(h) * nv[6] + dp_r7(h) * nv[7];
+}
+
+}  // namespace rks

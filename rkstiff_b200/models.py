@@ -1,0 +1,90 @@
+"""Model zoo: linear operators and nonlinear terms of the reference's spectral equations, with the
+nonlinear term available both as a fused CUDA kernel (K4, csrc/fft.cuh) and as a torch callable.
+
+Reference formulations (file:line):
+  kdv_ops ........ rkstiff/models.py:113-145   L = i k^3,        N = -6 F{u u_x}
+  burgers_ops .... rkstiff/models.py:153-194   L = -mu k^2,      N = -F{u u_x}
+  ks_ops ......... README.md:86-97             L = k^2 (1-k^2),  N = -F{u u_x}
+  nls_ops ........ demos/nls.ipynb             L = -i k^2,       N = i gamma F{|u|^2 u}
+  kdv_soliton .... rkstiff/models.py:32, kdv_multi_soliton models.py:76-110
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _abi
+
+
+class FusedNL:
+    """Handle of a fused spectral nonlinearity.
+
+    Passed as ``nl_func`` it makes the solver run the hand-written shared-memory FFT kernel;
+    called like a function it evaluates the same expression with ``torch.fft`` (used by tests
+    and wherever a plain callable is wanted).
+    """
+
+    def __init__(self, model_id: int, n: int, kx: Optional[torch.Tensor], param: float, name: str) -> None:
+        if n < 16 or n & (n - 1):
+            raise ValueError("fused nonlinearities need a power-of-two grid with n >= 16")
+        self.model_id = model_id
+        self.n = int(n)
+        self.kx = kx
+        self.param = float(param)
+        self.name = name
+
+    def __call__(self, uf: torch.Tensor) -> torch.Tensor:
+        if self.model_id == _abi.MODEL_UUX_RFFT:
+            u = torch.fft.irfft(uf, n=self.n, dim=-1)
+            ux = torch.fft.irfft(1j * self.kx * uf, n=self.n, dim=-1)
+            return -self.param * torch.fft.rfft(u * ux, dim=-1)
+        f = torch.fft.ifft(uf, dim=-1)
+        f2 = f.real ** 2 + f.imag ** 2
+        return 1j * self.param * torch.fft.fft(f2 * f, dim=-1)
+
+    def __repr__(self) -> str:
+        return f"FusedNL({self.name}, n={self.n}, param={self.param})"
+
+
+def _n_from_rfft_kx(kx: torch.Tensor) -> int:
+    return 2 * (kx.shape[-1] - 1)
+
+
+def kdv_ops(kx: torch.Tensor) -> Tuple[torch.Tensor, FusedNL]:
+    """KdV u_t = -u_xxx - 6 u u_x in rfft space (models.py:113-145)."""
+    lin_op = 1j * kx.to(torch.complex128) ** 3
+    return lin_op, FusedNL(_abi.MODEL_UUX_RFFT, _n_from_rfft_kx(kx), kx, 6.0, "kdv")
+
+
+def burgers_ops(kx: torch.Tensor, mu: float) -> Tuple[torch.Tensor, FusedNL]:
+    """Viscous Burgers u_t = mu u_xx - u u_x in rfft space (models.py:153-194)."""
+    lin_op = -mu * kx ** 2
+    return lin_op, FusedNL(_abi.MODEL_UUX_RFFT, _n_from_rfft_kx(kx), kx, 1.0, "burgers")
+
+
+def ks_ops(kx: torch.Tensor) -> Tuple[torch.Tensor, FusedNL]:
+    """Kuramoto-Sivashinsky u_t = -u_xx - u_xxxx - u u_x in rfft space (README.md:86-97)."""
+    lin_op = kx ** 2 * (1 - kx ** 2)
+    return lin_op, FusedNL(_abi.MODEL_UUX_RFFT, _n_from_rfft_kx(kx), kx, 1.0, "ks")
+
+
+def nls_ops(kx: torch.Tensor, gamma: float = 2.0) -> Tuple[torch.Tensor, FusedNL]:
+    """Cubic NLS u_t = i u_xx + i gamma |u|^2 u in fft space (demos/nls.ipynb)."""
+    lin_op = -1j * kx.to(torch.complex128) ** 2
+    return lin_op, FusedNL(_abi.MODEL_NLS_FFT, kx.shape[-1], kx, gamma, "nls")
+
+
+def kdv_soliton(x: torch.Tensor, ampl: float = 0.5, x0: float = 0.0, t: float = 0.0) -> torch.Tensor:
+    """Single KdV soliton 0.5 a^2 sech^2(a (x - x0 - a^2 t)/2) (models.py:32)."""
+    return 0.5 * ampl ** 2 / torch.cosh(ampl * (x - x0 - ampl ** 2 * t) / 2) ** 2
+
+
+def kdv_multi_soliton(x: torch.Tensor, ampl: Sequence[float], x0: Sequence[float], t: float = 0.0) -> torch.Tensor:
+    """Superposition of KdV solitons (models.py:76-110)."""
+    if len(x0) != len(ampl):
+        raise ValueError("Lengths of ampl and x0 must match.")
+    out = torch.zeros_like(x)
+    for a, c in zip(ampl, x0):
+        out = out + kdv_soliton(x, a, c, t)
+    return out

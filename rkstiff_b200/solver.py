@@ -1,0 +1,102 @@
+"""BaseSolver: the API shell shared by every solver class (rkstiff/solver.py:30-213).
+
+Differences from the reference, all extensions:
+  * ``lin_op`` and ``u`` are CUDA tensors (complex128 state, float64 or complex128 operator);
+  * ``lin_op`` is always a *diagonal* operator: it may be ``(n,)`` broadcast over leading batch
+    dimensions of ``u`` or have any rank matching the trailing dimensions of ``u`` (N-D grids).
+    Dense-matrix operators (the reference's 2-D ``lin_op``) are out of scope and rejected via
+    ``diagonalize=True`` / ``matrix=True`` -> NotImplementedError;
+  * ``nl_func`` is a torch callable or a fused-kernel handle from :mod:`rkstiff_b200.models`.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from typing import Callable, Dict, Optional, Union
+
+import torch
+
+from . import _abi
+from ._engine import Engine
+from .util.loghelper import get_level_name, get_solver_logger, set_log_level
+
+
+class BaseSolver(ABC):
+    METHOD: str = ""
+
+    def __init__(self, lin_op: torch.Tensor, nl_func: Callable[[torch.Tensor], torch.Tensor],
+                 loglevel: Union[str, int] = "WARNING", group=None) -> None:
+        if not torch.is_tensor(lin_op):
+            raise TypeError("lin_op must be a torch tensor on a CUDA device")
+        if lin_op.dim() < 1:
+            raise ValueError("lin_op must have at least one dimension")
+        if not lin_op.is_cuda:
+            raise ValueError("lin_op must live on a CUDA device: rkstiff_b200 has no CPU path")
+        if lin_op.dtype not in (torch.float64, torch.complex128):
+            raise TypeError("lin_op must be float64 or complex128")
+        self.lin_op = lin_op
+        self.nl_func = nl_func
+        self.logger = get_solver_logger(self.__class__, loglevel)
+        self.logger.info("Initialized %s solver", self.__class__.__name__)
+        self.t, self.u = [], []
+        self._diag = True
+        self._group = group
+        self._engines: Dict[tuple, Engine] = {}
+        self._engine: Optional[Engine] = None
+        self.logger.debug("Linear operator shape: %s, diagonal: %s", tuple(lin_op.shape), self._diag)
+
+    # -- engine plumbing ------------------------------------------------------------------
+    def _rks_config(self) -> _abi.RksConfig:
+        cfg = getattr(self, "config", None)
+        etd = getattr(self, "etd_config", None)
+        return _abi.RksConfig(
+            epsilon=cfg.epsilon if cfg else 1e-4, incr_f=cfg.incr_f if cfg else 1.25,
+            decr_f=cfg.decr_f if cfg else 0.85, safety_f=cfg.safety_f if cfg else 0.8,
+            adapt_cutoff=cfg.adapt_cutoff if cfg else 0.01, minh=cfg.minh if cfg else 1e-16,
+            modecutoff=etd.modecutoff if etd else 0.01, contour_radius=etd.contour_radius if etd else 1.0,
+            contour_points=etd.contour_points if etd else 32,
+            if45dp_r4_fix=int(bool(getattr(self, "r4_fix", False))))
+
+    def _fused(self):
+        from .models import FusedNL
+        return self.nl_func if isinstance(self.nl_func, FusedNL) else None
+
+    def _callable(self):
+        """None when the fused CUDA nonlinearity is used, else the torch callable."""
+        return None if self._fused() is not None else self.nl_func
+
+    def _get_engine(self, u: torch.Tensor) -> Engine:
+        key = tuple(u.shape)
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = Engine(self.METHOD, self.lin_op, u.shape, self._rks_config(), fused=self._fused(),
+                         group=self._group)
+            self._engines = {key: eng}           # one live plan per solver: a new shape replaces the old
+            self._cfg_sig = self._config_signature()
+        elif self._cfg_sig != self._config_signature():
+            # config objects are read live on every trial by the reference (solveras.py:452-454)
+            eng.set_config(self._rks_config())
+            self._cfg_sig = self._config_signature()
+        self._engine = eng
+        return eng
+
+    def _config_signature(self):
+        c = self._rks_config()
+        return tuple(getattr(c, f) for f, _ in c._fields_)
+
+    # -- reference API ---------------------------------------------------------------------
+    @property
+    @abstractmethod
+    def solver_type(self):
+        """SolverType.CONSTANT_STEP or SolverType.ADAPTIVE_STEP."""
+
+    def set_loglevel(self, loglevel: Union[str, int]) -> None:
+        set_log_level(self.logger, loglevel)
+        self.logger.info("Log level changed to %s", get_level_name(self.logger.level))
+
+    @abstractmethod
+    def reset(self) -> None:
+        """Clear stored snapshots and internal stepping state."""
+
+    @abstractmethod
+    def _reset(self) -> None:
+        """Method-specific part of reset()."""

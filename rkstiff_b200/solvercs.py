@@ -1,0 +1,104 @@
+"""BaseSolverCS: constant-step driver (rkstiff/solvercs.py:31-279) on the CUDA engine."""
+from __future__ import annotations
+
+from typing import Callable, Union
+
+import torch
+
+from .solver import BaseSolver
+from .util.solver_type import SolverType
+
+
+class BaseSolverCS(BaseSolver):
+    """Fixed-step evolve()/step().  With a fused nonlinearity evolve() enqueues every step
+    without a single host sync; snapshots are device-to-device clones on the same stream."""
+
+    def __init__(self, lin_op, nl_func, loglevel: Union[str, int] = "WARNING", group=None) -> None:
+        super().__init__(lin_op, nl_func, loglevel, group=group)
+        self._last_out = None
+
+    @property
+    def solver_type(self) -> SolverType:
+        return SolverType.CONSTANT_STEP
+
+    def reset(self) -> None:
+        self.logger.debug("Resetting constant-step solver state")
+        self.t, self.u = [], []
+        self._reset()
+
+    def _reset(self) -> None:
+        """solvercs.py: subclasses clear n1_init and the cached h (etd4.py:382-385)."""
+        self._h_coeff = None
+        self._last_out = None
+        if self._engine is not None:
+            self._engine.begin(0.0, 0.0, 0.0, 0, True, keep_fsal=False)
+
+    def _load_state(self, eng, u: torch.Tensor) -> None:
+        """Copy u into the plan unless it is the (unmodified) tensor the last step returned."""
+        tag = self._last_out
+        if tag is not None and tag[0] is eng and tag[1] == u.data_ptr() and tag[2] == u._version:
+            return
+        eng.set_u(u)
+
+    def _remember(self, eng, out: torch.Tensor) -> None:
+        self._last_out = (eng, out.data_ptr(), out._version)
+
+    def _update_stages(self, u: torch.Tensor, h: float) -> torch.Tensor:
+        eng = self._get_engine(u)
+        eng.ensure_fixed_coeffs(h)
+        self._h_coeff = h
+        self._load_state(eng, u)
+        eng.fixed_step(self._callable())
+        out = eng.get_u()
+        self._remember(eng, out)
+        return out
+
+    def step(self, u: torch.Tensor, h: float) -> torch.Tensor:
+        assert h >= 0.0
+        self.logger.debug("Executing constant step with h=%s", h)
+        return self._update_stages(u, h)
+
+    def evolve(self, u: torch.Tensor, t0: float, tf: float, h: float, store_data: bool = True,
+               store_freq: int = 1) -> torch.Tensor:
+        self.reset()
+        self.logger.info("Starting constant-step evolution from t=%s to t=%s", t0, tf)
+        tc = t0
+        if store_data:
+            self.t.append(t0)
+            self.u.append(u)
+        if tc + h > tf:
+            raise ValueError("Step size h must be <= (tf - t0); reduce h or extend tf.")
+        self.logger.debug("Step size h=%s, store_freq=%s", h, store_freq)
+        if not tc < tf:
+            return u
+        eng = self._get_engine(u)
+        eng.begin(t0, tf, h, 0, True, keep_fsal=False)
+        eng.ensure_fixed_coeffs(h)
+        self._h_coeff = h
+        eng.set_u(u)
+        nl = self._callable()
+        step_count = 0
+        pending = 0                                  # fused path: steps not yet enqueued
+        while tc < tf:                               # float-accumulated loop count, solvercs.py:258-261
+            if nl is None:
+                pending += 1
+            else:
+                eng.fixed_step(nl)
+            tc += h
+            step_count += 1
+            if step_count % 100 == 0:
+                self.logger.info("Progress: t=%.6f/%.6f (%.1f%%), steps=%d", tc, tf, 100 * tc / tf, step_count)
+            if store_data and step_count % store_freq == 0:
+                if pending:
+                    eng.run_fixed(pending)
+                    pending = 0
+                self.t.append(tc)
+                self.u.append(eng.get_u())           # clone: plan buffers are reused
+                self.logger.debug("Stored snapshot at t=%.6f (step %d)", tc, step_count)
+        if pending:
+            eng.run_fixed(pending)
+        self.logger.info("Evolution complete after %d steps", step_count)
+        self.logger.info("Stored %d snapshots", len(self.u))
+        out = eng.get_u()
+        self._remember(eng, out)
+        return out

@@ -1,0 +1,192 @@
+// CPU harness for the __host__ __device__ math of rkstiff_b200/csrc (tests only).
+// It compiles the SAME headers the CUDA kernels use with g++ and drives the per-thread
+// phase functions serially (one "thread" at a time, a barrier being the end of the loop),
+// so the device algorithms (FFT passes, psi/tableau formulas, stage combinations,
+// controller state machine) can be checked against the oracle without a GPU.
+// This is not a product path: nothing in rkstiff_b200/ loads it.
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+
+#include "../../rkstiff_b200/csrc/common.cuh"
+#include "../../rkstiff_b200/csrc/coeffs.cuh"
+#include "../../rkstiff_b200/csrc/stages.cuh"
+#include "../../rkstiff_b200/csrc/errctl.cuh"
+#include "../../rkstiff_b200/csrc/fft.cuh"
+
+using namespace rks;
+
+template <int M, int S>
+static void stage_all(int n, const cplx* u, const cplx* const* N, const cplx* coef, double h, cplx* out, cplx* err) {
+    constexpr int NC = method_ncoef(M);
+    for (int i = 0; i < n; ++i) {
+        cplx nv[8], cv[NC];
+        for (int j = 1; j <= 7; ++j) nv[j] = N[j] ? N[j][i] : mk(0, 0);
+        for (int s = 0; s < NC; ++s) cv[s] = coef[s * n + i];
+        out[i] = stage_combine<M, S, cplx>(u[i], nv, cv, h);
+        if (M == M_ETD35 && S == 6 && err) err[i] = etd35_err<cplx>(nv, cv);
+    }
+}
+
+extern "C" {
+
+// fused NL of one row, emulating `nthreads` threads
+void hc_nl(int model, int n, const double* in, const double* kx, double p0, double* out, int nthreads) {
+    int log2n = 0;
+    while ((1 << log2n) < n) ++log2n;
+    std::vector<cplx> tw(n), x(n);
+    for (int j = 0; j < n; ++j) tw[j] = mk(cos(-2.0 * M_PI * j / n), sin(-2.0 * M_PI * j / n));
+    const cplx* cin = reinterpret_cast<const cplx*>(in);
+    cplx* cout = reinterpret_cast<cplx*>(out);
+    for (int t = 0; t < nthreads; ++t) {
+        if (model == 1) uux_load(x.data(), cin, kx, n, t, nthreads);
+        else nls_load(x.data(), cin, n, t, nthreads);
+    }
+    const int np = fft_num_passes(log2n);
+    for (int q = 0; q < np; ++q)
+        for (int t = 0; t < nthreads; ++t) ifft_dif_pass(x.data(), log2n, q, tw.data(), t, nthreads);
+    for (int t = 0; t < nthreads; ++t) {
+        if (model == 1) uux_pointwise(x.data(), n, t, nthreads);
+        else nls_pointwise(x.data(), n, t, nthreads);
+    }
+    for (int q = 0; q < np; ++q)
+        for (int t = 0; t < nthreads; ++t) fft_dit_pass(x.data(), log2n, q, tw.data(), t, nthreads);
+    for (int t = 0; t < nthreads; ++t) {
+        if (model == 1) uux_store(cout, x.data(), p0, n, t, nthreads);
+        else nls_store(cout, x.data(), p0, n, t, nthreads);
+    }
+}
+
+// inverse-DIF followed by forward-DIT must be n * identity; also exposes the raw transforms
+void hc_fft_roundtrip(int n, const double* in, double* out) {
+    int log2n = 0;
+    while ((1 << log2n) < n) ++log2n;
+    std::vector<cplx> tw(n), x(n);
+    for (int j = 0; j < n; ++j) tw[j] = mk(cos(-2.0 * M_PI * j / n), sin(-2.0 * M_PI * j / n));
+    memcpy(x.data(), in, sizeof(cplx) * n);
+    const int np = fft_num_passes(log2n);
+    for (int q = 0; q < np; ++q) ifft_dif_pass(x.data(), log2n, q, tw.data(), 0, 1);
+    for (int q = 0; q < np; ++q) fft_dit_pass(x.data(), log2n, q, tw.data(), 0, 1);
+    memcpy(out, x.data(), sizeof(cplx) * n);
+}
+
+// coefficient arrays of one method: out is [ncoef][n] complex (IF real coefficients are widened)
+int hc_coeffs(int method, int n, const double* lin, int lin_complex, double h, double modecutoff,
+              int contour_points, double contour_radius, int r4_fix, double* out) {
+    cplx* o = reinterpret_cast<cplx*>(out);
+    const int nc = method_ncoef(method);
+    for (int i = 0; i < n; ++i) {
+        const cplx L = lin_complex ? mk(lin[2 * i], lin[2 * i + 1]) : mk(lin[i], 0.0);
+        if (method == M_IF4 || method == M_IF34) {
+            if (lin_complex) {
+                const cplx z = scale(h, L);
+                o[ifc::E * n + i] = cexp_t(z);
+                o[ifc::E2 * n + i] = cexp_t(z / 2.0);
+            } else {
+                const double z = h * L.x;
+                o[ifc::E * n + i] = mk(exp(z), 0.0);
+                o[ifc::E2 * n + i] = mk(exp(z / 2.0), 0.0);
+            }
+        } else if (method == M_IF45DP) {
+            if (lin_complex) {
+                cplx arr[dp::COUNT];
+                tableau_if45dp<cplx>(scale(h, L), h, r4_fix, arr);
+                for (int s = 0; s < nc; ++s) o[s * n + i] = arr[s];
+            } else {
+                double arr[dp::COUNT];
+                tableau_if45dp<double>(h * L.x, h, r4_fix, arr);
+                for (int s = 0; s < nc; ++s) o[s * n + i] = mk(arr[s], 0.0);
+            }
+        } else {
+            const bool five = (method == M_ETD5 || method == M_ETD35);
+            const cplx z = lin_complex ? scale(h, L) : mk(h * L.x, 0.0);
+            PsiSet ps = psi_zero();
+            if (hypot(z.x, z.y) < modecutoff) {
+                for (int j = 0; j < contour_points; ++j) {
+                    const cplx w = z + contour_node(contour_radius, j, contour_points);
+                    if (five) psi_accumulate<true>(ps, w); else psi_accumulate<false>(ps, w);
+                }
+                psi_scale(ps, h, (double)contour_points);
+            } else {
+                if (five) psi_accumulate<true>(ps, z); else psi_accumulate<false>(ps, z);
+                psi_scale(ps, h, 1.0);
+            }
+            if (five) {
+                cplx arr[e5::COUNT];
+                arr[e5::E14] = cexp(z / 4.0); arr[e5::E12] = cexp(z / 2.0);
+                arr[e5::E34] = cexp((3.0 * z) / 4.0); arr[e5::E] = cexp(z);
+                tableau_etd5(ps, arr);
+                for (int s = 0; s < nc; ++s) o[s * n + i] = arr[s];
+            } else {
+                cplx arr[kro::COUNT];
+                arr[kro::E] = cexp(z); arr[kro::E2] = cexp(z / 2.0);
+                tableau_krogstad(ps, arr);
+                for (int s = 0; s < nc; ++s) o[s * n + i] = arr[s];
+            }
+        }
+    }
+    return nc;
+}
+
+#define HC_STAGE(M, S) if (method == M && stage == S) { stage_all<M, S>(n, cu, Np, cc, h, co, ce); return 0; }
+// one stage combine with complex coefficients; N is 8 pointers (index 1..7, may be null)
+int hc_stage(int method, int stage, int n, const double* u, const double* const* N, const double* coef, double h,
+             double* out, double* err) {
+    const cplx* cu = reinterpret_cast<const cplx*>(u);
+    const cplx* Np[8];
+    for (int j = 0; j < 8; ++j) Np[j] = reinterpret_cast<const cplx*>(N[j]);
+    const cplx* cc = reinterpret_cast<const cplx*>(coef);
+    cplx* co = reinterpret_cast<cplx*>(out);
+    cplx* ce = reinterpret_cast<cplx*>(err);
+    HC_STAGE(M_IF4, 1) HC_STAGE(M_IF4, 2) HC_STAGE(M_IF4, 3) HC_STAGE(M_IF4, 4)
+    HC_STAGE(M_IF34, 1) HC_STAGE(M_IF34, 2) HC_STAGE(M_IF34, 3) HC_STAGE(M_IF34, 4)
+    HC_STAGE(M_ETD4, 1) HC_STAGE(M_ETD4, 2) HC_STAGE(M_ETD4, 3) HC_STAGE(M_ETD4, 4)
+    HC_STAGE(M_ETD34, 1) HC_STAGE(M_ETD34, 2) HC_STAGE(M_ETD34, 3) HC_STAGE(M_ETD34, 4)
+    HC_STAGE(M_ETD5, 1) HC_STAGE(M_ETD5, 2) HC_STAGE(M_ETD5, 3) HC_STAGE(M_ETD5, 4) HC_STAGE(M_ETD5, 5) HC_STAGE(M_ETD5, 6)
+    HC_STAGE(M_ETD35, 1) HC_STAGE(M_ETD35, 2) HC_STAGE(M_ETD35, 3) HC_STAGE(M_ETD35, 4) HC_STAGE(M_ETD35, 5) HC_STAGE(M_ETD35, 6)
+    HC_STAGE(M_IF45DP, 1) HC_STAGE(M_IF45DP, 2) HC_STAGE(M_IF45DP, 3) HC_STAGE(M_IF45DP, 4) HC_STAGE(M_IF45DP, 5) HC_STAGE(M_IF45DP, 6)
+    return -1;
+}
+
+// embedded error estimate formed inside the norm kernel (IF34 / ETD34 / IF45DP)
+int hc_embedded_err(int method, int n, const double* const* N, const double* coef, double h, double* err) {
+    const cplx* Np[8];
+    for (int j = 0; j < 8; ++j) Np[j] = reinterpret_cast<const cplx*>(N[j]);
+    const cplx* cc = reinterpret_cast<const cplx*>(coef);
+    cplx* ce = reinterpret_cast<cplx*>(err);
+    for (int i = 0; i < n; ++i) {
+        cplx nv[8], cv[32];
+        for (int j = 1; j <= 7; ++j) nv[j] = Np[j] ? Np[j][i] : mk(0, 0);
+        for (int s = 0; s < method_ncoef(method); ++s) cv[s] = cc[s * n + i];
+        if (method == M_IF34) ce[i] = embedded_err<M_IF34, cplx>(nv, cv, h);
+        else if (method == M_ETD34) ce[i] = embedded_err<M_ETD34, cplx>(nv, cv, h);
+        else if (method == M_IF45DP) ce[i] = embedded_err<M_IF45DP, cplx>(nv, cv, h);
+        else return -1;
+    }
+    return 0;
+}
+
+// controller: feed (sum_u2, sum_e2) of one trial; state is a caller-held opaque Ctrl blob
+int hc_ctrl_size(void) { return (int)sizeof(Ctrl); }
+void hc_ctrl_init(void* blob, double t0, double tf, double h, long long store_freq, int step_mode, int n1_refresh,
+                  double epsilon, double incr_f, double decr_f, double safety_f, double minh, int q) {
+    Ctrl* c = reinterpret_cast<Ctrl*>(blob);
+    memset(c, 0, sizeof(Ctrl));
+    c->t = t0; c->tf = tf; c->h = h; c->h_last = h; c->store_freq = store_freq; c->step_mode = step_mode;
+    c->n1_refresh = n1_refresh; c->need_n1 = 1;
+    c->epsilon = epsilon; c->incr_f = incr_f; c->decr_f = decr_f; c->safety_f = safety_f; c->minh = minh;
+    c->inv_q = 1.0 / (double)q;
+    c->h_coeff = NAN;
+}
+// out: {h, h_last, t, s_last, status, accept, numloops, u_sel, n_sel, need_n1, step_count, snap_pending, snap_count}
+void hc_ctrl_advance(void* blob, double sum_u2, double sum_e2, double* out) {
+    static TrialRec log[LOG_CAP];
+    Ctrl* c = reinterpret_cast<Ctrl*>(blob);
+    c->red[1] = sum_u2; c->red[2] = sum_e2;
+    controller_advance(*c, log);
+    out[0] = c->h; out[1] = c->h_last; out[2] = c->t; out[3] = c->s_last; out[4] = c->status; out[5] = c->accept;
+    out[6] = c->numloops; out[7] = c->u_sel; out[8] = c->n_sel; out[9] = c->need_n1; out[10] = (double)c->step_count;
+    out[11] = c->snap_pending; out[12] = c->snap_count;
+}
+
+}  // extern "C"

@@ -1,0 +1,251 @@
+"""CPU checks of the device math: the __host__ __device__ headers of rkstiff_b200/csrc are
+compiled with g++ (tests/host_check) and compared with the oracle.  No GPU, no CUDA runtime.
+These tests pin the algorithms (FFT pass structure, psi/tableau formulas, stage formulas,
+controller state machine); the `-m gpu` tests then check the kernels that wrap them.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import problems
+from oracle.rk_oracle import (ADAPTIVE, FIXED, METHODS, Config, MaxLoopsExceeded, MinimumStepReached,
+                              OracleSolver, coefficients)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MID = {"IF4": 0, "ETD4": 1, "ETD5": 2, "IF34": 3, "ETD34": 4, "ETD35": 5, "IF45DP": 6}
+SLOTS = {
+    "kro": ["E", "E2", "a21", "a31", "a32", "a41", "a43", "a51", "a52", "a54"],
+    "e5": ["E14", "E12", "E34", "E", "a21", "a31", "a32", "a41", "a43", "a51", "a52", "a54", "a61", "a62", "a63",
+           "a65", "a71", "a73", "a74", "a75", "a76"],
+    "if": ["E", "E2"],
+    "dp": ["E15", "E310", "E45", "E89", "E", "a21", "a31", "a32", "a41", "a42", "a43", "a51", "a52", "a53", "a54",
+           "a61", "a62", "a63", "a64", "a65", "a71", "a73", "a74", "a75", "r1", "r3", "r4", "r5"],
+}
+FAMILY = {"IF4": "if", "IF34": "if", "ETD4": "kro", "ETD34": "kro", "ETD5": "e5", "ETD35": "e5", "IF45DP": "dp"}
+STAGES = {"IF4": 4, "IF34": 4, "ETD4": 4, "ETD34": 4, "ETD5": 6, "ETD35": 6, "IF45DP": 6}
+
+
+@pytest.fixture(scope="module")
+def hc():
+    src = os.path.join(HERE, "host_check", "host_check.cpp")
+    lib = os.path.join(HERE, "host_check", "libhostcheck.so")
+    deps = [src] + [os.path.join(HERE, "..", "rkstiff_b200", "csrc", f)
+                    for f in ("common.cuh", "coeffs.cuh", "stages.cuh", "errctl.cuh", "fft.cuh")]
+    if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", lib, src])
+    return ctypes.CDLL(lib)
+
+
+def ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("n", [16, 32, 64, 128, 512, 1024, 2048, 8192])
+def test_fft_dif_dit_roundtrip(hc, n):
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    y = np.empty_like(x)
+    hc.hc_fft_roundtrip(n, ptr(x), ptr(y))
+    assert rel(y / n, x) < 5e-16 * np.log2(n)
+
+
+@pytest.mark.parametrize("n", [16, 64, 256, 1024, 8192])
+@pytest.mark.parametrize("nthreads", [1, 7, 64])
+def test_nl_uux_matches_numpy(hc, n, nthreads):
+    p = problems.ks(n) if n >= 64 else problems.kdv(n)
+    rng = np.random.default_rng(n)
+    uf = p.u0 + 1e-3 * (rng.standard_normal(p.u0.shape) + 1j * rng.standard_normal(p.u0.shape))
+    uf[-1] += 0.3j          # Nyquist with an imaginary part: irfft must ignore it
+    for c in (1.0, 6.0):
+        ref = -c * np.fft.rfft(np.fft.irfft(uf) * np.fft.irfft(1j * p.kx * uf))
+        out = np.empty_like(uf)
+        hc.hc_nl(1, n, ptr(uf), ptr(p.kx), ctypes.c_double(c), ptr(out), nthreads)
+        assert rel(out, ref) < 1e-14 * np.log2(n)
+
+
+@pytest.mark.parametrize("n", [16, 128, 2048, 8192])
+def test_nl_nls_matches_numpy(hc, n):
+    p = problems.nls(n, batch=2, half_width=20.0)
+    for row in p.u0:
+        out = np.empty_like(row)
+        hc.hc_nl(2, n, ptr(np.ascontiguousarray(row)), None, ctypes.c_double(2.0), ptr(out), 32)
+        assert rel(out, p.nl_func(row)) < 1e-14 * np.log2(n)
+
+
+def device_coeffs(hc, method, lin, h, cfg=Config()):
+    lin = np.ascontiguousarray(lin)
+    n = lin.shape[0]
+    names = SLOTS[FAMILY[method]]
+    out = np.zeros((len(names), n), dtype=np.complex128)
+    nc = hc.hc_coeffs(MID[method], n, ptr(lin), int(np.iscomplexobj(lin)), ctypes.c_double(h),
+                      ctypes.c_double(cfg.modecutoff), cfg.contour_points, ctypes.c_double(cfg.contour_radius),
+                      int(cfg.if45dp_r4_fix), ptr(out))
+    assert nc == len(names)
+    return dict(zip(names, out)), out
+
+
+@pytest.mark.parametrize("prob,h", [(problems.ks(256), 0.05), (problems.nls(256, half_width=20.0), 0.013),
+                                    (problems.kdv(256), 0.025), (problems.burgers(256, mu=0.01), 0.005)])
+@pytest.mark.parametrize("method", METHODS)
+def test_coefficients_match_oracle(hc, prob, h, method):
+    mine, _ = device_coeffs(hc, method, prob.lin_op, h)
+    ref = coefficients(method, prob.lin_op, h, Config())
+    z = np.abs(h * prob.lin_op)
+    for name, arr in mine.items():
+        r = np.asarray(ref[name], dtype=np.complex128)
+        # cancellation band just above modecutoff: the reference itself carries ~1e-9 relative
+        # rounding noise there; elsewhere the two agree to rounding
+        band = (z >= 0.01) & (z < 0.5)
+        np.testing.assert_allclose(arr[~band], r[~band], rtol=2e-13, atol=4e-16 * h, err_msg=f"{method}.{name}")
+        np.testing.assert_allclose(arr[band], r[band], rtol=5e-8, atol=4e-16 * h, err_msg=f"{method}.{name} band")
+
+
+def test_if45dp_r4_quirk_and_fix(hc):
+    p = problems.ks(64)
+    quirk, _ = device_coeffs(hc, "IF45DP", p.lin_op, 0.1)
+    fixed, _ = device_coeffs(hc, "IF45DP", p.lin_op, 0.1, Config(if45dp_r4_fix=True))
+    np.testing.assert_allclose(fixed["r4"] / quirk["r4"], 71.0 / 17.0, rtol=1e-15)
+
+
+def device_trial(hc, method, prob, u, h, N1=None):
+    """One pass over the stages with device formulas + NumPy nl_func; returns (u_new, err, N dict)."""
+    lin = prob.lin_op
+    mine, coef = device_coeffs(hc, method, lin, h)
+    n = u.shape[0]
+    N = {1: prob.nl_func(u) if N1 is None else N1}
+    S = STAGES[method]
+    k = None
+    err = np.zeros(n, dtype=np.complex128)
+    for s in range(1, S + 1):
+        arr = (ctypes.c_void_p * 8)()
+        for j in range(1, 8):
+            arr[j] = ptr(N[j]) if j in N else None
+        out = np.empty(n, dtype=np.complex128)
+        rc = hc.hc_stage(MID[method], s, n, ptr(u), arr, ptr(coef), ctypes.c_double(h), ptr(out), ptr(err))
+        assert rc == 0
+        k = out
+        if s < S:
+            N[s + 1] = prob.nl_func(k)
+    if method in ("IF34", "ETD34", "IF45DP"):
+        N[S + 1] = prob.nl_func(k)
+        arr = (ctypes.c_void_p * 8)()
+        for j in range(1, 8):
+            arr[j] = ptr(N[j]) if j in N else None
+        assert hc.hc_embedded_err(MID[method], n, arr, ptr(coef), ctypes.c_double(h), ptr(err)) == 0
+    return k, err, N
+
+
+@pytest.mark.parametrize("prob,h", [(problems.ks(256), 0.05), (problems.nls(256, half_width=20.0), 0.004),
+                                    (problems.kdv(256), 0.025)])
+@pytest.mark.parametrize("method", METHODS)
+def test_one_trial_state_matches_oracle(hc, prob, h, method):
+    """Fixed-step parity bar: <= 1e-12 relative per step (BASELINE north_star)."""
+    sol = OracleSolver(method, prob.lin_op, prob.nl_func)
+    ref = sol.trial(prob.u0, h)
+    k, err, _ = device_trial(hc, method, prob, prob.u0, h)
+    if method in ADAPTIVE:
+        assert rel(k, ref[0]) < 1e-13
+        # err is a difference of O(|N|) terms, so the two agree absolutely (rounding of N), not relatively
+        assert np.linalg.norm(err - ref[1]) < 1e-14 * np.linalg.norm(k)
+    else:
+        assert rel(k, ref) < 1e-13
+
+
+class _Canned(OracleSolver):
+    """Oracle controller fed with canned (u, err) pairs: checks the state machine alone."""
+
+    def __init__(self, method, pairs, cfg):
+        super().__init__(method, np.zeros(1), lambda v: v, cfg)
+        self.pairs = list(pairs)
+        self.i = 0
+
+    def trial(self, u, h):
+        x, y = self.pairs[self.i % len(self.pairs)]
+        self.i += 1
+        return np.array([x + 0j]), np.array([y + 0j])
+
+
+@pytest.mark.parametrize("method", ADAPTIVE)
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_controller_matches_oracle(hc, method, seed):
+    rng = np.random.default_rng(seed)
+    cfg = Config(epsilon=1e-4)
+    q = 5 if method == "IF45DP" else 4
+    # error/tolerance ratios spread around the accept threshold, with occasional NaN/inf/zero
+    pairs = []
+    for _ in range(400):
+        x = rng.uniform(0.5, 2.0)
+        ratio = 10 ** rng.uniform(-1.2, 1.2)
+        y = cfg.epsilon * x / ratio
+        r = rng.uniform()
+        if r < 0.02:
+            y = 0.0                 # ||err|| = 0 -> s = inf -> rejected
+        elif r < 0.04:
+            x = float("nan")
+        pairs.append((x, y))
+    sol = _Canned(method, pairs, cfg)
+    t0, tf, store_freq = 0.0, 3.0, 3
+    expect_status = 1
+    with np.errstate(all="ignore"):
+        try:
+            sol.evolve(np.zeros(1, dtype=complex), t0, tf, None, store_freq=store_freq)
+        except MinimumStepReached:
+            expect_status = 3
+        except MaxLoopsExceeded:
+            expect_status = 2
+    size = hc.hc_ctrl_size()
+    blob = ctypes.create_string_buffer(size)
+    h0 = (tf - t0) / 100.0
+    hc.hc_ctrl_init(blob, ctypes.c_double(t0), ctypes.c_double(tf), ctypes.c_double(h0), ctypes.c_longlong(store_freq),
+                    0, int(method == "ETD35"), ctypes.c_double(cfg.epsilon), ctypes.c_double(cfg.incr_f),
+                    ctypes.c_double(cfg.decr_f), ctypes.c_double(cfg.safety_f), ctypes.c_double(cfg.minh), q)
+    out = np.zeros(13)
+    hs, accs, ts, snaps = [], [], [], [t0]
+    h = h0
+    i = 0
+    status = 0
+    while status == 0:
+        x, y = pairs[i % len(pairs)]
+        i += 1
+        hs.append(h)
+        hc.hc_ctrl_advance(blob, ctypes.c_double(x * x), ctypes.c_double(y * y), ptr(out))
+        h, status = out[0], int(out[4])
+        accs.append(bool(out[5]))
+        if out[5]:
+            ts.append(out[2])
+        if out[11]:
+            snaps.append(out[2])
+    assert status == expect_status
+    # numpy's pow is its own SIMD kernel (not libm's), so h agrees to rounding, not bitwise
+    np.testing.assert_allclose(np.array(hs), np.array([r.h for r in sol.log]), rtol=1e-13, atol=0)
+    np.testing.assert_array_equal(np.array(accs), np.array([r.accepted for r in sol.log]))
+    ref_ts = np.array([r.t_after for r in sol.log if r.accepted])
+    np.testing.assert_allclose(np.array(ts)[:len(ref_ts)], ref_ts, rtol=1e-13, atol=0)
+    np.testing.assert_allclose(np.array(snaps), np.array(sol.t), rtol=1e-13, atol=0)
+
+
+def test_controller_failure_paths(hc):
+    """||err|| never small enough: MinimumStepReached / MaxLoopsExceeded (solveras.py:399-410)."""
+    size = hc.hc_ctrl_size()
+    out = np.zeros(13)
+    for minh, expect in ((1e-3, 3), (1e-300, 2)):
+        blob = ctypes.create_string_buffer(size)
+        hc.hc_ctrl_init(blob, ctypes.c_double(0.0), ctypes.c_double(1.0), ctypes.c_double(0.01), ctypes.c_longlong(1),
+                        0, 0, ctypes.c_double(1e-4), ctypes.c_double(1.25), ctypes.c_double(0.85),
+                        ctypes.c_double(0.8), ctypes.c_double(minh), 4)
+        n = 0
+        while True:
+            hc.hc_ctrl_advance(blob, ctypes.c_double(1.0), ctypes.c_double(1.0), ptr(out))
+            n += 1
+            if out[4] != 0:
+                break
+        assert int(out[4]) == expect
+        if expect == 2:
+            assert n == 51      # numloops > MAX_LOOPS on the 51st rejection

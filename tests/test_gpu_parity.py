@@ -1,0 +1,287 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the reference goldens.
+
+Bars (BASELINE.json north_star):
+  * fixed-step states within 1e-12 relative per step in FP64;
+  * adaptive runs reproduce the reference's accepted/rejected dt sequence over the compared
+    horizon (flags identical, dt within 1e-9 relative) with the final state within 1e-9 relative.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import problems  # noqa: E402
+from oracle.rk_oracle import ADAPTIVE, FIXED, METHODS, Config, OracleSolver, coefficients  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+STEP_TOL = 1e-12        # fixed-step relative tolerance per step
+DT_TOL = 1e-9           # adaptive dt-sequence relative tolerance
+FINAL_TOL = 1e-9        # adaptive final-state relative tolerance
+
+
+@pytest.fixture(scope="module")
+def rk():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import rkstiff_b200
+    return rkstiff_b200
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b))
+
+
+def fused_for(rk, prob):
+    kx = dev(prob.kx)
+    if prob.model == "nls":
+        return rk.models.FusedNL(2, prob.n, kx, prob.params["gamma"], "nls")
+    return rk.models.FusedNL(1, prob.n, kx, prob.params["c"], prob.model)
+
+
+def torch_callable(rk, prob):
+    f = fused_for(rk, prob)
+    return lambda v: f(v)          # plain callable => torch.fft path
+
+
+def make(rk, method, prob, nl, epsilon=None):
+    cls = getattr(rk, method)
+    lin = dev(prob.lin_op)
+    if method in ADAPTIVE:
+        cfg = rk.SolverConfig() if epsilon is None else rk.SolverConfig(epsilon=epsilon)
+        return cls(lin, nl, config=cfg)
+    return cls(lin, nl)
+
+
+# --------------------------------------------------------------------------------------------
+# K4: fused nonlinearity
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [16, 64, 256, 1024, 4096, 8192])
+@pytest.mark.parametrize("batch", [1, 3, 40])
+def test_fused_uux_matches_numpy(rk, n, batch):
+    p = problems.ks(n, batch=batch, seed=n) if n >= 64 else problems.kdv(n, batch=batch, seed=n)
+    sol = rk.ETD4(dev(p.lin_op), fused_for(rk, p))
+    u = dev(p.u0)
+    eng = sol._get_engine(u)
+    eng.set_u(u)
+    eng.nl(1)
+    got = host(eng.state_view("N1"))
+    assert rel(got, p.nl_func(p.u0)) < 2e-14 * np.log2(n)
+
+
+@pytest.mark.parametrize("n", [16, 128, 2048, 8192])
+@pytest.mark.parametrize("batch", [1, 5])
+def test_fused_nls_matches_numpy(rk, n, batch):
+    p = problems.nls(n, batch=batch, seed=n, half_width=20.0)
+    sol = rk.ETD4(dev(p.lin_op), fused_for(rk, p))
+    u = dev(p.u0)
+    eng = sol._get_engine(u)
+    eng.set_u(u)
+    eng.nl(1)
+    assert rel(host(eng.state_view("N1")), p.nl_func(p.u0)) < 2e-14 * np.log2(n)
+
+
+# --------------------------------------------------------------------------------------------
+# K2: coefficient arrays
+# --------------------------------------------------------------------------------------------
+NAMES = {
+    "ETD4": ["E", "E2", "a21", "a31", "a32", "a41", "a43", "a51", "a52", "a54"],
+    "ETD5": ["E14", "E12", "E34", "E", "a21", "a31", "a32", "a41", "a43", "a51", "a52", "a54", "a61", "a62", "a63",
+             "a65", "a71", "a73", "a74", "a75", "a76"],
+    "IF4": ["E", "E2"],
+    "IF45DP": ["E15", "E310", "E45", "E89", "E", "a21", "a31", "a32", "a41", "a42", "a43", "a51", "a52", "a53", "a54",
+               "a61", "a62", "a63", "a64", "a65", "a71", "a73", "a74", "a75", "r1", "r3", "r4", "r5"],
+}
+NAMES["ETD34"] = NAMES["ETD4"]
+NAMES["ETD35"] = NAMES["ETD5"]
+NAMES["IF34"] = NAMES["IF4"]
+
+
+@pytest.mark.parametrize("probname,h", [("ks", 0.05), ("nls", 0.013), ("kdv", 0.025)])
+@pytest.mark.parametrize("method", METHODS)
+def test_coefficient_kernel_matches_oracle(rk, probname, h, method):
+    p = {"ks": lambda: problems.ks(256), "nls": lambda: problems.nls(256, half_width=20.0),
+         "kdv": lambda: problems.kdv(256)}[probname]()
+    sol = make(rk, method, p, torch_callable(rk, p))
+    u = dev(p.u0)
+    eng = sol._get_engine(u)
+    eng.set_h(h)
+    from rkstiff_b200._abi import check, lib
+    check(lib.rks_update_coeffs(eng.plan, eng.st))
+    ref = coefficients(method, p.lin_op, h, Config())
+    z = np.abs(h * p.lin_op)
+    band = (z >= 0.01) & (z < 0.5)        # cancellation band of the closed forms
+    for name in NAMES[method]:
+        got = host(eng.coef_view(name)).astype(np.complex128)
+        want = np.asarray(ref[name], dtype=np.complex128)
+        np.testing.assert_allclose(got[~band], want[~band], rtol=5e-13, atol=1e-15 * h, err_msg=f"{method}.{name}")
+        np.testing.assert_allclose(got[band], want[band], rtol=1e-7, atol=1e-15 * h, err_msg=f"{method}.{name}")
+
+
+# --------------------------------------------------------------------------------------------
+# fixed step: per-step parity and reference goldens
+# --------------------------------------------------------------------------------------------
+FIXED_CASES = {"kdv": lambda: problems.kdv(256), "ks": lambda: problems.ks(256),
+               "burgers": lambda: problems.burgers(256, mu=0.01), "nls": lambda: problems.nls(256, half_width=20.0),
+               "ksb": lambda: problems.ks(128, batch=3, seed=0)}
+
+
+@pytest.mark.parametrize("path", ["fused", "callable"])
+@pytest.mark.parametrize("tag", list(FIXED_CASES))
+@pytest.mark.parametrize("method", FIXED)
+def test_fixed_step_parity_per_step(rk, golden, tag, method, path):
+    """Feed the SAME input state to both sides every step; <= 1e-12 relative per step."""
+    g = golden("fixed_runs.npz")
+    p = FIXED_CASES[tag]()
+    pre = f"{tag}_{method}_"
+    h = float(g[pre + "h"])
+    nl = fused_for(rk, p) if path == "fused" else torch_callable(rk, p)
+    sol = make(rk, method, p, nl)
+    got1 = host(sol.step(dev(p.u0), h))
+    assert rel(got1, g[pre + "u_step1"]) < STEP_TOL
+    # 20 more steps, oracle advanced from the engine's state each time
+    u = dev(p.u0)
+    for _ in range(20):
+        ref = OracleSolver(method, p.lin_op, p.nl_func).step(host(u), h)
+        sol.reset()
+        u = sol.step(u, h)
+        assert rel(host(u), ref) < STEP_TOL
+
+
+@pytest.mark.parametrize("path", ["fused", "callable"])
+@pytest.mark.parametrize("tag", list(FIXED_CASES))
+@pytest.mark.parametrize("method", FIXED)
+def test_fixed_evolve_matches_reference_golden(rk, golden, tag, method, path):
+    g = golden("fixed_runs.npz")
+    p = FIXED_CASES[tag]()
+    pre = f"{tag}_{method}_"
+    h, tf, steps = float(g[pre + "h"]), float(g[pre + "tf"]), int(g[pre + "steps"])
+    nl = fused_for(rk, p) if path == "fused" else torch_callable(rk, p)
+    sol = make(rk, method, p, nl)
+    uf = sol.evolve(dev(p.u0), 0.0, tf, h, store_freq=max(1, steps // 4))
+    np.testing.assert_array_equal(np.array(sol.t), g[pre + "t"])          # float-accumulated loop count
+    assert len(sol.u) == int(g[pre + "n_snap"])
+    tol = 1e-9 if tag.startswith("ks") else steps * STEP_TOL               # KS is chaotic: looser over 60 steps
+    assert rel(host(uf), g[pre + "u_final"]) < tol
+    assert rel(host(sol.u[1]), g[pre + "u_snap_1"]) < tol
+
+
+def test_fixed_step_h_larger_than_interval_raises(rk):
+    p = problems.kdv(64)
+    sol = rk.ETD4(dev(p.lin_op), fused_for(rk, p))
+    with pytest.raises(ValueError):
+        sol.evolve(dev(p.u0), 0.0, 0.1, 0.2)
+    with pytest.raises(AssertionError):
+        sol.step(dev(p.u0), -0.1)
+
+
+# --------------------------------------------------------------------------------------------
+# adaptive: dt sequence + final state against the reference goldens
+# --------------------------------------------------------------------------------------------
+AD_CASES = {"kdv": lambda: problems.kdv(256), "ks": lambda: problems.ks(256),
+            "burgers": lambda: problems.burgers(256, mu=0.01), "nls": lambda: problems.nls(256, half_width=20.0),
+            "nlsb": lambda: problems.nls(128, batch=3, seed=2, half_width=20.0),
+            "ksb": lambda: problems.ks(128, batch=4, seed=0)}
+
+
+@pytest.mark.parametrize("path", ["fused", "callable"])
+@pytest.mark.parametrize("tag", list(AD_CASES))
+@pytest.mark.parametrize("method", ADAPTIVE)
+def test_adaptive_dt_sequence_and_final_state(rk, golden, tag, method, path):
+    g = golden("adaptive_runs.npz")
+    p = AD_CASES[tag]()
+    pre = f"{tag}_{method}_"
+    h0 = float(g[pre + "h_init"])
+    nl = fused_for(rk, p) if path == "fused" else torch_callable(rk, p)
+    sol = make(rk, method, p, nl, float(g[pre + "epsilon"]))
+    uf = sol.evolve(dev(p.u0), 0.0, float(g[pre + "tf"]), None if np.isnan(h0) else h0,
+                    store_freq=int(g[pre + "store_freq"]))
+    hs = np.array([r[0] for r in sol.trial_log])
+    acc = np.array([r[2] for r in sol.trial_log])
+    ref_h, ref_acc = g[pre + "trial_h"], g[pre + "trial_accepted"]
+    assert len(hs) == len(ref_h), f"{len(hs)} trials vs {len(ref_h)} in the reference"
+    np.testing.assert_array_equal(acc, ref_acc)
+    np.testing.assert_allclose(hs, ref_h, rtol=DT_TOL, atol=0)
+    np.testing.assert_allclose(np.array(sol.t), g[pre + "t"], rtol=DT_TOL, atol=0)
+    assert len(sol.u) == int(g[pre + "n_snap"])
+    assert rel(host(uf), g[pre + "u_final"]) < FINAL_TOL
+    assert rel(host(sol.u[-1]), g[pre + "u_snap_last"]) < FINAL_TOL
+
+
+def test_cfg1_readme_quickstart(rk, golden):
+    """BASELINE cfg 1: KS n=1024, IF34, t 0->50, store_freq=20.  The run is chaotic, so the dt
+    sequence is compared over the short horizon the north_star allows and the totals loosely."""
+    g = golden("ks1024_if34_cfg1.npz")
+    p = problems.ks(1024)
+    sol = rk.IF34(dev(p.lin_op), fused_for(rk, p))
+    uf = sol.evolve(dev(p.u0), 0.0, 50.0, store_freq=20)
+    hs = np.array([r[0] for r in sol.trial_log])
+    acc = np.array([r[2] for r in sol.trial_log])
+    k = 150                                         # t <~ 12
+    np.testing.assert_array_equal(acc[:k], g["trial_accepted"][:k])
+    np.testing.assert_allclose(hs[:k], g["trial_h"][:k], rtol=1e-7)
+    assert abs(len(hs) - len(g["trial_h"])) <= 30
+    assert abs(len(sol.u) - int(g["n_snap"])) <= 2
+    assert torch.isfinite(uf.real).all()
+
+
+@pytest.mark.parametrize("method", ADAPTIVE)
+def test_step_api_matches_oracle(rk, method):
+    """User-driven step() loop (demos/ks.ipynb cell 14): u, h, h_suggest = solver.step(u, h)."""
+    p = problems.kdv(256)
+    sol = make(rk, method, p, fused_for(rk, p), 1e-5)
+    ora = OracleSolver(method, p.lin_op, p.nl_func, Config(epsilon=1e-5))
+    u, uo = dev(p.u0), p.u0
+    h = ho = 0.025
+    for _ in range(12):
+        u, hu, h = sol.step(u, h)
+        uo, huo, ho = ora.step(uo, ho)
+        assert hu == pytest.approx(huo, rel=DT_TOL)
+        assert h == pytest.approx(ho, rel=DT_TOL)
+        assert rel(host(u), uo) < FINAL_TOL
+
+
+def test_explosive_nonlinearity_raises_minimum_step(rk):
+    """tests/test_etd35.py:111-121: an explosive N drives h below minh."""
+    p = problems.kdv(64)
+    sol = rk.ETD35(dev(p.lin_op), lambda v: 1e20 * v * v.abs() ** 2 + 1e30,
+                   config=rk.SolverConfig(minh=1e-4))
+    with pytest.raises(rk.solveras.BaseSolverAS.SolverError):
+        sol.evolve(dev(p.u0), 0.0, 1.0)
+
+
+def test_tf_before_t0_returns_input(rk):
+    p = problems.kdv(64)
+    sol = rk.ETD35(dev(p.lin_op), fused_for(rk, p))
+    u0 = dev(p.u0)
+    out = sol.evolve(u0, 1.0, 0.5)
+    assert out is u0 and len(sol.t) == 1
+
+
+def test_if45dp_r4_fix_changes_step_count(rk):
+    p = problems.kdv(256)
+    counts = {}
+    for fix in (False, True):
+        sol = rk.IF45DP(dev(p.lin_op), fused_for(rk, p), r4_fix=fix)
+        sol.evolve(dev(p.u0), 0.0, 1.0, store_data=False)
+        counts[fix] = len(sol.trial_log)
+    assert counts[False] > 5 * counts[True]        # the shipped 17/1920 weight makes the estimate O(h)
+
+
+def test_real_linop_if_coefficients_stay_real(rk):
+    """if34.py:71: IF strategies do not cast lin_op; real L gives real exponentials."""
+    p = problems.ks(64)
+    sol = rk.IF34(dev(p.lin_op), fused_for(rk, p))
+    eng = sol._get_engine(dev(p.u0))
+    assert eng.coef_view("E").dtype == torch.float64
+    p2 = problems.kdv(64)
+    sol2 = rk.IF34(dev(p2.lin_op), fused_for(rk, p2))
+    assert sol2._get_engine(dev(p2.u0)).coef_view("E").dtype == torch.complex128
