@@ -147,7 +147,8 @@ struct DevPlan {
     void* coef;        // ncoef arrays of lin_elems entries (double or cplx)
     const void* lin;   // lin_op copy (double or cplx)
     double* partials;  // per-block partial sums of the norm kernel (2 per block)
-    const cplx* tw;    // twiddles exp(-2 pi i j / n), j < n
+    const cplx* tw;    // twiddles exp(-2 pi i j / n), j < n (generic NL kernel)
+    const cplx* twf;   // fast-path twiddle tables (fft_fast.cuh: o | a | b)
     const double* kx;  // wavenumbers of the fused model
     long long batch, n_c, lin_elems, n;
     double model_p0;   // c (u u_x models) or gamma (NLS)

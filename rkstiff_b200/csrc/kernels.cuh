@@ -5,6 +5,7 @@
 #include "stages.cuh"
 #include "errctl.cuh"
 #include "fft.cuh"
+#include "fft_fast.cuh"
 
 namespace rks {
 
@@ -73,6 +74,11 @@ __global__ void set_config_kernel(Ctrl* c, CfgArgs a) {
     c->adapt_cutoff = a.adapt_cutoff; c->minh = a.minh; c->inv_q = a.inv_q;
     c->modecutoff = a.modecutoff; c->contour_radius = a.contour_radius;
     c->contour_points = a.contour_points; c->r4_fix = a.r4_fix;
+}
+
+__global__ void fast_twiddle_kernel(cplx* twf, int n) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < fast::TW_TOTAL) twf[idx] = fast::twiddle_table_entry(idx, n);
 }
 
 __global__ void twiddle_kernel(cplx* tw, int n) {
@@ -350,6 +356,88 @@ __global__ void __launch_bounds__(1024) nl_kernel(DevPlan p, int j, int force, i
     if (active) {
         if (MODEL == 1) uux_store(out, x, p.model_p0, n, tid, tpr);
         else nls_store(out, x, p.model_p0, n, tid, tpr);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// K4 fast path (fft_fast.cuh): n = 512 W, W warps per row, 16 values per thread in registers,
+// persistent CTAs looping over row groups.  RPC rows share one CTA when rows are short.
+// ---------------------------------------------------------------------------------------
+template <int TR>
+RKS_D void row_barrier(int lrow, int rpc) {
+    if (TR == 32) { __syncwarp(); return; }
+    if (rpc == 1) { __syncthreads(); return; }
+    asm volatile("bar.sync %0, %1;" ::"r"(lrow + 1), "r"(TR) : "memory");
+}
+
+template <int W, int MODEL>
+__global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_fast_kernel(DevPlan p, int j, int force) {
+    constexpr int TR = 32 * W;                       // threads per row
+    constexpr int RPC = (W == 16 ? 512 : 256) / TR;  // rows per CTA
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const NlRoles roles = nl_roles(p, j, force);
+    if (!roles.run) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&p.ctrl->nl_evals, 1ull);
+
+    const int lrow = threadIdx.x / TR, T = threadIdx.x - lrow * TR, l = T & 31, w = T >> 5;
+    cplx* sm = reinterpret_cast<cplx*>(smem_raw) + (size_t)lrow * (512 * W);
+    cplx* chunk = sm + 512 * w;
+    const fast::Twiddles tw{p.twf + fast::TW_O, p.twf + fast::TW_A, p.twf + fast::TW_B};
+    const int n = 512 * W;
+    const long long groups = (p.batch + RPC - 1) / RPC;
+    for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
+        const long long row = g * RPC + lrow;
+        const bool on = row < p.batch;
+        const long long rr = on ? row : p.batch - 1;
+        const long long nrow = row + (long long)gridDim.x * RPC;     // the row this slot handles next
+        cplx v[16];
+        if (MODEL == 1) {
+            const fast::UuxModel m{roles.in + rr * p.n_c, roles.out + rr * p.n_c, p.kx, p.model_p0, n, on};
+            fast::p0_load_outer_dif<W>(v, sm, T, tw, m);
+            if (nrow < p.batch) {        // pull the next row from HBM into L2 while this one is transformed
+                const char* nxt = reinterpret_cast<const char*>(roles.in + nrow * p.n_c);
+                const int lines = (int)((p.n_c * 16 + 127) >> 7);
+                for (int q = T; q < lines; q += TR) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t)q << 7)));
+            }
+            row_barrier<TR>(lrow, RPC);
+            fast::read_chunk<W>(v, sm, T);
+            __syncwarp();
+            fast::p1_dif_a<W>(v, chunk, l, tw);  __syncwarp();
+            fast::read_b(v, chunk, l);           __syncwarp();
+            fast::p2_dif_b<W>(v, chunk, l, tw);  __syncwarp();
+            fast::read_c(v, chunk, l);           __syncwarp();
+            fast::p3_core(v, chunk, l, m);       __syncwarp();
+            fast::read_b(v, chunk, l);           __syncwarp();
+            fast::p4_dit_b<W>(v, chunk, l, tw);  __syncwarp();
+            fast::read_a(v, chunk, l);           __syncwarp();
+            fast::p5_dit_a<W>(v, sm, T, tw);
+            row_barrier<TR>(lrow, RPC);
+            fast::p6_outer_dit_store<W>(v, sm, T, tw, m);
+        } else {
+            const fast::NlsModel m{roles.in + rr * p.n_c, roles.out + rr * p.n_c, p.model_p0, n, on};
+            fast::p0_load_outer_dif<W>(v, sm, T, tw, m);
+            if (nrow < p.batch) {        // pull the next row from HBM into L2 while this one is transformed
+                const char* nxt = reinterpret_cast<const char*>(roles.in + nrow * p.n_c);
+                const int lines = (int)((p.n_c * 16 + 127) >> 7);
+                for (int q = T; q < lines; q += TR) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t)q << 7)));
+            }
+            row_barrier<TR>(lrow, RPC);
+            fast::read_chunk<W>(v, sm, T);
+            __syncwarp();
+            fast::p1_dif_a<W>(v, chunk, l, tw);  __syncwarp();
+            fast::read_b(v, chunk, l);           __syncwarp();
+            fast::p2_dif_b<W>(v, chunk, l, tw);  __syncwarp();
+            fast::read_c(v, chunk, l);           __syncwarp();
+            fast::p3_core(v, chunk, l, m);       __syncwarp();
+            fast::read_b(v, chunk, l);           __syncwarp();
+            fast::p4_dit_b<W>(v, chunk, l, tw);  __syncwarp();
+            fast::read_a(v, chunk, l);           __syncwarp();
+            fast::p5_dit_a<W>(v, sm, T, tw);
+            row_barrier<TR>(lrow, RPC);
+            fast::p6_outer_dit_store<W>(v, sm, T, tw, m);
+        }
+        row_barrier<TR>(lrow, RPC);          // p6 reads of the slab vs the next row's p0 writes
     }
 }
 

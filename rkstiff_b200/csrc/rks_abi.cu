@@ -2,6 +2,7 @@
 // Declared in include/rkstiff_b200.h.  No C++ exception crosses this boundary.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 
@@ -35,7 +36,7 @@ constexpr long long MODEL_MAX_N = 16384;        // longest row the smem-resident
 static size_t align_up(size_t v) { return (v + ALIGN - 1) / ALIGN * ALIGN; }
 
 struct Layout {
-    size_t ctrl, log, partials, tw, kx, lin, coef, U[2], K, ERR, NL[8], total;
+    size_t ctrl, log, partials, tw, twf, kx, lin, coef, U[2], K, ERR, NL[8], total;
 };
 
 static Layout make_layout(int method, long long batch, long long n_c, long long lin_elems, int lin_is_complex) {
@@ -51,6 +52,7 @@ static Layout make_layout(int method, long long batch, long long n_c, long long 
     L.partials = take(sizeof(double) * 2 * NORM_MAX_BLOCKS);
     const long long nmax = n_c <= MODEL_MAX_N ? 2 * n_c : 0;
     L.tw = take(sizeof(cplx) * (size_t)nmax);
+    L.twf = take(sizeof(cplx) * (size_t)(n_c <= MODEL_MAX_N ? fast::TW_TOTAL : 0));
     L.kx = take(sizeof(double) * (size_t)(n_c <= MODEL_MAX_N ? n_c : 0));
     L.lin = take((lin_is_complex ? sizeof(cplx) : sizeof(double)) * (size_t)lin_elems);
     L.coef = take(coef_elem * (size_t)lin_elems * method_ncoef(method));
@@ -78,8 +80,31 @@ struct rks_plan {
     bool have_h_coeff_host;
     int roles_u_sel, roles_n_sel;   // host mirror refreshed by rks_read_ctrl
     int nl_rows_per_cta, nl_threads;
+    bool nl_fast;                   // n in {512..8192}: register-resident FFT kernel (fft_fast.cuh)
     size_t nl_smem;
 };
+
+template <int W>
+static void launch_nl_fast(rks_plan* p, int j, int force, cudaStream_t stream) {
+    const DevPlan& d = p->d;
+    constexpr int THREADS = W == 16 ? 512 : 256;
+    constexpr int RPC = THREADS / (32 * W);
+    const size_t smem = (size_t)RPC * 512 * W * sizeof(cplx);
+    const long long groups = (d.batch + RPC - 1) / RPC;
+    const long long resident = (long long)p->sm_count * (W == 16 ? 1 : 2);
+    const unsigned grid = (unsigned)(groups < resident ? groups : resident);
+    if (d.model == RKS_MODEL_UUX_RFFT) nl_fast_kernel<W, 1><<<grid, THREADS, smem, stream>>>(d, j, force);
+    else nl_fast_kernel<W, 2><<<grid, THREADS, smem, stream>>>(d, j, force);
+}
+
+template <int W>
+static cudaError_t prepare_nl_fast(int model) {
+    constexpr int THREADS = W == 16 ? 512 : 256;
+    const int smem = THREADS / (32 * W) * 512 * W * (int)sizeof(cplx);
+    if (model == RKS_MODEL_UUX_RFFT)
+        return cudaFuncSetAttribute(nl_fast_kernel<W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    return cudaFuncSetAttribute(nl_fast_kernel<W, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
 
 extern "C" int rks_abi_version(void) { return RKS_ABI_VERSION; }
 extern "C" const char* rks_last_error(void) { return g_err; }
@@ -152,6 +177,7 @@ extern "C" int rks_plan_create(rks_plan** out, int method, int64_t batch, int64_
     d.log = (TrialRec*)(w + L.log);
     d.partials = (double*)(w + L.partials);
     d.tw = (const cplx*)(w + L.tw);
+    d.twf = (const cplx*)(w + L.twf);
     d.kx = (const double*)(w + L.kx);
     d.lin = w + L.lin;
     d.coef = w + L.coef;
@@ -217,7 +243,16 @@ extern "C" int rks_set_model(rks_plan* p, int model, int64_t n, const double* kx
     twiddle_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((cplx*)(p->ws + p->lay.tw), (int)n);
     p->launches += 1;
     if (kx) CUDA_TRY(cudaMemcpyAsync(p->ws + p->lay.kx, kx, sizeof(double) * (size_t)d.n_c, cudaMemcpyDeviceToDevice, stream));
-    // launch shape of the NL kernel: one row per CTA for long rows, several for short ones
+    p->nl_fast = (n >= 512 && n <= 8192) && !getenv("RKS_NL_GENERIC");
+    if (p->nl_fast) {
+        cudaError_t e = n == 512 ? prepare_nl_fast<1>(model) : n == 1024 ? prepare_nl_fast<2>(model)
+                      : n == 2048 ? prepare_nl_fast<4>(model) : n == 4096 ? prepare_nl_fast<8>(model)
+                      : prepare_nl_fast<16>(model);
+        CUDA_TRY(e);
+        fast_twiddle_kernel<<<(fast::TW_TOTAL + 255) / 256, 256, 0, stream>>>((cplx*)(p->ws + p->lay.twf), (int)n);
+        p->launches += 1;
+    }
+    // launch shape of the generic NL kernel: one row per CTA for long rows, several for short ones
     const size_t row_bytes = (size_t)n * sizeof(cplx);
     int tpr = (int)(n / 4);                       // one radix-4 butterfly per thread per pass
     if (tpr > 512) tpr = 512;
@@ -371,6 +406,17 @@ extern "C" int rks_stage(rks_plan* p, int s, void* stream_v) {
 // ---------------------------------------------------------------------------------------
 static int launch_nl(rks_plan* p, int j, int force, cudaStream_t stream) {
     const DevPlan& d = p->d;
+    if (p->nl_fast) {
+        switch (d.n) {
+            case 512: launch_nl_fast<1>(p, j, force, stream); break;
+            case 1024: launch_nl_fast<2>(p, j, force, stream); break;
+            case 2048: launch_nl_fast<4>(p, j, force, stream); break;
+            case 4096: launch_nl_fast<8>(p, j, force, stream); break;
+            default: launch_nl_fast<16>(p, j, force, stream); break;
+        }
+        p->launches += 1;
+        return RKS_OK;
+    }
     const unsigned grid = (unsigned)((d.batch + p->nl_rows_per_cta - 1) / p->nl_rows_per_cta);
     if (d.model == RKS_MODEL_UUX_RFFT)
         nl_kernel<1><<<grid, p->nl_threads, p->nl_smem, stream>>>(d, j, force, p->nl_rows_per_cta);

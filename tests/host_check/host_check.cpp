@@ -6,6 +6,7 @@
 // This is not a product path: nothing in rkstiff_b200/ loads it.
 #include <stdint.h>
 #include <string.h>
+#include <array>
 #include <vector>
 
 #include "../../rkstiff_b200/csrc/common.cuh"
@@ -13,6 +14,7 @@
 #include "../../rkstiff_b200/csrc/stages.cuh"
 #include "../../rkstiff_b200/csrc/errctl.cuh"
 #include "../../rkstiff_b200/csrc/fft.cuh"
+#include "../../rkstiff_b200/csrc/fft_fast.cuh"
 
 using namespace rks;
 
@@ -28,7 +30,51 @@ static void stage_all(int n, const cplx* u, const cplx* const* N, const cplx* co
     }
 }
 
+
+// serial emulation of the register-resident fast NL kernel (fft_fast.cuh): one row, 32 W threads
+template <int W, class Model>
+static void fast_row(const Model& m, const fast::Twiddles& tw) {
+    constexpr int TR = 32 * W;
+    std::vector<cplx> sm(512 * W);
+    std::vector<std::array<cplx, 16>> regs(TR);
+    auto V = [&](int T) -> cplx(&)[16] { return *reinterpret_cast<cplx(*)[16]>(regs[T].data()); };
+    for (int T = 0; T < TR; ++T) fast::p0_load_outer_dif<W>(V(T), sm.data(), T, tw, m);
+    for (int T = 0; T < TR; ++T) fast::read_chunk<W>(V(T), sm.data(), T);
+    for (int T = 0; T < TR; ++T) fast::p1_dif_a<W>(V(T), sm.data() + 512 * (T >> 5), T & 31, tw);
+    for (int T = 0; T < TR; ++T) fast::read_b(V(T), sm.data() + 512 * (T >> 5), T & 31);
+    for (int T = 0; T < TR; ++T) fast::p2_dif_b<W>(V(T), sm.data() + 512 * (T >> 5), T & 31, tw);
+    for (int T = 0; T < TR; ++T) fast::read_c(V(T), sm.data() + 512 * (T >> 5), T & 31);
+    for (int T = 0; T < TR; ++T) fast::p3_core(V(T), sm.data() + 512 * (T >> 5), T & 31, m);
+    for (int T = 0; T < TR; ++T) fast::read_b(V(T), sm.data() + 512 * (T >> 5), T & 31);
+    for (int T = 0; T < TR; ++T) fast::p4_dit_b<W>(V(T), sm.data() + 512 * (T >> 5), T & 31, tw);
+    for (int T = 0; T < TR; ++T) fast::read_a(V(T), sm.data() + 512 * (T >> 5), T & 31);
+    for (int T = 0; T < TR; ++T) fast::p5_dit_a<W>(V(T), sm.data(), T, tw);
+    for (int T = 0; T < TR; ++T) fast::p6_outer_dit_store<W>(V(T), sm.data(), T, tw, m);
+}
+template <class Model>
+static int fast_dispatch(int n, const Model& m, const fast::Twiddles& tw) {
+    switch (n) {
+        case 512: fast_row<1>(m, tw); return 0;
+        case 1024: fast_row<2>(m, tw); return 0;
+        case 2048: fast_row<4>(m, tw); return 0;
+        case 4096: fast_row<8>(m, tw); return 0;
+        case 8192: fast_row<16>(m, tw); return 0;
+    }
+    return -1;
+}
+
 extern "C" {
+
+int hc_nl_fast(int model, int n, const double* in, const double* kx, double p0, double* out) {
+    std::vector<cplx> tab(fast::TW_TOTAL);
+    for (int j = 0; j < fast::TW_TOTAL; ++j) tab[j] = fast::twiddle_table_entry(j, n);
+    const fast::Twiddles tw{tab.data() + fast::TW_O, tab.data() + fast::TW_A, tab.data() + fast::TW_B};
+    const cplx* cin = reinterpret_cast<const cplx*>(in);
+    cplx* co = reinterpret_cast<cplx*>(out);
+    if (model == 1) { fast::UuxModel m{cin, co, kx, p0, n, true}; return fast_dispatch(n, m, tw); }
+    fast::NlsModel m{cin, co, p0, n, true};
+    return fast_dispatch(n, m, tw);
+}
 
 // fused NL of one row, emulating `nthreads` threads
 void hc_nl(int model, int n, const double* in, const double* kx, double p0, double* out, int nthreads) {

@@ -33,7 +33,7 @@ def hc():
     src = os.path.join(HERE, "host_check", "host_check.cpp")
     lib = os.path.join(HERE, "host_check", "libhostcheck.so")
     deps = [src] + [os.path.join(HERE, "..", "rkstiff_b200", "csrc", f)
-                    for f in ("common.cuh", "coeffs.cuh", "stages.cuh", "errctl.cuh", "fft.cuh")]
+                    for f in ("common.cuh", "coeffs.cuh", "stages.cuh", "errctl.cuh", "fft.cuh", "fft_fast.cuh")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", lib, src])
     return ctypes.CDLL(lib)
@@ -77,6 +77,24 @@ def test_nl_nls_matches_numpy(hc, n):
         out = np.empty_like(row)
         hc.hc_nl(2, n, ptr(np.ascontiguousarray(row)), None, ctypes.c_double(2.0), ptr(out), 32)
         assert rel(out, p.nl_func(row)) < 1e-14 * np.log2(n)
+
+
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096, 8192])
+def test_fast_register_fft_nl_matches_numpy(hc, n):
+    """fft_fast.cuh: the register-resident W x 8 x 8 x 8 pipeline, emulated thread by thread."""
+    p = problems.nls(n, batch=2, half_width=20.0)
+    row = np.ascontiguousarray(p.u0[1])
+    out = np.empty_like(row)
+    assert hc.hc_nl_fast(2, n, ptr(row), None, ctypes.c_double(2.0), ptr(out)) == 0
+    assert rel(out, p.nl_func(row)) < 2e-15 * np.log2(n)
+    p = problems.ks(n)
+    rng = np.random.default_rng(n)
+    uf = p.u0 + 1e-3 * (rng.standard_normal(p.u0.shape) + 1j * rng.standard_normal(p.u0.shape))
+    uf[-1] += 0.3j
+    out = np.empty_like(uf)
+    assert hc.hc_nl_fast(1, n, ptr(uf), ptr(p.kx), ctypes.c_double(6.0), ptr(out)) == 0
+    ref = -6 * np.fft.rfft(np.fft.irfft(uf) * np.fft.irfft(1j * p.kx * uf))
+    assert rel(out, ref) < 1e-14 * np.log2(n)
 
 
 def device_coeffs(hc, method, lin, h, cfg=Config()):

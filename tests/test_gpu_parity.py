@@ -64,8 +64,8 @@ def make(rk, method, prob, nl, epsilon=None):
 # --------------------------------------------------------------------------------------------
 # K4: fused nonlinearity
 # --------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n", [16, 64, 256, 1024, 4096, 8192])
-@pytest.mark.parametrize("batch", [1, 3, 40])
+@pytest.mark.parametrize("n", [16, 64, 256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("batch", [1, 3, 40, 301])
 def test_fused_uux_matches_numpy(rk, n, batch):
     p = problems.ks(n, batch=batch, seed=n) if n >= 64 else problems.kdv(n, batch=batch, seed=n)
     sol = rk.ETD4(dev(p.lin_op), fused_for(rk, p))
@@ -77,8 +77,8 @@ def test_fused_uux_matches_numpy(rk, n, batch):
     assert rel(got, p.nl_func(p.u0)) < 2e-14 * np.log2(n)
 
 
-@pytest.mark.parametrize("n", [16, 128, 2048, 8192])
-@pytest.mark.parametrize("batch", [1, 5])
+@pytest.mark.parametrize("n", [16, 128, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("batch", [1, 5, 150])
 def test_fused_nls_matches_numpy(rk, n, batch):
     p = problems.nls(n, batch=batch, seed=n, half_width=20.0)
     sol = rk.ETD4(dev(p.lin_op), fused_for(rk, p))
