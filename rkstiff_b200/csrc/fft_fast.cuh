@@ -203,148 +203,130 @@ struct UuxModel {          // N = -c rfft(irfft(u^) irfft(i kx u^))       (model
 };
 
 // ---------------------------------------------------------------------------------------
-// phases.  T = thread index within the row (0 .. 32 W - 1); sm = the row's n-element smem slab.
-// Each phase is "compute + write"; the matching read_* runs after the synchronisation point.
+// phases.  T = thread index within the row (0 .. 32 W - 1); sm = the row's n-element smem slab;
+// chunk = the 512-element slice owned by this warp; l = lane.
+//
+// Every inner pass is IN PLACE: a butterfly writes its 8 results to the 8 positions it read, so
+// a thread only ever keeps one butterfly (8 values) in registers, and the only hazards are
+// between passes (separated by __syncwarp / the row barrier).
+// Inverse-direction passes read twiddle copy `ti`, forward ones copy `tf` (two identical tables at
+// different addresses: otherwise the compiler keeps the inverse half's twiddles alive in local
+// memory across the whole transform instead of re-reading them from L1).
 // ---------------------------------------------------------------------------------------
 template <int W, class Model>
-RKS_HD void p0_load_outer_dif(cplx (&v)[16], cplx* sm, int T, const Twiddles& tw, const Model& m) {
+RKS_HD void p0_load_outer_dif(cplx* sm, int T, const Twiddles& ti, const Model& m) {
     constexpr int TR = 32 * W, NB = 16 / W;
-    if (W == 1) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = m.load(T + 32 * j);
-        return;
-    }
-#pragma unroll
-    for (int b = 0; b < NB; ++b)
-#pragma unroll
-        for (int s = 0; s < W; ++s) v[b * W + s] = m.load(T + TR * b + 512 * s);
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        const int i = T + TR * b;
-        dftR<W, true>(&v[b * W]);
-        twiddle_scale<W, true>(&v[b * W], tw.o, 512, i, SlotPerm<W>());
-#pragma unroll
-        for (int r = 0; r < W; ++r) sm[swz(r * 512 + i)] = v[b * W + perm<W>(r)];
-    }
-}
-template <int W>
-RKS_HD void read_chunk(cplx (&v)[16], const cplx* sm, int T) {
-    if (W == 1) return;                                   // values already in place
-    const int w = T >> 5, l = T & 31;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = sm[swz(w * 512 + l + 32 * j)];
-}
-// inner DIF pass A (stride 64) : v[j] <-> chunk[l + 32 j]
-template <int W>
-RKS_HD void p1_dif_a(cplx (&v)[16], cplx* chunk, int l, const Twiddles& tw) {
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        const int i = l + 32 * b;
-        cplx a[8];
-#pragma unroll
-        for (int s = 0; s < 8; ++s) a[s] = v[b + 2 * s];
-        dft8<true>(a);
-        twiddle_scale<8, true>(a, tw.a, 64, i, SlotPerm<8>());
-#pragma unroll
-        for (int r = 0; r < 8; ++r) chunk[swz(r * 64 + i)] = a[perm8(r)];
-    }
-}
-RKS_HD void read_b(cplx (&v)[16], const cplx* chunk, int l) {
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        const int q = l + 32 * b, blk = q >> 3, ii = q & 7;
-#pragma unroll
-        for (int s = 0; s < 8; ++s) v[b * 8 + s] = chunk[swz(blk * 64 + ii + 8 * s)];
-    }
-}
-template <int W>
-RKS_HD void p2_dif_b(cplx (&v)[16], cplx* chunk, int l, const Twiddles& tw) {
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        const int q = l + 32 * b, blk = q >> 3, ii = q & 7;
-        dft8<true>(&v[b * 8]);
-        twiddle_scale<8, true>(&v[b * 8], tw.b, 8, ii, SlotPerm<8>());
-#pragma unroll
-        for (int r = 0; r < 8; ++r) chunk[swz(blk * 64 + r * 8 + ii)] = v[b * 8 + perm8(r)];
-    }
-}
-RKS_HD void read_c(cplx (&v)[16], const cplx* chunk, int l) {
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        const int q = l + 32 * b;
-#pragma unroll
-        for (int s = 0; s < 8; ++s) v[b * 8 + s] = chunk[swz(q * 8 + s)];
-    }
-}
-// innermost: DIF radix-8, pointwise nonlinearity, DIT radix-8 -- all in registers
-template <class Model>
-RKS_HD void p3_core(cplx (&v)[16], cplx* chunk, int l, const Model& m) {
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        const int q = l + 32 * b;
-        dft8<true>(&v[b * 8]);
-        cplx a[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) a[r] = m.pointwise(v[b * 8 + perm8(r)]);
-        dft8<false>(a);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) chunk[swz(q * 8 + k)] = a[perm8(k)];
-    }
-}
-// read for DIT pass B' is read_b (same positions), for A' the positions r*64 + i
-template <int W>
-RKS_HD void p4_dit_b(cplx (&v)[16], cplx* chunk, int l, const Twiddles& tw) {
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        const int q = l + 32 * b, blk = q >> 3, ii = q & 7;
-        twiddle_scale<8, false>(&v[b * 8], tw.b, 8, ii, SlotId());
-        dft8<false>(&v[b * 8]);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) chunk[swz(blk * 64 + ii + 8 * k)] = v[b * 8 + perm8(k)];
-    }
-}
-RKS_HD void read_a(cplx (&v)[16], const cplx* chunk, int l) {
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        const int i = l + 32 * b;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) v[b * 8 + r] = chunk[swz(r * 64 + i)];
-    }
-}
-// DIT pass A' : leaves v[j] <-> chunk[l + 32 j]; for W > 1 also writes the row slab for the outer pass
-template <int W>
-RKS_HD void p5_dit_a(cplx (&v)[16], cplx* sm, int T, const Twiddles& tw) {
-    const int w = T >> 5, l = T & 31;
-    cplx o[16];
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        const int i = l + 32 * b;
-        twiddle_scale<8, false>(&v[b * 8], tw.a, 64, i, SlotId());
-        dft8<false>(&v[b * 8]);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o[b + 2 * k] = v[b * 8 + perm8(k)];
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        v[j] = o[j];
-        if (W > 1) sm[swz(w * 512 + l + 32 * j)] = o[j];
-    }
-}
-template <int W, class Model>
-RKS_HD void p6_outer_dit_store(cplx (&v)[16], const cplx* sm, int T, const Twiddles& tw, const Model& m) {
-    constexpr int TR = 32 * W, NB = 16 / W;
-    if (W == 1) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) m.store(T + 32 * j, v[j]);
-        return;
-    }
+    if (W == 1) return;                                   // pass A reads global memory directly
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const int i = T + TR * b;
         cplx a[W];
 #pragma unroll
-        for (int r = 0; r < W; ++r) a[r] = sm[swz(r * 512 + i)];
-        twiddle_scale<W, false>(a, tw.o, 512, i, SlotId());
+        for (int s = 0; s < W; ++s) a[s] = m.load(i + 512 * s);
+        dftR<W, true>(a);
+        twiddle_scale<W, true>(a, ti.o, 512, i, SlotPerm<W>());
+        cplx* dst = sm + swz(i);                          // swz(r*512 + i) = swz(i) + r*512
+#pragma unroll
+        for (int r = 0; r < W; ++r) dst[r * 512] = a[perm<W>(r)];
+    }
+}
+
+// inner DIF pass A: butterflies i = l, l + 32 over positions i + 64 s
+template <int W, class Model>
+RKS_HD void p1_dif_a(cplx* chunk, int l, const Twiddles& ti, const Model& m) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        const int i = l + 32 * b;
+        cplx* pos = chunk + swz(i);                       // swz(i + 64 s) = swz(i) + 64 s
+        cplx a[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) a[s] = (W == 1) ? m.load(i + 64 * s) : pos[64 * s];
+        dft8<true>(a);
+        twiddle_scale<8, true>(a, ti.a, 64, i, SlotPerm<8>());
+#pragma unroll
+        for (int r = 0; r < 8; ++r) pos[64 * r] = a[perm8(r)];
+    }
+}
+// inner DIF pass B: butterflies (blk, ii) over positions blk*64 + ii + 8 s
+RKS_HD void p2_dif_b(cplx* chunk, int l, const Twiddles& ti) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        const int q = l + 32 * b, blk = q >> 3, ii = q & 7;
+        cplx* base = chunk + blk * 64;
+        cplx a[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) a[s] = base[8 * s + (ii ^ s)];          // swz: low bits ^ ((p >> 3) & 7) = ii ^ s
+        dft8<true>(a);
+        twiddle_scale<8, true>(a, ti.b, 8, ii, SlotPerm<8>());
+#pragma unroll
+        for (int r = 0; r < 8; ++r) base[8 * r + (ii ^ r)] = a[perm8(r)];
+    }
+}
+// innermost: DIF radix-8, pointwise nonlinearity, DIT radix-8 on positions q*8 + s
+template <class Model>
+RKS_HD void p3_core(cplx* chunk, int l, const Model& m) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        const int q = l + 32 * b;
+        cplx* base = chunk + q * 8;
+        const int x = q & 7;                                                // (p >> 3) & 7 for p = q*8 + s
+        cplx a[8], c[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) a[s] = base[s ^ x];
+        dft8<true>(a);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) c[r] = m.pointwise(a[perm8(r)]);
+        dft8<false>(c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) base[k ^ x] = c[perm8(k)];
+    }
+}
+// inner DIT pass B': inputs blk*64 + r*8 + ii (sub-block r), outputs blk*64 + ii + 8 k: same positions
+RKS_HD void p4_dit_b(cplx* chunk, int l, const Twiddles& tf) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        const int q = l + 32 * b, blk = q >> 3, ii = q & 7;
+        cplx* base = chunk + blk * 64;
+        cplx a[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) a[r] = base[8 * r + (ii ^ r)];
+        twiddle_scale<8, false>(a, tf.b, 8, ii, SlotId());
+        dft8<false>(a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) base[8 * k + (ii ^ k)] = a[perm8(k)];
+    }
+}
+// inner DIT pass A': inputs r*64 + i, outputs i + 64 k.  W == 1 stores straight to global memory.
+template <int W, class Model>
+RKS_HD void p5_dit_a(cplx* chunk, int l, const Twiddles& tf, const Model& m) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        const int i = l + 32 * b;
+        cplx* pos = chunk + swz(i);
+        cplx a[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) a[r] = pos[64 * r];
+        twiddle_scale<8, false>(a, tf.a, 64, i, SlotId());
+        dft8<false>(a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (W == 1) m.store(i + 64 * k, a[perm8(k)]);
+            else pos[64 * k] = a[perm8(k)];
+        }
+    }
+}
+template <int W, class Model>
+RKS_HD void p6_outer_dit_store(const cplx* sm, int T, const Twiddles& tf, const Model& m) {
+    constexpr int TR = 32 * W, NB = 16 / W;
+    if (W == 1) return;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int i = T + TR * b;
+        const cplx* src = sm + swz(i);
+        cplx a[W];
+#pragma unroll
+        for (int r = 0; r < W; ++r) a[r] = src[r * 512];
+        twiddle_scale<W, false>(a, tf.o, 512, i, SlotId());
         dftR<W, false>(a);
 #pragma unroll
         for (int k = 0; k < W; ++k) m.store(i + 512 * k, a[perm<W>(k)]);

@@ -78,7 +78,7 @@ __global__ void set_config_kernel(Ctrl* c, CfgArgs a) {
 
 __global__ void fast_twiddle_kernel(cplx* twf, int n) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < fast::TW_TOTAL) twf[idx] = fast::twiddle_table_entry(idx, n);
+    if (idx < 2 * fast::TW_TOTAL) twf[idx] = fast::twiddle_table_entry(idx % fast::TW_TOTAL, n);   // two copies
 }
 
 __global__ void twiddle_kernel(cplx* tw, int n) {
@@ -371,73 +371,60 @@ RKS_D void row_barrier(int lrow, int rpc) {
     asm volatile("bar.sync %0, %1;" ::"r"(lrow + 1), "r"(TR) : "memory");
 }
 
+template <int W, class Model>
+RKS_D void nl_fast_row(cplx* sm, cplx* chunk, int T, int l, int lrow, int rpc, const fast::Twiddles& ti,
+                       const fast::Twiddles& tf, const Model& m, const char* next_row, int next_lines) {
+    constexpr int TR = 32 * W;
+    fast::p0_load_outer_dif<W>(sm, T, ti, m);
+    // pull the next row from HBM into L2 while this one is transformed
+    for (int q = T; q < next_lines; q += TR) asm volatile("prefetch.global.L2 [%0];" ::"l"(next_row + ((size_t)q << 7)));
+    if (W > 1) row_barrier<TR>(lrow, rpc);
+    fast::p1_dif_a<W>(chunk, l, ti, m);   __syncwarp();
+    fast::p2_dif_b(chunk, l, ti);         __syncwarp();
+    fast::p3_core(chunk, l, m);           __syncwarp();
+    fast::p4_dit_b(chunk, l, tf);         __syncwarp();
+    fast::p5_dit_a<W>(chunk, l, tf, m);
+    if (W > 1) {
+        row_barrier<TR>(lrow, rpc);
+        fast::p6_outer_dit_store<W>(sm, T, tf, m);
+        row_barrier<TR>(lrow, rpc);          // slab reads of p6 vs the next row's p0 writes
+    } else {
+        __syncwarp();
+    }
+}
+
 template <int W, int MODEL>
 __global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_fast_kernel(DevPlan p, int j, int force) {
     constexpr int TR = 32 * W;                       // threads per row
     constexpr int RPC = (W == 16 ? 512 : 256) / TR;  // rows per CTA
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     const NlRoles roles = nl_roles(p, j, force);
     if (!roles.run) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&p.ctrl->nl_evals, 1ull);
 
-    const int lrow = threadIdx.x / TR, T = threadIdx.x - lrow * TR, l = T & 31, w = T >> 5;
+    const int lrow = threadIdx.x / TR, T = threadIdx.x - lrow * TR, l = T & 31;
     cplx* sm = reinterpret_cast<cplx*>(smem_raw) + (size_t)lrow * (512 * W);
-    cplx* chunk = sm + 512 * w;
-    const fast::Twiddles tw{p.twf + fast::TW_O, p.twf + fast::TW_A, p.twf + fast::TW_B};
+    cplx* chunk = sm + 512 * (T >> 5);
+    const fast::Twiddles ti{p.twf + fast::TW_O, p.twf + fast::TW_A, p.twf + fast::TW_B};
+    const cplx* twf2 = p.twf + fast::TW_TOTAL;
+    const fast::Twiddles tf{twf2 + fast::TW_O, twf2 + fast::TW_A, twf2 + fast::TW_B};
     const int n = 512 * W;
+    const int lines = (int)((p.n_c * 16 + 127) >> 7);
     const long long groups = (p.batch + RPC - 1) / RPC;
     for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
         const long long row = g * RPC + lrow;
         const bool on = row < p.batch;
         const long long rr = on ? row : p.batch - 1;
         const long long nrow = row + (long long)gridDim.x * RPC;     // the row this slot handles next
-        cplx v[16];
+        const char* nxt = reinterpret_cast<const char*>(roles.in + (nrow < p.batch ? nrow : rr) * p.n_c);
+        const int nlines = nrow < p.batch ? lines : 0;
         if (MODEL == 1) {
             const fast::UuxModel m{roles.in + rr * p.n_c, roles.out + rr * p.n_c, p.kx, p.model_p0, n, on};
-            fast::p0_load_outer_dif<W>(v, sm, T, tw, m);
-            if (nrow < p.batch) {        // pull the next row from HBM into L2 while this one is transformed
-                const char* nxt = reinterpret_cast<const char*>(roles.in + nrow * p.n_c);
-                const int lines = (int)((p.n_c * 16 + 127) >> 7);
-                for (int q = T; q < lines; q += TR) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t)q << 7)));
-            }
-            row_barrier<TR>(lrow, RPC);
-            fast::read_chunk<W>(v, sm, T);
-            __syncwarp();
-            fast::p1_dif_a<W>(v, chunk, l, tw);  __syncwarp();
-            fast::read_b(v, chunk, l);           __syncwarp();
-            fast::p2_dif_b<W>(v, chunk, l, tw);  __syncwarp();
-            fast::read_c(v, chunk, l);           __syncwarp();
-            fast::p3_core(v, chunk, l, m);       __syncwarp();
-            fast::read_b(v, chunk, l);           __syncwarp();
-            fast::p4_dit_b<W>(v, chunk, l, tw);  __syncwarp();
-            fast::read_a(v, chunk, l);           __syncwarp();
-            fast::p5_dit_a<W>(v, sm, T, tw);
-            row_barrier<TR>(lrow, RPC);
-            fast::p6_outer_dit_store<W>(v, sm, T, tw, m);
+            nl_fast_row<W>(sm, chunk, T, l, lrow, RPC, ti, tf, m, nxt, nlines);
         } else {
             const fast::NlsModel m{roles.in + rr * p.n_c, roles.out + rr * p.n_c, p.model_p0, n, on};
-            fast::p0_load_outer_dif<W>(v, sm, T, tw, m);
-            if (nrow < p.batch) {        // pull the next row from HBM into L2 while this one is transformed
-                const char* nxt = reinterpret_cast<const char*>(roles.in + nrow * p.n_c);
-                const int lines = (int)((p.n_c * 16 + 127) >> 7);
-                for (int q = T; q < lines; q += TR) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ((size_t)q << 7)));
-            }
-            row_barrier<TR>(lrow, RPC);
-            fast::read_chunk<W>(v, sm, T);
-            __syncwarp();
-            fast::p1_dif_a<W>(v, chunk, l, tw);  __syncwarp();
-            fast::read_b(v, chunk, l);           __syncwarp();
-            fast::p2_dif_b<W>(v, chunk, l, tw);  __syncwarp();
-            fast::read_c(v, chunk, l);           __syncwarp();
-            fast::p3_core(v, chunk, l, m);       __syncwarp();
-            fast::read_b(v, chunk, l);           __syncwarp();
-            fast::p4_dit_b<W>(v, chunk, l, tw);  __syncwarp();
-            fast::read_a(v, chunk, l);           __syncwarp();
-            fast::p5_dit_a<W>(v, sm, T, tw);
-            row_barrier<TR>(lrow, RPC);
-            fast::p6_outer_dit_store<W>(v, sm, T, tw, m);
+            nl_fast_row<W>(sm, chunk, T, l, lrow, RPC, ti, tf, m, nxt, nlines);
         }
-        row_barrier<TR>(lrow, RPC);          // p6 reads of the slab vs the next row's p0 writes
     }
 }
 

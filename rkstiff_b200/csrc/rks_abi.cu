@@ -52,7 +52,7 @@ static Layout make_layout(int method, long long batch, long long n_c, long long 
     L.partials = take(sizeof(double) * 2 * NORM_MAX_BLOCKS);
     const long long nmax = n_c <= MODEL_MAX_N ? 2 * n_c : 0;
     L.tw = take(sizeof(cplx) * (size_t)nmax);
-    L.twf = take(sizeof(cplx) * (size_t)(n_c <= MODEL_MAX_N ? fast::TW_TOTAL : 0));
+    L.twf = take(sizeof(cplx) * (size_t)(n_c <= MODEL_MAX_N ? 2 * fast::TW_TOTAL : 0));
     L.kx = take(sizeof(double) * (size_t)(n_c <= MODEL_MAX_N ? n_c : 0));
     L.lin = take((lin_is_complex ? sizeof(cplx) : sizeof(double)) * (size_t)lin_elems);
     L.coef = take(coef_elem * (size_t)lin_elems * method_ncoef(method));
@@ -249,7 +249,7 @@ extern "C" int rks_set_model(rks_plan* p, int model, int64_t n, const double* kx
                       : n == 2048 ? prepare_nl_fast<4>(model) : n == 4096 ? prepare_nl_fast<8>(model)
                       : prepare_nl_fast<16>(model);
         CUDA_TRY(e);
-        fast_twiddle_kernel<<<(fast::TW_TOTAL + 255) / 256, 256, 0, stream>>>((cplx*)(p->ws + p->lay.twf), (int)n);
+        fast_twiddle_kernel<<<(2 * fast::TW_TOTAL + 255) / 256, 256, 0, stream>>>((cplx*)(p->ws + p->lay.twf), (int)n);
         p->launches += 1;
     }
     // launch shape of the generic NL kernel: one row per CTA for long rows, several for short ones

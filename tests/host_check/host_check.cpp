@@ -31,25 +31,18 @@ static void stage_all(int n, const cplx* u, const cplx* const* N, const cplx* co
 }
 
 
-// serial emulation of the register-resident fast NL kernel (fft_fast.cuh): one row, 32 W threads
+// serial emulation of the fast NL kernel (fft_fast.cuh): one row, 32 W threads, phase by phase
 template <int W, class Model>
 static void fast_row(const Model& m, const fast::Twiddles& tw) {
     constexpr int TR = 32 * W;
     std::vector<cplx> sm(512 * W);
-    std::vector<std::array<cplx, 16>> regs(TR);
-    auto V = [&](int T) -> cplx(&)[16] { return *reinterpret_cast<cplx(*)[16]>(regs[T].data()); };
-    for (int T = 0; T < TR; ++T) fast::p0_load_outer_dif<W>(V(T), sm.data(), T, tw, m);
-    for (int T = 0; T < TR; ++T) fast::read_chunk<W>(V(T), sm.data(), T);
-    for (int T = 0; T < TR; ++T) fast::p1_dif_a<W>(V(T), sm.data() + 512 * (T >> 5), T & 31, tw);
-    for (int T = 0; T < TR; ++T) fast::read_b(V(T), sm.data() + 512 * (T >> 5), T & 31);
-    for (int T = 0; T < TR; ++T) fast::p2_dif_b<W>(V(T), sm.data() + 512 * (T >> 5), T & 31, tw);
-    for (int T = 0; T < TR; ++T) fast::read_c(V(T), sm.data() + 512 * (T >> 5), T & 31);
-    for (int T = 0; T < TR; ++T) fast::p3_core(V(T), sm.data() + 512 * (T >> 5), T & 31, m);
-    for (int T = 0; T < TR; ++T) fast::read_b(V(T), sm.data() + 512 * (T >> 5), T & 31);
-    for (int T = 0; T < TR; ++T) fast::p4_dit_b<W>(V(T), sm.data() + 512 * (T >> 5), T & 31, tw);
-    for (int T = 0; T < TR; ++T) fast::read_a(V(T), sm.data() + 512 * (T >> 5), T & 31);
-    for (int T = 0; T < TR; ++T) fast::p5_dit_a<W>(V(T), sm.data(), T, tw);
-    for (int T = 0; T < TR; ++T) fast::p6_outer_dit_store<W>(V(T), sm.data(), T, tw, m);
+    for (int T = 0; T < TR; ++T) fast::p0_load_outer_dif<W>(sm.data(), T, tw, m);
+    for (int T = 0; T < TR; ++T) fast::p1_dif_a<W>(sm.data() + 512 * (T >> 5), T & 31, tw, m);
+    for (int T = 0; T < TR; ++T) fast::p2_dif_b(sm.data() + 512 * (T >> 5), T & 31, tw);
+    for (int T = 0; T < TR; ++T) fast::p3_core(sm.data() + 512 * (T >> 5), T & 31, m);
+    for (int T = 0; T < TR; ++T) fast::p4_dit_b(sm.data() + 512 * (T >> 5), T & 31, tw);
+    for (int T = 0; T < TR; ++T) fast::p5_dit_a<W>(sm.data() + 512 * (T >> 5), T & 31, tw, m);
+    for (int T = 0; T < TR; ++T) fast::p6_outer_dit_store<W>(sm.data(), T, tw, m);
 }
 template <class Model>
 static int fast_dispatch(int n, const Model& m, const fast::Twiddles& tw) {
