@@ -178,11 +178,9 @@ class Engine:
             check(lib.rks_error_control(self.plan, self.st))
             return
         # shared-dt ensemble sharded by batch: reference-exact global norms (solveras.py:451-454)
-        import torch.distributed as dist
-        red = self._red_view()
-        dist.all_reduce(red[0:1], op=dist.ReduceOp.MAX, group=self.group)
-        check(lib.rks_error_sums(self.plan, self.st))
-        dist.all_reduce(red[1:3], op=dist.ReduceOp.SUM, group=self.group)
+        from .dist import allreduce_error_scalars
+        allreduce_error_scalars(self._red_view(), self.group,
+                                between=lambda: check(lib.rks_error_sums(self.plan, self.st)))
         check(lib.rks_controller(self.plan, self.st))
 
     def read_ctrl(self) -> RksCtrl:
