@@ -157,6 +157,11 @@ int rks_update_coeffs(rks_plan* plan, void* stream);
 int rks_stage(rks_plan* plan, int stage, void* stream);
 /* K4: N_j = N(input_j), j in 1..S+1 (see DESIGN.md for the input of each j); predicated on device */
 int rks_nl(rks_plan* plan, int j, void* stream);
+/* K1+K4: stage `stage` and the nonlinear evaluation it feeds (N_{stage+1}; after the last stage N1
+ * for fixed-step methods, N_last for FSAL methods, none for ETD35).  One fused kernel when the plan
+ * has a fused model with n in 512..8192: the stage value k is formed in the load prologue of the
+ * FFT kernel and never written to HBM unless it is the new state. */
+int rks_stage_nl(rks_plan* plan, int stage, void* stream);
 /* for caller-supplied nl_func: device pointers valid for the roles last read by rks_read_ctrl */
 void* rks_nl_input(rks_plan* plan, int j);
 void* rks_nl_output(rks_plan* plan, int j);

@@ -125,3 +125,53 @@ def nls(n: int = 8192, batch: int = 0, seed: int = 2, gamma: float = 2.0,
 
 
 BUILDERS = {"ks": ks, "kdv": kdv, "burgers": burgers, "nls": nls}
+
+
+# ----------------------------------------------------------------------------------------------
+# N-D grids, formulated the way the reference's demos do it: lin_op and u FLATTENED to 1-D and
+# reshaped inside nl_func (demos/nls.ipynb:496-511).  These are the oracles for
+# "lin_op shaped like u" on the engine side.
+# ----------------------------------------------------------------------------------------------
+def allen_cahn_2d(n: int = 256, eps: float = 0.01, seed: int = 1234) -> Problem:
+    """Periodic Allen-Cahn u_t = eps lap(u) + u - u^3 on [0, 2 pi)^2, rfft2 half spectrum (n, n/2+1):
+    L = 1 - eps (kx^2 + ky^2), N = -rfft2(irfft2(u^)^3)   (SURVEY.md 8d cfg 4)."""
+    x = np.arange(n) * (2 * np.pi / n)
+    ky = 2 * np.pi * np.fft.fftfreq(n, d=2 * np.pi / n)
+    kx = 2 * np.pi * np.fft.rfftfreq(n, d=2 * np.pi / n)
+    KY, KX = np.meshgrid(ky, kx, indexing="ij")
+    shape = KX.shape
+    lin = (1.0 - eps * (KX ** 2 + KY ** 2)).ravel()
+    rng = np.random.default_rng(seed)
+    Y, X = np.meshgrid(x, x, indexing="ij")
+    u0 = np.zeros((n, n))
+    for _ in range(16):
+        g, m, p, th = rng.standard_normal(), rng.integers(-4, 5), rng.integers(-4, 5), rng.uniform(0, 2 * np.pi)
+        u0 += 0.1 * g * np.cos(m * X + p * Y + th)
+
+    def nl(uf):
+        u = np.fft.irfft2(uf.reshape(shape), s=(n, n))
+        return -np.fft.rfft2(u ** 3).ravel()
+
+    prob = Problem("allen_cahn_2d", lin, nl, np.fft.rfft2(u0).ravel(), "none", n * n, kx, {"eps": eps}, x)
+    prob.params["shape"] = shape
+    return prob
+
+
+def nls_3d(n: int = 32, gamma: float = 2.0, half_width: float = 6.0) -> Problem:
+    """3-D NLS u_t = i lap(u) + i gamma |u|^2 u on [-W, W)^3: L = -i |k|^2, N = i gamma fftn(|f|^2 f)
+    with a Gaussian initial condition (SURVEY.md 8d cfg 5)."""
+    x, k = x_kx_fft(n, -half_width, half_width)
+    KX, KY, KZ = np.meshgrid(k, k, k, indexing="ij")
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    shape = (n, n, n)
+    lin = (-1j * (KX ** 2 + KY ** 2 + KZ ** 2)).ravel()
+    u0 = np.exp(-(X ** 2 + Y ** 2 + Z ** 2)).astype(np.complex128)
+
+    def nl(uf):
+        f = np.fft.ifftn(uf.reshape(shape))
+        f2 = f.real ** 2 + f.imag ** 2
+        return (1j * gamma * np.fft.fftn(f2 * f)).ravel()
+
+    prob = Problem("nls_3d", lin, nl, np.fft.fftn(u0).ravel(), "none", n ** 3, k, {"gamma": gamma}, x)
+    prob.params["shape"] = shape
+    return prob

@@ -68,6 +68,7 @@ def _load():
         "rks_update_coeffs": (c_int, [P, P]),
         "rks_stage": (c_int, [P, c_int, P]),
         "rks_nl": (c_int, [P, c_int, P]),
+        "rks_stage_nl": (c_int, [P, c_int, P]),
         "rks_nl_input": (P, [P, c_int]),
         "rks_nl_output": (P, [P, c_int]),
         "rks_error_control": (c_int, [P, P]),

@@ -7,7 +7,8 @@ import subprocess
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "librkstiff_b200.so")
+# RKS_LIB selects another build of the same ABI (kernel tuning experiments)
+LIB_PATH = os.environ.get("RKS_LIB") or os.path.join(PKG_DIR, "librkstiff_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

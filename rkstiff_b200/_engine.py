@@ -205,11 +205,11 @@ class Engine:
         elif self.ctrl.need_n1:
             self.nl_apply(1, nl_func)
         for s in range(1, S + 1):
-            self.stage(s)
-            if s < S or self.fsal:
-                if nl_func is None:
-                    self.nl(s + 1)
-                else:
+            if nl_func is None:
+                check(lib.rks_stage_nl(self.plan, s, self.st))      # fused K1+K4 where available
+            else:
+                self.stage(s)
+                if s < S or self.fsal:
                     self.nl_apply(s + 1, nl_func)
         self.error_control()
         if ring is not None:

@@ -1,18 +1,21 @@
-// K4 fast path -- register-resident FP64 FFT pair (inverse, pointwise nonlinearity, forward)
-// for rows of n = 512*W points, W in {1,2,4,8,16}  (n = 512 ... 8192).
+// K4 fast path -- shared-memory FP64 FFT pair (inverse, pointwise nonlinearity, forward) for rows
+// of n = 512 ... 8192 points, built from IN-PLACE radix-8/16 passes.
 //
-// Layout.  A row is owned by W warps; every thread keeps 16 complex values in registers.
-//   outer pass   radix-W across the W chunks of 512 points   (row-level exchange through smem)
-//   inner passes radix-8 x 8 x 8 on each 512-point chunk, one warp per chunk, exchanges through
-//                the warp's own 8 KB smem slice, synchronised with __syncwarp only
+// A row of n = 512 W points is owned by W warps (32 W threads) and lives in one smem slab.
+//   pass 1       radix R1 over stride Q1 = n / R1, global memory -> smem (row-level barrier after it)
+//   middle       radix R_k over stride Q_k inside blocks of R_k Q_k points; every block lies inside
+//                one warp's 512-point slice, so these passes need __syncwarp only
+//   core         the innermost radix-R_m butterfly of the inverse transform, the pointwise
+//                nonlinearity, and the innermost butterfly of the forward transform, in registers
 // The inverse transform is decimation-in-frequency and the forward one its mirrored
-// decimation-in-time, so the time-domain data stay in digit-reversed order and the pointwise
-// nonlinearity sits between the two innermost radix-8 butterflies without any exchange:
-//   load -> [W] -x- [8] -x- [8] -x- [8] -> N(.) -> [8] -x- [8] -x- [8] -x- [W] -> store
-// (-x- = shared-memory exchange: 2 row-level, 4 warp-level per nonlinear evaluation).
-// Shared-memory positions are XOR-swizzled (swz) so that every 128-bit access of a quarter-warp
-// is bank-conflict free.  The functions are __host__ __device__: tests/host_check executes the
-// same phase sequence serially on the CPU.
+// decimation-in-time, so the time-domain data stay digit-reversed and nothing is ever reordered:
+//   n = 512  : [8] [8] core8          n = 2048 : [16] [16] core8        n = 8192 : [16] [8] [8] core8
+//   n = 1024 : [16] [8] core8         n = 4096 : [16] [16] core16
+// i.e. 5 in-place smem passes per nonlinear evaluation (7 for n = 8192).  Every butterfly writes
+// its results to the positions it read, so a thread holds one or two butterflies in registers.
+// Positions are XOR-swizzled (swz<SH>) so that the 128-bit accesses of every quarter-warp are bank
+// conflict free.  All functions are __host__ __device__: tests/host_check runs the same phase
+// sequence serially on the CPU.
 #pragma once
 #include "common.cuh"
 
@@ -23,7 +26,14 @@ constexpr double SQH = 0.70710678118654752440;   // sqrt(1/2)
 constexpr double C8 = 0.92387953251128675613;    // cos(pi/8)
 constexpr double S8 = 0.38268343236508977173;    // sin(pi/8)
 
-RKS_HD int swz(int p) { return p ^ ((p >> 3) & 7); }
+#ifndef RKS_TW_SQUARE
+#define RKS_TW_SQUARE 1        // 1: read w^1 only and square; 0: read w^1, w^2, w^4, w^8 from tables
+#endif
+#ifndef RKS_LOADS_FIRST
+#define RKS_LOADS_FIRST 0      // 1: issue the loads of both butterflies of a thread before computing (measured slower)
+#endif
+
+template <int SH> RKS_HD int swz(int p) { return p ^ ((p >> SH) & 7); }
 
 template <bool INV> RKS_HD cplx rot(cplx a) { return INV ? mul_i(a) : mul_mi(a); }     // * (+-i)
 // multiply by exp(-+ i pi/4 * k)-type constants: w = (c, -s) forward, (c, +s) inverse
@@ -76,19 +86,25 @@ template <int R, bool INV> RKS_HD void dftR(cplx* v) {
     else if (R == 16) dft16<INV>(v);
 }
 
-// Twiddle tables, laid out so that the lanes of a warp read consecutive entries (a gather
-// tw[r*i] costs up to 32 L1 wavefronts per load, a contiguous read 4).  Only the powers
-// 1, 2, 4, 8 are stored; the others are products of at most three of them.
-//   o[k][i] = w_n^(k i),   k in {1,2,4,8}, i < 512     (outer radix-W pass)
-//   a[k][i] = w_512^(k i), k in {1,2,4},   i < 64      (inner pass A)
-//   b[k][i] = w_64^(k i),  k in {1,2,4},   i < 8       (inner pass B)
-// with w_m = exp(-2 pi i / m).
+// Twiddle tables: for every pass k with stride Q_k > 1 the Q_k values w_{L_k}^j, j < Q_k
+// (L_k = R_k Q_k, w_m = exp(-2 pi i / m)), contiguous so that the lanes of a warp read consecutive
+// entries.  Only the first power is stored; twiddle_scale builds the others by squaring/products.
 struct Twiddles {
-    const cplx* o;      // 4 x 512
-    const cplx* a;      // 3 x 64
-    const cplx* b;      // 3 x 8
+    const cplx* t1;     // pass 1
+    const cplx* t2;     // pass 2
+    const cplx* t3;     // pass 3 (n = 8192 only)
 };
-constexpr int TW_O = 0, TW_A = 4 * 512, TW_B = TW_A + 3 * 64, TW_TOTAL = TW_B + 3 * 8;
+// each pass table holds the powers k = 1, 2, 4, 8 as four rows of TW_S{1,2,3} entries
+constexpr int TW_S1 = 512, TW_S2 = 64, TW_S3 = 16;
+constexpr int TW_T1 = 0, TW_T2 = 4 * TW_S1, TW_T3 = TW_T2 + 4 * TW_S2, TW_TOTAL = TW_T3 + 4 * TW_S3;
+
+// static plan of an n-point row
+template <int N> struct Plan;
+template <> struct Plan<512>  { static constexpr int W = 1,  SH = 3, R1 = 8,  R2 = 8,  R3 = 8,  R4 = 1; };
+template <> struct Plan<1024> { static constexpr int W = 2,  SH = 3, R1 = 16, R2 = 8,  R3 = 8,  R4 = 1; };
+template <> struct Plan<2048> { static constexpr int W = 4,  SH = 3, R1 = 16, R2 = 16, R3 = 8,  R4 = 1; };
+template <> struct Plan<4096> { static constexpr int W = 8,  SH = 4, R1 = 16, R2 = 16, R3 = 16, R4 = 1; };
+template <> struct Plan<8192> { static constexpr int W = 16, SH = 3, R1 = 16, R2 = 8,  R3 = 8,  R4 = 8; };
 
 RKS_HD cplx tw_ld(const cplx* p) {
 #if defined(__CUDA_ARCH__)
@@ -102,41 +118,57 @@ template <bool INV> RKS_HD cplx cj(cplx w) { return INV ? conj(w) : w; }
 struct SlotId { RKS_HD int operator()(int r) const { return r; } };
 template <int R> struct SlotPerm { RKS_HD int operator()(int r) const { return perm<R>(r); } };
 
-// entry `idx` of the concatenated table block [o | a | b] for an n-point row
-RKS_HD cplx twiddle_table_entry(int idx, int n) {
-    int k, i, m;
-    if (idx < TW_A) { k = 1 << (idx / 512); i = idx % 512; m = n; }
-    else if (idx < TW_B) { const int t = idx - TW_A; k = 1 << (t / 64); i = t % 64; m = 512; }
-    else { const int t = idx - TW_B; k = 1 << (t / 8); i = t % 8; m = 64; }
-    const long long e = ((long long)k * i) % m;
+// entry `idx` of the concatenated table block [t1 | t2 | t3] for an n-point row
+template <int N>
+RKS_HD cplx twiddle_table_entry_n(int idx) {
+    using P = Plan<N>;
+    constexpr int Q1 = N / P::R1, Q2 = Q1 / P::R2, Q3 = Q2 / P::R3;
+    int j, m, k, q;
+    if (idx < TW_T2) { k = idx / TW_S1; j = idx % TW_S1; m = N; q = Q1; }
+    else if (idx < TW_T3) { k = (idx - TW_T2) / TW_S2; j = (idx - TW_T2) % TW_S2; m = Q1; q = Q2; }
+    else { k = (idx - TW_T3) / TW_S3; j = (idx - TW_T3) % TW_S3; m = Q2; q = Q3; }
+    if (j >= q) j = 0;
+    j = (int)(((long long)j << k) % m);              // w^(2^k j)
     double s, c;
 #if defined(__CUDA_ARCH__)
-    sincospi(-2.0 * (double)e / (double)m, &s, &c);
+    sincospi(-2.0 * (double)j / (double)m, &s, &c);
 #else
-    s = sin(-2.0 * M_PI * (double)e / (double)m); c = cos(-2.0 * M_PI * (double)e / (double)m);
+    s = sin(-2.0 * M_PI * (double)j / (double)m); c = cos(-2.0 * M_PI * (double)j / (double)m);
 #endif
     return mk(c, s);
 }
+RKS_HD cplx twiddle_table_entry(int idx, int n) {
+    switch (n) {
+        case 512: return twiddle_table_entry_n<512>(idx);
+        case 1024: return twiddle_table_entry_n<1024>(idx);
+        case 2048: return twiddle_table_entry_n<2048>(idx);
+        case 4096: return twiddle_table_entry_n<4096>(idx);
+        default: return twiddle_table_entry_n<8192>(idx);
+    }
+}
 
-// v[slot(r)] *= w^r for r = 1..R-1, with w^1, w^2, w^4, w^8 read from tab[k*stride + i]
+// v[slot(r)] *= w^r for r = 1..R-1.  RKS_TW_SQUARE: only w^1 is read and w^2, w^4, w^8 are
+// squarings (error <= ~8 ulp on the twiddle); otherwise the four powers are read from the table
+// rows.  The remaining powers are products of at most three of them.  Twiddle loads compete with
+// the shared-memory passes for the LSU pipe.
 template <int R, bool INV, class Slot>
 RKS_HD void twiddle_scale(cplx* v, const cplx* tab, int stride, int i, Slot slot) {
     if (R == 1) return;
     const cplx w1 = cj<INV>(tw_ld(tab + i));
     v[slot(1)] = v[slot(1)] * w1;
     if (R == 2) return;
-    const cplx w2 = cj<INV>(tw_ld(tab + stride + i));
+    const cplx w2 = RKS_TW_SQUARE ? w1 * w1 : cj<INV>(tw_ld(tab + stride + i));
     const cplx w3 = w1 * w2;
     v[slot(2)] = v[slot(2)] * w2;
     v[slot(3)] = v[slot(3)] * w3;
     if (R == 4) return;
-    const cplx w4 = cj<INV>(tw_ld(tab + 2 * stride + i));
+    const cplx w4 = RKS_TW_SQUARE ? w2 * w2 : cj<INV>(tw_ld(tab + 2 * stride + i));
     v[slot(4)] = v[slot(4)] * w4;
     v[slot(5)] = v[slot(5)] * (w4 * w1);
     v[slot(6)] = v[slot(6)] * (w4 * w2);
     v[slot(7)] = v[slot(7)] * (w4 * w3);
     if (R == 8) return;
-    const cplx w8 = cj<INV>(tw_ld(tab + 3 * stride + i));
+    const cplx w8 = RKS_TW_SQUARE ? w4 * w4 : cj<INV>(tw_ld(tab + 3 * stride + i));
     v[slot(8)] = v[slot(8)] * w8;
     v[slot(9)] = v[slot(9)] * (w8 * w1);
     v[slot(10)] = v[slot(10)] * (w8 * w2);
@@ -168,9 +200,39 @@ RKS_HD void row_st(cplx* p, cplx v) {
 #endif
 }
 
-struct NlsModel {          // N = i gamma fft(|f|^2 f), f = ifft(u^)      (demos/nls.ipynb)
-    const cplx* in; cplx* out; double gamma; int n; bool on;
-    RKS_HD cplx load(int p) const { return row_ld(in + p); }
+// Where a row's input comes from: an existing array (plain evaluation) or the stage combine
+// evaluated on the fly (fuse.cuh).  `sink` optionally stores the value as the new state u+ and
+// tracks max |u+|^2 for the error controller.
+struct ArraySource {
+    const cplx* in;
+    RKS_HD cplx value(long long p) const { return row_ld(in + p); }
+};
+struct StateSink {
+    cplx* kout;                     // nullptr: the stage value is not a state
+    unsigned long long* mx;         // nullptr: no max tracking; else running max of the bit pattern of |k|^2
+    RKS_HD void operator()(long long p, cplx v) const {
+        if (kout) row_st(kout + p, v);
+        if (mx) {
+            const double a = v.x * v.x + v.y * v.y;
+            unsigned long long bits;
+#if defined(__CUDA_ARCH__)
+            bits = (a != a) ? 0x7ff8000000000000ull : (unsigned long long)__double_as_longlong(a);
+#else
+            bits = 0; (void)a;
+#endif
+            if (bits > *mx) *mx = bits;
+        }
+    }
+};
+
+template <class Src>
+struct NlsModelT {          // N = i gamma fft(|f|^2 f), f = ifft(u^)      (demos/nls.ipynb)
+    Src src; StateSink sink; cplx* out; double gamma; int n; bool on;
+    RKS_HD cplx load(int p) const {
+        const cplx v = src.value(p);
+        if (on) sink(p, v);
+        return v;
+    }
     RKS_HD cplx pointwise(cplx z) const {
         const double sc = 1.0 / (double)n;
         const cplx f = mk(z.x * sc, z.y * sc);
@@ -179,17 +241,30 @@ struct NlsModel {          // N = i gamma fft(|f|^2 f), f = ifft(u^)      (demos
     }
     RKS_HD void store(int p, cplx v) const { if (on) row_st(out + p, mk(-(gamma * v.y), gamma * v.x)); }
 };
-struct UuxModel {          // N = -c rfft(irfft(u^) irfft(i kx u^))       (models.py:140-143)
-    const cplx* in; cplx* out; const double* kx; double c; int n; bool on;
+using NlsModel = NlsModelT<ArraySource>;
+
+// N = -c rfft(irfft(u^) irfft(i kx u^))  (models.py:140-143).  `Half` yields the half spectrum value at
+// index k <= n/2: a global array (plain evaluation) or the smem staging row of the fused kernel.
+struct GlobalHalf {
+    const cplx* in;
+    RKS_HD cplx get(int k) const { return row_ld(in + k); }
+};
+struct SmemHalf {
+    const cplx* stage;
+    RKS_HD cplx get(int k) const { return stage[k]; }
+};
+template <class Half>
+struct UuxModelT {
+    Half half; cplx* out; const double* kx; double c; int n; bool on;
     RKS_HD cplx load(int p) const {
-        const int half = n >> 1;
-        if (p <= half) {
-            const cplx v = row_ld(in + p);
+        const int hn = n >> 1;
+        if (p <= hn) {
+            const cplx v = half.get(p);
             const double kk = kx[p];
-            if (p == 0 || p == half) return mk(v.x, -(kk * v.y));       // c2r ignores Im of DC / Nyquist
+            if (p == 0 || p == hn) return mk(v.x, -(kk * v.y));         // c2r ignores Im of DC / Nyquist
             return mk(v.x - kk * v.x, v.y - kk * v.y);                  // U^ + i (i k U^)
         }
-        const cplx v = row_ld(in + (n - p));
+        const cplx v = half.get(n - p);
         const double kk = kx[n - p];
         return mk(v.x + kk * v.x, -(v.y + kk * v.y));                   // Hermitian partner
     }
@@ -201,137 +276,139 @@ struct UuxModel {          // N = -c rfft(irfft(u^) irfft(i kx u^))       (model
         if (on && p <= (n >> 1)) row_st(out + p, mk(-c * v.x, -c * v.y));
     }
 };
+using UuxModel = UuxModelT<GlobalHalf>;
 
 // ---------------------------------------------------------------------------------------
-// phases.  T = thread index within the row (0 .. 32 W - 1); sm = the row's n-element smem slab;
-// chunk = the 512-element slice owned by this warp; l = lane.
-//
-// Every inner pass is IN PLACE: a butterfly writes its 8 results to the 8 positions it read, so
-// a thread only ever keeps one butterfly (8 values) in registers, and the only hazards are
-// between passes (separated by __syncwarp / the row barrier).
+// generic in-place passes.  A butterfly is identified by the logical position p0 of its first
+// element (elements p0 + Q s) and its twiddle index j (w_L^(r j), L = R Q).  NB butterflies of one
+// thread are loaded first and then transformed/stored one after the other.
 // Inverse-direction passes read twiddle copy `ti`, forward ones copy `tf` (two identical tables at
 // different addresses: otherwise the compiler keeps the inverse half's twiddles alive in local
 // memory across the whole transform instead of re-reading them from L1).
 // ---------------------------------------------------------------------------------------
-template <int W, class Model>
-RKS_HD void p0_load_outer_dif(cplx* sm, int T, const Twiddles& ti, const Model& m) {
-    constexpr int TR = 32 * W, NB = 16 / W;
-    if (W == 1) return;                                   // pass A reads global memory directly
+template <int R, int Q, int SH, int NB, int TS, bool GLOBAL_IN, class Model>
+RKS_HD void dif_pass(cplx* sm, const int (&p0)[NB], const int (&j)[NB], const cplx* tab, const Model& m) {
+    cplx a[NB][R];
+#pragma unroll
+    for (int b = 0; b < (RKS_LOADS_FIRST ? NB : 0); ++b)
+#pragma unroll
+        for (int s = 0; s < R; ++s) a[b][s] = GLOBAL_IN ? m.load(p0[b] + Q * s) : sm[swz<SH>(p0[b] + Q * s)];
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-        const int i = T + TR * b;
-        cplx a[W];
+        if (!RKS_LOADS_FIRST) {
 #pragma unroll
-        for (int s = 0; s < W; ++s) a[s] = m.load(i + 512 * s);
-        dftR<W, true>(a);
-        twiddle_scale<W, true>(a, ti.o, 512, i, SlotPerm<W>());
-        cplx* dst = sm + swz(i);                          // swz(r*512 + i) = swz(i) + r*512
+            for (int s = 0; s < R; ++s) a[b][s] = GLOBAL_IN ? m.load(p0[b] + Q * s) : sm[swz<SH>(p0[b] + Q * s)];
+        }
+        dftR<R, true>(a[b]);
+        if (Q > 1) twiddle_scale<R, true>(a[b], tab, TS, j[b], SlotPerm<R>());
 #pragma unroll
-        for (int r = 0; r < W; ++r) dst[r * 512] = a[perm<W>(r)];
+        for (int r = 0; r < R; ++r) sm[swz<SH>(p0[b] + Q * r)] = a[b][perm<R>(r)];
     }
 }
-
-// inner DIF pass A: butterflies i = l, l + 32 over positions i + 64 s
-template <int W, class Model>
-RKS_HD void p1_dif_a(cplx* chunk, int l, const Twiddles& ti, const Model& m) {
+template <int R, int Q, int SH, int NB, int TS, bool GLOBAL_OUT, class Model>
+RKS_HD void dit_pass(cplx* sm, const int (&p0)[NB], const int (&j)[NB], const cplx* tab, const Model& m) {
+    cplx a[NB][R];
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        const int i = l + 32 * b;
-        cplx* pos = chunk + swz(i);                       // swz(i + 64 s) = swz(i) + 64 s
-        cplx a[8];
+    for (int b = 0; b < (RKS_LOADS_FIRST ? NB : 0); ++b)
 #pragma unroll
-        for (int s = 0; s < 8; ++s) a[s] = (W == 1) ? m.load(i + 64 * s) : pos[64 * s];
-        dft8<true>(a);
-        twiddle_scale<8, true>(a, ti.a, 64, i, SlotPerm<8>());
+        for (int r = 0; r < R; ++r) a[b][r] = sm[swz<SH>(p0[b] + Q * r)];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) pos[64 * r] = a[perm8(r)];
-    }
-}
-// inner DIF pass B: butterflies (blk, ii) over positions blk*64 + ii + 8 s
-RKS_HD void p2_dif_b(cplx* chunk, int l, const Twiddles& ti) {
+    for (int b = 0; b < NB; ++b) {
+        if (!RKS_LOADS_FIRST) {
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        const int q = l + 32 * b, blk = q >> 3, ii = q & 7;
-        cplx* base = chunk + blk * 64;
-        cplx a[8];
+            for (int r = 0; r < R; ++r) a[b][r] = sm[swz<SH>(p0[b] + Q * r)];
+        }
+        if (Q > 1) twiddle_scale<R, false>(a[b], tab, TS, j[b], SlotId());
+        dftR<R, false>(a[b]);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) a[s] = base[8 * s + (ii ^ s)];          // swz: low bits ^ ((p >> 3) & 7) = ii ^ s
-        dft8<true>(a);
-        twiddle_scale<8, true>(a, ti.b, 8, ii, SlotPerm<8>());
-#pragma unroll
-        for (int r = 0; r < 8; ++r) base[8 * r + (ii ^ r)] = a[perm8(r)];
-    }
-}
-// innermost: DIF radix-8, pointwise nonlinearity, DIT radix-8 on positions q*8 + s
-template <class Model>
-RKS_HD void p3_core(cplx* chunk, int l, const Model& m) {
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        const int q = l + 32 * b;
-        cplx* base = chunk + q * 8;
-        const int x = q & 7;                                                // (p >> 3) & 7 for p = q*8 + s
-        cplx a[8], c[8];
-#pragma unroll
-        for (int s = 0; s < 8; ++s) a[s] = base[s ^ x];
-        dft8<true>(a);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) c[r] = m.pointwise(a[perm8(r)]);
-        dft8<false>(c);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) base[k ^ x] = c[perm8(k)];
-    }
-}
-// inner DIT pass B': inputs blk*64 + r*8 + ii (sub-block r), outputs blk*64 + ii + 8 k: same positions
-RKS_HD void p4_dit_b(cplx* chunk, int l, const Twiddles& tf) {
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        const int q = l + 32 * b, blk = q >> 3, ii = q & 7;
-        cplx* base = chunk + blk * 64;
-        cplx a[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) a[r] = base[8 * r + (ii ^ r)];
-        twiddle_scale<8, false>(a, tf.b, 8, ii, SlotId());
-        dft8<false>(a);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) base[8 * k + (ii ^ k)] = a[perm8(k)];
-    }
-}
-// inner DIT pass A': inputs r*64 + i, outputs i + 64 k.  W == 1 stores straight to global memory.
-template <int W, class Model>
-RKS_HD void p5_dit_a(cplx* chunk, int l, const Twiddles& tf, const Model& m) {
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        const int i = l + 32 * b;
-        cplx* pos = chunk + swz(i);
-        cplx a[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) a[r] = pos[64 * r];
-        twiddle_scale<8, false>(a, tf.a, 64, i, SlotId());
-        dft8<false>(a);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (W == 1) m.store(i + 64 * k, a[perm8(k)]);
-            else pos[64 * k] = a[perm8(k)];
+        for (int k = 0; k < R; ++k) {
+            if (GLOBAL_OUT) m.store(p0[b] + Q * k, a[b][perm<R>(k)]);
+            else sm[swz<SH>(p0[b] + Q * k)] = a[b][perm<R>(k)];
         }
     }
 }
-template <int W, class Model>
-RKS_HD void p6_outer_dit_store(const cplx* sm, int T, const Twiddles& tf, const Model& m) {
-    constexpr int TR = 32 * W, NB = 16 / W;
-    if (W == 1) return;
+// innermost butterflies + pointwise nonlinearity (stride 1, no twiddles)
+template <int R, int SH, int NB, class Model>
+RKS_HD void core_pass(cplx* sm, const int (&p0)[NB], const Model& m) {
+    cplx a[NB][R];
+#pragma unroll
+    for (int b = 0; b < (RKS_LOADS_FIRST ? NB : 0); ++b)
+#pragma unroll
+        for (int s = 0; s < R; ++s) a[b][s] = sm[swz<SH>(p0[b] + s)];
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-        const int i = T + TR * b;
-        const cplx* src = sm + swz(i);
-        cplx a[W];
+        if (!RKS_LOADS_FIRST) {
 #pragma unroll
-        for (int r = 0; r < W; ++r) a[r] = src[r * 512];
-        twiddle_scale<W, false>(a, tf.o, 512, i, SlotId());
-        dftR<W, false>(a);
+            for (int s = 0; s < R; ++s) a[b][s] = sm[swz<SH>(p0[b] + s)];
+        }
+        cplx c[R];
+        dftR<R, true>(a[b]);
 #pragma unroll
-        for (int k = 0; k < W; ++k) m.store(i + 512 * k, a[perm<W>(k)]);
+        for (int r = 0; r < R; ++r) c[r] = m.pointwise(a[b][perm<R>(r)]);
+        dftR<R, false>(c);
+#pragma unroll
+        for (int k = 0; k < R; ++k) sm[swz<SH>(p0[b] + k)] = c[perm<R>(k)];
     }
 }
+
+// butterfly assignment of a warp-local pass: the warp's 512-point slice holds 512/R butterflies,
+// lane l takes u = l + 32 c;  u -> (block u / Q, offset u % Q)
+template <int R, int Q, int NB>
+RKS_HD void warp_butterflies(int chunk0, int l, int (&p0)[NB], int (&j)[NB]) {
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+        const int u = l + 32 * c;
+        j[c] = u % Q;
+        p0[c] = chunk0 + (u / Q) * (R * Q) + j[c];
+    }
+}
+
+// ---- the phase sequence of one row (T = thread index within the row, W = warps per row) ----
+// phase ids for the host emulation: 0 first DIF pass, 1..: middle DIF, core, middle DIT, last DIT
+template <int N, class Model>
+RKS_HD void phase_first(cplx* sm, int T, const Twiddles& ti, const Model& m) {
+    using P = Plan<N>;
+    constexpr int Q1 = N / P::R1, NB = Q1 / (32 * P::W);
+    int p0[NB], j[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) { p0[c] = T + 32 * P::W * c; j[c] = p0[c]; }
+    dif_pass<P::R1, Q1, P::SH, NB, TW_S1, true>(sm, p0, j, ti.t1, m);
+}
+template <int N, class Model>
+RKS_HD void phase_last(cplx* sm, int T, const Twiddles& tf, const Model& m) {
+    using P = Plan<N>;
+    constexpr int Q1 = N / P::R1, NB = Q1 / (32 * P::W);
+    int p0[NB], j[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) { p0[c] = T + 32 * P::W * c; j[c] = p0[c]; }
+    dit_pass<P::R1, Q1, P::SH, NB, TW_S1, true>(sm, p0, j, tf.t1, m);
+}
+// middle pass k = 2 (and 3 for n = 8192); DIR: true = inverse/DIF, false = forward/DIT
+template <int N, int K, bool DIF, class Model>
+RKS_HD void phase_middle(cplx* sm, int T, const Twiddles& tw, const Model& m) {
+    using P = Plan<N>;
+    constexpr int Q1 = N / P::R1;
+    constexpr int R = K == 2 ? P::R2 : P::R3;
+    constexpr int Q = K == 2 ? Q1 / P::R2 : Q1 / P::R2 / P::R3;
+    constexpr int NB = 16 / R;
+    int p0[NB], j[NB];
+    warp_butterflies<R, Q, NB>((T >> 5) * 512, T & 31, p0, j);
+    const cplx* tab = K == 2 ? tw.t2 : tw.t3;
+    constexpr int TS = K == 2 ? TW_S2 : TW_S3;
+    if (DIF) dif_pass<R, Q, P::SH, NB, TS, false>(sm, p0, j, tab, m);
+    else dit_pass<R, Q, P::SH, NB, TS, false>(sm, p0, j, tab, m);
+}
+template <int N, class Model>
+RKS_HD void phase_core(cplx* sm, int T, const Model& m) {
+    using P = Plan<N>;
+    constexpr int R = P::R4 > 1 ? P::R4 : P::R3;
+    constexpr int NB = 16 / R;
+    int p0[NB], j[NB];
+    warp_butterflies<R, 1, NB>((T >> 5) * 512, T & 31, p0, j);
+    core_pass<R, P::SH, NB>(sm, p0, m);
+}
+// number of warp-local middle passes per direction
+template <int N> RKS_HD constexpr int middle_passes() { return Plan<N>::R4 > 1 ? 2 : 1; }
 
 }  // namespace fast
 }  // namespace rks

@@ -1,11 +1,13 @@
 // Device kernels of the rkstiff_b200 engine (sm_100a).  See DESIGN.md for the byte model of each.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 #include "coeffs.cuh"
 #include "stages.cuh"
 #include "errctl.cuh"
 #include "fft.cuh"
 #include "fft_fast.cuh"
+#include "fuse.cuh"
 
 namespace rks {
 
@@ -371,59 +373,145 @@ RKS_D void row_barrier(int lrow, int rpc) {
     asm volatile("bar.sync %0, %1;" ::"r"(lrow + 1), "r"(TR) : "memory");
 }
 
-template <int W, class Model>
-RKS_D void nl_fast_row(cplx* sm, cplx* chunk, int T, int l, int lrow, int rpc, const fast::Twiddles& ti,
-                       const fast::Twiddles& tf, const Model& m, const char* next_row, int next_lines) {
-    constexpr int TR = 32 * W;
-    fast::p0_load_outer_dif<W>(sm, T, ti, m);
-    // pull the next row from HBM into L2 while this one is transformed
-    for (int q = T; q < next_lines; q += TR) asm volatile("prefetch.global.L2 [%0];" ::"l"(next_row + ((size_t)q << 7)));
-    if (W > 1) row_barrier<TR>(lrow, rpc);
-    fast::p1_dif_a<W>(chunk, l, ti, m);   __syncwarp();
-    fast::p2_dif_b(chunk, l, ti);         __syncwarp();
-    fast::p3_core(chunk, l, m);           __syncwarp();
-    fast::p4_dit_b(chunk, l, tf);         __syncwarp();
-    fast::p5_dit_a<W>(chunk, l, tf, m);
-    if (W > 1) {
-        row_barrier<TR>(lrow, rpc);
-        fast::p6_outer_dit_store<W>(sm, T, tf, m);
-        row_barrier<TR>(lrow, rpc);          // slab reads of p6 vs the next row's p0 writes
-    } else {
-        __syncwarp();
-    }
+template <int N, class Model>
+RKS_D void nl_fast_row(cplx* sm, int T, int lrow, int rpc, const fast::Twiddles& ti, const fast::Twiddles& tf,
+                       const Model& m) {
+    constexpr int W = fast::Plan<N>::W, TR = 32 * W;
+    fast::phase_first<N>(sm, T, ti, m);
+    row_barrier<TR>(lrow, rpc);
+    fast::phase_middle<N, 2, true>(sm, T, ti, m);   __syncwarp();
+    if (fast::middle_passes<N>() == 2) { fast::phase_middle<N, 3, true>(sm, T, ti, m);   __syncwarp(); }
+    fast::phase_core<N>(sm, T, m);                  __syncwarp();
+    if (fast::middle_passes<N>() == 2) { fast::phase_middle<N, 3, false>(sm, T, tf, m);  __syncwarp(); }
+    fast::phase_middle<N, 2, false>(sm, T, tf, m);
+    row_barrier<TR>(lrow, rpc);
+    fast::phase_last<N>(sm, T, tf, m);
+    row_barrier<TR>(lrow, rpc);              // slab reads of the last pass vs the next row's first pass
 }
 
-template <int W, int MODEL>
-__global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_fast_kernel(DevPlan p, int j, int force) {
+// pull a row that will be needed soon from HBM into L2 (no registers, no smem)
+template <int TR>
+RKS_D void prefetch_row_l2(const void* row, int lines, int T) {
+    const char* base = reinterpret_cast<const char*>(row);
+    for (int q = T; q < lines; q += TR) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ((size_t)q << 7)));
+}
+
+// FK = 0: N_j = N(existing array).  FK = 1 / 2: the stage combine (fuse.cuh, complex / real
+// coefficient arrays) is evaluated in the load prologue, so the stage value k never goes to HBM
+// unless it is a state (fd.write_k: final stage of fixed-step and FSAL methods).
+template <int W, int MODEL, int FK>
+__global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2))
+nl_fast_kernel(DevPlan p, int j, int force, FuseDesc fd) {
+    using CT = typename std::conditional<FK == 2, double, cplx>::type;
+    constexpr int N = 512 * W;
     constexpr int TR = 32 * W;                       // threads per row
-    constexpr int RPC = (W == 16 ? 512 : 256) / TR;  // rows per CTA
+    constexpr int THREADS = W == 16 ? 512 : 256;
+    constexpr int RPC = THREADS / TR;                // rows per CTA
+    constexpr int STAGE_LD = N / 2 + 8;              // staging row of the fused u u_x models (half spectrum)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const NlRoles roles = nl_roles(p, j, force);
     if (!roles.run) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&p.ctrl->nl_evals, 1ull);
 
-    const int lrow = threadIdx.x / TR, T = threadIdx.x - lrow * TR, l = T & 31;
-    cplx* sm = reinterpret_cast<cplx*>(smem_raw) + (size_t)lrow * (512 * W);
-    cplx* chunk = sm + 512 * (T >> 5);
-    const fast::Twiddles ti{p.twf + fast::TW_O, p.twf + fast::TW_A, p.twf + fast::TW_B};
+    const int lrow = threadIdx.x / TR, T = threadIdx.x - lrow * TR;
+    cplx* sm = reinterpret_cast<cplx*>(smem_raw) + (size_t)lrow * N;
+    cplx* stage = reinterpret_cast<cplx*>(smem_raw) + (size_t)RPC * N + (size_t)lrow * STAGE_LD;
+    const fast::Twiddles ti{p.twf + fast::TW_T1, p.twf + fast::TW_T2, p.twf + fast::TW_T3};
     const cplx* twf2 = p.twf + fast::TW_TOTAL;
-    const fast::Twiddles tf{twf2 + fast::TW_O, twf2 + fast::TW_A, twf2 + fast::TW_B};
-    const int n = 512 * W;
+    const fast::Twiddles tf{twf2 + fast::TW_T1, twf2 + fast::TW_T2, twf2 + fast::TW_T3};
     const int lines = (int)((p.n_c * 16 + 127) >> 7);
     const long long groups = (p.batch + RPC - 1) / RPC;
+
+    // fused mode: resolve the term list once (roles and h are fixed for the whole launch)
+    const cplx* xbase[FUSE_MAX_TERMS];
+    const CT* cbase[FUSE_MAX_TERMS];
+    double sc[FUSE_MAX_TERMS];
+    cplx* kbase = nullptr;
+    unsigned long long mx = 0ull;
+    if (FK > 0) {
+        const Ctrl* c = p.ctrl;
+        const bool adapt = method_adaptive(p.method);
+        const int u_sel = adapt ? c->u_sel : 0, n_sel = adapt ? c->n_sel : 0;
+        const double h = c->h;
+#pragma unroll
+        for (int t = 0; t < FUSE_MAX_TERMS; ++t) {
+            if (t < fd.nterms) {
+                xbase[t] = fd.src[t] == 0 ? p.U[u_sel] : p.NL[nl_phys(p.method, fd.src[t], n_sel)];
+                cbase[t] = fd.slot[t] < 0 ? nullptr : (const CT*)p.coef + (size_t)fd.slot[t] * p.lin_elems;
+                sc[t] = fd.c0[t] + fd.c1[t] * h;
+            }
+        }
+        if (fd.write_k) kbase = adapt ? p.U[1 - u_sel] : p.U[0];
+    }
+
     for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
         const long long row = g * RPC + lrow;
         const bool on = row < p.batch;
         const long long rr = on ? row : p.batch - 1;
         const long long nrow = row + (long long)gridDim.x * RPC;     // the row this slot handles next
-        const char* nxt = reinterpret_cast<const char*>(roles.in + (nrow < p.batch ? nrow : rr) * p.n_c);
         const int nlines = nrow < p.batch ? lines : 0;
-        if (MODEL == 1) {
-            const fast::UuxModel m{roles.in + rr * p.n_c, roles.out + rr * p.n_c, p.kx, p.model_p0, n, on};
-            nl_fast_row<W>(sm, chunk, T, l, lrow, RPC, ti, tf, m, nxt, nlines);
+        cplx* out = roles.out + rr * p.n_c;
+        if (FK == 0) {
+            prefetch_row_l2<TR>(roles.in + (nlines ? nrow : rr) * p.n_c, nlines, T);
+            if (MODEL == 1) {
+                const fast::UuxModel m{fast::GlobalHalf{roles.in + rr * p.n_c}, out, p.kx, p.model_p0, N, on};
+                nl_fast_row<N>(sm, T, lrow, RPC, ti, tf, m);
+            } else {
+                const fast::NlsModel m{fast::ArraySource{roles.in + rr * p.n_c}, fast::StateSink{nullptr, nullptr}, out,
+                                       p.model_p0, N, on};
+                nl_fast_row<N>(sm, T, lrow, RPC, ti, tf, m);
+            }
         } else {
-            const fast::NlsModel m{roles.in + rr * p.n_c, roles.out + rr * p.n_c, p.model_p0, n, on};
-            nl_fast_row<W>(sm, chunk, T, l, lrow, RPC, ti, tf, m, nxt, nlines);
+            FuseSource<CT> src;
+            src.nterms = fd.nterms;
+#pragma unroll
+            for (int t = 0; t < FUSE_MAX_TERMS; ++t) {
+                if (t < fd.nterms) {
+                    src.x[t] = xbase[t] + rr * p.n_c;
+                    src.c[t] = cbase[t];
+                    src.sc[t] = sc[t];
+                    prefetch_row_l2<TR>(xbase[t] + (nlines ? nrow : rr) * p.n_c, nlines, T);
+                }
+            }
+            const fast::StateSink sink{kbase ? kbase + rr * p.n_c : nullptr, fd.track_max ? &mx : nullptr};
+            if (MODEL == 1) {
+                // half spectrum of the stage value: computed once per mode, staged in smem (the
+                // inverse transform needs every mode twice: k and its Hermitian partner n - k)
+                constexpr int HALF = N / 2 + 1;
+                for (int q0 = T; q0 < HALF; q0 += 2 * TR) {      // two modes per iteration: more loads in flight
+                    const int q1 = q0 + TR;
+                    const cplx v0 = src.value(q0);
+                    const cplx v1 = src.value(q1 < HALF ? q1 : q0);
+                    if (on) sink(q0, v0);
+                    stage[q0] = v0;
+                    if (q1 < HALF) {
+                        if (on) sink(q1, v1);
+                        stage[q1] = v1;
+                    }
+                }
+                row_barrier<TR>(lrow, RPC);
+                const fast::UuxModelT<fast::SmemHalf> m{fast::SmemHalf{stage}, out, p.kx, p.model_p0, N, on};
+                nl_fast_row<N>(sm, T, lrow, RPC, ti, tf, m);
+            } else {
+                const fast::NlsModelT<FuseSource<CT>> m{src, sink, out, p.model_p0, N, on};
+                nl_fast_row<N>(sm, T, lrow, RPC, ti, tf, m);
+            }
+        }
+    }
+    if (FK > 0 && fd.track_max) {
+        // block max of |u+|^2 -> one atomicMax per block (solveras.py:451: magu.max())
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, mx, o);
+            mx = t > mx ? t : mx;
+        }
+        __shared__ unsigned long long smx[THREADS / 32];
+        if ((threadIdx.x & 31) == 0) smx[threadIdx.x >> 5] = mx;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long m = smx[0];
+            for (int i = 1; i < THREADS / 32; ++i) m = smx[i] > m ? smx[i] : m;
+            if (m) atomicMax((unsigned long long*)&p.ctrl->red[0], m);
         }
     }
 }

@@ -81,29 +81,55 @@ struct rks_plan {
     int roles_u_sel, roles_n_sel;   // host mirror refreshed by rks_read_ctrl
     int nl_rows_per_cta, nl_threads;
     bool nl_fast;                   // n in {512..8192}: register-resident FFT kernel (fft_fast.cuh)
+    bool no_fuse;                   // default: K1 and K4 as separate kernels (north_star decomposition); RKS_FUSE=1 fuses
     size_t nl_smem;
 };
 
+// smem of a fast NL launch: the row slabs plus, for the fused u u_x models, one staging row each
 template <int W>
-static void launch_nl_fast(rks_plan* p, int j, int force, cudaStream_t stream) {
+static size_t nl_fast_smem(int model, int fk) {
+    constexpr int THREADS = W == 16 ? 512 : 256;
+    constexpr int RPC = THREADS / (32 * W);
+    size_t elems = (size_t)RPC * 512 * W;
+    if (fk > 0 && model == RKS_MODEL_UUX_RFFT) elems += (size_t)RPC * (512 * W / 2 + 8);
+    return elems * sizeof(cplx);
+}
+
+template <int W, int MODEL, int FK>
+static void launch_nl_fast_t(rks_plan* p, int j, int force, const FuseDesc& fd, cudaStream_t stream) {
     const DevPlan& d = p->d;
     constexpr int THREADS = W == 16 ? 512 : 256;
     constexpr int RPC = THREADS / (32 * W);
-    const size_t smem = (size_t)RPC * 512 * W * sizeof(cplx);
+    const size_t smem = nl_fast_smem<W>(MODEL, FK);
     const long long groups = (d.batch + RPC - 1) / RPC;
     const long long resident = (long long)p->sm_count * (W == 16 ? 1 : 2);
     const unsigned grid = (unsigned)(groups < resident ? groups : resident);
-    if (d.model == RKS_MODEL_UUX_RFFT) nl_fast_kernel<W, 1><<<grid, THREADS, smem, stream>>>(d, j, force);
-    else nl_fast_kernel<W, 2><<<grid, THREADS, smem, stream>>>(d, j, force);
+    nl_fast_kernel<W, MODEL, FK><<<grid, THREADS, smem, stream>>>(d, j, force, fd);
+}
+
+// fk: 0 plain, 1 fused with complex coefficient arrays, 2 fused with real ones
+template <int W>
+static void launch_nl_fast(rks_plan* p, int j, int force, const FuseDesc& fd, int fk, cudaStream_t stream) {
+    const bool uux = p->d.model == RKS_MODEL_UUX_RFFT;
+    if (fk == 0) uux ? launch_nl_fast_t<W, 1, 0>(p, j, force, fd, stream) : launch_nl_fast_t<W, 2, 0>(p, j, force, fd, stream);
+    else if (fk == 1) uux ? launch_nl_fast_t<W, 1, 1>(p, j, force, fd, stream) : launch_nl_fast_t<W, 2, 1>(p, j, force, fd, stream);
+    else uux ? launch_nl_fast_t<W, 1, 2>(p, j, force, fd, stream) : launch_nl_fast_t<W, 2, 2>(p, j, force, fd, stream);
 }
 
 template <int W>
 static cudaError_t prepare_nl_fast(int model) {
-    constexpr int THREADS = W == 16 ? 512 : 256;
-    const int smem = THREADS / (32 * W) * 512 * W * (int)sizeof(cplx);
-    if (model == RKS_MODEL_UUX_RFFT)
-        return cudaFuncSetAttribute(nl_fast_kernel<W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    return cudaFuncSetAttribute(nl_fast_kernel<W, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaSuccess;
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    if (model == RKS_MODEL_UUX_RFFT) {
+        e = cudaFuncSetAttribute(nl_fast_kernel<W, 1, 0>, attr, (int)nl_fast_smem<W>(model, 0));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 1, 1>, attr, (int)nl_fast_smem<W>(model, 1));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 1, 2>, attr, (int)nl_fast_smem<W>(model, 2));
+    } else {
+        e = cudaFuncSetAttribute(nl_fast_kernel<W, 2, 0>, attr, (int)nl_fast_smem<W>(model, 0));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 2, 1>, attr, (int)nl_fast_smem<W>(model, 1));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 2, 2>, attr, (int)nl_fast_smem<W>(model, 2));
+    }
+    return e;
 }
 
 extern "C" int rks_abi_version(void) { return RKS_ABI_VERSION; }
@@ -244,6 +270,7 @@ extern "C" int rks_set_model(rks_plan* p, int model, int64_t n, const double* kx
     p->launches += 1;
     if (kx) CUDA_TRY(cudaMemcpyAsync(p->ws + p->lay.kx, kx, sizeof(double) * (size_t)d.n_c, cudaMemcpyDeviceToDevice, stream));
     p->nl_fast = (n >= 512 && n <= 8192) && !getenv("RKS_NL_GENERIC");
+    p->no_fuse = getenv("RKS_FUSE") == nullptr;       // fused K1+K4 is opt-in (RKS_FUSE=1): see DESIGN.md 4
     if (p->nl_fast) {
         cudaError_t e = n == 512 ? prepare_nl_fast<1>(model) : n == 1024 ? prepare_nl_fast<2>(model)
                       : n == 2048 ? prepare_nl_fast<4>(model) : n == 4096 ? prepare_nl_fast<8>(model)
@@ -404,17 +431,23 @@ extern "C" int rks_stage(rks_plan* p, int s, void* stream_v) {
 // ---------------------------------------------------------------------------------------
 // K4 dispatch
 // ---------------------------------------------------------------------------------------
+static void dispatch_nl_fast(rks_plan* p, int j, int force, const FuseDesc& fd, int fk, cudaStream_t stream) {
+    switch (p->d.n) {
+        case 512: launch_nl_fast<1>(p, j, force, fd, fk, stream); break;
+        case 1024: launch_nl_fast<2>(p, j, force, fd, fk, stream); break;
+        case 2048: launch_nl_fast<4>(p, j, force, fd, fk, stream); break;
+        case 4096: launch_nl_fast<8>(p, j, force, fd, fk, stream); break;
+        default: launch_nl_fast<16>(p, j, force, fd, fk, stream); break;
+    }
+    p->launches += 1;
+}
+
 static int launch_nl(rks_plan* p, int j, int force, cudaStream_t stream) {
     const DevPlan& d = p->d;
     if (p->nl_fast) {
-        switch (d.n) {
-            case 512: launch_nl_fast<1>(p, j, force, stream); break;
-            case 1024: launch_nl_fast<2>(p, j, force, stream); break;
-            case 2048: launch_nl_fast<4>(p, j, force, stream); break;
-            case 4096: launch_nl_fast<8>(p, j, force, stream); break;
-            default: launch_nl_fast<16>(p, j, force, stream); break;
-        }
-        p->launches += 1;
+        FuseDesc none;
+        memset(&none, 0, sizeof(none));
+        dispatch_nl_fast(p, j, force, none, 0, stream);
         return RKS_OK;
     }
     const unsigned grid = (unsigned)((d.batch + p->nl_rows_per_cta - 1) / p->nl_rows_per_cta);
@@ -434,6 +467,39 @@ extern "C" int rks_nl(rks_plan* p, int j, void* stream) {
     if (j < 1 || j > jmax) return fail(RKS_ERR_ARG, "N index out of range");
     // fixed-step methods have no device predicate: the caller decides when N1 is (re)computed
     launch_nl(p, j, method_adaptive(p->method) ? 0 : 1, (cudaStream_t)stream);
+    CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
+// Stage s followed by the nonlinear evaluation it feeds.  With a fast fused model the combine is
+// evaluated in the load prologue of the NL kernel (one launch, the stage value never goes to HBM
+// unless it is a state); otherwise this is rks_stage + rks_nl.
+static bool can_fuse_stage(const rks_plan* p, int s) {
+    const int m = p->method, S = method_stages(m);
+    if (!p->nl_fast || p->no_fuse || p->d.lin_elems != p->d.n_c) return false;
+    if (s == S && m == M_ETD35) return false;              // last ETD35 stage emits err and feeds no N
+    return true;
+}
+
+extern "C" int rks_stage_nl(rks_plan* p, int s, void* stream_v) {
+    if (!p) return fail(RKS_ERR_ARG, "plan is null");
+    if (p->d.model == RKS_MODEL_NONE) return fail(RKS_ERR_UNSUPPORTED, "no fused model set (rks_set_model)");
+    const int m = p->method, S = method_stages(m);
+    if (s < 1 || s > S) return fail(RKS_ERR_ARG, "stage out of range");
+    const bool adapt = method_adaptive(m);
+    // which N the evaluation after stage s produces: N_{s+1}; after the last stage N1 (fixed step,
+    // etd4.py:174) or N_last (FSAL methods, if34.py:129); none for ETD35
+    const int j = s < S ? s + 1 : (adapt ? (method_fsal(m) ? S + 1 : 0) : 1);
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    if (!can_fuse_stage(p, s)) {
+        if (int rc = rks_stage(p, s, stream_v)) return rc;
+        return j ? rks_nl(p, j, stream_v) : RKS_OK;
+    }
+    FuseDesc fd = fuse_desc(m, s);
+    fd.write_k = (s == S) ? 1 : 0;
+    fd.track_max = (s == S && adapt) ? 1 : 0;
+    const int fk = (method_is_if(m) && !p->d.lin_complex) ? 2 : 1;
+    dispatch_nl_fast(p, j, adapt ? 0 : 1, fd, fk, stream);
     CUDA_TRY(cudaGetLastError());
     return RKS_OK;
 }
@@ -526,12 +592,8 @@ static int enqueue_trial(rks_plan* p, void* ring, double* ring_t, int cap, void*
     int rc;
     if ((rc = rks_update_coeffs(p, stream))) return rc;
     if ((rc = rks_nl(p, 1, stream))) return rc;                 // runs only when ctrl.need_n1
-    for (int s = 1; s <= S; ++s) {
-        if ((rc = rks_stage(p, s, stream))) return rc;
-        if (s < S || method_fsal(m)) {
-            if ((rc = rks_nl(p, s + 1, stream))) return rc;
-        }
-    }
+    for (int s = 1; s <= S; ++s)
+        if ((rc = rks_stage_nl(p, s, stream))) return rc;
     if ((rc = rks_error_control(p, stream))) return rc;
     if (ring) return rks_snapshot(p, ring, ring_t, cap, stream);
     return RKS_OK;
@@ -553,11 +615,9 @@ extern "C" int rks_run_fixed(rks_plan* p, int nsteps, void* stream) {
     const int S = method_stages(p->method);
     int rc;
     for (int i = 0; i < nsteps; ++i) {
-        for (int s = 1; s <= S; ++s) {
-            if ((rc = rks_stage(p, s, stream))) return rc;
-            // after the last stage U holds u+ and N1 <- N(u+)  (etd4.py:174)
-            if ((rc = rks_nl(p, s < S ? s + 1 : 1, stream))) return rc;
-        }
+        // after the last stage U holds u+ and N1 <- N(u+)  (etd4.py:174)
+        for (int s = 1; s <= S; ++s)
+            if ((rc = rks_stage_nl(p, s, stream))) return rc;
     }
     return RKS_OK;
 }

@@ -88,3 +88,45 @@ def kdv_multi_soliton(x: torch.Tensor, ampl: Sequence[float], x0: Sequence[float
     for a, c in zip(ampl, x0):
         out = out + kdv_soliton(x, a, c, t)
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# N-D Fourier-diagonal models.  lin_op has the shape of the spectral grid and u
+# that shape (plus optional leading batch dims): the engine's "lin_op shaped like u" path.  The
+# nonlinear term is a torch callable here (library FFT for the N-D transform; K1/K2/K3 are the
+# engine's kernels) -- the hand-written fused kernels cover the 1-D models above.
+# ----------------------------------------------------------------------------------------------
+def allen_cahn_fourier_ops(n: int, eps: float = 0.01, length: float = 2 * 3.141592653589793, device="cuda"):
+    """Periodic 2-D Allen-Cahn u_t = eps lap(u) + u - u^3 on an n x n grid, rfft2 half spectrum:
+    L = 1 - eps |k|^2 (float64, shape (n, n/2+1)), N(u^) = -rfft2(irfft2(u^)^3).  The +u goes into L,
+    mirroring the split of rkstiff/models.py:240-244."""
+    d = length / n
+    ky = 2 * 3.141592653589793 * torch.fft.fftfreq(n, d=d, dtype=torch.float64, device=device)
+    kx = 2 * 3.141592653589793 * torch.fft.rfftfreq(n, d=d, dtype=torch.float64, device=device)
+    lin_op = 1.0 - eps * (kx[None, :] ** 2 + ky[:, None] ** 2)
+
+    def nl_func(uf: torch.Tensor) -> torch.Tensor:
+        u = torch.fft.irfft2(uf, s=(n, n))
+        return -torch.fft.rfft2(u * u * u)
+
+    return lin_op, nl_func
+
+
+def nls_nd_ops(k_axes: Sequence[torch.Tensor], gamma: float = 2.0):
+    """N-D cubic NLS u_t = i lap(u) + i gamma |u|^2 u (demos/nls.ipynb:496-508 is the 2-D case):
+    L = -i sum_d k_d^2 on the full fft grid, N(u^) = i gamma fftn(|f|^2 f), f = ifftn(u^)."""
+    nd = len(k_axes)
+    k2 = 0
+    for d, k in enumerate(k_axes):
+        shape = [1] * nd
+        shape[d] = k.shape[0]
+        k2 = k2 + (k.to(torch.float64) ** 2).reshape(shape)
+    lin_op = -1j * k2.to(torch.complex128)
+    dims = tuple(range(-nd, 0))
+
+    def nl_func(uf: torch.Tensor) -> torch.Tensor:
+        f = torch.fft.ifftn(uf, dim=dims)
+        f2 = f.real ** 2 + f.imag ** 2
+        return 1j * gamma * torch.fft.fftn(f2 * f, dim=dims)
+
+    return lin_op, nl_func

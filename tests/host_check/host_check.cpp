@@ -15,6 +15,7 @@
 #include "../../rkstiff_b200/csrc/errctl.cuh"
 #include "../../rkstiff_b200/csrc/fft.cuh"
 #include "../../rkstiff_b200/csrc/fft_fast.cuh"
+#include "../../rkstiff_b200/csrc/fuse.cuh"
 
 using namespace rks;
 
@@ -32,26 +33,28 @@ static void stage_all(int n, const cplx* u, const cplx* const* N, const cplx* co
 
 
 // serial emulation of the fast NL kernel (fft_fast.cuh): one row, 32 W threads, phase by phase
-template <int W, class Model>
+template <int N, class Model>
 static void fast_row(const Model& m, const fast::Twiddles& tw) {
-    constexpr int TR = 32 * W;
-    std::vector<cplx> sm(512 * W);
-    for (int T = 0; T < TR; ++T) fast::p0_load_outer_dif<W>(sm.data(), T, tw, m);
-    for (int T = 0; T < TR; ++T) fast::p1_dif_a<W>(sm.data() + 512 * (T >> 5), T & 31, tw, m);
-    for (int T = 0; T < TR; ++T) fast::p2_dif_b(sm.data() + 512 * (T >> 5), T & 31, tw);
-    for (int T = 0; T < TR; ++T) fast::p3_core(sm.data() + 512 * (T >> 5), T & 31, m);
-    for (int T = 0; T < TR; ++T) fast::p4_dit_b(sm.data() + 512 * (T >> 5), T & 31, tw);
-    for (int T = 0; T < TR; ++T) fast::p5_dit_a<W>(sm.data() + 512 * (T >> 5), T & 31, tw, m);
-    for (int T = 0; T < TR; ++T) fast::p6_outer_dit_store<W>(sm.data(), T, tw, m);
+    constexpr int TR = 32 * fast::Plan<N>::W;
+    std::vector<cplx> sm(N);
+    for (int T = 0; T < TR; ++T) fast::phase_first<N>(sm.data(), T, tw, m);
+    for (int T = 0; T < TR; ++T) fast::phase_middle<N, 2, true>(sm.data(), T, tw, m);
+    if (fast::middle_passes<N>() == 2)
+        for (int T = 0; T < TR; ++T) fast::phase_middle<N, 3, true>(sm.data(), T, tw, m);
+    for (int T = 0; T < TR; ++T) fast::phase_core<N>(sm.data(), T, m);
+    if (fast::middle_passes<N>() == 2)
+        for (int T = 0; T < TR; ++T) fast::phase_middle<N, 3, false>(sm.data(), T, tw, m);
+    for (int T = 0; T < TR; ++T) fast::phase_middle<N, 2, false>(sm.data(), T, tw, m);
+    for (int T = 0; T < TR; ++T) fast::phase_last<N>(sm.data(), T, tw, m);
 }
 template <class Model>
 static int fast_dispatch(int n, const Model& m, const fast::Twiddles& tw) {
     switch (n) {
-        case 512: fast_row<1>(m, tw); return 0;
-        case 1024: fast_row<2>(m, tw); return 0;
-        case 2048: fast_row<4>(m, tw); return 0;
-        case 4096: fast_row<8>(m, tw); return 0;
-        case 8192: fast_row<16>(m, tw); return 0;
+        case 512: fast_row<512>(m, tw); return 0;
+        case 1024: fast_row<1024>(m, tw); return 0;
+        case 2048: fast_row<2048>(m, tw); return 0;
+        case 4096: fast_row<4096>(m, tw); return 0;
+        case 8192: fast_row<8192>(m, tw); return 0;
     }
     return -1;
 }
@@ -61,11 +64,11 @@ extern "C" {
 int hc_nl_fast(int model, int n, const double* in, const double* kx, double p0, double* out) {
     std::vector<cplx> tab(fast::TW_TOTAL);
     for (int j = 0; j < fast::TW_TOTAL; ++j) tab[j] = fast::twiddle_table_entry(j, n);
-    const fast::Twiddles tw{tab.data() + fast::TW_O, tab.data() + fast::TW_A, tab.data() + fast::TW_B};
+    const fast::Twiddles tw{tab.data() + fast::TW_T1, tab.data() + fast::TW_T2, tab.data() + fast::TW_T3};
     const cplx* cin = reinterpret_cast<const cplx*>(in);
     cplx* co = reinterpret_cast<cplx*>(out);
-    if (model == 1) { fast::UuxModel m{cin, co, kx, p0, n, true}; return fast_dispatch(n, m, tw); }
-    fast::NlsModel m{cin, co, p0, n, true};
+    if (model == 1) { fast::UuxModel m{fast::GlobalHalf{cin}, co, kx, p0, n, true}; return fast_dispatch(n, m, tw); }
+    fast::NlsModel m{fast::ArraySource{cin}, fast::StateSink{nullptr, nullptr}, co, p0, n, true};
     return fast_dispatch(n, m, tw);
 }
 
@@ -203,6 +206,24 @@ int hc_embedded_err(int method, int n, const double* const* N, const double* coe
         else return -1;
     }
     return 0;
+}
+
+// the run-time term list of fuse.cuh evaluated for one stage (complex coefficients): must agree
+// with stage_combine of stages.cuh
+int hc_fused_stage(int method, int stage, int n, const double* u, const double* const* N, const double* coef, double h,
+                   double* out) {
+    const FuseDesc d = fuse_desc(method, stage);
+    FuseSource<cplx> src;
+    src.nterms = d.nterms;
+    for (int t = 0; t < d.nterms; ++t) {
+        src.x[t] = reinterpret_cast<const cplx*>(d.src[t] == 0 ? u : N[d.src[t]]);
+        src.c[t] = d.slot[t] < 0 ? nullptr : reinterpret_cast<const cplx*>(coef) + (size_t)d.slot[t] * n;
+        src.sc[t] = d.c0[t] + d.c1[t] * h;
+        if (!src.x[t]) return -1;
+    }
+    cplx* co = reinterpret_cast<cplx*>(out);
+    for (int i = 0; i < n; ++i) co[i] = src.value(i);
+    return d.nterms;
 }
 
 // controller: feed (sum_u2, sum_e2) of one trial; state is a caller-held opaque Ctrl blob

@@ -285,3 +285,57 @@ def test_real_linop_if_coefficients_stay_real(rk):
     p2 = problems.kdv(64)
     sol2 = rk.IF34(dev(p2.lin_op), fused_for(rk, p2))
     assert sol2._get_engine(dev(p2.u0)).coef_view("E").dtype == torch.complex128
+
+
+# --------------------------------------------------------------------------------------------
+# N-D grids (BASELINE cfg 4 / cfg 5 at reduced size): "lin_op shaped like u" against the
+# reference's own formulation, which flattens lin_op/u to 1-D (demos/nls.ipynb:496-511)
+# --------------------------------------------------------------------------------------------
+def test_cfg4_allen_cahn_2d_if45dp_matches_flattened_oracle(rk):
+    n = 64
+    p = problems.allen_cahn_2d(n)
+    shape = p.params["shape"]
+    lin, nl = rk.models.allen_cahn_fourier_ops(n, eps=0.01)
+    np.testing.assert_allclose(host(lin).ravel(), p.lin_op, rtol=1e-14)
+    sol = rk.IF45DP(lin, nl, config=rk.SolverConfig(epsilon=1e-4))
+    uf = sol.evolve(dev(p.u0.reshape(shape)), 0.0, 0.1, store_freq=5)
+    ora = OracleSolver("IF45DP", p.lin_op, p.nl_func, Config(epsilon=1e-4))
+    uo = ora.evolve(p.u0, 0.0, 0.1, store_freq=5)
+    assert [r[2] for r in sol.trial_log] == [r.accepted for r in ora.log]
+    np.testing.assert_allclose([r[0] for r in sol.trial_log], [r.h for r in ora.log], rtol=DT_TOL)
+    np.testing.assert_allclose(sol.t, ora.t, rtol=DT_TOL)
+    assert rel(host(uf).ravel(), uo) < FINAL_TOL
+    assert sol.u[-1].shape == tuple(shape)
+
+
+def test_cfg5_nls_3d_etd35_matches_flattened_oracle(rk):
+    n = 16
+    p = problems.nls_3d(n)
+    k = dev(p.kx)
+    lin, nl = rk.models.nls_nd_ops([k, k, k], gamma=2.0)
+    np.testing.assert_allclose(host(lin).ravel(), p.lin_op, rtol=1e-14)
+    sol = rk.ETD35(lin, nl, config=rk.SolverConfig(epsilon=1e-5))
+    uf = sol.evolve(dev(p.u0.reshape(n, n, n)), 0.0, 0.2)
+    ora = OracleSolver("ETD35", p.lin_op, p.nl_func, Config(epsilon=1e-5))
+    uo = ora.evolve(p.u0, 0.0, 0.2)
+    assert [r[2] for r in sol.trial_log] == [r.accepted for r in ora.log]
+    np.testing.assert_allclose([r[0] for r in sol.trial_log], [r.h for r in ora.log], rtol=DT_TOL)
+    assert rel(host(uf).ravel(), uo) < FINAL_TOL
+
+
+def test_batched_2d_grid_shares_one_dt(rk):
+    """leading batch dim over a 2-D spectral grid: lin_op (n, n/2+1), u (B, n, n/2+1)."""
+    n = 32
+    p = problems.allen_cahn_2d(n)
+    shape = p.params["shape"]
+    lin, nl = rk.models.allen_cahn_fourier_ops(n, eps=0.01)
+    u0 = np.stack([p.u0.reshape(shape), 0.5 * p.u0.reshape(shape)])
+    sol = rk.IF34(lin, nl)
+    uf = sol.evolve(dev(u0), 0.0, 0.5)
+    # oracle: reference broadcast semantics with the batch flattened alongside (lin_op tiled)
+    def nl_b(v):
+        return np.concatenate([p.nl_func(v[: p.lin_op.size]), p.nl_func(v[p.lin_op.size:])])
+    ora = OracleSolver("IF34", np.tile(p.lin_op, 2), nl_b)
+    uo = ora.evolve(u0.ravel(), 0.0, 0.5)
+    assert [r[2] for r in sol.trial_log] == [r.accepted for r in ora.log]
+    assert rel(host(uf).ravel(), uo) < FINAL_TOL

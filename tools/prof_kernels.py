@@ -34,7 +34,10 @@ else:
     eng.set_u(u0)
     eng.run_fixed(2)
 torch.cuda.synchronize()
+from rkstiff_b200._abi import check, lib  # noqa: E402
 for _ in range(reps):
+    for s in range(1, eng.stages):
+        check(lib.rks_stage_nl(eng.plan, s, eng.st))      # fused K1+K4
     eng.nl(2)
     for s in range(1, eng.stages + (0 if workload == "cfg3" else 1)):
         eng.stage(s)
