@@ -75,3 +75,35 @@ def test_shard_bounds_cover_every_row_once():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_bounds(4, 2, 2)
+
+
+def _fft_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from rkstiff_b200.dist_fft import SlabFFT
+    shape = (8, 4, 6)
+    g = torch.Generator().manual_seed(0)
+    full = torch.randn(shape, dtype=torch.float64, generator=g) + 1j * torch.randn(shape, dtype=torch.float64, generator=g)
+    fft = SlabFFT(shape)
+    spec = fft.forward(fft.real_slice(full))
+    want = fft.spec_slice(torch.fft.fftn(full))
+    back = fft.inverse(spec)
+    q.put((rank, float((spec - want).abs().max()), float((back - fft.real_slice(full)).abs().max())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_slab_fft_matches_fftn_and_round_trips():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fft_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    for _, e_fwd, e_back in res:
+        assert e_fwd < 1e-12 and e_back < 1e-13
