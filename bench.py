@@ -34,7 +34,12 @@ METRIC = "rk_step_gridpoints_per_s"
 UNIT = "gridpoint*steps/s"
 
 # algorithmic bytes per complex element per trial (SURVEY.md 8d / DESIGN.md 4)
-BYTES_PER_ELEM = {"ETD35": 736, "ETD4": 400}
+BYTES_PER_ELEM = {"IF4": 368, "ETD4": 400, "IF34": 416, "ETD34": 448, "ETD5": 688, "ETD35": 736, "IF45DP": 816}
+# passes (reads + writes of a full state array) of each stage-combine kernel, from the reference formulas
+STAGE_PASSES = {"IF4": [3, 3, 3, 6], "IF34": [3, 3, 3, 6], "ETD4": [3, 4, 4, 6], "ETD34": [3, 4, 4, 6],
+                "ETD5": [3, 4, 4, 6, 7, 7], "ETD35": [3, 4, 4, 6, 7, 8], "IF45DP": [3, 4, 5, 6, 7, 7]}
+NORM_PASSES = {"IF34": 3, "ETD34": 3, "ETD35": 2, "IF45DP": 7}
+ADAPTIVE = ("IF34", "ETD34", "ETD35", "IF45DP")
 
 
 # ------------------------------------------------------------------------------------------
@@ -120,15 +125,19 @@ class ClockSampler:
 # CPU baseline: the oracle (NumPy port of the reference path), bounded sample
 # ------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    workload, rows, seed, steps, warmup = args
+    workload, rows, seed, steps, warmup, method = args
     import numpy as np
     from oracle import problems
     from oracle.rk_oracle import Config, OracleSolver
     if workload == "cfg2":
         p = problems.nls(N_NLS, batch=rows, seed=seed)
-        sol = OracleSolver("ETD35", p.lin_op, p.nl_func, Config(epsilon=1e-6))
-        u, h = p.u0, 0.01
-        n = N_NLS
+        cfg, h, n = Config(epsilon=1e-6), (0.002 if method == "IF45DP" else 0.01), N_NLS
+    else:
+        p = problems.ks(N_KS, batch=rows, seed=seed)
+        cfg, h, n = Config(epsilon=1e-4), 0.05, N_KS
+    sol = OracleSolver(method, p.lin_op, p.nl_func, cfg)
+    u = p.u0
+    if method in ADAPTIVE:
         for _ in range(warmup):
             u, _, h = sol.step(u, h)
         sol.log.clear()
@@ -138,24 +147,21 @@ def _cpu_worker(args):
         dt = time.perf_counter() - t0
         trials = len(sol.log)
     else:
-        p = problems.ks(N_KS, batch=rows, seed=seed)
-        sol = OracleSolver("ETD4", p.lin_op, p.nl_func)
-        u, n = p.u0, N_KS
         for _ in range(warmup):
-            u = sol.step(u, 0.05)
+            u = sol.step(u, h)
         t0 = time.perf_counter()
         for _ in range(steps):
-            u = sol.step(u, 0.05)
+            u = sol.step(u, h)
         dt = time.perf_counter() - t0
         trials = steps
     assert np.isfinite(u).all()
     return trials * rows * n, dt
 
 
-def cpu_baseline(workload, cores, steps, warmup, rows):
+def cpu_baseline(workload, cores, steps, warmup, rows, method):
     """gp*steps/s of the oracle on `cores` processes, each stepping its own `rows`-trajectory shard."""
     import multiprocessing as mp
-    jobs = [(workload, rows, 100 + i, steps, warmup) for i in range(cores)]
+    jobs = [(workload, rows, 100 + i, steps, warmup, method) for i in range(cores)]
     if cores == 1:
         res = [_cpu_worker(jobs[0])]
     else:
@@ -177,20 +183,29 @@ def run_reference(args):
     rows = 16 if args.workload == "cfg2" else 256
     steps = max(1, min(args.steps, 12 if args.workload == "cfg2" else 40))
     warm = max(1, min(args.warmup, 2))
-    value, wall = cpu_baseline(args.workload, cores, steps, warm, rows)
+    method = args.method or ("ETD35" if args.workload == "cfg2" else "ETD4")
+    value, wall = cpu_baseline(args.workload, cores, steps, warm, rows, method)
     sample = (f"{cores} processes x {rows} trajectories x {steps} steps of the oracle "
-              f"({'NLS n=8192 ETD35 adaptive' if args.workload == 'cfg2' else 'KS n=1024 ETD4 h=0.05'})")
+              f"({'NLS n=8192' if args.workload == 'cfg2' else 'KS n=1024'} {method})")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.workload, args.gpus),
+            "config": workload_config(args.workload, args.gpus, method),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
-def workload_config(workload, gpus):
+def workload_config(workload, gpus, method=None):
+    cfg = _workload_config(workload, gpus)
+    if method and method != cfg["method"]:
+        cfg["workload"] = cfg["workload"].replace(cfg["method"], method) + " [method overridden]"
+        cfg["method"] = method
+    return cfg
+
+
+def _workload_config(workload, gpus):
     if workload == "cfg2":
         return {"workload": "cfg2: NLS 1-D n=8192 complex128, ETD35 adaptive eps=1e-6, 4096 soliton trajectories "
                             "per GPU, one shared dt", "method": "ETD35", "n": N_NLS, "batch_per_gpu": B_NLS,
@@ -312,26 +327,33 @@ def run_ours(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
 
     K, W = args.steps, max(3, args.warmup)
+    method = args.method or ("ETD35" if args.workload == "cfg2" else "ETD4")
+    adaptive = method in ADAPTIVE
     if args.workload == "cfg2":
-        method, n, batch, n_c = "ETD35", N_NLS, B_NLS, N_NLS
+        n, batch, n_c = N_NLS, B_NLS, N_NLS
         kx, u0 = nls_inputs(torch, batch, device, seed=2 + rank)
         lin, nl = rk.models.nls_ops(kx, gamma=2.0)
-        sol = rk.ETD35(lin, nl, config=rk.SolverConfig(epsilon=1e-6), group=group)
+        h0 = 0.002 if method == "IF45DP" else 0.01
     else:
-        method, n, batch, n_c = "ETD4", N_KS, B_KS, N_KS // 2 + 1
+        n, batch, n_c = N_KS, B_KS, N_KS // 2 + 1
         kx, u0 = ks_inputs(torch, batch, device, seed=rank)
         lin, nl = rk.models.ks_ops(kx)
-        sol = rk.ETD4(lin, nl, group=group)
+        h0 = 0.05
+    cls = getattr(rk, method)
+    if adaptive:
+        sol = cls(lin, nl, config=rk.SolverConfig(epsilon=1e-6 if args.workload == "cfg2" else 1e-4), group=group)
+    else:
+        sol = cls(lin, nl, group=group)
     eng = sol._get_engine(u0)
 
     # ---- device-resident throughput: K steps, inputs already in HBM --------------------------
-    if args.workload == "cfg2":
-        eng.begin(0.0, 1e9, 0.01, 0, False)
+    if adaptive:
+        eng.begin(0.0, 1e9, h0, 0, False)
         eng.set_u(u0)
         run = eng.run_trials
     else:
-        eng.begin(0.0, 0.0, 0.05, 0, True)
-        eng.ensure_fixed_coeffs(0.05)
+        eng.begin(0.0, 0.0, h0, 0, True)
+        eng.ensure_fixed_coeffs(h0)
         eng.set_u(u0)
         run = eng.run_fixed
     run(W)
@@ -346,7 +368,7 @@ def run_ours(args):
     secs = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
     launches = eng.launches() - l0
     clocks = sampler.stop() if sampler else None
-    if args.workload == "cfg2":
+    if adaptive:
         c = eng.read_ctrl()
         assert c.status == 0 and c.trial_count == K + W, (c.status, c.trial_count)
         accepted = int(c.step_count)
@@ -360,22 +382,31 @@ def run_ours(args):
     reps = 10
     kern = {}
     S = eng.stages
-    t_nl = time_kernel(torch, lambda: eng.nl(2), reps)
-    kern["nl (K4 fused spectral nonlinearity)"] = (t_nl, 2 * 16 * elems, S)
-    stage_bytes = {"ETD35": [3, 4, 4, 6, 7, 8], "ETD4": [3, 4, 4, 6]}[method]   # passes (reads + writes)
-    for s in range(1, S + 1):
-        if method == "ETD4" and s == S:
-            continue            # in place: timing it alone would overwrite u repeatedly (harmless, but skip)
-        t = time_kernel(torch, lambda s=s: eng.stage(s), reps)
-        kern[f"stage{s} (K1 combine)"] = (t, stage_bytes[s - 1] * 16 * elems, 1)
+    n_nl = S if (not adaptive or method in ("IF34", "ETD34", "IF45DP")) else S - 1
     if method == "ETD35":
+        n_nl = S                                   # 5 stage NLs + N1 = N(u) after an accept
+    t_nl = time_kernel(torch, lambda: eng.nl(2), reps)
+    kern["nl (K4 fused spectral nonlinearity)"] = (t_nl, 2 * 16 * elems, n_nl)
+    for s in range(1, S + 1):
+        if not adaptive and s == S:
+            continue            # in place: timing it alone would advance u repeatedly
+        t = time_kernel(torch, lambda s=s: eng.stage(s), reps)
+        kern[f"stage{s} (K1 combine)"] = (t, STAGE_PASSES[method][s - 1] * 16 * elems, 1)
+    if adaptive:
         t = time_kernel(torch, lambda: rk._abi.check(rk._abi.lib.rks_error_sums(eng.plan, eng.st)), reps)
-        kern["norm (K3 masked norms)"] = (t, 2 * 16 * elems, 1)
+        kern["norm (K3 masked norms)"] = (t, NORM_PASSES[method] * 16 * elems, 1)
     shares = {k: v[0] * v[2] for k, v in kern.items()}
     top = max(shares, key=shares.get)
     t_top, b_top, _ = kern[top]
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
+    # ncu --set full captures under profiles/ (same geometry); None when that kernel/geometry was not captured
+    traffic = None
+    if top.startswith("nl") and batch * n_c == 4096 * 8192:
+        traffic = 536.98e6 + 478.76e6           # profiles/r01_v4_nl_fast_ncu_raw.csv
+    elif top.startswith("nl") and batch * n_c == 65536 * 513:
+        traffic = 540.44e6 + 480.53e6           # profiles/r01_v4_nl_fast_cfg3_ncu_raw.csv
     roofline = {"bound": "hbm", "kernel": top, "achieved": b_top / t_top / 1e9, "peak": peak_gbs, "unit": "GB/s",
-                "frac": b_top / t_top / 1e9 / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "frac": b_top / t_top / 1e9 / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                 "share_of_step": shares[top] / sum(shares.values()),
                 "whole_step": {"algorithmic_bytes_per_elem": BYTES_PER_ELEM[method],
                                "achieved": BYTES_PER_ELEM[method] * elems * K / secs / 1e9,
@@ -391,14 +422,17 @@ def run_ours(args):
 
     def e2e_once():
         ud = u_host.to(device, non_blocking=True)
-        if args.workload == "cfg2":
-            uf = sol.evolve(ud, 0.0, 1.0, store_data=False)
+        if adaptive:
+            # IF45DP: the reference's r4 weight makes the error estimate O(h) (~40x more trials): shorter horizon
+            horizon = (1.0 if args.workload == "cfg2" else 2.0) * (0.02 if method == "IF45DP" else 1.0)
+            uf = sol.evolve(ud, 0.0, horizon, store_data=False)
             steps_done = len(sol.trial_log)
         else:
-            uf = sol.evolve(ud, 0.0, 2.0, 0.05, store_data=False)
+            tf_e2e = 2.0 if args.workload == "cfg3" else 0.4
+            uf = sol.evolve(ud, 0.0, tf_e2e, h0, store_data=False)
             steps_done, tc = 0, 0.0
-            while tc < 2.0:                      # the reference's float-accumulated loop count
-                tc += 0.05
+            while tc < tf_e2e:                   # the reference's float-accumulated loop count
+                tc += h0
                 steps_done += 1
         out_host.copy_(uf, non_blocking=True)
         torch.cuda.synchronize()
@@ -414,15 +448,15 @@ def run_ours(args):
     e2e_secs = max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": world * batch * n * steps_e2e / e2e_secs, "unit": UNIT,
            "h2d_bytes_per_step": state_bytes * reps_e2e / steps_e2e, "d2h_bytes_per_step": state_bytes * reps_e2e / steps_e2e,
-           "call": ("ETD35.evolve(u0, 0, 1)" if args.workload == "cfg2" else "ETD4.evolve(u0, 0, 2, h=0.05)")
-                   + " with u0 copied from pinned host memory and the final state copied back, per call",
+           "call": f"{method}.evolve(u0, ...) of the workload's horizon with u0 copied from pinned host memory and the "
+                   "final state copied back, per call",
            "steps_per_call": steps_e2e / reps_e2e, "h2d_bytes_per_call": state_bytes, "d2h_bytes_per_call": state_bytes}
 
     # ---- CPU baseline on rank 0, N = 1 only ---------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rows, cs, cw = (16, 6, 1) if args.workload == "cfg2" else (256, 40, 2)
-        v, wall = cpu_baseline(args.workload, 1, cs, cw, rows)
+        v, wall = cpu_baseline(args.workload, 1, cs, cw, rows, method)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"oracle (NumPy port of the reference path), 1 process, {rows} trajectories x {cs} steps, "
                          f"{wall:.1f} s"}
@@ -430,7 +464,7 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": 1e3 * secs / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": workload_config(args.workload, world),
+                "dtype": "f64", "data": "synthetic", "config": workload_config(args.workload, world, method),
                 "accepted_steps": accepted, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line))
@@ -445,6 +479,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5"])
+    ap.add_argument("--method", default=None, help="override the method of cfg2/cfg3 (IF4 ETD4 ETD5 IF34 ETD34 ETD35 IF45DP)")
     ap.add_argument("--size", type=int, default=256, help="cfg5: points per axis of the 3-D grid")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
