@@ -29,9 +29,6 @@ constexpr double S8 = 0.38268343236508977173;    // sin(pi/8)
 #ifndef RKS_TW_SQUARE
 #define RKS_TW_SQUARE 1        // 1: read w^1 only and square; 0: read w^1, w^2, w^4, w^8 from tables
 #endif
-#ifndef RKS_LOADS_FIRST
-#define RKS_LOADS_FIRST 0      // 1: issue the loads of both butterflies of a thread before computing (measured slower)
-#endif
 
 template <int SH> RKS_HD int swz(int p) { return p ^ ((p >> SH) & 7); }
 
@@ -286,68 +283,81 @@ using UuxModel = UuxModelT<GlobalHalf>;
 // different addresses: otherwise the compiler keeps the inverse half's twiddles alive in local
 // memory across the whole transform instead of re-reading them from L1).
 // ---------------------------------------------------------------------------------------
+// ---- butterfly-level primitives (one butterfly = R values `a` of one thread) ----
+template <int R, int Q, int SH>
+RKS_HD void bf_load(const cplx* sm, int p0, cplx* a) {
+#pragma unroll
+    for (int s = 0; s < R; ++s) a[s] = sm[swz<SH>(p0 + Q * s)];
+}
+template <int R, int Q, class Model>
+RKS_HD void bf_load_global(const Model& m, int p0, cplx* a) {
+#pragma unroll
+    for (int s = 0; s < R; ++s) a[s] = m.load(p0 + Q * s);
+}
+// results of bf_dif / bf_dit / bf_core sit in slot perm<R>(r); both stores undo that
+template <int R, int Q, int SH>
+RKS_HD void bf_store(cplx* sm, int p0, const cplx* a) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) sm[swz<SH>(p0 + Q * r)] = a[perm<R>(r)];
+}
+template <int R, int Q, class Model>
+RKS_HD void bf_store_global(const Model& m, int p0, const cplx* a) {
+#pragma unroll
+    for (int k = 0; k < R; ++k) m.store(p0 + Q * k, a[perm<R>(k)]);
+}
+template <int R, int Q, int TS>
+RKS_HD void bf_dif(cplx* a, const cplx* tab, int j) {          // inverse butterfly, then twiddles on the outputs
+    dftR<R, true>(a);
+    if (Q > 1) twiddle_scale<R, true>(a, tab, TS, j, SlotPerm<R>());
+}
+template <int R, int Q, int TS>
+RKS_HD void bf_dit(cplx* a, const cplx* tab, int j) {          // twiddles on the inputs, then forward butterfly
+    if (Q > 1) twiddle_scale<R, false>(a, tab, TS, j, SlotId());
+    dftR<R, false>(a);
+}
+template <int R, class Model>
+RKS_HD void bf_core(cplx* a, const Model& m) {                  // innermost inverse bf, N(.), innermost forward bf
+    cplx c[R];
+    dftR<R, true>(a);
+#pragma unroll
+    for (int r = 0; r < R; ++r) c[r] = m.pointwise(a[perm<R>(r)]);
+    dftR<R, false>(c);
+#pragma unroll
+    for (int r = 0; r < R; ++r) a[r] = c[r];
+}
+
+// ---- whole passes: NB butterflies per thread, one after the other ----
 template <int R, int Q, int SH, int NB, int TS, bool GLOBAL_IN, class Model>
 RKS_HD void dif_pass(cplx* sm, const int (&p0)[NB], const int (&j)[NB], const cplx* tab, const Model& m) {
-    cplx a[NB][R];
-#pragma unroll
-    for (int b = 0; b < (RKS_LOADS_FIRST ? NB : 0); ++b)
-#pragma unroll
-        for (int s = 0; s < R; ++s) a[b][s] = GLOBAL_IN ? m.load(p0[b] + Q * s) : sm[swz<SH>(p0[b] + Q * s)];
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-        if (!RKS_LOADS_FIRST) {
-#pragma unroll
-            for (int s = 0; s < R; ++s) a[b][s] = GLOBAL_IN ? m.load(p0[b] + Q * s) : sm[swz<SH>(p0[b] + Q * s)];
-        }
-        dftR<R, true>(a[b]);
-        if (Q > 1) twiddle_scale<R, true>(a[b], tab, TS, j[b], SlotPerm<R>());
-#pragma unroll
-        for (int r = 0; r < R; ++r) sm[swz<SH>(p0[b] + Q * r)] = a[b][perm<R>(r)];
+        cplx a[R];
+        if (GLOBAL_IN) bf_load_global<R, Q>(m, p0[b], a);
+        else bf_load<R, Q, SH>(sm, p0[b], a);
+        bf_dif<R, Q, TS>(a, tab, j[b]);
+        bf_store<R, Q, SH>(sm, p0[b], a);
     }
 }
 template <int R, int Q, int SH, int NB, int TS, bool GLOBAL_OUT, class Model>
 RKS_HD void dit_pass(cplx* sm, const int (&p0)[NB], const int (&j)[NB], const cplx* tab, const Model& m) {
-    cplx a[NB][R];
-#pragma unroll
-    for (int b = 0; b < (RKS_LOADS_FIRST ? NB : 0); ++b)
-#pragma unroll
-        for (int r = 0; r < R; ++r) a[b][r] = sm[swz<SH>(p0[b] + Q * r)];
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-        if (!RKS_LOADS_FIRST) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) a[b][r] = sm[swz<SH>(p0[b] + Q * r)];
-        }
-        if (Q > 1) twiddle_scale<R, false>(a[b], tab, TS, j[b], SlotId());
-        dftR<R, false>(a[b]);
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-            if (GLOBAL_OUT) m.store(p0[b] + Q * k, a[b][perm<R>(k)]);
-            else sm[swz<SH>(p0[b] + Q * k)] = a[b][perm<R>(k)];
-        }
+        cplx a[R];
+        bf_load<R, Q, SH>(sm, p0[b], a);
+        bf_dit<R, Q, TS>(a, tab, j[b]);
+        if (GLOBAL_OUT) bf_store_global<R, Q>(m, p0[b], a);
+        else bf_store<R, Q, SH>(sm, p0[b], a);
     }
 }
 // innermost butterflies + pointwise nonlinearity (stride 1, no twiddles)
 template <int R, int SH, int NB, class Model>
 RKS_HD void core_pass(cplx* sm, const int (&p0)[NB], const Model& m) {
-    cplx a[NB][R];
-#pragma unroll
-    for (int b = 0; b < (RKS_LOADS_FIRST ? NB : 0); ++b)
-#pragma unroll
-        for (int s = 0; s < R; ++s) a[b][s] = sm[swz<SH>(p0[b] + s)];
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-        if (!RKS_LOADS_FIRST) {
-#pragma unroll
-            for (int s = 0; s < R; ++s) a[b][s] = sm[swz<SH>(p0[b] + s)];
-        }
-        cplx c[R];
-        dftR<R, true>(a[b]);
-#pragma unroll
-        for (int r = 0; r < R; ++r) c[r] = m.pointwise(a[b][perm<R>(r)]);
-        dftR<R, false>(c);
-#pragma unroll
-        for (int k = 0; k < R; ++k) sm[swz<SH>(p0[b] + k)] = c[perm<R>(k)];
+        cplx a[R];
+        bf_load<R, 1, SH>(sm, p0[b], a);
+        bf_core<R>(a, m);
+        bf_store<R, 1, SH>(sm, p0[b], a);
     }
 }
 

@@ -75,28 +75,18 @@ struct FuseSource {
     double sc[FUSE_MAX_TERMS];
     int nterms;
     RKS_HD cplx value(long long p) const {
-        // all loads first (memory-level parallelism), then the combine
-        cplx xv[FUSE_MAX_TERMS];
-        CT cv[FUSE_MAX_TERMS];
+        cplx acc = mk(0.0, 0.0);
 #pragma unroll
         for (int t = 0; t < FUSE_MAX_TERMS; ++t) {
             if (t < nterms) {
 #if defined(__CUDA_ARCH__)
                 const double2 v = __ldcs(reinterpret_cast<const double2*>(x[t] + p));
-                xv[t] = mk(v.x, v.y);
-                if (c[t]) cv[t] = ld_coef(c[t] + p);
+                cplx term = mk(v.x, v.y);
+                if (c[t]) term = cmul(ld_coef(c[t] + p), term);
 #else
-                xv[t] = x[t][p];
-                if (c[t]) cv[t] = c[t][p];
+                cplx term = x[t][p];
+                if (c[t]) term = cmul(c[t][p], term);
 #endif
-            }
-        }
-        cplx acc = mk(0.0, 0.0);
-#pragma unroll
-        for (int t = 0; t < FUSE_MAX_TERMS; ++t) {
-            if (t < nterms) {
-                cplx term = xv[t];
-                if (c[t]) term = cmul(cv[t], term);
                 if (sc[t] != 1.0) term = sc[t] * term;
                 acc = t == 0 ? term : acc + term;
             }

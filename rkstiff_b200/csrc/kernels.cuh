@@ -373,17 +373,76 @@ RKS_D void row_barrier(int lrow, int rpc) {
     asm volatile("bar.sync %0, %1;" ::"r"(lrow + 1), "r"(TR) : "memory");
 }
 
+#ifndef RKS_PINGPONG
+#define RKS_PINGPONG 0
+#endif
+
+// EXPERIMENT, off by default (measured slower: 459 us vs 370 us per launch at 4096 x 8192).
+// n = 8192 runs one CTA per SM and ncu shows FP64 ~50 % and LSU ~63 % busy with little overlap.  Here
+// the warp-local part of the transform is run by two groups of 8 warps (two per scheduler each) that
+// hand an "LSU token" back and forth through two named barriers: while one group moves data between
+// registers and shared memory, the other computes.  Strict alternation loses more (two warps per
+// scheduler cannot fill the FP64 pipe, barrier bubbles) than the overlap wins.
+struct LsuToken {
+    int g;
+    RKS_D void acquire() const { asm volatile("bar.sync %0, 512;" ::"r"(1 + g) : "memory"); }
+    RKS_D void release() const { asm volatile("bar.arrive %0, 512;" ::"r"(2 - g) : "memory"); }
+    RKS_D void prime() const { if (g == 1) asm volatile("bar.arrive 1, 512;" ::: "memory"); }   // group 0 starts
+};
+
+template <class Model>
+RKS_D void inner_pingpong_8192(cplx* sm, int T, const fast::Twiddles& ti, const fast::Twiddles& tf, const Model& m) {
+    using namespace fast;
+    constexpr int SH = 3;
+    const int w = T >> 5, l = T & 31;
+    const LsuToken tok{(w >> 2) & 1};
+    const int c0 = w * 512;
+    // first elements / twiddle indices of this lane's two butterflies in each pass
+    const int u0 = l, u1 = l + 32;
+    const int a0 = c0 + u0, a1 = c0 + u1;                                        // pass 2: R 8, Q 64
+    const int b0 = c0 + (u0 >> 3) * 64 + (u0 & 7), b1 = c0 + (u1 >> 3) * 64 + (u1 & 7);   // pass 3: R 8, Q 8
+    const int k0 = c0 + u0 * 8, k1 = c0 + u1 * 8;                                // core:   R 8, Q 1
+    cplx a[8];
+    tok.prime();
+    tok.acquire(); bf_load<8, 64, SH>(sm, a0, a); tok.release();
+    bf_dif<8, 64, TW_S2>(a, ti.t2, u0);
+    tok.acquire(); bf_store<8, 64, SH>(sm, a0, a); bf_load<8, 64, SH>(sm, a1, a); tok.release();
+    bf_dif<8, 64, TW_S2>(a, ti.t2, u1);
+    tok.acquire(); bf_store<8, 64, SH>(sm, a1, a); __syncwarp(); bf_load<8, 8, SH>(sm, b0, a); tok.release();
+    bf_dif<8, 8, TW_S3>(a, ti.t3, u0 & 7);
+    tok.acquire(); bf_store<8, 8, SH>(sm, b0, a); bf_load<8, 8, SH>(sm, b1, a); tok.release();
+    bf_dif<8, 8, TW_S3>(a, ti.t3, u1 & 7);
+    tok.acquire(); bf_store<8, 8, SH>(sm, b1, a); __syncwarp(); bf_load<8, 1, SH>(sm, k0, a); tok.release();
+    bf_core<8>(a, m);
+    tok.acquire(); bf_store<8, 1, SH>(sm, k0, a); bf_load<8, 1, SH>(sm, k1, a); tok.release();
+    bf_core<8>(a, m);
+    tok.acquire(); bf_store<8, 1, SH>(sm, k1, a); __syncwarp(); bf_load<8, 8, SH>(sm, b0, a); tok.release();
+    bf_dit<8, 8, TW_S3>(a, tf.t3, u0 & 7);
+    tok.acquire(); bf_store<8, 8, SH>(sm, b0, a); bf_load<8, 8, SH>(sm, b1, a); tok.release();
+    bf_dit<8, 8, TW_S3>(a, tf.t3, u1 & 7);
+    tok.acquire(); bf_store<8, 8, SH>(sm, b1, a); __syncwarp(); bf_load<8, 64, SH>(sm, a0, a); tok.release();
+    bf_dit<8, 64, TW_S2>(a, tf.t2, u0);
+    tok.acquire(); bf_store<8, 64, SH>(sm, a0, a); bf_load<8, 64, SH>(sm, a1, a); tok.release();
+    bf_dit<8, 64, TW_S2>(a, tf.t2, u1);
+    tok.acquire(); bf_store<8, 64, SH>(sm, a1, a);
+    if (tok.g == 0) tok.release();           // group 1 primed one extra arrival: it skips its last release
+}
+
 template <int N, class Model>
 RKS_D void nl_fast_row(cplx* sm, int T, int lrow, int rpc, const fast::Twiddles& ti, const fast::Twiddles& tf,
                        const Model& m) {
     constexpr int W = fast::Plan<N>::W, TR = 32 * W;
     fast::phase_first<N>(sm, T, ti, m);
     row_barrier<TR>(lrow, rpc);
-    fast::phase_middle<N, 2, true>(sm, T, ti, m);   __syncwarp();
-    if (fast::middle_passes<N>() == 2) { fast::phase_middle<N, 3, true>(sm, T, ti, m);   __syncwarp(); }
-    fast::phase_core<N>(sm, T, m);                  __syncwarp();
-    if (fast::middle_passes<N>() == 2) { fast::phase_middle<N, 3, false>(sm, T, tf, m);  __syncwarp(); }
-    fast::phase_middle<N, 2, false>(sm, T, tf, m);
+    if (N == 8192 && RKS_PINGPONG) {
+        inner_pingpong_8192(sm, T, ti, tf, m);
+    } else {
+        fast::phase_middle<N, 2, true>(sm, T, ti, m);   __syncwarp();
+        if (fast::middle_passes<N>() == 2) { fast::phase_middle<N, 3, true>(sm, T, ti, m);   __syncwarp(); }
+        fast::phase_core<N>(sm, T, m);                  __syncwarp();
+        if (fast::middle_passes<N>() == 2) { fast::phase_middle<N, 3, false>(sm, T, tf, m);  __syncwarp(); }
+        fast::phase_middle<N, 2, false>(sm, T, tf, m);
+    }
     row_barrier<TR>(lrow, rpc);
     fast::phase_last<N>(sm, T, tf, m);
     row_barrier<TR>(lrow, rpc);              // slab reads of the last pass vs the next row's first pass
