@@ -285,9 +285,54 @@ def run_cfg5(args):
         dist.destroy_process_group()
 
 
+def run_cfg4(args):
+    """2-D periodic Allen-Cahn, rfft2 half spectrum, IF45DP adaptive with device-side dt control and on-device
+    exp() coefficient recompute (BASELINE cfg 4).  Single GPU; N-D transform through the torch-callable path
+    (cuFFT), K1/K2/K3 from this engine on the (n, n/2+1) 'lin_op shaped like u' layout."""
+    import torch
+
+    import rkstiff_b200 as rk
+
+    torch.cuda.set_device(0)
+    n = args.size if args.size != 256 else 4096
+    lin, nl = rk.models.allen_cahn_fourier_ops(n, eps=0.01)
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    x = torch.arange(n, dtype=torch.float64, device="cuda") * (2 * math.pi / n)
+    u0 = torch.zeros(n, n, dtype=torch.float64, device="cuda")
+    for _ in range(16):
+        amp = float(torch.randn(1, generator=g))
+        m, q = int(torch.randint(-4, 5, (1,), generator=g)), int(torch.randint(-4, 5, (1,), generator=g))
+        th = float(torch.rand(1, generator=g)) * 2 * math.pi
+        u0 += 0.1 * amp * torch.cos(m * x[None, :] + q * x[:, None] + th)
+    uf0 = torch.fft.rfft2(u0)
+    sol = rk.IF45DP(lin, nl, config=rk.SolverConfig(epsilon=1e-4))
+    sol.evolve(uf0, 0.0, 0.01, store_data=False)          # warm-up
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sol.evolve(uf0, 0.0, 0.2, store_data=False)
+    e1.record()
+    torch.cuda.synchronize()
+    secs = e0.elapsed_time(e1) * 1e-3
+    trials = len(sol.trial_log)
+    n_c = n * (n // 2 + 1)
+    alg = (16 * 87 + 8 * 29) * n_c * trials            # SURVEY 8d: P = 87 passes + 29 real coefficient reads
+    print(json.dumps({"metric": METRIC, "value": n * n * trials / secs, "unit": UNIT, "n_gpus": 1, "steps": trials,
+                      "warmup": 0, "ms_per_step": 1e3 * secs / trials, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": f"cfg4: Allen-Cahn 2-D {n}^2 Fourier grid (rfft2 half spectrum), IF45DP adaptive "
+                                             "eps=1e-4, t 0->0.2, NL through cuFFT (torch callable)", "method": "IF45DP", "n": n},
+                      "accepted_steps": sum(1 for r in sol.trial_log if r[2]),
+                      "roofline": {"bound": "hbm", "kernel": "whole trial (model of SURVEY 8d)", "achieved": alg / secs / 1e9,
+                                   "peak": 6549.8, "unit": "GB/s", "frac": alg / secs / 1e9 / 6549.8, "traffic": None},
+                      "gpu_launches": sol._engine.launches()}))
+
+
 def run_ours(args):
     if args.workload == "cfg5":
         return run_cfg5(args)
+    if args.workload == "cfg4":
+        return run_cfg4(args)
     import torch
     import torch.distributed as dist
 
@@ -478,9 +523,9 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--method", default=None, help="override the method of cfg2/cfg3 (IF4 ETD4 ETD5 IF34 ETD34 ETD35 IF45DP)")
-    ap.add_argument("--size", type=int, default=256, help="cfg5: points per axis of the 3-D grid")
+    ap.add_argument("--size", type=int, default=256, help="cfg4/cfg5: points per axis of the 2-D/3-D grid (cfg4 default 4096)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
