@@ -65,8 +65,18 @@ static Layout make_layout(int method, long long batch, long long n_c, long long 
     return L;
 }
 
+struct GraphCache {
+    cudaGraphExec_t exec = nullptr;
+    void* ring = nullptr;
+    double* ring_t = nullptr;
+    int cap = 0, kernels = 0;
+    cudaStream_t stream = nullptr;
+};
+
 struct rks_plan {
     DevPlan d;
+    GraphCache graph;
+    bool use_graph;                 // replay one captured trial/step (RKS_NO_GRAPH=1 disables)
     Layout lay;
     unsigned char* ws;
     rks_config cfg;
@@ -192,6 +202,7 @@ extern "C" int rks_plan_create(rks_plan** out, int method, int64_t batch, int64_
     p->launches = 0;
     p->have_h_coeff_host = false;
     p->roles_u_sel = p->roles_n_sel = 0;
+    p->use_graph = getenv("RKS_NO_GRAPH") == nullptr;
     CUDA_TRY(cudaGetDevice(&p->device));
     CUDA_TRY(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device));
     CUDA_TRY(cudaMallocHost((void**)&p->pinned_raw, sizeof(Ctrl)));
@@ -232,6 +243,8 @@ extern "C" int rks_plan_create(rks_plan** out, int method, int64_t batch, int64_
 
 extern "C" void rks_plan_destroy(rks_plan* p) {
     if (!p) return;
+    if (p->graph.exec) cudaGraphExecDestroy(p->graph.exec);
+    if (p->graph.stream) cudaStreamDestroy(p->graph.stream);
     cudaFreeHost(p->pinned_raw);
     cudaFreeHost(p->pinned_log);
     delete p;
@@ -266,6 +279,7 @@ extern "C" int rks_set_model(rks_plan* p, int model, int64_t n, const double* kx
     int log2n = 0;
     while ((1ll << log2n) < n) ++log2n;
     d.n = n; d.log2n = log2n; d.model = model; d.model_p0 = params_host[0];
+    if (p->graph.exec) { cudaGraphExecDestroy(p->graph.exec); p->graph.exec = nullptr; }
     twiddle_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((cplx*)(p->ws + p->lay.tw), (int)n);
     p->launches += 1;
     if (kx) CUDA_TRY(cudaMemcpyAsync(p->ws + p->lay.kx, kx, sizeof(double) * (size_t)d.n_c, cudaMemcpyDeviceToDevice, stream));
@@ -599,10 +613,47 @@ static int enqueue_trial(rks_plan* p, void* ring, double* ring_t, int cap, void*
     return RKS_OK;
 }
 
+// One trial / one fixed step is ~12 launches whose arguments never change (roles, h and predicates
+// are read from the control block on the device), so the sequence is captured once into a CUDA
+// graph and replayed: small problems are launch-latency bound (BASELINE cfg 1: 8 KB of state).
+static int graph_replay(rks_plan* p, int count, int adaptive, void* ring, double* ring_t, int cap, cudaStream_t stream) {
+    const int S = method_stages(p->method);
+    GraphCache& g = p->graph;
+    if (g.exec && (g.ring != ring || g.ring_t != ring_t || g.cap != cap)) {
+        cudaGraphExecDestroy(g.exec);
+        g.exec = nullptr;
+    }
+    if (!g.exec) {
+        // capture on a plan-owned stream (the caller's may be the legacy default stream, which cannot
+        // capture); the instantiated graph is then launched into the caller's stream
+        if (!g.stream) CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        const long long before = p->launches;
+        CUDA_TRY(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeRelaxed));
+        int rc = RKS_OK;
+        if (adaptive) rc = enqueue_trial(p, ring, ring_t, cap, g.stream);
+        else
+            for (int s = 1; s <= S && rc == RKS_OK; ++s) rc = rks_stage_nl(p, s, g.stream);
+        cudaError_t e = cudaStreamEndCapture(g.stream, &graph);
+        g.kernels = (int)(p->launches - before);
+        p->launches = before;
+        if (rc != RKS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) return fail(RKS_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { g.exec = nullptr; return fail(RKS_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+        g.ring = ring; g.ring_t = ring_t; g.cap = cap;
+    }
+    for (int i = 0; i < count; ++i) CUDA_TRY(cudaGraphLaunch(g.exec, stream));
+    p->launches += (long long)count * g.kernels;
+    return RKS_OK;
+}
+
 extern "C" int rks_run_trials(rks_plan* p, int ntrials, void* ring, double* ring_t, int cap, void* stream) {
     if (!p) return fail(RKS_ERR_ARG, "plan is null");
     if (!method_adaptive(p->method)) return fail(RKS_ERR_UNSUPPORTED, "rks_run_trials needs an adaptive method");
     if (p->d.model == RKS_MODEL_NONE) return fail(RKS_ERR_UNSUPPORTED, "no fused model set (rks_set_model)");
+    if (p->use_graph) return graph_replay(p, ntrials, 1, ring, ring_t, cap, (cudaStream_t)stream);
     for (int i = 0; i < ntrials; ++i)
         if (int rc = enqueue_trial(p, ring, ring_t, cap, stream)) return rc;
     return RKS_OK;
@@ -612,6 +663,7 @@ extern "C" int rks_run_fixed(rks_plan* p, int nsteps, void* stream) {
     if (!p) return fail(RKS_ERR_ARG, "plan is null");
     if (method_adaptive(p->method)) return fail(RKS_ERR_UNSUPPORTED, "rks_run_fixed needs a fixed-step method");
     if (p->d.model == RKS_MODEL_NONE) return fail(RKS_ERR_UNSUPPORTED, "no fused model set (rks_set_model)");
+    if (p->use_graph) return graph_replay(p, nsteps, 0, nullptr, nullptr, 0, (cudaStream_t)stream);
     const int S = method_stages(p->method);
     int rc;
     for (int i = 0; i < nsteps; ++i) {
