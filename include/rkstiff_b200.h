@@ -55,7 +55,11 @@ enum rks_model {
     RKS_MODEL_NONE = 0,
     RKS_MODEL_UUX_RFFT = 1, /* N = -c * rfft(irfft(u^) * irfft(i kx u^)); KS/Burgers c=1, KdV c=6
                                models.py:140-143,189-192, README.md:94-97. n_c = n/2+1, params[0]=c */
-    RKS_MODEL_NLS_FFT = 2   /* N = i*gamma * fft(|ifft u^|^2 ifft u^); demos/nls.ipynb. n_c = n, params[0]=gamma */
+    RKS_MODEL_NLS_FFT = 2,  /* N = i*gamma * fft(|ifft u^|^2 ifft u^); demos/nls.ipynb. n_c = n, params[0]=gamma */
+    RKS_MODEL_CUBIC_RFFT = 3,   /* N = c * rfft(irfft(u^)^3): Fourier-diagonal Allen-Cahn (c = -1, L = 1 - eps k^2, the
+                                   split of models.py:240-244). n_c = n/2+1, params[0]=c, kx unused */
+    RKS_MODEL_SINE_GORDON = 4   /* psi = phi_t + i Omega phi: N = fft(phi - sin phi), phi^ = (psi^(k) - conj psi^(-k))/(2 i Omega);
+                                   n_c = n, kx = Omega(k) = sqrt(1 + k^2) */
 };
 
 enum rks_status {

@@ -175,3 +175,56 @@ def nls_3d(n: int = 32, gamma: float = 2.0, half_width: float = 6.0) -> Problem:
     prob = Problem("nls_3d", lin, nl, np.fft.fftn(u0).ravel(), "none", n ** 3, k, {"gamma": gamma}, x)
     prob.params["shape"] = shape
     return prob
+
+
+# ----------------------------------------------------------------------------------------------
+# Fourier-diagonal models without a reference formulation: the oracle is the
+# reference's solver classes (restated in rk_oracle.py) driven by these NumPy closures.
+# ----------------------------------------------------------------------------------------------
+def allen_cahn_1d(n: int = 256, eps: float = 0.01, batch: int = 0, seed: int = 5) -> Problem:
+    """Periodic 1-D Allen-Cahn u_t = eps u_xx + u - u^3 on [0, 2 pi): L = 1 - eps k^2 (the +u goes into L,
+    like rkstiff/models.py:240-244), N = -rfft(irfft(u^)^3)."""
+    x, kx = x_kx_rfft(n, 0.0, 2 * np.pi)
+    lin = 1.0 - eps * kx ** 2
+    rng = np.random.default_rng(seed)
+
+    def ic():
+        u = np.zeros(n)
+        for m in range(1, 6):
+            u += 0.3 * rng.standard_normal() * np.cos(m * x + rng.uniform(0, 2 * np.pi))
+        return u
+
+    u0 = np.stack([ic() for _ in range(batch)]) if batch else ic()
+
+    def nl(uf):
+        u = np.fft.irfft(uf, axis=-1)
+        return -np.fft.rfft(u ** 3, axis=-1)
+
+    return Problem("allen_cahn_1d", lin, nl, np.fft.rfft(u0, axis=-1), "cubic", n, kx, {"c": -1.0, "eps": eps}, x)
+
+
+def sine_gordon(n: int = 256, batch: int = 0, half_width: float = 20.0, seed: int = 7) -> Problem:
+    """Sine-Gordon phi_tt = phi_xx - sin(phi) in first-order complex form psi = phi_t + i Omega phi,
+    Omega = sqrt(1 + k^2):  L = i Omega,  N(psi^) = fft(phi - sin phi),
+    phi^(k) = (psi^(k) - conj(psi^(-k))) / (2 i Omega(k)).  Initial data: breathers at rest."""
+    x, k = x_kx_fft(n, -half_width, half_width)
+    omega = np.sqrt(1.0 + k ** 2)
+    lin = 1j * omega
+    rev = (-np.arange(n)) % n
+
+    def nl(pf):
+        phi_hat = (pf - np.conj(pf[..., rev])) / (2j * omega)
+        phi = np.fft.ifft(phi_hat, axis=-1).real
+        return np.fft.fft(phi - np.sin(phi), axis=-1)
+
+    def breather(w, x0):
+        s = np.sqrt(1 - w * w)
+        return 4 * np.arctan(s / w / np.cosh(s * (x - x0)))
+
+    if batch:
+        rng = np.random.default_rng(seed)
+        phi0 = np.stack([breather(rng.uniform(0.3, 0.8), rng.uniform(-5, 5)) for _ in range(batch)])
+    else:
+        phi0 = breather(0.5, 0.0)
+    psi0 = 1j * omega * np.fft.fft(phi0, axis=-1)            # phi_t = 0
+    return Problem("sine_gordon", lin, nl, psi0, "sine_gordon", n, omega, {}, x)

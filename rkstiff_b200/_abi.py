@@ -14,7 +14,7 @@ from . import _build
 RKS_ABI_VERSION = 1
 
 METHOD_IDS = {"IF4": 0, "ETD4": 1, "ETD5": 2, "IF34": 3, "ETD34": 4, "ETD35": 5, "IF45DP": 6}
-MODEL_NONE, MODEL_UUX_RFFT, MODEL_NLS_FFT = 0, 1, 2
+MODEL_NONE, MODEL_UUX_RFFT, MODEL_NLS_FFT, MODEL_CUBIC_RFFT, MODEL_SINE_GORDON = 0, 1, 2, 3, 4
 CTRL_RUNNING, CTRL_DONE, CTRL_MAX_LOOPS, CTRL_MIN_STEP = 0, 1, 2, 3
 LOG_CAP = 4096
 

@@ -83,63 +83,4 @@ RKS_HD void fft_dit_pass(cplx* x, int log2n, int p, const cplx* tw, int tid, int
     fft_dit4_pass(x, n, 2 * (k + 1) + odd, tw, tid, nthreads);
 }
 
-// ---------------------------------------------------------------------------------------
-// model phases.  in/out are one trajectory's spectrum in global memory; x is the smem row.
-// ---------------------------------------------------------------------------------------
-
-// u u_x models (KS, Burgers, KdV): N = -c rfft(irfft(u^) irfft(i kx u^)), models.py:140-143.
-// Load phase: build Z = U^ + i W^ on the full circle, W^ = i kx U^, with c2r semantics
-// (imaginary parts of the DC and Nyquist inputs are ignored, as numpy.fft.irfft does), so that
-// one complex inverse transform returns u in the real part and u_x in the imaginary part.
-RKS_HD void uux_load(cplx* x, const cplx* in, const double* kx, int n, int tid, int nthreads) {
-    const int half = n >> 1;
-    for (int k = tid; k <= half; k += nthreads) {
-        const cplx v = in[k];
-        const double kk = kx[k];
-        if (k == 0) {
-            x[0] = mk(v.x, -(kk * v.y));
-        } else if (k == half) {
-            x[half] = mk(v.x, -(kk * v.y));
-        } else {
-            // Z[k] = v (1 - kk),  Z[n-k] = conj(v) (1 + kk)
-            x[k] = mk(v.x - kk * v.x, v.y - kk * v.y);
-            x[n - k] = mk(v.x + kk * v.x, -(v.y + kk * v.y));
-        }
-    }
-}
-// pointwise: z holds n*(u + i u_x) (unnormalised inverse); product u*u_x, scaled by 1/n^2
-RKS_HD void uux_pointwise(cplx* x, int n, int tid, int nthreads) {
-    const double sc = 1.0 / ((double)n * (double)n);       // exact: n is a power of two
-    for (int i = tid; i < n; i += nthreads) {
-        const cplx z = x[i];
-        x[i] = mk((z.x * z.y) * sc, 0.0);
-    }
-}
-RKS_HD void uux_store(cplx* out, const cplx* x, double c, int n, int tid, int nthreads) {
-    const int half = n >> 1;
-    for (int k = tid; k <= half; k += nthreads) {
-        const cplx v = x[k];
-        out[k] = mk(-c * v.x, -c * v.y);
-    }
-}
-
-// NLS: N = i gamma fft(|f|^2 f), f = ifft(u^)  (demos/nls.ipynb)
-RKS_HD void nls_load(cplx* x, const cplx* in, int n, int tid, int nthreads) {
-    for (int k = tid; k < n; k += nthreads) x[k] = in[k];
-}
-RKS_HD void nls_pointwise(cplx* x, int n, int tid, int nthreads) {
-    const double sc = 1.0 / (double)n;
-    for (int i = tid; i < n; i += nthreads) {
-        const cplx f = mk(x[i].x * sc, x[i].y * sc);
-        const double f2 = f.x * f.x + f.y * f.y;
-        x[i] = mk(f2 * f.x, f2 * f.y);
-    }
-}
-RKS_HD void nls_store(cplx* out, const cplx* x, double gamma, int n, int tid, int nthreads) {
-    for (int k = tid; k < n; k += nthreads) {
-        const cplx v = x[k];
-        out[k] = mk(-(gamma * v.y), gamma * v.x);           // i*gamma*v
-    }
-}
-
 }  // namespace rks

@@ -275,6 +275,74 @@ struct UuxModelT {
 };
 using UuxModel = UuxModelT<GlobalHalf>;
 
+// N = c rfft(irfft(u^)^3): the cubic term of the Fourier-diagonal Allen-Cahn equation
+// u_t = eps u_xx + u - u^3 (L = 1 - eps k^2 carries the +u, mirroring rkstiff/models.py:240-244; c = -1).
+template <class Half>
+struct CubicModelT {
+    Half half; cplx* out; double c; int n; bool on;
+    RKS_HD cplx load(int p) const {
+        const int hn = n >> 1;
+        if (p <= hn) {
+            const cplx v = half.get(p);
+            if (p == 0 || p == hn) return mk(v.x, 0.0);                 // c2r ignores Im of DC / Nyquist
+            return v;
+        }
+        return conj(half.get(n - p));                                   // Hermitian partner
+    }
+    RKS_HD cplx pointwise(cplx z) const {
+        const double x = z.x * (1.0 / (double)n);
+        return mk(x * x * x, 0.0);
+    }
+    RKS_HD void store(int p, cplx v) const {
+        if (on && p <= (n >> 1)) row_st(out + p, mk(c * v.x, c * v.y));
+    }
+};
+using CubicModel = CubicModelT<GlobalHalf>;
+
+// Sine-Gordon phi_tt = phi_xx - sin(phi) in the first-order complex form psi = phi_t + i Omega phi,
+// Omega = sqrt(1 + k^2):  psi^_t = i Omega psi^ + F{phi - sin phi},
+// phi^(k) = (psi^(k) - conj(psi^(-k))) / (2 i Omega(k))   (`omega` holds Omega(k)).
+struct SineGordonModel {
+    const cplx* in; cplx* out; const double* omega; int n; bool on;
+    RKS_HD cplx load(int p) const {
+        const cplx a = row_ld(in + p), b = row_ld(in + ((n - p) & (n - 1)));
+        const double scl = 1.0 / (2.0 * omega[p]);
+        return mk((a.y + b.y) * scl, -((a.x - b.x) * scl));             // (a - conj b) / (2 i Omega)
+    }
+    RKS_HD cplx pointwise(cplx z) const {
+        const double phi = z.x * (1.0 / (double)n);
+        return mk(phi - sin(phi), 0.0);
+    }
+    RKS_HD void store(int p, cplx v) const { if (on) row_st(out + p, v); }
+};
+
+// model ids of include/rkstiff_b200.h -> model objects reading/writing plain arrays
+template <int MODEL> struct ModelOf;
+template <> struct ModelOf<1> {
+    using type = UuxModel;
+    RKS_HD static type make(const cplx* in, cplx* out, const double* kx, double p0, int n, bool on) {
+        return type{GlobalHalf{in}, out, kx, p0, n, on};
+    }
+};
+template <> struct ModelOf<2> {
+    using type = NlsModel;
+    RKS_HD static type make(const cplx* in, cplx* out, const double*, double p0, int n, bool on) {
+        return type{ArraySource{in}, StateSink{nullptr, nullptr}, out, p0, n, on};
+    }
+};
+template <> struct ModelOf<3> {
+    using type = CubicModel;
+    RKS_HD static type make(const cplx* in, cplx* out, const double*, double p0, int n, bool on) {
+        return type{GlobalHalf{in}, out, p0, n, on};
+    }
+};
+template <> struct ModelOf<4> {
+    using type = SineGordonModel;
+    RKS_HD static type make(const cplx* in, cplx* out, const double* kx, double, int n, bool on) {
+        return type{in, out, kx, n, on};
+    }
+};
+
 // ---------------------------------------------------------------------------------------
 // generic in-place passes.  A butterfly is identified by the logical position p0 of its first
 // element (elements p0 + Q s) and its twiddle index j (w_L^(r j), L = R Q).  NB butterflies of one

@@ -333,32 +333,27 @@ __global__ void __launch_bounds__(1024) nl_kernel(DevPlan p, int j, int force, i
     const long long row = (long long)blockIdx.x * rows_per_cta + lrow;
     const bool active = row < p.batch;
     cplx* x = smem + (size_t)lrow * n;
-    const cplx* in = roles.in + row * p.n_c;
-    cplx* out = roles.out + row * p.n_c;
-
-    if (active) {
-        if (MODEL == 1) uux_load(x, in, p.kx, n, tid, tpr);
-        else nls_load(x, in, n, tid, tpr);
-    }
+    const long long rr = active ? row : p.batch - 1;
+    const cplx* in = roles.in + rr * p.n_c;
+    cplx* out = roles.out + rr * p.n_c;
+    const auto m = fast::ModelOf<MODEL>::make(in, out, p.kx, p.model_p0, n, active);
+    if (active)
+        for (int q = tid; q < n; q += tpr) x[q] = m.load(q);
     __syncthreads();
     const int np = fft_num_passes(log2n);
     for (int q = 0; q < np; ++q) {
         if (active) ifft_dif_pass(x, log2n, q, p.tw, tid, tpr);
         __syncthreads();
     }
-    if (active) {
-        if (MODEL == 1) uux_pointwise(x, n, tid, tpr);
-        else nls_pointwise(x, n, tid, tpr);
-    }
+    if (active)
+        for (int q = tid; q < n; q += tpr) x[q] = m.pointwise(x[q]);
     __syncthreads();
     for (int q = 0; q < np; ++q) {
         if (active) fft_dit_pass(x, log2n, q, p.tw, tid, tpr);
         __syncthreads();
     }
-    if (active) {
-        if (MODEL == 1) uux_store(out, x, p.model_p0, n, tid, tpr);
-        else nls_store(out, x, p.model_p0, n, tid, tpr);
-    }
+    if (active)
+        for (int q = tid; q < n; q += tpr) m.store(q, x[q]);
 }
 
 
@@ -512,14 +507,8 @@ nl_fast_kernel(DevPlan p, int j, int force, FuseDesc fd) {
         cplx* out = roles.out + rr * p.n_c;
         if (FK == 0) {
             prefetch_row_l2<TR>(roles.in + (nlines ? nrow : rr) * p.n_c, nlines, T);
-            if (MODEL == 1) {
-                const fast::UuxModel m{fast::GlobalHalf{roles.in + rr * p.n_c}, out, p.kx, p.model_p0, N, on};
-                nl_fast_row<N>(sm, T, lrow, RPC, ti, tf, m);
-            } else {
-                const fast::NlsModel m{fast::ArraySource{roles.in + rr * p.n_c}, fast::StateSink{nullptr, nullptr}, out,
-                                       p.model_p0, N, on};
-                nl_fast_row<N>(sm, T, lrow, RPC, ti, tf, m);
-            }
+            const auto m = fast::ModelOf<MODEL>::make(roles.in + rr * p.n_c, out, p.kx, p.model_p0, N, on);
+            nl_fast_row<N>(sm, T, lrow, RPC, ti, tf, m);
         } else {
             FuseSource<CT> src;
             src.nterms = fd.nterms;
@@ -533,7 +522,9 @@ nl_fast_kernel(DevPlan p, int j, int force, FuseDesc fd) {
                 }
             }
             const fast::StateSink sink{kbase ? kbase + rr * p.n_c : nullptr, fd.track_max ? &mx : nullptr};
-            if (MODEL == 1) {
+            if (MODEL != 1 && MODEL != 2) {
+                // fused combine is only instantiated for the u u_x and NLS models
+            } else if (MODEL == 1) {
                 // half spectrum of the stage value: computed once per mode, staged in smem (the
                 // inverse transform needs every mode twice: k and its Hermitian partner n - k)
                 constexpr int HALF = N / 2 + 1;

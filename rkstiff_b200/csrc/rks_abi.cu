@@ -117,10 +117,13 @@ static void launch_nl_fast_t(rks_plan* p, int j, int force, const FuseDesc& fd, 
     nl_fast_kernel<W, MODEL, FK><<<grid, THREADS, smem, stream>>>(d, j, force, fd);
 }
 
-// fk: 0 plain, 1 fused with complex coefficient arrays, 2 fused with real ones
+// fk: 0 plain, 1 fused with complex coefficient arrays, 2 fused with real ones (models 1 and 2 only)
 template <int W>
 static void launch_nl_fast(rks_plan* p, int j, int force, const FuseDesc& fd, int fk, cudaStream_t stream) {
-    const bool uux = p->d.model == RKS_MODEL_UUX_RFFT;
+    const int model = p->d.model;
+    if (model == RKS_MODEL_CUBIC_RFFT) { launch_nl_fast_t<W, 3, 0>(p, j, force, fd, stream); return; }
+    if (model == RKS_MODEL_SINE_GORDON) { launch_nl_fast_t<W, 4, 0>(p, j, force, fd, stream); return; }
+    const bool uux = model == RKS_MODEL_UUX_RFFT;
     if (fk == 0) uux ? launch_nl_fast_t<W, 1, 0>(p, j, force, fd, stream) : launch_nl_fast_t<W, 2, 0>(p, j, force, fd, stream);
     else if (fk == 1) uux ? launch_nl_fast_t<W, 1, 1>(p, j, force, fd, stream) : launch_nl_fast_t<W, 2, 1>(p, j, force, fd, stream);
     else uux ? launch_nl_fast_t<W, 1, 2>(p, j, force, fd, stream) : launch_nl_fast_t<W, 2, 2>(p, j, force, fd, stream);
@@ -134,10 +137,14 @@ static cudaError_t prepare_nl_fast(int model) {
         e = cudaFuncSetAttribute(nl_fast_kernel<W, 1, 0>, attr, (int)nl_fast_smem<W>(model, 0));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 1, 1>, attr, (int)nl_fast_smem<W>(model, 1));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 1, 2>, attr, (int)nl_fast_smem<W>(model, 2));
-    } else {
+    } else if (model == RKS_MODEL_NLS_FFT) {
         e = cudaFuncSetAttribute(nl_fast_kernel<W, 2, 0>, attr, (int)nl_fast_smem<W>(model, 0));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 2, 1>, attr, (int)nl_fast_smem<W>(model, 1));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 2, 2>, attr, (int)nl_fast_smem<W>(model, 2));
+    } else if (model == RKS_MODEL_CUBIC_RFFT) {
+        e = cudaFuncSetAttribute(nl_fast_kernel<W, 3, 0>, attr, (int)nl_fast_smem<W>(model, 0));
+    } else {
+        e = cudaFuncSetAttribute(nl_fast_kernel<W, 4, 0>, attr, (int)nl_fast_smem<W>(model, 0));
     }
     return e;
 }
@@ -269,13 +276,14 @@ extern "C" int rks_set_model(rks_plan* p, int model, int64_t n, const double* kx
     cudaStream_t stream = (cudaStream_t)stream_v;
     DevPlan& d = p->d;
     if (model == RKS_MODEL_NONE) { d.model = 0; return RKS_OK; }
-    if (model != RKS_MODEL_UUX_RFFT && model != RKS_MODEL_NLS_FFT) return fail(RKS_ERR_ARG, "unknown model id");
+    if (model < RKS_MODEL_UUX_RFFT || model > RKS_MODEL_SINE_GORDON) return fail(RKS_ERR_ARG, "unknown model id");
     if (d.lin_elems != d.n_c) return fail(RKS_ERR_UNSUPPORTED, "fused 1-D models need lin_op of n_c elements");
     if (n < 16 || n > MODEL_MAX_N || (n & (n - 1))) return fail(RKS_ERR_UNSUPPORTED, "n must be a power of two in [16, 16384]");
-    const long long want_nc = model == RKS_MODEL_UUX_RFFT ? n / 2 + 1 : n;
+    const bool half_spectrum = model == RKS_MODEL_UUX_RFFT || model == RKS_MODEL_CUBIC_RFFT;
+    const long long want_nc = half_spectrum ? n / 2 + 1 : n;
     if (want_nc != d.n_c) return fail(RKS_ERR_ARG, "n does not match n_c for this model");
     if (nparams < 1 || !params_host) return fail(RKS_ERR_ARG, "model needs one parameter");
-    if (model == RKS_MODEL_UUX_RFFT && !kx) return fail(RKS_ERR_ARG, "kx is null");
+    if ((model == RKS_MODEL_UUX_RFFT || model == RKS_MODEL_SINE_GORDON) && !kx) return fail(RKS_ERR_ARG, "kx is null");
     int log2n = 0;
     while ((1ll << log2n) < n) ++log2n;
     d.n = n; d.log2n = log2n; d.model = model; d.model_p0 = params_host[0];
@@ -305,10 +313,11 @@ extern "C" int rks_set_model(rks_plan* p, int model, int64_t n, const double* kx
     p->nl_threads = rows * tpr;
     p->nl_smem = row_bytes * rows;
     if (p->nl_smem > 227 * 1024) return fail(RKS_ERR_UNSUPPORTED, "row does not fit in shared memory");
-    if (model == RKS_MODEL_UUX_RFFT)
-        CUDA_TRY(cudaFuncSetAttribute(nl_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->nl_smem));
-    else
-        CUDA_TRY(cudaFuncSetAttribute(nl_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->nl_smem));
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    if (model == RKS_MODEL_UUX_RFFT) CUDA_TRY(cudaFuncSetAttribute(nl_kernel<1>, attr, (int)p->nl_smem));
+    else if (model == RKS_MODEL_NLS_FFT) CUDA_TRY(cudaFuncSetAttribute(nl_kernel<2>, attr, (int)p->nl_smem));
+    else if (model == RKS_MODEL_CUBIC_RFFT) CUDA_TRY(cudaFuncSetAttribute(nl_kernel<3>, attr, (int)p->nl_smem));
+    else CUDA_TRY(cudaFuncSetAttribute(nl_kernel<4>, attr, (int)p->nl_smem));
     CUDA_TRY(cudaGetLastError());
     return RKS_OK;
 }
@@ -465,10 +474,10 @@ static int launch_nl(rks_plan* p, int j, int force, cudaStream_t stream) {
         return RKS_OK;
     }
     const unsigned grid = (unsigned)((d.batch + p->nl_rows_per_cta - 1) / p->nl_rows_per_cta);
-    if (d.model == RKS_MODEL_UUX_RFFT)
-        nl_kernel<1><<<grid, p->nl_threads, p->nl_smem, stream>>>(d, j, force, p->nl_rows_per_cta);
-    else
-        nl_kernel<2><<<grid, p->nl_threads, p->nl_smem, stream>>>(d, j, force, p->nl_rows_per_cta);
+    if (d.model == RKS_MODEL_UUX_RFFT) nl_kernel<1><<<grid, p->nl_threads, p->nl_smem, stream>>>(d, j, force, p->nl_rows_per_cta);
+    else if (d.model == RKS_MODEL_NLS_FFT) nl_kernel<2><<<grid, p->nl_threads, p->nl_smem, stream>>>(d, j, force, p->nl_rows_per_cta);
+    else if (d.model == RKS_MODEL_CUBIC_RFFT) nl_kernel<3><<<grid, p->nl_threads, p->nl_smem, stream>>>(d, j, force, p->nl_rows_per_cta);
+    else nl_kernel<4><<<grid, p->nl_threads, p->nl_smem, stream>>>(d, j, force, p->nl_rows_per_cta);
     p->launches += 1;
     return RKS_OK;
 }
@@ -491,6 +500,7 @@ extern "C" int rks_nl(rks_plan* p, int j, void* stream) {
 static bool can_fuse_stage(const rks_plan* p, int s) {
     const int m = p->method, S = method_stages(m);
     if (!p->nl_fast || p->no_fuse || p->d.lin_elems != p->d.n_c) return false;
+    if (p->d.model != RKS_MODEL_UUX_RFFT && p->d.model != RKS_MODEL_NLS_FFT) return false;
     if (s == S && m == M_ETD35) return false;              // last ETD35 stage emits err and feeds no N
     return true;
 }

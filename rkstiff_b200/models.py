@@ -39,6 +39,14 @@ class FusedNL:
             u = torch.fft.irfft(uf, n=self.n, dim=-1)
             ux = torch.fft.irfft(1j * self.kx * uf, n=self.n, dim=-1)
             return -self.param * torch.fft.rfft(u * ux, dim=-1)
+        if self.model_id == _abi.MODEL_CUBIC_RFFT:
+            u = torch.fft.irfft(uf, n=self.n, dim=-1)
+            return self.param * torch.fft.rfft(u * u * u, dim=-1)
+        if self.model_id == _abi.MODEL_SINE_GORDON:
+            rev = (-torch.arange(self.n, device=uf.device)) % self.n
+            phi_hat = (uf - torch.conj(uf[..., rev])) / (2j * self.kx)
+            phi = torch.fft.ifft(phi_hat, dim=-1).real
+            return torch.fft.fft(phi - torch.sin(phi), dim=-1)
         f = torch.fft.ifft(uf, dim=-1)
         f2 = f.real ** 2 + f.imag ** 2
         return 1j * self.param * torch.fft.fft(f2 * f, dim=-1)
@@ -73,6 +81,23 @@ def nls_ops(kx: torch.Tensor, gamma: float = 2.0) -> Tuple[torch.Tensor, FusedNL
     """Cubic NLS u_t = i u_xx + i gamma |u|^2 u in fft space (demos/nls.ipynb)."""
     lin_op = -1j * kx.to(torch.complex128) ** 2
     return lin_op, FusedNL(_abi.MODEL_NLS_FFT, kx.shape[-1], kx, gamma, "nls")
+
+
+def allen_cahn_1d_ops(kx: torch.Tensor, eps: float = 0.01) -> Tuple[torch.Tensor, FusedNL]:
+    """Periodic 1-D Allen-Cahn u_t = eps u_xx + u - u^3 in rfft space: L = 1 - eps k^2 (the +u goes into
+    L, mirroring the split of rkstiff/models.py:240-244), N = -F{u^3}."""
+    lin_op = 1.0 - eps * kx ** 2
+    return lin_op, FusedNL(_abi.MODEL_CUBIC_RFFT, _n_from_rfft_kx(kx), None, -1.0, "allen_cahn")
+
+
+def sine_gordon_ops(kx: torch.Tensor) -> Tuple[torch.Tensor, FusedNL]:
+    """Sine-Gordon phi_tt = phi_xx - sin(phi) on the full fft grid in first-order complex form
+    psi = phi_t + i Omega phi, Omega = sqrt(1 + k^2) (the reference's own SG demo is a Chebyshev dense
+    system; this Fourier-diagonal restatement is SURVEY.md 8f-1):  L = i Omega,  N = F{phi - sin phi}.
+    State: psi^ = F{phi_t} + i Omega F{phi};  phi^ = (psi^(k) - conj(psi^(-k))) / (2 i Omega)."""
+    omega = torch.sqrt(1.0 + kx.to(torch.float64) ** 2)
+    lin_op = 1j * omega.to(torch.complex128)
+    return lin_op, FusedNL(_abi.MODEL_SINE_GORDON, kx.shape[-1], omega, 0.0, "sine_gordon")
 
 
 def kdv_soliton(x: torch.Tensor, ampl: float = 0.5, x0: float = 0.0, t: float = 0.0) -> torch.Tensor:

@@ -59,6 +59,23 @@ static int fast_dispatch(int n, const Model& m, const fast::Twiddles& tw) {
     return -1;
 }
 
+// fused NL of one row through the generic radix-4 passes (fft.cuh), emulating `nthreads` threads
+template <class Model>
+static void generic_row(const Model& m, int n, int nthreads) {
+    int log2n = 0;
+    while ((1 << log2n) < n) ++log2n;
+    std::vector<cplx> tw(n), x(n);
+    for (int j = 0; j < n; ++j) tw[j] = mk(cos(-2.0 * M_PI * j / n), sin(-2.0 * M_PI * j / n));
+    for (int t = 0; t < nthreads; ++t)
+        for (int q = t; q < n; q += nthreads) x[q] = m.load(q);
+    const int np = fft_num_passes(log2n);
+    for (int q = 0; q < np; ++q)
+        for (int t = 0; t < nthreads; ++t) ifft_dif_pass(x.data(), log2n, q, tw.data(), t, nthreads);
+    for (int q = 0; q < n; ++q) x[q] = m.pointwise(x[q]);
+    for (int q = 0; q < np; ++q)
+        for (int t = 0; t < nthreads; ++t) fft_dit_pass(x.data(), log2n, q, tw.data(), t, nthreads);
+    for (int q = 0; q < n; ++q) m.store(q, x[q]);
+}
 extern "C" {
 
 int hc_nl_fast(int model, int n, const double* in, const double* kx, double p0, double* out) {
@@ -67,36 +84,19 @@ int hc_nl_fast(int model, int n, const double* in, const double* kx, double p0, 
     const fast::Twiddles tw{tab.data() + fast::TW_T1, tab.data() + fast::TW_T2, tab.data() + fast::TW_T3};
     const cplx* cin = reinterpret_cast<const cplx*>(in);
     cplx* co = reinterpret_cast<cplx*>(out);
-    if (model == 1) { fast::UuxModel m{fast::GlobalHalf{cin}, co, kx, p0, n, true}; return fast_dispatch(n, m, tw); }
-    fast::NlsModel m{fast::ArraySource{cin}, fast::StateSink{nullptr, nullptr}, co, p0, n, true};
-    return fast_dispatch(n, m, tw);
+    if (model == 1) return fast_dispatch(n, fast::ModelOf<1>::make(cin, co, kx, p0, n, true), tw);
+    if (model == 2) return fast_dispatch(n, fast::ModelOf<2>::make(cin, co, kx, p0, n, true), tw);
+    if (model == 3) return fast_dispatch(n, fast::ModelOf<3>::make(cin, co, kx, p0, n, true), tw);
+    return fast_dispatch(n, fast::ModelOf<4>::make(cin, co, kx, p0, n, true), tw);
 }
 
-// fused NL of one row, emulating `nthreads` threads
 void hc_nl(int model, int n, const double* in, const double* kx, double p0, double* out, int nthreads) {
-    int log2n = 0;
-    while ((1 << log2n) < n) ++log2n;
-    std::vector<cplx> tw(n), x(n);
-    for (int j = 0; j < n; ++j) tw[j] = mk(cos(-2.0 * M_PI * j / n), sin(-2.0 * M_PI * j / n));
     const cplx* cin = reinterpret_cast<const cplx*>(in);
-    cplx* cout = reinterpret_cast<cplx*>(out);
-    for (int t = 0; t < nthreads; ++t) {
-        if (model == 1) uux_load(x.data(), cin, kx, n, t, nthreads);
-        else nls_load(x.data(), cin, n, t, nthreads);
-    }
-    const int np = fft_num_passes(log2n);
-    for (int q = 0; q < np; ++q)
-        for (int t = 0; t < nthreads; ++t) ifft_dif_pass(x.data(), log2n, q, tw.data(), t, nthreads);
-    for (int t = 0; t < nthreads; ++t) {
-        if (model == 1) uux_pointwise(x.data(), n, t, nthreads);
-        else nls_pointwise(x.data(), n, t, nthreads);
-    }
-    for (int q = 0; q < np; ++q)
-        for (int t = 0; t < nthreads; ++t) fft_dit_pass(x.data(), log2n, q, tw.data(), t, nthreads);
-    for (int t = 0; t < nthreads; ++t) {
-        if (model == 1) uux_store(cout, x.data(), p0, n, t, nthreads);
-        else nls_store(cout, x.data(), p0, n, t, nthreads);
-    }
+    cplx* co = reinterpret_cast<cplx*>(out);
+    if (model == 1) generic_row(fast::ModelOf<1>::make(cin, co, kx, p0, n, true), n, nthreads);
+    else if (model == 2) generic_row(fast::ModelOf<2>::make(cin, co, kx, p0, n, true), n, nthreads);
+    else if (model == 3) generic_row(fast::ModelOf<3>::make(cin, co, kx, p0, n, true), n, nthreads);
+    else generic_row(fast::ModelOf<4>::make(cin, co, kx, p0, n, true), n, nthreads);
 }
 
 // inverse-DIF followed by forward-DIT must be n * identity; also exposes the raw transforms

@@ -97,6 +97,31 @@ def test_fast_register_fft_nl_matches_numpy(hc, n):
     assert rel(out, ref) < 1e-14 * np.log2(n)
 
 
+@pytest.mark.parametrize("n", [64, 256, 1024, 4096])
+def test_nl_cubic_and_sine_gordon_match_numpy(hc, n):
+    """models 3 (Allen-Cahn cubic, rfft) and 4 (sine-Gordon, first-order complex form): generic and fast paths."""
+    p = problems.allen_cahn_1d(n)
+    uf = p.u0.copy()
+    uf[-1] += 0.2j
+    ref = p.nl_func(uf)
+    out = np.empty_like(uf)
+    hc.hc_nl(3, n, ptr(uf), None, ctypes.c_double(-1.0), ptr(out), 32)
+    assert rel(out, ref) < 2e-14 * np.log2(n)
+    if n >= 512:
+        assert hc.hc_nl_fast(3, n, ptr(uf), None, ctypes.c_double(-1.0), ptr(out)) == 0
+        assert rel(out, ref) < 2e-14 * np.log2(n)
+    p = problems.sine_gordon(n)
+    rng = np.random.default_rng(n)
+    pf = p.u0 + 0.01 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    ref = p.nl_func(pf)
+    out = np.empty_like(pf)
+    hc.hc_nl(4, n, ptr(pf), ptr(p.kx), ctypes.c_double(0.0), ptr(out), 32)
+    assert rel(out, ref) < 2e-14 * np.log2(n)
+    if n >= 512:
+        assert hc.hc_nl_fast(4, n, ptr(pf), ptr(p.kx), ctypes.c_double(0.0), ptr(out)) == 0
+        assert rel(out, ref) < 2e-14 * np.log2(n)
+
+
 def device_coeffs(hc, method, lin, h, cfg=Config()):
     lin = np.ascontiguousarray(lin)
     n = lin.shape[0]

@@ -42,6 +42,10 @@ def rel(a, b):
 
 def fused_for(rk, prob):
     kx = dev(prob.kx)
+    if prob.model == "cubic":
+        return rk.models.FusedNL(3, prob.n, None, prob.params["c"], "allen_cahn")
+    if prob.model == "sine_gordon":
+        return rk.models.FusedNL(4, prob.n, kx, 0.0, "sine_gordon")
     if prob.model == "nls":
         return rk.models.FusedNL(2, prob.n, kx, prob.params["gamma"], "nls")
     return rk.models.FusedNL(1, prob.n, kx, prob.params["c"], prob.model)
@@ -339,3 +343,48 @@ def test_batched_2d_grid_shares_one_dt(rk):
     uo = ora.evolve(u0.ravel(), 0.0, 0.5)
     assert [r[2] for r in sol.trial_log] == [r.accepted for r in ora.log]
     assert rel(host(uf).ravel(), uo) < FINAL_TOL
+
+
+# --------------------------------------------------------------------------------------------
+# fused Allen-Cahn (cubic) and sine-Gordon models: oracle = the reference's solver
+# logic driven by a NumPy nl_func of the same model
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [64, 512, 2048])
+@pytest.mark.parametrize("name", ["allen_cahn_1d", "sine_gordon"])
+def test_fused_new_models_match_numpy(rk, name, n):
+    p = getattr(problems, name)(n, batch=5)
+    sol = rk.ETD4(dev(p.lin_op), fused_for(rk, p))
+    u = dev(p.u0)
+    eng = sol._get_engine(u)
+    eng.set_u(u)
+    eng.nl(1)
+    assert rel(host(eng.state_view("N1")), p.nl_func(p.u0)) < 2e-14 * np.log2(n)
+    f = fused_for(rk, p)
+    assert rel(host(f(u)), p.nl_func(p.u0)) < 1e-13          # the torch.fft restatement of the same model
+
+
+@pytest.mark.parametrize("path", ["fused", "callable"])
+@pytest.mark.parametrize("name,method,tf,eps", [("allen_cahn_1d", "IF45DP", 0.5, 1e-4), ("allen_cahn_1d", "ETD35", 3.0, 1e-5),
+                                                ("sine_gordon", "ETD35", 2.0, 1e-6), ("sine_gordon", "IF34", 2.0, 1e-5)])
+def test_new_models_adaptive_parity(rk, name, method, tf, eps, path):
+    p = getattr(problems, name)(512, batch=3)
+    nl = fused_for(rk, p) if path == "fused" else torch_callable(rk, p)
+    sol = make(rk, method, p, nl, eps)
+    uf = sol.evolve(dev(p.u0), 0.0, tf, store_freq=4)
+    ora = OracleSolver(method, p.lin_op, p.nl_func, Config(epsilon=eps))
+    uo = ora.evolve(p.u0, 0.0, tf, store_freq=4)
+    assert [r[2] for r in sol.trial_log] == [r.accepted for r in ora.log]
+    np.testing.assert_allclose([r[0] for r in sol.trial_log], [r.h for r in ora.log], rtol=DT_TOL)
+    np.testing.assert_allclose(sol.t, ora.t, rtol=DT_TOL)
+    assert rel(host(uf), uo) < FINAL_TOL
+
+
+def test_sine_gordon_breather_returns_after_one_period(rk):
+    """physics check of the first-order restatement: a breather of frequency w is 2 pi / w periodic."""
+    n, w = 1024, 0.5
+    p = problems.sine_gordon(n)
+    lin, nl = rk.models.sine_gordon_ops(dev(np.sqrt(p.kx ** 2 - 1.0) * np.sign(np.fft.fftfreq(n))))
+    np.testing.assert_allclose(host(lin), p.lin_op, rtol=1e-13)
+    sol = rk.ETD35(lin, nl, config=rk.SolverConfig(epsilon=1e-8))
+    uf = sol.evolve(dev(p.u0), 0.0, 2 * np.pi / w, store_data=False)
+    assert rel(host(uf), p.u0) < 1e-5
