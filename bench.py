@@ -218,6 +218,43 @@ def _workload_config(workload, gpus):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+def parity_sample(torch, rk, workload, method, device):
+    """Same small sample through the oracle and through the engine: relative state error after a few steps and,
+    for adaptive methods, whether the accept/reject sequence and the dt sequence (1e-9) agree."""
+    import numpy as np
+    from oracle import problems
+    from oracle.rk_oracle import Config, OracleSolver
+    rows = 4
+    if workload == "cfg2":
+        p = problems.nls(N_NLS, batch=rows, seed=11)
+        lin, nl = rk.models.nls_ops(torch.from_numpy(p.kx).to(device), 2.0)
+        eps, tf, h = 1e-6, 0.1, 0.002
+    else:
+        p = problems.ks(N_KS, batch=rows, seed=11)
+        lin, nl = rk.models.ks_ops(torch.from_numpy(p.kx).to(device))
+        eps, tf, h = 1e-4, 1.0, 0.05
+    u0 = torch.from_numpy(p.u0).to(device)
+    ora = OracleSolver(method, p.lin_op, p.nl_func, Config(epsilon=eps))
+    if method in ADAPTIVE:
+        if method == "IF45DP":
+            tf *= 0.05
+        sol = getattr(rk, method)(lin, nl, config=rk.SolverConfig(epsilon=eps))
+        uf = sol.evolve(u0, 0.0, tf, store_data=False).cpu().numpy()
+        uo = ora.evolve(p.u0, 0.0, tf, store_data=False)
+        hs, acc = [r[0] for r in sol.trial_log], [r[2] for r in sol.trial_log]
+        same = acc == [r.accepted for r in ora.log] and bool(np.allclose(hs, [r.h for r in ora.log], rtol=1e-9, atol=0))
+        return {"rel_err_final": float(np.linalg.norm(uf - uo) / np.linalg.norm(uo)), "trials": len(hs),
+                "dt_sequence_matches_oracle": same}
+    sol = getattr(rk, method)(lin, nl)
+    worst, u = 0.0, u0
+    for _ in range(5):
+        ref = OracleSolver(method, p.lin_op, p.nl_func).step(u.cpu().numpy(), h)
+        sol.reset()
+        u = sol.step(u, h)
+        worst = max(worst, float(np.linalg.norm(u.cpu().numpy() - ref) / np.linalg.norm(ref)))
+    return {"rel_err_per_step_max": worst, "steps": 5}
+
+
 def time_kernel(torch, fn, reps):
     fn()
     torch.cuda.synchronize()
@@ -497,14 +534,15 @@ def run_ours(args):
                    "final state copied back, per call",
            "steps_per_call": steps_e2e / reps_e2e, "h2d_bytes_per_call": state_bytes, "d2h_bytes_per_call": state_bytes}
 
-    # ---- CPU baseline on rank 0, N = 1 only ---------------------------------------------------
+    # ---- CPU baseline on rank 0, N = 1 only (the oracle also serves as the checker of a small sample) --
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rows, cs, cw = (16, 6, 1) if args.workload == "cfg2" else (256, 40, 2)
         v, wall = cpu_baseline(args.workload, 1, cs, cw, rows, method)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"oracle (NumPy port of the reference path), 1 process, {rows} trajectories x {cs} steps, "
-                         f"{wall:.1f} s"}
+                         f"{wall:.1f} s",
+               "parity": parity_sample(torch, rk, args.workload, method, device)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
