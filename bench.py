@@ -537,7 +537,8 @@ def run_ours(args):
     # ---- CPU baseline on rank 0, N = 1 only (the oracle also serves as the checker of a small sample) --
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rows, cs, cw = (16, 6, 1) if args.workload == "cfg2" else (256, 40, 2)
+        # ~10-20 s of single-core NumPy work (cfg 2 at B=64, cfg 3 at B=1024)
+        rows, cs, cw = (64, 24, 1) if args.workload == "cfg2" else (1024, 60, 2)
         v, wall = cpu_baseline(args.workload, 1, cs, cw, rows, method)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"oracle (NumPy port of the reference path), 1 process, {rows} trajectories x {cs} steps, "
