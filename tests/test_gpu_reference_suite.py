@@ -1,0 +1,119 @@
+"""The reference's own accuracy tests, run through the B200 classes:
+  * KdV soliton against the exact solution, evolve() and step() (tests/testing_util.py:42-124) with the
+    reference's tolerances (test_etd4.py:12,19; test_etd5.py:14,21; test_if4.py:28,35; test_if34.py:141,148;
+    test_etd34.py:32,40; test_etd35.py:27,33);
+  * Burgers norm invariant (test_if34.py:15-21, test_if45dp.py:10-16);
+  * convergence order by log-log least squares (test_order_convergence.py:221-295);
+  * structural checks: snapshot cadence, h caching, tf < t0, explosive nonlinearity."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rk():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import rkstiff_b200
+    return rkstiff_b200
+
+
+def kdv_setup(rk):
+    x, kx = rk.grids.construct_x_kx_rfft(256, -30.0, 30.0)
+    h, steps = 0.025, 200
+    u0 = torch.fft.rfft(rk.models.kdv_soliton(x, ampl=1.0, x0=-5.0, t=0.0))
+    exact = torch.fft.rfft(rk.models.kdv_soliton(x, ampl=1.0, x0=-5.0, t=h * steps))
+    lin, nl = rk.models.kdv_ops(kx)
+    return u0, lin, nl, exact, h, steps
+
+
+def relerr(a, b):
+    return float(torch.linalg.norm(a - b) / torch.linalg.norm(b))
+
+
+FIXED_TOL = {"ETD4": 1e-6, "ETD5": 1e-6, "IF4": 1e-5}
+ADAPT = {"IF34": 1e-5, "ETD34": 1e-4, "ETD35": 1e-4}      # epsilon used by the reference tests; bound 1e-4
+
+
+@pytest.mark.parametrize("method", list(FIXED_TOL))
+def test_kdv_soliton_fixed_step_evolve_and_step(rk, method):
+    u0, lin, nl, exact, h, steps = kdv_setup(rk)
+    sol = getattr(rk, method)(lin, nl)
+    assert relerr(sol.evolve(u0, 0.0, h * steps, h, store_data=False), exact) < FIXED_TOL[method]
+    sol = getattr(rk, method)(lin, nl)
+    u = u0.clone()
+    for _ in range(steps):
+        u = sol.step(u, h)
+    assert relerr(u, exact) < FIXED_TOL[method]
+
+
+@pytest.mark.parametrize("method", list(ADAPT))
+def test_kdv_soliton_adaptive_evolve_and_step(rk, method):
+    u0, lin, nl, exact, h, steps = kdv_setup(rk)
+    sol = getattr(rk, method)(lin, nl, config=rk.SolverConfig(epsilon=ADAPT[method]))
+    assert relerr(sol.evolve(u0, 0.0, h * steps, h_init=h, store_data=False), exact) < 1e-4
+    # step(): with a loose tolerance the controller must not change h (testing_util.py:110-117)
+    sol = getattr(rk, method)(lin, nl, config=rk.SolverConfig(epsilon=0.1))
+    u = u0.clone()
+    for _ in range(steps):
+        u, h_actual, _ = sol.step(u, h)
+        assert abs(h_actual - h) < 1e-10
+    assert relerr(u, exact) < 1e-4
+
+
+@pytest.mark.parametrize("method", ["IF34", "IF45DP", "ETD35"])
+def test_burgers_norm_invariant(rk, method):
+    x, kx = rk.grids.construct_x_kx_rfft(1024, -np.pi, np.pi)
+    lin, nl = rk.models.burgers_ops(kx, 0.0005)
+    u0 = torch.fft.rfft(torch.exp(-10 * torch.sin(x / 2) ** 2))
+    sol = getattr(rk, method)(lin, nl)
+    uf = sol.evolve(u0, 0.0, 0.85, store_data=False)
+    assert abs(float(torch.linalg.norm(uf) / torch.linalg.norm(u0)) - 1.0) < 1e-2
+
+
+@pytest.mark.parametrize("method,expected", [("ETD4", 4), ("IF4", 4), ("ETD5", 5)])
+def test_convergence_order_on_kdv(rk, method, expected):
+    u0, lin, nl, _, _, _ = kdv_setup(rk)
+    hs = [0.05, 0.025, 0.0125] if expected == 4 else [0.1, 0.05, 0.025]
+    tf = 1.0
+
+    def run(h):
+        # fixed number of step() calls like the reference's order tests (evolve() counts steps by float
+        # accumulation and may take one more, solvercs.py:258-261)
+        sol = getattr(rk, method)(lin, nl)
+        u = u0.clone()
+        for _ in range(int(round(tf / h))):
+            u = sol.step(u, h)
+        return u
+
+    ref = run(hs[-1] / 4)
+    errs = [relerr(run(h), ref) for h in hs]
+    order = np.polyfit(np.log(hs), np.log(errs), 1)[0]
+    assert order > expected - 0.5, (order, errs)
+
+
+def test_snapshot_cadence_and_reset(rk):
+    u0, lin, nl, _, h, _ = kdv_setup(rk)
+    sol = rk.ETD4(lin, nl)
+    sol.evolve(u0, 0.0, 10 * h, h, store_data=True, store_freq=2)
+    assert len(sol.t) == len(sol.u) == 6 and sol.t[0] == 0.0
+    assert sol.u[0] is u0                                  # the reference stores the caller's array
+    sol.reset()
+    assert sol.t == [] and sol.u == []
+    sol.evolve(u0, 0.0, 10 * h, h, store_data=False)
+    assert sol.t == []
+
+
+def test_step_size_cache_key_and_live_config(rk):
+    u0, lin, nl, _, h, _ = kdv_setup(rk)
+    sol = rk.ETD35(lin, nl, config=rk.SolverConfig(epsilon=1e-3))
+    sol.evolve(u0, 0.0, 0.5, store_data=False)
+    updates_loose = sol._engine.read_ctrl().coeff_updates
+    trials_loose = len(sol.trial_log)
+    assert 0 < updates_loose <= trials_loose              # coefficients rebuilt only when h changes (etd35.py:851)
+    sol.config.epsilon = 1e-7                              # config is read live (solveras.py:452-454)
+    sol.evolve(u0, 0.0, 0.5, store_data=False)
+    assert len(sol.trial_log) > trials_loose

@@ -1,0 +1,97 @@
+"""Host-side API checks that mirror the reference's own unit tests (no GPU needed):
+SolverConfig / ETDConfig validation (tests/test_solveras.py:43-85, tests/test_etd.py:68-104),
+SolverType (tests/test_solver_type.py), logger naming (tests/test_loghelper.py), module surface."""
+import logging
+
+import pytest
+
+import rkstiff_b200 as rk
+from rkstiff_b200.etd import ETDConfig
+from rkstiff_b200.solveras import BaseSolverAS, SolverConfig
+from rkstiff_b200.util.loghelper import get_solver_logger, set_log_level
+from rkstiff_b200.util.solver_type import SolverType
+
+
+def test_solverconfig_valid_defaults():
+    cfg = SolverConfig()
+    assert (cfg.epsilon, cfg.incr_f, cfg.decr_f, cfg.safety_f, cfg.adapt_cutoff, cfg.minh) == \
+        (1e-4, 1.25, 0.85, 0.8, 0.01, 1e-16)
+
+
+@pytest.mark.parametrize("kw", [dict(epsilon=0.0), dict(epsilon=-1e-3), dict(incr_f=1.0), dict(incr_f=0.5),
+                                dict(decr_f=1.0), dict(decr_f=2.0), dict(safety_f=1.01), dict(adapt_cutoff=1.0),
+                                dict(minh=0), dict(minh=-1e-5)])
+def test_solverconfig_rejects_out_of_range(kw):
+    with pytest.raises(ValueError):
+        SolverConfig(**kw)
+
+
+def test_solverconfig_setters_validate_and_fresh_default_per_solver():
+    cfg = SolverConfig()
+    cfg.epsilon = 1e-6
+    assert cfg.epsilon == 1e-6
+    with pytest.raises(ValueError):
+        cfg.decr_f = 1.5
+    assert SolverConfig().epsilon == 1e-4          # no shared mutable default (SURVEY.md 4 hazard)
+
+
+def test_etdconfig_validation():
+    assert ETDConfig(modecutoff=0.5).modecutoff == 0.5
+    assert ETDConfig(contour_points=8).contour_points == 8
+    assert ETDConfig(contour_radius=2.5).contour_radius == 2.5
+    for bad in (dict(modecutoff=1.5), dict(modecutoff=0.0), dict(contour_points=1), dict(contour_radius=0.0),
+                dict(contour_radius=-1.0)):
+        with pytest.raises(ValueError):
+            ETDConfig(**bad)
+    with pytest.raises(TypeError):
+        ETDConfig(contour_points=3.14)
+
+
+def test_solver_type_enum():
+    assert SolverType.CS is SolverType.CONSTANT_STEP and SolverType.AS is SolverType.ADAPTIVE_STEP
+    assert str(SolverType.ADAPTIVE_STEP) == "Adaptive Step"
+    with pytest.raises(TypeError):
+        SolverType.from_solver(object())
+
+
+def test_logger_names_and_levels():
+    lg = get_solver_logger(rk.ETD35, "INFO")
+    assert lg.name == "rkstiff.ETD35" and lg.level == logging.INFO
+    set_log_level(lg, "debug")
+    assert lg.level == logging.DEBUG
+    with pytest.raises(ValueError):
+        set_log_level(lg, "NOT_A_LEVEL")
+
+
+def test_controller_limits_and_exceptions_exposed():
+    assert (BaseSolverAS.MAX_LOOPS, BaseSolverAS.MAX_S, BaseSolverAS.MIN_S) == (50, 4.0, 0.25)
+    assert issubclass(BaseSolverAS.MaxLoopsExceeded, BaseSolverAS.SolverError)
+    assert issubclass(BaseSolverAS.MinimumStepReached, BaseSolverAS.SolverError)
+    assert issubclass(BaseSolverAS.SolverError, RuntimeError)
+
+
+def test_module_surface_matches_reference_imports():
+    """import paths the reference's demos and tests use."""
+    from rkstiff_b200.etd import SolverConfig as a  # noqa: F401
+    from rkstiff_b200.etd34 import ETD34, ETDConfig as b, SolverConfig as c  # noqa: F401
+    from rkstiff_b200.etd35 import ETD35, ETDConfig as d, SolverConfig as e  # noqa: F401
+    from rkstiff_b200.etd4 import ETD4  # noqa: F401
+    from rkstiff_b200.etd5 import ETD5  # noqa: F401
+    from rkstiff_b200.if4 import IF4  # noqa: F401
+    from rkstiff_b200.if34 import IF34  # noqa: F401
+    from rkstiff_b200.if45dp import IF45DP  # noqa: F401
+    from rkstiff_b200 import grids, models  # noqa: F401
+    for cls in (rk.IF34, rk.ETD34, rk.ETD35, rk.IF45DP):
+        assert issubclass(cls, BaseSolverAS)
+
+
+def test_matrix_operators_are_rejected_not_emulated():
+    torch = pytest.importorskip("torch")
+    if torch.cuda.is_available():
+        lin = torch.zeros(8, dtype=torch.float64, device="cuda")
+        with pytest.raises(NotImplementedError):
+            rk.ETD35(lin, lambda v: v, diagonalize=True)
+        with pytest.raises(NotImplementedError):
+            rk.IF34(lin, lambda v: v, diagonalize=True)
+    with pytest.raises(TypeError):
+        rk.ETD4([1.0, 2.0], lambda v: v)
