@@ -38,6 +38,11 @@ class BaseSolver(ABC):
         self.logger = get_solver_logger(self.__class__, loglevel)
         self.logger.info("Initialized %s solver", self.__class__.__name__)
         self.t, self.u = [], []
+        #: where evolve() keeps the snapshots of solver.u: "cuda" (device clones) or "cpu" (pinned host
+        #: tensors filled by asynchronous device-to-host copies on a side stream, so that storing multi-GB
+        #: states neither stalls the stepping stream nor fills HBM; call solver.sync_snapshots() before use)
+        self.snapshot_device = "cuda"
+        self._snap_stream = None
         self._diag = True
         self._group = group
         self._engines: Dict[tuple, Engine] = {}
@@ -82,6 +87,29 @@ class BaseSolver(ABC):
     def _config_signature(self):
         c = self._rks_config()
         return tuple(getattr(c, f) for f, _ in c._fields_)
+
+    # -- snapshot pipeline -----------------------------------------------------------------
+    def _store_snapshot(self, t: float, u_dev: torch.Tensor) -> None:
+        """Append (t, u) to solver.t / solver.u; u_dev is a device tensor the caller will not modify."""
+        self.t.append(t)
+        if self.snapshot_device == "cuda":
+            self.u.append(u_dev)
+            return
+        if self.snapshot_device != "cpu":
+            raise ValueError("snapshot_device must be 'cuda' or 'cpu'")
+        if self._snap_stream is None:
+            self._snap_stream = torch.cuda.Stream(device=u_dev.device)
+        host = torch.empty(u_dev.shape, dtype=u_dev.dtype, pin_memory=True)
+        self._snap_stream.wait_stream(torch.cuda.current_stream(u_dev.device))
+        with torch.cuda.stream(self._snap_stream):
+            host.copy_(u_dev, non_blocking=True)
+        u_dev.record_stream(self._snap_stream)            # keep the device clone alive until the copy ran
+        self.u.append(host)
+
+    def sync_snapshots(self) -> None:
+        """Wait for outstanding snapshot copies (snapshot_device == "cpu")."""
+        if self._snap_stream is not None:
+            self._snap_stream.synchronize()
 
     # -- reference API ---------------------------------------------------------------------
     @property

@@ -244,8 +244,7 @@ class BaseSolverAS(BaseSolver):
                 times = ring_t.cpu()
                 cap = ring.shape[0]
                 for i in range(snaps, c.snap_count):
-                    self.t.append(float(times[i % cap]))
-                    self.u.append(ring[i % cap].clone())
+                    self._store_snapshot(float(times[i % cap]), ring[i % cap].clone())
                     self.logger.debug("Stored solution at t=%.6f", self.t[-1])
                 snaps = c.snap_count
             if c.status != _abi.CTRL_RUNNING:
@@ -253,6 +252,7 @@ class BaseSolverAS(BaseSolver):
         self._raise_on_failure(c.status)
         self._accept = bool(c.accept)
         self._h_coeff = c.h_coeff
+        self.sync_snapshots()
         self.logger.info("Evolution complete after %d steps", c.step_count)
         self.logger.info("Stored %d solution snapshots", len(self.u))
         return eng.get_u()

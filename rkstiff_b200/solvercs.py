@@ -92,11 +92,11 @@ class BaseSolverCS(BaseSolver):
                 if pending:
                     eng.run_fixed(pending)
                     pending = 0
-                self.t.append(tc)
-                self.u.append(eng.get_u())           # clone: plan buffers are reused
+                self._store_snapshot(tc, eng.get_u())     # clone: plan buffers are reused
                 self.logger.debug("Stored snapshot at t=%.6f (step %d)", tc, step_count)
         if pending:
             eng.run_fixed(pending)
+        self.sync_snapshots()
         self.logger.info("Evolution complete after %d steps", step_count)
         self.logger.info("Stored %d snapshots", len(self.u))
         out = eng.get_u()

@@ -388,3 +388,20 @@ def test_sine_gordon_breather_returns_after_one_period(rk):
     sol = rk.ETD35(lin, nl, config=rk.SolverConfig(epsilon=1e-8))
     uf = sol.evolve(dev(p.u0), 0.0, 2 * np.pi / w, store_data=False)
     assert rel(host(uf), p.u0) < 1e-5
+
+
+def test_cfg2b_independent_dt_matches_per_trajectory_reference_runs(rk):
+    """cfg 2b: every trajectory keeps its own dt sequence == B separate reference runs (subset of 8)."""
+    from rkstiff_b200.ensemble import evolve_independent
+    p = problems.nls(512, batch=8, seed=2, half_width=20.0)
+    lin, nl = rk.models.nls_ops(dev(p.kx), 2.0)
+    uf, logs = evolve_independent(lambda: rk.ETD35(lin, nl, config=rk.SolverConfig(epsilon=1e-6)), dev(p.u0), 0.0, 0.2)
+    lengths = set()
+    for b in range(8):
+        ora = OracleSolver("ETD35", p.lin_op, p.nl_func, Config(epsilon=1e-6))
+        uo = ora.evolve(p.u0[b], 0.0, 0.2)
+        assert [r[2] for r in logs[b]] == [r.accepted for r in ora.log]
+        np.testing.assert_allclose([r[0] for r in logs[b]], [r.h for r in ora.log], rtol=DT_TOL)
+        assert rel(host(uf[b]), uo) < FINAL_TOL
+        lengths.add(tuple(round(r.h, 12) for r in ora.log))
+    assert len(lengths) > 1                     # the trajectories really take different dt sequences

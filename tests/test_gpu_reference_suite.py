@@ -117,3 +117,17 @@ def test_step_size_cache_key_and_live_config(rk):
     sol.config.epsilon = 1e-7                              # config is read live (solveras.py:452-454)
     sol.evolve(u0, 0.0, 0.5, store_data=False)
     assert len(sol.trial_log) > trials_loose
+
+
+def test_host_snapshot_pipeline_matches_device_snapshots(rk):
+    """snapshot_device="cpu": pinned-host snapshots through an asynchronous side-stream copy."""
+    u0, lin, nl, _, h, _ = kdv_setup(rk)
+    for cls, kw in ((rk.ETD4, dict(h=h)), (rk.ETD35, dict(h_init=h))):
+        dev_sol, host_sol = cls(lin, nl), cls(lin, nl)
+        host_sol.snapshot_device = "cpu"
+        dev_sol.evolve(u0, 0.0, 20 * h, store_freq=3, **kw)
+        host_sol.evolve(u0, 0.0, 20 * h, store_freq=3, **kw)
+        assert host_sol.t == dev_sol.t and len(host_sol.u) == len(dev_sol.u) > 2
+        for a, b in zip(host_sol.u[1:], dev_sol.u[1:]):
+            assert not a.is_cuda and a.is_pinned()
+            assert torch.equal(a, b.cpu())
