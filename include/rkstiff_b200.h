@@ -185,6 +185,11 @@ int rks_run_fixed(rks_plan* plan, int nsteps, void* stream);
  * controller call asked for one (solveras.py:643-645) */
 int rks_snapshot(rks_plan* plan, void* snap_ring, double* snap_t, int snap_cap, void* stream);
 
+/* Pointwise nonlinearity alone, for N-D grids whose transforms are done by a library FFT between
+ * the engine's kernels: RKS_MODEL_NLS_FFT: out = i*p0*|in|^2 in (count complex128);
+ * RKS_MODEL_CUBIC_RFFT: out = p0*in^3 (count float64).  in == out is allowed.  No plan needed. */
+int rks_pointwise(int model, const void* in, void* out, int64_t count, double p0, void* stream);
+
 /* the only syncing calls */
 int rks_read_ctrl(rks_plan* plan, rks_ctrl_host* out, void* stream);
 int rks_read_log(rks_plan* plan, rks_trial_rec* out_host, int first, int count, void* stream);

@@ -162,7 +162,12 @@ class Engine:
         """N_j = nl_func(input_j) for a caller-supplied torch callable (roles from the last read_ctrl)."""
         src = self._view(lib.rks_nl_input(self.plan, j))
         dst = self._view(lib.rks_nl_output(self.plan, j))
-        res = nl_func(src)
+        if getattr(nl_func, "supports_out", False):
+            res = nl_func(src, out=dst)                  # the callable writes N_j itself (no copy pass)
+            if res.data_ptr() == dst.data_ptr():
+                return
+        else:
+            res = nl_func(src)
         if not torch.is_tensor(res):
             raise TypeError("nl_func must return a torch tensor")
         dst.copy_(res.reshape(self.u_shape))

@@ -150,8 +150,9 @@ __global__ void __launch_bounds__(128) coef_kernel(DevPlan p, int force) {
         }
         const bool small = valid && (hypot(z.x, z.y) < c->modecutoff);    // np.abs(z) < modecutoff
         PsiSet ps = psi_zero();
+        const ExpSet ez = exp_set<FIVE>(z);               // exp(z/4), exp(z/2), exp(3z/4), exp(z): one cexp
         if (valid && !small) {
-            psi_accumulate<FIVE>(ps, z);
+            psi_accumulate<FIVE>(ps, z, ez);
             psi_scale(ps, h, 1.0);
         }
         // contour mean for the small modes of this warp (etd35.py:239-269)
@@ -178,17 +179,17 @@ __global__ void __launch_bounds__(128) coef_kernel(DevPlan p, int force) {
         if (!valid) return;
         if (FIVE) {
             cplx arr[e5::COUNT];
-            arr[e5::E14] = cexp(z / 4.0);
-            arr[e5::E12] = cexp(z / 2.0);
-            arr[e5::E34] = cexp((3.0 * z) / 4.0);
-            arr[e5::E] = cexp(z);
+            arr[e5::E14] = ez.q;
+            arr[e5::E12] = ez.h;
+            arr[e5::E34] = ez.t;
+            arr[e5::E] = ez.f;
             tableau_etd5(ps, arr);
 #pragma unroll
             for (int s = 0; s < e5::COUNT; ++s) stg(out + s * stride + i, arr[s]);
         } else {
             cplx arr[kro::COUNT];
-            arr[kro::E] = cexp(z);
-            arr[kro::E2] = cexp(z / 2.0);
+            arr[kro::E] = ez.f;
+            arr[kro::E2] = ez.h;
             tableau_krogstad(ps, arr);
 #pragma unroll
             for (int s = 0; s < kro::COUNT; ++s) stg(out + s * stride + i, arr[s]);
@@ -672,6 +673,27 @@ __global__ void controller_kernel(DevPlan p) {
     Ctrl local = *c;
     controller_advance(local, p.log);
     *c = local;
+}
+
+// pointwise nonlinearity of the N-D models, applied between two library transforms (one read + one
+// write instead of the half-dozen elementwise passes a torch expression costs)
+__global__ void __launch_bounds__(256) pointwise_nls_kernel(const cplx* in, cplx* out, long long count, double gamma) {
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < count; e += (long long)gridDim.x * 256) {
+        const cplx f = ldcs(in + e);
+        const double f2 = f.x * f.x + f.y * f.y;
+        stg(out + e, mk(-(gamma * (f2 * f.y)), gamma * (f2 * f.x)));          // i gamma |f|^2 f
+    }
+}
+__global__ void __launch_bounds__(256) pointwise_cubic_kernel(const double* in, double* out, long long count, double c) {
+    const long long pairs = count >> 1;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < pairs; e += (long long)gridDim.x * 256) {
+        const double2 u = __ldcs(reinterpret_cast<const double2*>(in) + e);
+        reinterpret_cast<double2*>(out)[e] = make_double2(c * (u.x * u.x * u.x), c * (u.y * u.y * u.y));
+    }
+    if ((count & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const double u = in[count - 1];
+        out[count - 1] = c * (u * u * u);
+    }
 }
 
 // snapshot of the accepted state into the ring (solveras.py:643-645)

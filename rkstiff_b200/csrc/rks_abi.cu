@@ -715,6 +715,25 @@ extern "C" int rks_read_log(rks_plan* p, rks_trial_rec* out, int first, int coun
 }
 
 // ---------------------------------------------------------------------------------------
+// pointwise nonlinearities for N-D models whose transforms are done by a library FFT
+// ---------------------------------------------------------------------------------------
+extern "C" int rks_pointwise(int model, const void* in, void* out, int64_t count, double p0, void* stream_v) {
+    if (!in || !out || count <= 0) return fail(RKS_ERR_ARG, "bad pointwise arguments");
+    if (((uintptr_t)in | (uintptr_t)out) & 15) return fail(RKS_ERR_ARG, "pointwise arrays must be 16-byte aligned");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long blocks = (count + 255) / 256;
+    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+    if (model == RKS_MODEL_NLS_FFT) pointwise_nls_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const cplx*)in, (cplx*)out, count, p0);
+    else if (model == RKS_MODEL_CUBIC_RFFT) pointwise_cubic_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const double*)in, (double*)out, count, p0);
+    else return fail(RKS_ERR_UNSUPPORTED, "no pointwise kernel for this model");
+    CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // introspection
 // ---------------------------------------------------------------------------------------
 static int coef_slot(int m, const std::string& s) {

@@ -121,6 +121,17 @@ def kdv_multi_soliton(x: torch.Tensor, ampl: Sequence[float], x0: Sequence[float
 # nonlinear term is a torch callable here (library FFT for the N-D transform; K1/K2/K3 are the
 # engine's kernels) -- the hand-written fused kernels cover the 1-D models above.
 # ----------------------------------------------------------------------------------------------
+def pointwise_(model_id: int, x: torch.Tensor, p0: float) -> torch.Tensor:
+    """In-place pointwise nonlinearity of an N-D model in one CUDA kernel (rks_pointwise):
+    MODEL_NLS_FFT: x <- i p0 |x|^2 x (complex128);  MODEL_CUBIC_RFFT: x <- p0 x^3 (float64)."""
+    from ctypes import c_void_p
+    if not x.is_contiguous():
+        raise ValueError("pointwise_ needs a contiguous tensor")
+    st = c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    _abi.check(_abi.lib.rks_pointwise(model_id, c_void_p(x.data_ptr()), c_void_p(x.data_ptr()), x.numel(), float(p0), st))
+    return x
+
+
 def allen_cahn_fourier_ops(n: int, eps: float = 0.01, length: float = 2 * 3.141592653589793, device="cuda"):
     """Periodic 2-D Allen-Cahn u_t = eps lap(u) + u - u^3 on an n x n grid, rfft2 half spectrum:
     L = 1 - eps |k|^2 (float64, shape (n, n/2+1)), N(u^) = -rfft2(irfft2(u^)^3).  The +u goes into L,
@@ -130,10 +141,11 @@ def allen_cahn_fourier_ops(n: int, eps: float = 0.01, length: float = 2 * 3.1415
     kx = 2 * 3.141592653589793 * torch.fft.rfftfreq(n, d=d, dtype=torch.float64, device=device)
     lin_op = 1.0 - eps * (kx[None, :] ** 2 + ky[:, None] ** 2)
 
-    def nl_func(uf: torch.Tensor) -> torch.Tensor:
-        u = torch.fft.irfft2(uf, s=(n, n))
-        return -torch.fft.rfft2(u * u * u)
+    def nl_func(uf: torch.Tensor, out=None) -> torch.Tensor:
+        u = torch.fft.irfft2(uf, s=(n, n)).contiguous()
+        return torch.fft.rfft2(pointwise_(_abi.MODEL_CUBIC_RFFT, u, -1.0), out=out)      # -(u^3), one kernel
 
+    nl_func.supports_out = True          # the engine lets the transform write N_j in place (no copy pass)
     return lin_op, nl_func
 
 
@@ -149,9 +161,9 @@ def nls_nd_ops(k_axes: Sequence[torch.Tensor], gamma: float = 2.0):
     lin_op = -1j * k2.to(torch.complex128)
     dims = tuple(range(-nd, 0))
 
-    def nl_func(uf: torch.Tensor) -> torch.Tensor:
-        f = torch.fft.ifftn(uf, dim=dims)
-        f2 = f.real ** 2 + f.imag ** 2
-        return 1j * gamma * torch.fft.fftn(f2 * f, dim=dims)
+    def nl_func(uf: torch.Tensor, out=None) -> torch.Tensor:
+        f = torch.fft.ifftn(uf, dim=dims).contiguous()
+        return torch.fft.fftn(pointwise_(_abi.MODEL_NLS_FFT, f, gamma), dim=dims, out=out)   # F{i gamma |f|^2 f}
 
+    nl_func.supports_out = True
     return lin_op, nl_func

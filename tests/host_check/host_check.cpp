@@ -155,13 +155,14 @@ int hc_coeffs(int method, int n, const double* lin, int lin_complex, double h, d
             }
             if (five) {
                 cplx arr[e5::COUNT];
-                arr[e5::E14] = cexp(z / 4.0); arr[e5::E12] = cexp(z / 2.0);
-                arr[e5::E34] = cexp((3.0 * z) / 4.0); arr[e5::E] = cexp(z);
+                const ExpSet ez = exp_set<true>(z);
+                arr[e5::E14] = ez.q; arr[e5::E12] = ez.h; arr[e5::E34] = ez.t; arr[e5::E] = ez.f;
                 tableau_etd5(ps, arr);
                 for (int s = 0; s < nc; ++s) o[s * n + i] = arr[s];
             } else {
                 cplx arr[kro::COUNT];
-                arr[kro::E] = cexp(z); arr[kro::E2] = cexp(z / 2.0);
+                const ExpSet ez = exp_set<false>(z);
+                arr[kro::E] = ez.f; arr[kro::E2] = ez.h;
                 tableau_krogstad(ps, arr);
                 for (int s = 0; s < nc; ++s) o[s * n + i] = arr[s];
             }

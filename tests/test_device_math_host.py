@@ -146,8 +146,8 @@ def test_coefficients_match_oracle(hc, prob, h, method):
         # cancellation band just above modecutoff: the reference itself carries ~1e-9 relative
         # rounding noise there; elsewhere the two agree to rounding
         band = (z >= 0.01) & (z < 0.5)
-        np.testing.assert_allclose(arr[~band], r[~band], rtol=2e-13, atol=4e-16 * h, err_msg=f"{method}.{name}")
-        np.testing.assert_allclose(arr[band], r[band], rtol=5e-8, atol=4e-16 * h, err_msg=f"{method}.{name} band")
+        np.testing.assert_allclose(arr[~band], r[~band], rtol=2e-13, atol=1e-15 * h, err_msg=f"{method}.{name}")
+        np.testing.assert_allclose(arr[band], r[band], rtol=5e-8, atol=1e-15 * h, err_msg=f"{method}.{name} band")
 
 
 def test_if45dp_r4_quirk_and_fix(hc):
