@@ -190,6 +190,14 @@ int rks_snapshot(rks_plan* plan, void* snap_ring, double* snap_t, int snap_cap, 
  * RKS_MODEL_CUBIC_RFFT: out = p0*in^3 (count float64).  in == out is allowed.  No plan needed. */
 int rks_pointwise(int model, const void* in, void* out, int64_t count, double p0, void* stream);
 
+/* Standalone fused row transform: out_row = F{ N( F^-1{ in_row } ) } along the contiguous axis of any
+ * (batch, n_c) complex128 array -- the innermost-axis part of an N-D nonlinear term (the caller
+ * transforms the outer axes).  Same kernels as rks_nl; no stepping plan.  in == out is allowed. */
+typedef struct rks_rows rks_rows;
+int rks_rows_create(rks_rows** out, int model, int64_t n, const double* kx, double p0, void* stream);
+int rks_rows_apply(rks_rows* rows, const void* in, void* out, int64_t batch, void* stream);
+void rks_rows_destroy(rks_rows* rows);
+
 /* the only syncing calls */
 int rks_read_ctrl(rks_plan* plan, rks_ctrl_host* out, void* stream);
 int rks_read_log(rks_plan* plan, rks_trial_rec* out_host, int first, int count, void* stream);

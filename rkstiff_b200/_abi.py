@@ -79,6 +79,9 @@ def _load():
         "rks_run_fixed": (c_int, [P, c_int, P]),
         "rks_snapshot": (c_int, [P, P, P, c_int, P]),
         "rks_pointwise": (c_int, [c_int, P, P, c_int64, c_double, P]),
+        "rks_rows_create": (c_int, [POINTER(P), c_int, c_int64, P, c_double, P]),
+        "rks_rows_apply": (c_int, [P, P, P, c_int64, P]),
+        "rks_rows_destroy": (None, [P]),
         "rks_read_ctrl": (c_int, [P, POINTER(RksCtrl), P]),
         "rks_read_log": (c_int, [P, POINTER(RksTrialRec), c_int, c_int, P]),
         "rks_array": (P, [P, c_char_p]),

@@ -306,6 +306,10 @@ struct NlRoles {
 RKS_D NlRoles nl_roles(const DevPlan& p, int j, int force) {
     const Ctrl* c = p.ctrl;
     NlRoles r;
+    if (c == nullptr) {                                  // standalone row transform (rks_rows_apply)
+        r.in = p.U[0]; r.out = p.NL[1]; r.run = true;
+        return r;
+    }
     const int m = p.method;
     const bool adapt = method_adaptive(m);
     const int S = method_stages(m);
@@ -325,7 +329,7 @@ __global__ void __launch_bounds__(1024) nl_kernel(DevPlan p, int j, int force, i
     cplx* smem = reinterpret_cast<cplx*>(smem_raw);
     const NlRoles roles = nl_roles(p, j, force);
     if (!roles.run) return;
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&p.ctrl->nl_evals, 1ull);
+    if (p.ctrl && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&p.ctrl->nl_evals, 1ull);
 
     const int n = (int)p.n;
     const int log2n = p.log2n;
@@ -466,7 +470,7 @@ nl_fast_kernel(DevPlan p, int j, int force, FuseDesc fd) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const NlRoles roles = nl_roles(p, j, force);
     if (!roles.run) return;
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&p.ctrl->nl_evals, 1ull);
+    if (p.ctrl && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&p.ctrl->nl_evals, 1ull);
 
     const int lrow = threadIdx.x / TR, T = threadIdx.x - lrow * TR;
     cplx* sm = reinterpret_cast<cplx*>(smem_raw) + (size_t)lrow * N;

@@ -270,6 +270,38 @@ extern "C" int rks_set_config(rks_plan* p, const rks_config* cfg, void* stream) 
     return RKS_OK;
 }
 
+static int prepare_nl_launch(rks_plan* p, int model, long long n, cplx* twf_dev, cudaStream_t stream) {
+    DevPlan& d = p->d;
+    p->nl_fast = (n >= 512 && n <= 8192) && !getenv("RKS_NL_GENERIC");
+    p->no_fuse = getenv("RKS_FUSE") == nullptr;       // fused K1+K4 is opt-in (RKS_FUSE=1): see DESIGN.md 4
+    if (p->nl_fast) {
+        cudaError_t e = n == 512 ? prepare_nl_fast<1>(model) : n == 1024 ? prepare_nl_fast<2>(model)
+                      : n == 2048 ? prepare_nl_fast<4>(model) : n == 4096 ? prepare_nl_fast<8>(model)
+                      : prepare_nl_fast<16>(model);
+        CUDA_TRY(e);
+        fast_twiddle_kernel<<<(2 * fast::TW_TOTAL + 255) / 256, 256, 0, stream>>>(twf_dev, (int)n);
+        p->launches += 1;
+    }
+    // launch shape of the generic NL kernel: one row per CTA for long rows, several for short ones
+    const size_t row_bytes = (size_t)n * sizeof(cplx);
+    int tpr = (int)(n / 4);                       // one radix-4 butterfly per thread per pass
+    if (tpr > 512) tpr = 512;
+    if (tpr < 32) tpr = 32;
+    int rows = 256 / tpr;
+    if (rows < 1) rows = 1;
+    while (rows > 1 && (long long)rows > d.batch) rows >>= 1;
+    p->nl_rows_per_cta = rows;
+    p->nl_threads = rows * tpr;
+    p->nl_smem = row_bytes * rows;
+    if (p->nl_smem > 227 * 1024) return fail(RKS_ERR_UNSUPPORTED, "row does not fit in shared memory");
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    if (model == RKS_MODEL_UUX_RFFT) CUDA_TRY(cudaFuncSetAttribute(nl_kernel<1>, attr, (int)p->nl_smem));
+    else if (model == RKS_MODEL_NLS_FFT) CUDA_TRY(cudaFuncSetAttribute(nl_kernel<2>, attr, (int)p->nl_smem));
+    else if (model == RKS_MODEL_CUBIC_RFFT) CUDA_TRY(cudaFuncSetAttribute(nl_kernel<3>, attr, (int)p->nl_smem));
+    else CUDA_TRY(cudaFuncSetAttribute(nl_kernel<4>, attr, (int)p->nl_smem));
+    return RKS_OK;
+}
+
 extern "C" int rks_set_model(rks_plan* p, int model, int64_t n, const double* kx, const double* params_host,
                              int nparams, void* stream_v) {
     if (!p) return fail(RKS_ERR_ARG, "plan is null");
@@ -291,33 +323,7 @@ extern "C" int rks_set_model(rks_plan* p, int model, int64_t n, const double* kx
     twiddle_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((cplx*)(p->ws + p->lay.tw), (int)n);
     p->launches += 1;
     if (kx) CUDA_TRY(cudaMemcpyAsync(p->ws + p->lay.kx, kx, sizeof(double) * (size_t)d.n_c, cudaMemcpyDeviceToDevice, stream));
-    p->nl_fast = (n >= 512 && n <= 8192) && !getenv("RKS_NL_GENERIC");
-    p->no_fuse = getenv("RKS_FUSE") == nullptr;       // fused K1+K4 is opt-in (RKS_FUSE=1): see DESIGN.md 4
-    if (p->nl_fast) {
-        cudaError_t e = n == 512 ? prepare_nl_fast<1>(model) : n == 1024 ? prepare_nl_fast<2>(model)
-                      : n == 2048 ? prepare_nl_fast<4>(model) : n == 4096 ? prepare_nl_fast<8>(model)
-                      : prepare_nl_fast<16>(model);
-        CUDA_TRY(e);
-        fast_twiddle_kernel<<<(2 * fast::TW_TOTAL + 255) / 256, 256, 0, stream>>>((cplx*)(p->ws + p->lay.twf), (int)n);
-        p->launches += 1;
-    }
-    // launch shape of the generic NL kernel: one row per CTA for long rows, several for short ones
-    const size_t row_bytes = (size_t)n * sizeof(cplx);
-    int tpr = (int)(n / 4);                       // one radix-4 butterfly per thread per pass
-    if (tpr > 512) tpr = 512;
-    if (tpr < 32) tpr = 32;
-    int rows = 256 / tpr;
-    if (rows < 1) rows = 1;
-    while (rows > 1 && (long long)rows > d.batch) rows >>= 1;
-    p->nl_rows_per_cta = rows;
-    p->nl_threads = rows * tpr;
-    p->nl_smem = row_bytes * rows;
-    if (p->nl_smem > 227 * 1024) return fail(RKS_ERR_UNSUPPORTED, "row does not fit in shared memory");
-    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    if (model == RKS_MODEL_UUX_RFFT) CUDA_TRY(cudaFuncSetAttribute(nl_kernel<1>, attr, (int)p->nl_smem));
-    else if (model == RKS_MODEL_NLS_FFT) CUDA_TRY(cudaFuncSetAttribute(nl_kernel<2>, attr, (int)p->nl_smem));
-    else if (model == RKS_MODEL_CUBIC_RFFT) CUDA_TRY(cudaFuncSetAttribute(nl_kernel<3>, attr, (int)p->nl_smem));
-    else CUDA_TRY(cudaFuncSetAttribute(nl_kernel<4>, attr, (int)p->nl_smem));
+    if (int rc = prepare_nl_launch(p, model, n, (cplx*)(p->ws + p->lay.twf), stream)) return rc;
     CUDA_TRY(cudaGetLastError());
     return RKS_OK;
 }
@@ -712,6 +718,75 @@ extern "C" int rks_read_log(rks_plan* p, rks_trial_rec* out, int first, int coun
     CUDA_TRY(cudaStreamSynchronize(stream));
     for (int i = 0; i < count; ++i) memcpy(&out[i], &p->pinned_log[(first + i) % LOG_CAP], sizeof(TrialRec));
     return RKS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// standalone fused row transform: out_row = F{ N( F^-1{in_row} ) } along the contiguous axis of
+// any array (the innermost-axis part of an N-D nonlinear term; the outer axes are transformed by the
+// caller).  Same kernels as rks_nl, no stepping plan / workspace.
+// ---------------------------------------------------------------------------------------
+struct rks_rows {
+    rks_plan plan;            // only d (model fields), sm_count and the launch shape are used
+    void* dev_mem;
+};
+
+extern "C" int rks_rows_create(rks_rows** out, int model, int64_t n, const double* kx, double p0, void* stream_v) {
+    if (!out) return fail(RKS_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (model < RKS_MODEL_UUX_RFFT || model > RKS_MODEL_SINE_GORDON) return fail(RKS_ERR_ARG, "unknown model id");
+    if (n < 16 || n > MODEL_MAX_N || (n & (n - 1))) return fail(RKS_ERR_UNSUPPORTED, "n must be a power of two in [16, 16384]");
+    if ((model == RKS_MODEL_UUX_RFFT || model == RKS_MODEL_SINE_GORDON) && !kx) return fail(RKS_ERR_ARG, "kx is null");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    rks_rows* r = new (std::nothrow) rks_rows();
+    if (!r) return fail(RKS_ERR_ARG, "out of host memory");
+    rks_plan* p = &r->plan;
+    memset(&p->d, 0, sizeof(DevPlan));
+    p->launches = 0; p->no_fuse = true; p->use_graph = false; p->pinned_raw = nullptr; p->pinned_log = nullptr;
+    const bool half = model == RKS_MODEL_UUX_RFFT || model == RKS_MODEL_CUBIC_RFFT;
+    const long long n_c = half ? n / 2 + 1 : n;
+    const size_t tw_b = align_up(sizeof(cplx) * (size_t)n), twf_b = align_up(sizeof(cplx) * 2 * fast::TW_TOTAL);
+    const size_t kx_b = align_up(sizeof(double) * (size_t)n_c);
+    CUDA_TRY(cudaGetDevice(&p->device));
+    CUDA_TRY(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device));
+    CUDA_TRY(cudaMalloc(&r->dev_mem, tw_b + twf_b + kx_b));
+    unsigned char* w = (unsigned char*)r->dev_mem;
+    DevPlan& d = p->d;
+    d.ctrl = nullptr;
+    d.tw = (const cplx*)w; d.twf = (const cplx*)(w + tw_b); d.kx = (const double*)(w + tw_b + twf_b);
+    d.n = n; d.n_c = n_c; d.lin_elems = n_c; d.batch = 1ll << 40; d.model = model; d.model_p0 = p0;   // batch: set per apply
+    d.method = M_ETD4;
+    int log2n = 0;
+    while ((1ll << log2n) < n) ++log2n;
+    d.log2n = log2n;
+    twiddle_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((cplx*)w, (int)n);
+    if (kx) CUDA_TRY(cudaMemcpyAsync(w + tw_b + twf_b, kx, sizeof(double) * (size_t)n_c, cudaMemcpyDeviceToDevice, stream));
+    if (int rc = prepare_nl_launch(p, model, n, (cplx*)(w + tw_b), stream)) { cudaFree(r->dev_mem); delete r; return rc; }
+    CUDA_TRY(cudaGetLastError());
+    *out = r;
+    return RKS_OK;
+}
+
+extern "C" int rks_rows_apply(rks_rows* r, const void* in, void* out, int64_t batch, void* stream) {
+    if (!r || !in || !out || batch <= 0) return fail(RKS_ERR_ARG, "bad row-transform arguments");
+    rks_plan* p = &r->plan;
+    p->d.batch = batch;
+    p->d.U[0] = (cplx*)in;
+    p->d.NL[1] = (cplx*)out;
+    // generic kernel: rows per CTA must not exceed the batch
+    if (!p->nl_fast) {
+        while (p->nl_rows_per_cta > 1 && p->nl_rows_per_cta > batch) {
+            p->nl_rows_per_cta >>= 1; p->nl_threads >>= 1; p->nl_smem >>= 1;
+        }
+    }
+    launch_nl(p, 1, 1, (cudaStream_t)stream);
+    CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
+extern "C" void rks_rows_destroy(rks_rows* r) {
+    if (!r) return;
+    cudaFree(r->dev_mem);
+    delete r;
 }
 
 // ---------------------------------------------------------------------------------------

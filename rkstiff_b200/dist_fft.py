@@ -54,24 +54,26 @@ class SlabFFT:
         return out
 
     # -- transforms -------------------------------------------------------------------------
-    def forward(self, f: torch.Tensor) -> torch.Tensor:
-        """real-space slab ``(n0/G, n1, ...)`` -> spectral block ``(n0, n1/G, ...)`` (unnormalised)."""
+    def forward(self, f: torch.Tensor, skip_last: bool = False) -> torch.Tensor:
+        """real-space slab ``(n0/G, n1, ...)`` -> spectral block ``(n0, n1/G, ...)`` (unnormalised).
+        ``skip_last``: the last axis is already in spectral space (fused row kernel did it)."""
         G, (n0, n1) = self.world, self.shape[:2]
         nd = len(self.shape)
-        a = torch.fft.fftn(f, dim=tuple(range(1, nd)))
+        a = torch.fft.fftn(f, dim=tuple(range(1, nd - 1 if skip_last and nd > 2 else nd)))
         # chunk j of axis 1 goes to rank j
         a = a.reshape((n0 // G, G, n1 // G) + self.rest).permute((1, 0, 2) + tuple(range(3, nd + 1))).contiguous()
         b = self._exchange(a).reshape(self.spec_shape)        # blocks arrive ordered by source rank = axis-0 order
         return torch.fft.fft(b, dim=0)
 
-    def inverse(self, s: torch.Tensor) -> torch.Tensor:
-        """spectral block -> real-space slab (normalised like numpy.fft.ifftn)."""
+    def inverse(self, s: torch.Tensor, skip_last: bool = False) -> torch.Tensor:
+        """spectral block -> real-space slab (normalised like numpy.fft.ifftn).
+        ``skip_last``: leave the last axis in spectral space (the fused row kernel transforms it)."""
         G, (n0, n1) = self.world, self.shape[:2]
         nd = len(self.shape)
         b = torch.fft.ifft(s, dim=0).reshape((G, n0 // G, n1 // G) + self.rest).contiguous()
         a = self._exchange(b)                                  # a[j] = my axis-0 planes of rank j's axis-1 chunk
         a = a.permute((1, 0, 2) + tuple(range(3, nd + 1))).reshape(self.real_shape)
-        return torch.fft.ifftn(a, dim=tuple(range(1, nd)))
+        return torch.fft.ifftn(a, dim=tuple(range(1, nd - 1 if skip_last and nd > 2 else nd)))
 
 
 def nls_slab_ops(k_axes: Sequence[torch.Tensor], gamma: float = 2.0, group=None) -> Tuple[torch.Tensor, Callable, SlabFFT]:
@@ -93,7 +95,18 @@ def nls_slab_ops(k_axes: Sequence[torch.Tensor], gamma: float = 2.0, group=None)
     lin_global = -1j * k2.to(torch.complex128)
     lin_op = fft.spec_slice(lin_global.expand(shape))
 
+    rows = None
+    if lin_op.is_cuda and nd == 2:        # see models.nls_nd_ops: the fused row kernel only pays off in 2-D
+        from . import _abi
+        from .models import RowNL, _pow2_in_range
+        if _pow2_in_range(shape[-1]):
+            rows = RowNL(_abi.MODEL_NLS_FFT, shape[-1], None, gamma, lin_op.device)
+
     def nl_func(uf: torch.Tensor) -> torch.Tensor:
+        if rows is not None:
+            # innermost axis: inverse transform, i gamma |f|^2 f and forward transform in ONE fused kernel
+            a = fft.inverse(uf, skip_last=True).contiguous()
+            return fft.forward(rows(a, out=a), skip_last=True)
         f = fft.inverse(uf).contiguous()
         if f.is_cuda:
             from .models import pointwise_
