@@ -95,18 +95,7 @@ def nls_slab_ops(k_axes: Sequence[torch.Tensor], gamma: float = 2.0, group=None)
     lin_global = -1j * k2.to(torch.complex128)
     lin_op = fft.spec_slice(lin_global.expand(shape))
 
-    rows = None
-    if lin_op.is_cuda and nd == 2:        # see models.nls_nd_ops: the fused row kernel only pays off in 2-D
-        from . import _abi
-        from .models import RowNL, _pow2_in_range
-        if _pow2_in_range(shape[-1]):
-            rows = RowNL(_abi.MODEL_NLS_FFT, shape[-1], None, gamma, lin_op.device)
-
     def nl_func(uf: torch.Tensor) -> torch.Tensor:
-        if rows is not None:
-            # innermost axis: inverse transform, i gamma |f|^2 f and forward transform in ONE fused kernel
-            a = fft.inverse(uf, skip_last=True).contiguous()
-            return fft.forward(rows(a, out=a), skip_last=True)
         f = fft.inverse(uf).contiguous()
         if f.is_cuda:
             from .models import pointwise_
