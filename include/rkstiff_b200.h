@@ -136,6 +136,19 @@ int rks_plan_create(rks_plan** out, int method, int64_t batch, int64_t n_c, cons
                     size_t workspace_bytes, void* stream);
 void rks_plan_destroy(rks_plan* plan);
 
+/* Independent-dt ensemble (BASELINE cfg 2b): `batch` trajectories of one 1-D problem, each with its
+ * own controller, dt, coefficient arrays and buffer roles -- B separate reference solvers
+ * (solveras.py:279-325 run once per trajectory) stepped by one set of launches (gridDim.z = row).
+ * Adaptive methods and fused models only; every other call takes the plan unchanged
+ * (rks_begin / rks_set_h broadcast to all rows, rks_set_u / rks_get_u move the (batch, n_c) block,
+ * rks_read_ctrl reports row 0 with status RUNNING until every row has finished, else the worst
+ * status of any row).  rks_snapshot, rks_controller and caller-side N evaluation are not available. */
+#define RKS_ROW_LOG_CAP 64
+size_t rks_workspace_bytes_independent(int method, int64_t batch, int64_t n_c, int lin_is_complex);
+int rks_plan_create_independent(rks_plan** out, int method, int64_t batch, int64_t n_c, const void* lin_op,
+                                int lin_is_complex, const rks_config* cfg, void* workspace,
+                                size_t workspace_bytes, void* stream);
+
 /* SolverConfig/ETDConfig are read live by the reference on every trial (solveras.py:452-454) */
 int rks_set_config(rks_plan* plan, const rks_config* cfg, void* stream);
 
@@ -201,8 +214,12 @@ void rks_rows_destroy(rks_rows* rows);
 /* the only syncing calls */
 int rks_read_ctrl(rks_plan* plan, rks_ctrl_host* out, void* stream);
 int rks_read_log(rks_plan* plan, rks_trial_rec* out_host, int first, int count, void* stream);
+/* independent-dt plans: control block of every row; trial records of one row (ring of RKS_ROW_LOG_CAP) */
+int rks_read_rows(rks_plan* plan, rks_ctrl_host* out_host, int64_t nrows, void* stream);
+int rks_read_row_log(rks_plan* plan, int64_t row, rks_trial_rec* out_host, int first, int count, void* stream);
 
-/* introspection for tests: device pointer of a named array ("E", "a21", ..., "N1".., "K", "ERR", "U0", "U1") */
+/* introspection for tests: device pointer of a named array ("E", "a21", ..., "N1".., "K", "ERR", "U0", "U1";
+ * independent-dt plans also "row_logs": [batch][RKS_ROW_LOG_CAP] rks_trial_rec) */
 void* rks_array(rks_plan* plan, const char* name);
 int64_t rks_kernel_launches(rks_plan* plan);   /* kernels launched through this plan so far */
 

@@ -17,6 +17,7 @@ METHOD_IDS = {"IF4": 0, "ETD4": 1, "ETD5": 2, "IF34": 3, "ETD34": 4, "ETD35": 5,
 MODEL_NONE, MODEL_UUX_RFFT, MODEL_NLS_FFT, MODEL_CUBIC_RFFT, MODEL_SINE_GORDON = 0, 1, 2, 3, 4
 CTRL_RUNNING, CTRL_DONE, CTRL_MAX_LOOPS, CTRL_MIN_STEP = 0, 1, 2, 3
 LOG_CAP = 4096
+ROW_LOG_CAP = 64
 
 
 class RksConfig(Structure):
@@ -59,6 +60,9 @@ def _load():
         "rks_plan_create": (c_int, [POINTER(P), c_int, c_int64, c_int64, P, c_int, c_int64, POINTER(RksConfig), P,
                                     c_size_t, P]),
         "rks_plan_destroy": (None, [P]),
+        "rks_workspace_bytes_independent": (c_size_t, [c_int, c_int64, c_int64, c_int]),
+        "rks_plan_create_independent": (c_int, [POINTER(P), c_int, c_int64, c_int64, P, c_int, POINTER(RksConfig), P,
+                                                c_size_t, P]),
         "rks_set_config": (c_int, [P, POINTER(RksConfig), P]),
         "rks_set_model": (c_int, [P, c_int, c_int64, P, POINTER(c_double), c_int, P]),
         "rks_begin": (c_int, [P, c_double, c_double, c_double, c_int64, c_int, c_int, P]),
@@ -84,6 +88,8 @@ def _load():
         "rks_rows_destroy": (None, [P]),
         "rks_read_ctrl": (c_int, [P, POINTER(RksCtrl), P]),
         "rks_read_log": (c_int, [P, POINTER(RksTrialRec), c_int, c_int, P]),
+        "rks_read_rows": (c_int, [P, POINTER(RksCtrl), c_int64, P]),
+        "rks_read_row_log": (c_int, [P, c_int64, POINTER(RksTrialRec), c_int, c_int, P]),
         "rks_array": (P, [P, c_char_p]),
         "rks_kernel_launches": (c_int64, [P]),
     }

@@ -25,7 +25,7 @@ class Engine:
     (update_coeffs / n1_init / update_stages of the reference) plus the device controller."""
 
     def __init__(self, method: str, lin_op: torch.Tensor, u_shape: torch.Size, cfg: RksConfig,
-                 fused=None, group=None):
+                 fused=None, group=None, independent: bool = False):
         if not lin_op.is_cuda:
             raise ValueError("lin_op must be a CUDA tensor: rkstiff_b200 has no CPU path")
         if lin_op.dtype not in (torch.float64, torch.complex128):
@@ -47,19 +47,38 @@ class Engine:
         self.fsal = method in ("IF34", "ETD34", "IF45DP")
         self.group = group
         self.fused = fused
+        self.independent = bool(independent)
+        if self.independent:
+            # one controller / dt / coefficient set per trajectory (include/rkstiff_b200.h, cfg 2b)
+            if not self.adaptive:
+                raise ValueError("independent dt needs an adaptive method")
+            if fused is None:
+                raise ValueError("independent dt needs a fused nonlinearity (models.*_ops)")
+            if group is not None:
+                raise ValueError("independent trajectories need no process group: shard u0 instead")
+            if nd != 1 or len(u_shape) != 2:
+                raise ValueError("independent dt takes u of shape (batch, n_c) and a 1-D lin_op")
         lin = lin_op.contiguous()
         is_cx = lin.dtype == torch.complex128
         self.lin_complex = is_cx      # coefficient arrays are real only for IF methods with a real lin_op
         with torch.cuda.device(self.device):
-            nbytes = lib.rks_workspace_bytes(self.mid, self.batch, self.n_c, self.n_c, int(is_cx))
+            if self.independent:
+                nbytes = lib.rks_workspace_bytes_independent(self.mid, self.batch, self.n_c, int(is_cx))
+            else:
+                nbytes = lib.rks_workspace_bytes(self.mid, self.batch, self.n_c, self.n_c, int(is_cx))
             if nbytes == 0:
                 raise ValueError("invalid plan geometry")
             self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             self.plan = c_void_p()
             self._cfg = cfg
-            check(lib.rks_plan_create(byref(self.plan), self.mid, self.batch, self.n_c, c_void_p(lin.data_ptr()),
-                                      int(is_cx), self.n_c, byref(cfg), c_void_p(self.ws.data_ptr()), nbytes,
-                                      _stream(self.device)))
+            if self.independent:
+                check(lib.rks_plan_create_independent(byref(self.plan), self.mid, self.batch, self.n_c,
+                                                      c_void_p(lin.data_ptr()), int(is_cx), byref(cfg),
+                                                      c_void_p(self.ws.data_ptr()), nbytes, _stream(self.device)))
+            else:
+                check(lib.rks_plan_create(byref(self.plan), self.mid, self.batch, self.n_c, c_void_p(lin.data_ptr()),
+                                          int(is_cx), self.n_c, byref(cfg), c_void_p(self.ws.data_ptr()), nbytes,
+                                          _stream(self.device)))
             if fused is not None:
                 kx = fused.kx.to(device=self.device, dtype=torch.float64).contiguous() if fused.kx is not None else None
                 params = (c_double * 1)(float(fused.param))
@@ -198,6 +217,22 @@ class Engine:
         buf = (RksTrialRec * count)()
         check(lib.rks_read_log(self.plan, buf, first, count, self.st))
         return list(buf)
+
+    # -- independent-dt ensembles -----------------------------------------------------------
+    def read_rows(self):
+        """Control block of every trajectory of an independent-dt plan (syncs)."""
+        rows = (RksCtrl * self.batch)()
+        check(lib.rks_read_rows(self.plan, rows, self.batch, self.st))
+        return rows
+
+    def row_logs(self):
+        """Host copy of every row's trial-record ring, as a (batch, ROW_LOG_CAP) structured array (syncs)."""
+        import numpy as np
+        rec = np.dtype([("h", "<f8"), ("s", "<f8"), ("t_after", "<f8"), ("accepted", "<i4"), ("pad", "<i4")])
+        off = self.array("row_logs") - self.ws.data_ptr()
+        nb = self.batch * _abi.ROW_LOG_CAP * rec.itemsize
+        raw = self.ws[off: off + nb].cpu().numpy()
+        return raw.view(rec).reshape(self.batch, _abi.ROW_LOG_CAP)
 
     # -- whole trials ---------------------------------------------------------------------
     def enqueue_trial(self, nl_func: Optional[Callable], ring=None, ring_t=None) -> None:

@@ -132,6 +132,7 @@ struct Ctrl {
     int contour_points, r4_fix;
     int status, accept, numloops, u_sel, n_sel, need_n1, n1_refresh, step_mode;
     int log_count, snap_count, snap_pending;
+    int log_cap;                     // capacity of this plan's trial-log ring
 };
 
 // ---------------------------------------------------------------------------------------

@@ -43,7 +43,13 @@ struct BeginArgs {
     int step_mode, keep_fsal, n1_refresh;
 };
 
-__global__ void begin_kernel(Ctrl* c, BeginArgs a) {
+RKS_D void begin_ctrl(Ctrl* c, const BeginArgs& a);
+__global__ void begin_kernel(Ctrl* c, BeginArgs a) { begin_ctrl(c, a); }
+__global__ void begin_multi_kernel(const DevPlan* plans, int nplans, BeginArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nplans) begin_ctrl(plans[i].ctrl, a);
+}
+RKS_D void begin_ctrl(Ctrl* c, const BeginArgs& a) {
     c->t = a.t0; c->tf = a.tf; c->h = a.h; c->h_last = a.h;
     c->store_freq = a.store_freq;
     c->step_mode = a.step_mode;
@@ -66,12 +72,46 @@ __global__ void set_h_kernel(Ctrl* c, double h) {
     c->status = ST_RUNNING;
     c->numloops = 0;
 }
+__global__ void set_h_multi_kernel(const DevPlan* plans, int nplans, double h) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nplans) return;
+    Ctrl* c = plans[i].ctrl;
+    c->h = h; c->status = ST_RUNNING; c->numloops = 0;
+}
 
 struct CfgArgs {
     double epsilon, incr_f, decr_f, safety_f, adapt_cutoff, minh, inv_q, modecutoff, contour_radius;
     int contour_points, r4_fix;
 };
-__global__ void set_config_kernel(Ctrl* c, CfgArgs a) {
+RKS_D void set_config_ctrl(Ctrl* c, const CfgArgs& a);
+__global__ void set_config_kernel(Ctrl* c, CfgArgs a) { set_config_ctrl(c, a); }
+__global__ void set_config_multi_kernel(const DevPlan* plans, int nplans, CfgArgs a, int log_cap) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nplans) return;
+    set_config_ctrl(plans[i].ctrl, a);
+    plans[i].ctrl->log_cap = log_cap;
+}
+// how many plans are still stepping (host polls this once per chunk of trials)
+__global__ void count_running_kernel(const DevPlan* plans, int nplans, int* out) {
+    // out[0] = rows still RUNNING, out[1] = worst status code of any row
+    int mine = 0, worst = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nplans; i += gridDim.x * blockDim.x) {
+        const int st = plans[i].ctrl->status;
+        mine += st == ST_RUNNING;
+        worst = st > worst ? st : worst;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        const int w = __shfl_xor_sync(0xffffffffu, worst, o);
+        worst = w > worst ? w : worst;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (mine) atomicAdd(out, mine);
+        if (worst) atomicMax(out + 1, worst);
+    }
+}
+RKS_D void set_config_ctrl(Ctrl* c, const CfgArgs& a) {
+    c->log_cap = LOG_CAP;
     c->epsilon = a.epsilon; c->incr_f = a.incr_f; c->decr_f = a.decr_f; c->safety_f = a.safety_f;
     c->adapt_cutoff = a.adapt_cutoff; c->minh = a.minh; c->inv_q = a.inv_q;
     c->modecutoff = a.modecutoff; c->contour_radius = a.contour_radius;
@@ -110,7 +150,7 @@ RKS_D cplx warp_sum(cplx v) {
 }
 
 template <int FAM, typename LT>
-__global__ void __launch_bounds__(128) coef_kernel(DevPlan p, int force) {
+RKS_D void coef_kernel_body(const DevPlan& p, int force) {
     Ctrl* c = p.ctrl;
     const double h = c->h;
     if (!force) {
@@ -196,6 +236,12 @@ __global__ void __launch_bounds__(128) coef_kernel(DevPlan p, int force) {
         }
     }
 }
+template <int FAM, typename LT>
+__global__ void __launch_bounds__(128) coef_kernel(DevPlan p, int force) { coef_kernel_body<FAM, LT>(p, force); }
+// one plan per blockIdx.z: ensembles whose trajectories keep their own dt (rks_multi_*)
+template <int FAM, typename LT>
+__global__ void __launch_bounds__(128) coef_kernel_multi(const DevPlan* plans, int force) { coef_kernel_body<FAM, LT>(plans[blockIdx.z], force); }
+
 
 // ---------------------------------------------------------------------------------------
 // K1: stage combine.  !FULL: block (32, 8), thread = one mode column x R batch rows, the
@@ -205,7 +251,7 @@ __global__ void __launch_bounds__(128) coef_kernel(DevPlan p, int force) {
 constexpr int STAGE_R = 2;
 
 template <int M, int S, typename CT, bool FULL>
-__global__ void __launch_bounds__(256) stage_kernel(DevPlan p) {
+RKS_D void stage_kernel_body(const DevPlan& p) {
     constexpr int R = STAGE_R;
     constexpr bool ADAPT = method_adaptive(M);
     constexpr int SMAX = method_stages(M);
@@ -292,6 +338,12 @@ __global__ void __launch_bounds__(256) stage_kernel(DevPlan p) {
         }
     }
 }
+template <int M, int S, typename CT, bool FULL>
+__global__ void __launch_bounds__(256) stage_kernel(DevPlan p) { stage_kernel_body<M, S, CT, FULL>(p); }
+// one plan per blockIdx.z: ensembles whose trajectories keep their own dt (rks_multi_*)
+template <int M, int S, typename CT, bool FULL>
+__global__ void __launch_bounds__(256) stage_kernel_multi(const DevPlan* plans) { stage_kernel_body<M, S, CT, FULL>(plans[blockIdx.z]); }
+
 
 // ---------------------------------------------------------------------------------------
 // K4: fused spectral nonlinearity, one trajectory row per CTA slot, row resident in smem.
@@ -324,8 +376,8 @@ RKS_D NlRoles nl_roles(const DevPlan& p, int j, int force) {
 }
 
 template <int MODEL>
-__global__ void __launch_bounds__(1024) nl_kernel(DevPlan p, int j, int force, int rows_per_cta) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+RKS_D void nl_kernel_body(const DevPlan& p, int j, int force, int rows_per_cta) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     cplx* smem = reinterpret_cast<cplx*>(smem_raw);
     const NlRoles roles = nl_roles(p, j, force);
     if (!roles.run) return;
@@ -360,6 +412,12 @@ __global__ void __launch_bounds__(1024) nl_kernel(DevPlan p, int j, int force, i
     if (active)
         for (int q = tid; q < n; q += tpr) m.store(q, x[q]);
 }
+template <int MODEL>
+__global__ void __launch_bounds__(1024) nl_kernel(DevPlan p, int j, int force, int rows_per_cta) { nl_kernel_body<MODEL>(p, j, force, rows_per_cta); }
+// one plan per blockIdx.z: ensembles whose trajectories keep their own dt (rks_multi_*)
+template <int MODEL>
+__global__ void __launch_bounds__(1024) nl_kernel_multi(const DevPlan* plans, int j, int force, int rows_per_cta) { nl_kernel_body<MODEL>(plans[blockIdx.z], j, force, rows_per_cta); }
+
 
 
 // ---------------------------------------------------------------------------------------
@@ -459,8 +517,7 @@ RKS_D void prefetch_row_l2(const void* row, int lines, int T) {
 // coefficient arrays) is evaluated in the load prologue, so the stage value k never goes to HBM
 // unless it is a state (fd.write_k: final stage of fixed-step and FSAL methods).
 template <int W, int MODEL, int FK>
-__global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2))
-nl_fast_kernel(DevPlan p, int j, int force, FuseDesc fd) {
+RKS_D void nl_fast_kernel_body(const DevPlan& p, int j, int force, FuseDesc fd) {
     using CT = typename std::conditional<FK == 2, double, cplx>::type;
     constexpr int N = 512 * W;
     constexpr int TR = 32 * W;                       // threads per row
@@ -570,6 +627,12 @@ nl_fast_kernel(DevPlan p, int j, int force, FuseDesc fd) {
         }
     }
 }
+template <int W, int MODEL, int FK>
+__global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_fast_kernel(DevPlan p, int j, int force, FuseDesc fd) { nl_fast_kernel_body<W, MODEL, FK>(p, j, force, fd); }
+// one plan per blockIdx.z: ensembles whose trajectories keep their own dt (rks_multi_*)
+template <int W, int MODEL, int FK>
+__global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_fast_kernel_multi(const DevPlan* plans, int j, int force, FuseDesc fd) { nl_fast_kernel_body<W, MODEL, FK>(plans[blockIdx.z], j, force, fd); }
+
 
 // ---------------------------------------------------------------------------------------
 // K3: masked norms (solveras.py:451-454) + controller tail.
@@ -592,7 +655,7 @@ RKS_D double block_sum(double v, double* sh) {
 }
 
 template <int M, typename CT, bool FULL>
-__global__ void __launch_bounds__(128) norm_kernel(DevPlan p, int fuse_controller) {
+RKS_D void norm_kernel_body(const DevPlan& p, int fuse_controller) {
     constexpr unsigned NMASK = err_nl_mask(M);
     constexpr unsigned CMASK = err_coef_mask(M);
     constexpr int NC = method_ncoef(M);
@@ -670,6 +733,12 @@ __global__ void __launch_bounds__(128) norm_kernel(DevPlan p, int fuse_controlle
         }
     }
 }
+template <int M, typename CT, bool FULL>
+__global__ void __launch_bounds__(128) norm_kernel(DevPlan p, int fuse_controller) { norm_kernel_body<M, CT, FULL>(p, fuse_controller); }
+// one plan per blockIdx.z: ensembles whose trajectories keep their own dt (rks_multi_*)
+template <int M, typename CT, bool FULL>
+__global__ void __launch_bounds__(128) norm_kernel_multi(const DevPlan* plans, int fuse_controller) { norm_kernel_body<M, CT, FULL>(plans[blockIdx.z], fuse_controller); }
+
 
 __global__ void controller_kernel(DevPlan p) {
     Ctrl* c = p.ctrl;
@@ -721,6 +790,17 @@ __global__ void __launch_bounds__(256) copy_u_kernel(DevPlan p, cplx* ext, int t
     for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
         if (to_plan) stg(mine + e, ldcs(ext + e));
         else stg(ext + e, ldcs(mine + e));
+    }
+}
+
+// row z of a caller array (nplans, n_c) <-> the state buffer of plan z
+__global__ void __launch_bounds__(256) copy_u_multi_kernel(const DevPlan* plans, cplx* ext, int to_plan) {
+    const DevPlan& p = plans[blockIdx.z];
+    cplx* mine = p.U[p.ctrl->u_sel];
+    cplx* row = ext + (size_t)blockIdx.z * p.n_c;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < p.n_c; e += (long long)gridDim.x * 256) {
+        if (to_plan) stg(mine + e, ldcs(row + e));
+        else stg(row + e, ldcs(mine + e));
     }
 }
 

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <vector>
 
 #include "../../include/rkstiff_b200.h"
 #include "kernels.cuh"
@@ -31,6 +32,8 @@ static_assert(RKS_LOG_CAP == LOG_CAP, "log capacity");
 // ---------------------------------------------------------------------------------------
 constexpr size_t ALIGN = 256;
 constexpr int NORM_MAX_BLOCKS = 4096;
+constexpr int MULTI_NORM_BLOCKS = 16;       // norm-kernel blocks per row in independent-dt mode
+constexpr int MULTI_LOG_CAP = RKS_ROW_LOG_CAP;          // trial records kept per row in independent-dt mode
 constexpr long long MODEL_MAX_N = 16384;        // longest row the smem-resident FFT handles
 
 static size_t align_up(size_t v) { return (v + ALIGN - 1) / ALIGN * ALIGN; }
@@ -77,6 +80,15 @@ struct rks_plan {
     DevPlan d;
     GraphCache graph;
     bool use_graph;                 // replay one captured trial/step (RKS_NO_GRAPH=1 disables)
+    // independent-dt ensembles: one single-row plan per trajectory, launched together (blockIdx.z = row)
+    DevPlan* multi_dev = nullptr;   // device array of per-row plans (nullptr: ordinary plan)
+    long long multi_n = 0;
+    int* multi_count_dev = nullptr; // running-row counter
+    int* multi_count_host = nullptr;
+    Ctrl* multi_ctrl_host = nullptr;    // pinned staging of all row control blocks
+    size_t multi_ctrl_stride = 0, multi_log_cap = 0;
+    unsigned char* multi_ctrl_base = nullptr; TrialRec* multi_log_base = nullptr;
+    std::vector<DevPlan> multi_host;
     Layout lay;
     unsigned char* ws;
     rks_config cfg;
@@ -111,6 +123,11 @@ static void launch_nl_fast_t(rks_plan* p, int j, int force, const FuseDesc& fd, 
     constexpr int THREADS = W == 16 ? 512 : 256;
     constexpr int RPC = THREADS / (32 * W);
     const size_t smem = nl_fast_smem<W>(MODEL, FK);
+    if (p->multi_n) {
+        if constexpr (FK == 0)
+            nl_fast_kernel_multi<W, MODEL, 0><<<dim3(1, 1, (unsigned)p->multi_n), THREADS, smem, stream>>>(p->multi_dev, j, force, fd);
+        return;
+    }
     const long long groups = (d.batch + RPC - 1) / RPC;
     const long long resident = (long long)p->sm_count * (W == 16 ? 1 : 2);
     const unsigned grid = (unsigned)(groups < resident ? groups : resident);
@@ -135,16 +152,20 @@ static cudaError_t prepare_nl_fast(int model) {
     const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
     if (model == RKS_MODEL_UUX_RFFT) {
         e = cudaFuncSetAttribute(nl_fast_kernel<W, 1, 0>, attr, (int)nl_fast_smem<W>(model, 0));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel_multi<W, 1, 0>, attr, (int)nl_fast_smem<W>(model, 0));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 1, 1>, attr, (int)nl_fast_smem<W>(model, 1));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 1, 2>, attr, (int)nl_fast_smem<W>(model, 2));
     } else if (model == RKS_MODEL_NLS_FFT) {
         e = cudaFuncSetAttribute(nl_fast_kernel<W, 2, 0>, attr, (int)nl_fast_smem<W>(model, 0));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel_multi<W, 2, 0>, attr, (int)nl_fast_smem<W>(model, 0));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 2, 1>, attr, (int)nl_fast_smem<W>(model, 1));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 2, 2>, attr, (int)nl_fast_smem<W>(model, 2));
     } else if (model == RKS_MODEL_CUBIC_RFFT) {
         e = cudaFuncSetAttribute(nl_fast_kernel<W, 3, 0>, attr, (int)nl_fast_smem<W>(model, 0));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel_multi<W, 3, 0>, attr, (int)nl_fast_smem<W>(model, 0));
     } else {
         e = cudaFuncSetAttribute(nl_fast_kernel<W, 4, 0>, attr, (int)nl_fast_smem<W>(model, 0));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel_multi<W, 4, 0>, attr, (int)nl_fast_smem<W>(model, 0));
     }
     return e;
 }
@@ -248,12 +269,147 @@ extern "C" int rks_plan_create(rks_plan** out, int method, int64_t batch, int64_
     return RKS_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// independent-dt ensembles (BASELINE cfg 2b): one single-row plan per trajectory -- its own control
+// block, coefficient arrays and buffer roles -- all launched together (gridDim.z = rows)
+// ---------------------------------------------------------------------------------------
+struct MultiLayout {
+    size_t tw, twf, kx, lin, plans, count, ctrl, ctrl_stride, log, partials, coef, coef_stride, U[2], K, ERR, NL[8], total;
+};
+
+static MultiLayout make_multi_layout(int method, long long batch, long long n_c, int lin_is_complex) {
+    MultiLayout L;
+    memset(&L, 0, sizeof(L));
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+    const size_t state = (size_t)batch * (size_t)n_c * sizeof(cplx);
+    const size_t coef_elem = (method_is_if(method) && !lin_is_complex) ? sizeof(double) : sizeof(cplx);
+    const long long nmax = n_c <= MODEL_MAX_N ? 2 * n_c : 0;
+    L.tw = take(sizeof(cplx) * (size_t)nmax);
+    L.twf = take(sizeof(cplx) * (size_t)(n_c <= MODEL_MAX_N ? 2 * fast::TW_TOTAL : 0));
+    L.kx = take(sizeof(double) * (size_t)(n_c <= MODEL_MAX_N ? n_c : 0));
+    L.lin = take((lin_is_complex ? sizeof(cplx) : sizeof(double)) * (size_t)n_c);
+    L.plans = take(sizeof(DevPlan) * (size_t)batch);
+    L.count = take(sizeof(int) * 4);
+    L.ctrl_stride = align_up(sizeof(Ctrl));
+    L.ctrl = take(L.ctrl_stride * (size_t)batch);
+    L.log = take(sizeof(TrialRec) * MULTI_LOG_CAP * (size_t)batch);
+    L.partials = take(sizeof(double) * 2 * MULTI_NORM_BLOCKS * (size_t)batch);
+    L.coef_stride = coef_elem * (size_t)n_c * method_ncoef(method);
+    L.coef = take(L.coef_stride * (size_t)batch);
+    L.U[0] = take(state);
+    L.U[1] = take(state);
+    L.K = take(state);
+    L.ERR = method == M_ETD35 ? take(state) : 0;
+    for (int j = 1; j <= method_nl_buffers(method); ++j) L.NL[j] = take(state);
+    L.total = off;
+    return L;
+}
+
+extern "C" size_t rks_workspace_bytes_independent(int method, int64_t batch, int64_t n_c, int lin_is_complex) {
+    if (!valid_method(method) || !method_adaptive(method) || batch <= 0 || batch > 65535 || n_c <= 0) return 0;
+    return make_multi_layout(method, batch, n_c, lin_is_complex).total;
+}
+
+static int upload_multi_plans(rks_plan* p, cudaStream_t stream) {
+    // every row shares the model fields of the prototype
+    for (auto& q : p->multi_host) {
+        q.model = p->d.model; q.n = p->d.n; q.log2n = p->d.log2n; q.model_p0 = p->d.model_p0;
+    }
+    CUDA_TRY(cudaMemcpyAsync(p->multi_dev, p->multi_host.data(), sizeof(DevPlan) * p->multi_host.size(),
+                             cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return RKS_OK;
+}
+
+extern "C" int rks_plan_create_independent(rks_plan** out, int method, int64_t batch, int64_t n_c, const void* lin_op,
+                                           int lin_is_complex, const rks_config* cfg, void* workspace,
+                                           size_t workspace_bytes, void* stream_v) {
+    if (!out) return fail(RKS_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (!valid_method(method) || !method_adaptive(method)) return fail(RKS_ERR_ARG, "independent dt needs an adaptive method");
+    if (batch <= 0 || batch > 65535 || n_c <= 0) return fail(RKS_ERR_ARG, "batch must be in 1..65535 and n_c positive");
+    if (!lin_op || !workspace) return fail(RKS_ERR_ARG, "null device pointer");
+    if (((uintptr_t)workspace) % ALIGN) return fail(RKS_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+    if (int rc = check_cfg(cfg)) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    const MultiLayout L = make_multi_layout(method, batch, n_c, lin_is_complex);
+    if (workspace_bytes < L.total) return fail(RKS_ERR_WORKSPACE, "workspace too small");
+    rks_plan* p = new (std::nothrow) rks_plan();
+    if (!p) return fail(RKS_ERR_ARG, "out of host memory");
+    memset(&p->d, 0, sizeof(DevPlan));
+    memset(&p->lay, 0, sizeof(Layout));
+    p->ws = (unsigned char*)workspace;
+    p->cfg = *cfg;
+    p->method = method;
+    p->launches = 0;
+    p->have_h_coeff_host = false;
+    p->roles_u_sel = p->roles_n_sel = 0;
+    p->use_graph = getenv("RKS_NO_GRAPH") == nullptr;
+    p->no_fuse = true;
+    p->nl_fast = false;
+    CUDA_TRY(cudaGetDevice(&p->device));
+    CUDA_TRY(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device));
+    CUDA_TRY(cudaMallocHost((void**)&p->pinned_raw, sizeof(Ctrl)));
+    CUDA_TRY(cudaMallocHost((void**)&p->pinned_log, sizeof(TrialRec) * LOG_CAP));
+    CUDA_TRY(cudaMallocHost((void**)&p->multi_ctrl_host, L.ctrl_stride * (size_t)batch));
+    CUDA_TRY(cudaMallocHost((void**)&p->multi_count_host, sizeof(int) * 4));
+    unsigned char* w = p->ws;
+    p->lay.tw = L.tw; p->lay.twf = L.twf; p->lay.kx = L.kx; p->lay.lin = L.lin;
+    p->multi_n = batch;
+    p->multi_dev = (DevPlan*)(w + L.plans);
+    p->multi_count_dev = (int*)(w + L.count);
+    p->multi_ctrl_base = w + L.ctrl;
+    p->multi_ctrl_stride = L.ctrl_stride;
+    p->multi_log_base = (TrialRec*)(w + L.log);
+    p->multi_log_cap = MULTI_LOG_CAP;
+    p->multi_host.resize((size_t)batch);
+    for (long long r = 0; r < batch; ++r) {
+        DevPlan& d = p->multi_host[(size_t)r];
+        memset(&d, 0, sizeof(DevPlan));
+        d.ctrl = (Ctrl*)(w + L.ctrl + L.ctrl_stride * (size_t)r);
+        d.log = (TrialRec*)(w + L.log) + (size_t)r * MULTI_LOG_CAP;
+        d.partials = (double*)(w + L.partials) + (size_t)r * 2 * MULTI_NORM_BLOCKS;
+        d.tw = (const cplx*)(w + L.tw);
+        d.twf = (const cplx*)(w + L.twf);
+        d.kx = (const double*)(w + L.kx);
+        d.lin = w + L.lin;
+        d.coef = w + L.coef + L.coef_stride * (size_t)r;
+        const size_t ro = (size_t)r * (size_t)n_c;
+        d.U[0] = (cplx*)(w + L.U[0]) + ro;
+        d.U[1] = (cplx*)(w + L.U[1]) + ro;
+        d.K = (cplx*)(w + L.K) + ro;
+        d.ERR = method == M_ETD35 ? (cplx*)(w + L.ERR) + ro : nullptr;
+        for (int j = 1; j <= method_nl_buffers(method); ++j) d.NL[j] = (cplx*)(w + L.NL[j]) + ro;
+        d.batch = 1; d.n_c = n_c; d.lin_elems = n_c; d.n = 0;
+        d.method = method; d.lin_complex = lin_is_complex; d.lin_full = 1;
+        d.model = RKS_MODEL_NONE;
+    }
+    p->d = p->multi_host[0];
+    CUDA_TRY(cudaMemsetAsync(w + L.count, 0, L.coef - L.count, stream));          // counters, ctrl, logs, partials
+    CUDA_TRY(cudaMemcpyAsync(w + L.lin, lin_op, (lin_is_complex ? sizeof(cplx) : sizeof(double)) * (size_t)n_c,
+                             cudaMemcpyDeviceToDevice, stream));
+    if (int rc = upload_multi_plans(p, stream)) return rc;
+    const unsigned g = (unsigned)((batch + 127) / 128);
+    set_config_multi_kernel<<<g, 128, 0, stream>>>(p->multi_dev, (int)batch, cfg_args(*cfg, method), MULTI_LOG_CAP);
+    BeginArgs b;
+    b.t0 = 0.0; b.tf = 0.0; b.h = 0.0; b.store_freq = 0; b.step_mode = 1; b.keep_fsal = 0;
+    b.n1_refresh = method == M_ETD35;
+    begin_multi_kernel<<<g, 128, 0, stream>>>(p->multi_dev, (int)batch, b);
+    p->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    *out = p;
+    return RKS_OK;
+}
+
 extern "C" void rks_plan_destroy(rks_plan* p) {
     if (!p) return;
     if (p->graph.exec) cudaGraphExecDestroy(p->graph.exec);
     if (p->graph.stream) cudaStreamDestroy(p->graph.stream);
     cudaFreeHost(p->pinned_raw);
     cudaFreeHost(p->pinned_log);
+    if (p->multi_ctrl_host) cudaFreeHost(p->multi_ctrl_host);
+    if (p->multi_count_host) cudaFreeHost(p->multi_count_host);
     delete p;
 }
 
@@ -264,7 +420,11 @@ extern "C" int rks_set_config(rks_plan* p, const rks_config* cfg, void* stream) 
                              cfg->contour_radius != p->cfg.contour_radius || cfg->if45dp_r4_fix != p->cfg.if45dp_r4_fix;
     p->cfg = *cfg;
     if (etd_changed) p->have_h_coeff_host = false;
-    set_config_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p->d.ctrl, cfg_args(*cfg, p->method));
+    if (p->multi_n)
+        set_config_multi_kernel<<<(unsigned)((p->multi_n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+            p->multi_dev, (int)p->multi_n, cfg_args(*cfg, p->method), MULTI_LOG_CAP);
+    else
+        set_config_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p->d.ctrl, cfg_args(*cfg, p->method));
     p->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return RKS_OK;
@@ -299,6 +459,10 @@ static int prepare_nl_launch(rks_plan* p, int model, long long n, cplx* twf_dev,
     else if (model == RKS_MODEL_NLS_FFT) CUDA_TRY(cudaFuncSetAttribute(nl_kernel<2>, attr, (int)p->nl_smem));
     else if (model == RKS_MODEL_CUBIC_RFFT) CUDA_TRY(cudaFuncSetAttribute(nl_kernel<3>, attr, (int)p->nl_smem));
     else CUDA_TRY(cudaFuncSetAttribute(nl_kernel<4>, attr, (int)p->nl_smem));
+    if (model == RKS_MODEL_UUX_RFFT) CUDA_TRY(cudaFuncSetAttribute(nl_kernel_multi<1>, attr, (int)p->nl_smem));
+    else if (model == RKS_MODEL_NLS_FFT) CUDA_TRY(cudaFuncSetAttribute(nl_kernel_multi<2>, attr, (int)p->nl_smem));
+    else if (model == RKS_MODEL_CUBIC_RFFT) CUDA_TRY(cudaFuncSetAttribute(nl_kernel_multi<3>, attr, (int)p->nl_smem));
+    else CUDA_TRY(cudaFuncSetAttribute(nl_kernel_multi<4>, attr, (int)p->nl_smem));
     return RKS_OK;
 }
 
@@ -324,6 +488,8 @@ extern "C" int rks_set_model(rks_plan* p, int model, int64_t n, const double* kx
     p->launches += 1;
     if (kx) CUDA_TRY(cudaMemcpyAsync(p->ws + p->lay.kx, kx, sizeof(double) * (size_t)d.n_c, cudaMemcpyDeviceToDevice, stream));
     if (int rc = prepare_nl_launch(p, model, n, (cplx*)(p->ws + p->lay.twf), stream)) return rc;
+    if (p->multi_n)
+        if (int rc = upload_multi_plans(p, stream)) return rc;
     CUDA_TRY(cudaGetLastError());
     return RKS_OK;
 }
@@ -335,7 +501,10 @@ extern "C" int rks_begin(rks_plan* p, double t0, double tf, double h, int64_t st
     b.t0 = t0; b.tf = tf; b.h = h; b.store_freq = store_freq; b.step_mode = step_mode; b.keep_fsal = keep_fsal;
     b.n1_refresh = p->method == M_ETD35;
     if (!keep_fsal) { p->have_h_coeff_host = false; p->roles_n_sel = 0; }
-    begin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p->d.ctrl, b);
+    if (p->multi_n)
+        begin_multi_kernel<<<(unsigned)((p->multi_n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p->multi_dev, (int)p->multi_n, b);
+    else
+        begin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p->d.ctrl, b);
     p->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return RKS_OK;
@@ -343,7 +512,10 @@ extern "C" int rks_begin(rks_plan* p, double t0, double tf, double h, int64_t st
 
 extern "C" int rks_set_h(rks_plan* p, double h, void* stream) {
     if (!p) return fail(RKS_ERR_ARG, "plan is null");
-    set_h_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p->d.ctrl, h);
+    if (p->multi_n)
+        set_h_multi_kernel<<<(unsigned)((p->multi_n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p->multi_dev, (int)p->multi_n, h);
+    else
+        set_h_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p->d.ctrl, h);
     p->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return RKS_OK;
@@ -358,7 +530,11 @@ static unsigned copy_grid(const rks_plan* p) {
 
 extern "C" int rks_set_u(rks_plan* p, const void* u, void* stream) {
     if (!p || !u) return fail(RKS_ERR_ARG, "null argument");
-    copy_u_kernel<<<copy_grid(p), 256, 0, (cudaStream_t)stream>>>(p->d, (cplx*)u, 1);
+    if (p->multi_n)
+        copy_u_multi_kernel<<<dim3((unsigned)((p->d.n_c + 255) / 256 > 64 ? 64 : (p->d.n_c + 255) / 256), 1, (unsigned)p->multi_n), 256, 0,
+                              (cudaStream_t)stream>>>(p->multi_dev, (cplx*)u, 1);
+    else
+        copy_u_kernel<<<copy_grid(p), 256, 0, (cudaStream_t)stream>>>(p->d, (cplx*)u, 1);
     p->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return RKS_OK;
@@ -366,7 +542,11 @@ extern "C" int rks_set_u(rks_plan* p, const void* u, void* stream) {
 
 extern "C" int rks_get_u(rks_plan* p, void* u_out, void* stream) {
     if (!p || !u_out) return fail(RKS_ERR_ARG, "null argument");
-    copy_u_kernel<<<copy_grid(p), 256, 0, (cudaStream_t)stream>>>(p->d, (cplx*)u_out, 0);
+    if (p->multi_n)
+        copy_u_multi_kernel<<<dim3((unsigned)((p->d.n_c + 255) / 256 > 64 ? 64 : (p->d.n_c + 255) / 256), 1, (unsigned)p->multi_n), 256, 0,
+                              (cudaStream_t)stream>>>(p->multi_dev, (cplx*)u_out, 0);
+    else
+        copy_u_kernel<<<copy_grid(p), 256, 0, (cudaStream_t)stream>>>(p->d, (cplx*)u_out, 0);
     p->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return RKS_OK;
@@ -375,21 +555,27 @@ extern "C" int rks_get_u(rks_plan* p, void* u_out, void* stream) {
 // ---------------------------------------------------------------------------------------
 // K2 dispatch
 // ---------------------------------------------------------------------------------------
-static int launch_coeffs(rks_plan* p, int force, cudaStream_t stream) {
+template <int FAM, typename LT>
+static void launch_coef_t(rks_plan* p, int force, cudaStream_t stream) {
     const DevPlan& d = p->d;
     const unsigned grid = (unsigned)((d.lin_elems + 127) / 128);
+    if (p->multi_n) coef_kernel_multi<FAM, LT><<<dim3(grid, 1, (unsigned)p->multi_n), 128, 0, stream>>>(p->multi_dev, force);
+    else coef_kernel<FAM, LT><<<grid, 128, 0, stream>>>(d, force);
+}
+
+static int launch_coeffs(rks_plan* p, int force, cudaStream_t stream) {
     const int m = p->method;
-    const bool cx = d.lin_complex != 0;
+    const bool cx = p->d.lin_complex != 0;
     if (m == M_IF4 || m == M_IF34) {
-        if (cx) coef_kernel<0, cplx><<<grid, 128, 0, stream>>>(d, force);
-        else coef_kernel<0, double><<<grid, 128, 0, stream>>>(d, force);
+        if (cx) launch_coef_t<0, cplx>(p, force, stream);
+        else launch_coef_t<0, double>(p, force, stream);
     } else if (m == M_ETD4 || m == M_ETD34) {
-        coef_kernel<1, cplx><<<grid, 128, 0, stream>>>(d, force);
+        launch_coef_t<1, cplx>(p, force, stream);
     } else if (m == M_ETD5 || m == M_ETD35) {
-        coef_kernel<2, cplx><<<grid, 128, 0, stream>>>(d, force);
+        launch_coef_t<2, cplx>(p, force, stream);
     } else {
-        if (cx) coef_kernel<3, cplx><<<grid, 128, 0, stream>>>(d, force);
-        else coef_kernel<3, double><<<grid, 128, 0, stream>>>(d, force);
+        if (cx) launch_coef_t<3, cplx>(p, force, stream);
+        else launch_coef_t<3, double>(p, force, stream);
     }
     p->launches += 1;
     return RKS_OK;
@@ -411,7 +597,10 @@ template <int M, int S, typename CT>
 static void launch_stage_t(rks_plan* p, cudaStream_t stream) {
     const DevPlan& d = p->d;
     const dim3 block(32, 8);
-    if (d.lin_full) {
+    if (p->multi_n) {
+        const unsigned gx = (unsigned)((d.n_c + 256 * STAGE_R - 1) / (256 * STAGE_R));
+        stage_kernel_multi<M, S, CT, true><<<dim3(gx, 1, (unsigned)p->multi_n), block, 0, stream>>>(p->multi_dev);
+    } else if (d.lin_full) {
         const long long total = d.batch * d.n_c;
         const unsigned gx = (unsigned)((total + 256 * STAGE_R - 1) / (256 * STAGE_R));
         stage_kernel<M, S, CT, true><<<dim3(gx), block, 0, stream>>>(d);
@@ -479,6 +668,15 @@ static int launch_nl(rks_plan* p, int j, int force, cudaStream_t stream) {
         dispatch_nl_fast(p, j, force, none, 0, stream);
         return RKS_OK;
     }
+    if (p->multi_n) {
+        const dim3 g(1, 1, (unsigned)p->multi_n);
+        if (d.model == RKS_MODEL_UUX_RFFT) nl_kernel_multi<1><<<g, p->nl_threads, p->nl_smem, stream>>>(p->multi_dev, j, force, p->nl_rows_per_cta);
+        else if (d.model == RKS_MODEL_NLS_FFT) nl_kernel_multi<2><<<g, p->nl_threads, p->nl_smem, stream>>>(p->multi_dev, j, force, p->nl_rows_per_cta);
+        else if (d.model == RKS_MODEL_CUBIC_RFFT) nl_kernel_multi<3><<<g, p->nl_threads, p->nl_smem, stream>>>(p->multi_dev, j, force, p->nl_rows_per_cta);
+        else nl_kernel_multi<4><<<g, p->nl_threads, p->nl_smem, stream>>>(p->multi_dev, j, force, p->nl_rows_per_cta);
+        p->launches += 1;
+        return RKS_OK;
+    }
     const unsigned grid = (unsigned)((d.batch + p->nl_rows_per_cta - 1) / p->nl_rows_per_cta);
     if (d.model == RKS_MODEL_UUX_RFFT) nl_kernel<1><<<grid, p->nl_threads, p->nl_smem, stream>>>(d, j, force, p->nl_rows_per_cta);
     else if (d.model == RKS_MODEL_NLS_FFT) nl_kernel<2><<<grid, p->nl_threads, p->nl_smem, stream>>>(d, j, force, p->nl_rows_per_cta);
@@ -505,7 +703,7 @@ extern "C" int rks_nl(rks_plan* p, int j, void* stream) {
 // unless it is a state); otherwise this is rks_stage + rks_nl.
 static bool can_fuse_stage(const rks_plan* p, int s) {
     const int m = p->method, S = method_stages(m);
-    if (!p->nl_fast || p->no_fuse || p->d.lin_elems != p->d.n_c) return false;
+    if (!p->nl_fast || p->no_fuse || p->multi_n || p->d.lin_elems != p->d.n_c) return false;
     if (p->d.model != RKS_MODEL_UUX_RFFT && p->d.model != RKS_MODEL_NLS_FFT) return false;
     if (s == S && m == M_ETD35) return false;              // last ETD35 stage emits err and feeds no N
     return true;
@@ -555,6 +753,12 @@ extern "C" void* rks_nl_output(rks_plan* p, int j) {
 template <int M, typename CT>
 static void launch_norm_t(rks_plan* p, int fuse, cudaStream_t stream) {
     const DevPlan& d = p->d;
+    if (p->multi_n) {
+        long long gx = (d.n_c + 127) / 128;
+        if (gx > MULTI_NORM_BLOCKS) gx = MULTI_NORM_BLOCKS;
+        norm_kernel_multi<M, CT, true><<<dim3((unsigned)gx, 1, (unsigned)p->multi_n), 128, 0, stream>>>(p->multi_dev, fuse);
+        return;
+    }
     const long long ncols = d.lin_full ? d.batch * d.n_c : d.n_c;
     const long long nrows = d.lin_full ? 1 : d.batch;
     const long long target = (long long)p->sm_count * 8;          // resident 128-thread CTAs we aim for
@@ -598,6 +802,7 @@ extern "C" int rks_error_sums(rks_plan* p, void* stream) {
 extern "C" int rks_controller(rks_plan* p, void* stream) {
     if (!p) return fail(RKS_ERR_ARG, "plan is null");
     if (!method_adaptive(p->method)) return fail(RKS_ERR_UNSUPPORTED, "fixed-step methods have no controller");
+    if (p->multi_n) return fail(RKS_ERR_UNSUPPORTED, "independent-dt plans run the controller inside rks_error_control");
     controller_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p->d);
     p->launches += 1;
     CUDA_TRY(cudaGetLastError());
@@ -611,6 +816,7 @@ extern "C" double* rks_reduction_scalars(rks_plan* p) { return p ? p->d.ctrl->re
 // ---------------------------------------------------------------------------------------
 extern "C" int rks_snapshot(rks_plan* p, void* ring, double* ring_t, int cap, void* stream) {
     if (!p || !ring || !ring_t || cap < 1) return fail(RKS_ERR_ARG, "bad snapshot ring");
+    if (p->multi_n) return fail(RKS_ERR_UNSUPPORTED, "snapshots are not available with independent dt");
     snapshot_kernel<<<copy_grid(p), 256, 0, (cudaStream_t)stream>>>(p->d, (cplx*)ring, ring_t, cap);
     p->launches += 1;
     CUDA_TRY(cudaGetLastError());
@@ -696,9 +902,19 @@ extern "C" int rks_run_fixed(rks_plan* p, int nsteps, void* stream) {
 extern "C" int rks_read_ctrl(rks_plan* p, rks_ctrl_host* out, void* stream_v) {
     if (!p || !out) return fail(RKS_ERR_ARG, "null argument");
     cudaStream_t stream = (cudaStream_t)stream_v;
+    int running = 0;
+    if (p->multi_n) {
+        // aggregate view: fields of row 0, status RUNNING while any row is still stepping
+        CUDA_TRY(cudaMemsetAsync(p->multi_count_dev, 0, 2 * sizeof(int), stream));
+        count_running_kernel<<<(unsigned)((p->multi_n + 255) / 256), 256, 0, stream>>>(p->multi_dev, (int)p->multi_n, p->multi_count_dev);
+        p->launches += 1;
+        CUDA_TRY(cudaMemcpyAsync(p->multi_count_host, p->multi_count_dev, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    }
     CUDA_TRY(cudaMemcpyAsync(p->pinned_raw, p->d.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
-    const Ctrl& c = *p->pinned_raw;
+    if (p->multi_n) running = p->multi_count_host[0];
+    Ctrl& c = *p->pinned_raw;
+    if (p->multi_n) c.status = running > 0 ? ST_RUNNING : p->multi_count_host[1];
     out->h = c.h; out->h_last = c.h_last; out->h_coeff = c.h_coeff; out->t = c.t; out->tf = c.tf;
     out->s_last = c.s_last;
     out->step_count = c.step_count; out->trial_count = c.trial_count; out->nl_evals = c.nl_evals;
@@ -708,6 +924,38 @@ extern "C" int rks_read_ctrl(rks_plan* p, rks_ctrl_host* out, void* stream_v) {
     out->log_count = c.log_count; out->snap_count = c.snap_count;
     p->roles_u_sel = c.u_sel;
     p->roles_n_sel = c.n_sel;
+    return RKS_OK;
+}
+
+static void ctrl_to_host(const Ctrl& c, rks_ctrl_host* out) {
+    out->h = c.h; out->h_last = c.h_last; out->h_coeff = c.h_coeff; out->t = c.t; out->tf = c.tf;
+    out->s_last = c.s_last;
+    out->step_count = c.step_count; out->trial_count = c.trial_count; out->nl_evals = c.nl_evals;
+    out->coeff_updates = c.coeff_updates;
+    out->status = c.status; out->accept = c.accept; out->numloops = c.numloops;
+    out->u_sel = c.u_sel; out->n_sel = c.n_sel; out->need_n1 = c.need_n1;
+    out->log_count = c.log_count; out->snap_count = c.snap_count;
+}
+
+// independent-dt ensembles: control block of every row, and the last trial records of one row
+extern "C" int rks_read_rows(rks_plan* p, rks_ctrl_host* out, int64_t nrows, void* stream_v) {
+    if (!p || !out || !p->multi_n || nrows != p->multi_n) return fail(RKS_ERR_ARG, "rks_read_rows needs an independent-dt plan and one slot per row");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    CUDA_TRY(cudaMemcpyAsync(p->multi_ctrl_host, p->multi_ctrl_base, p->multi_ctrl_stride * (size_t)nrows, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    for (int64_t r = 0; r < nrows; ++r)
+        ctrl_to_host(*(const Ctrl*)((const unsigned char*)p->multi_ctrl_host + p->multi_ctrl_stride * (size_t)r), &out[r]);
+    return RKS_OK;
+}
+
+extern "C" int rks_read_row_log(rks_plan* p, int64_t row, rks_trial_rec* out, int first, int count, void* stream_v) {
+    if (!p || !out || !p->multi_n || row < 0 || row >= p->multi_n || first < 0 || count < 0 || count > MULTI_LOG_CAP)
+        return fail(RKS_ERR_ARG, "bad row log range");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    CUDA_TRY(cudaMemcpyAsync(p->pinned_log, p->multi_log_base + (size_t)row * MULTI_LOG_CAP, sizeof(TrialRec) * MULTI_LOG_CAP,
+                             cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    for (int i = 0; i < count; ++i) memcpy(&out[i], &p->pinned_log[(first + i) % MULTI_LOG_CAP], sizeof(TrialRec));
     return RKS_OK;
 }
 
@@ -836,6 +1084,7 @@ extern "C" void* rks_array(rks_plan* p, const char* name) {
     if (s == "ERR") return d.ERR;
     if (s == "ctrl") return d.ctrl;
     if (s == "tw") return (void*)d.tw;
+    if (s == "row_logs") return p->multi_n ? (void*)p->multi_log_base : nullptr;
     if (s.size() == 2 && s[0] == 'N' && s[1] >= '1' && s[1] <= '7') {
         const int j = s[1] - '0';
         return j <= method_nl_buffers(p->method) ? d.NL[j] : nullptr;

@@ -6,10 +6,12 @@ Two ways to step a batch ``u0`` of shape ``(B, n_c)``:
   broadcast semantics apply -- one dt for everybody, global max / global 2-norms over the batch
   (solveras.py:451-454) -- and the batch may be sharded over GPUs (``group=``).
 * **independent dt** (cfg 2b): every trajectory is its own adaptive problem with its own controller.
-  ``evolve_independent`` below runs one plan per trajectory, round-robin on a few CUDA streams so
-  that the small kernels of different trajectories overlap.  Results are identical to B separate
-  reference runs.  This is the functional form; per-trajectory control blocks inside one set of
-  batched kernels (per-row h, roles and coefficient arrays) are not built yet.
+  With a fused nonlinearity use ``solver.evolve_independent(u0, t0, tf)`` (solveras.py): one plan
+  holds a control block, coefficient arrays and buffer roles per trajectory, and one set of launches
+  (``gridDim.z`` = trajectory) steps all of them.  ``evolve_independent`` below is the general form
+  for arbitrary torch ``nl_func`` callables: one plan per trajectory, round-robin on a few CUDA
+  streams so that the small kernels of different trajectories overlap.  Both give results identical
+  to B separate reference runs.
 """
 from __future__ import annotations
 

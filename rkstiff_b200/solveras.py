@@ -15,6 +15,7 @@ from typing import Callable, List, Optional, Tuple, Union
 import torch
 
 from . import _abi
+from ._engine import Engine
 from .solver import BaseSolver
 from .util.solver_type import SolverType
 
@@ -196,6 +197,61 @@ class BaseSolverAS(BaseSolver):
         self._last_out = (eng, out.data_ptr(), out._version)
         self.logger.debug("Step accepted, returning h=%s, h_suggest=%s", c.h_last, c.h)
         return out, c.h_last, c.h
+
+    # -- independent-dt ensembles (BASELINE cfg 2b) ---------------------------------------------
+    def evolve_independent(self, u: torch.Tensor, t0: float, tf: float, h_init: Optional[float] = None,
+                           keep_log: bool = True):
+        """Evolve every row of ``u`` (shape ``(B, n_c)``) as its own adaptive problem: B reference solvers
+        (solveras.py:279-325 per trajectory), each with its own dt sequence, accept/reject decisions and
+        coefficient arrays, stepped together by one set of kernel launches.  Needs a fused nonlinearity.
+
+        Returns ``(u_final, logs)`` with ``logs[b] = [(h, s, accepted, t_after), ...]`` of trajectory b
+        (empty lists with ``keep_log=False``).  A trajectory that fails raises the reference's exception.
+        ``solver.t`` / ``solver.u`` are not filled: rows are at different times in between."""
+        if self._fused() is None:
+            raise ValueError("evolve_independent needs a fused nonlinearity (rkstiff_b200.models.*_ops)")
+        if u.dim() != 2:
+            raise ValueError("u must have shape (batch, n_c)")
+        self.reset()
+        if h_init is None:
+            h_init = (tf - t0) / 100.0
+        h = h_init
+        if t0 + h > tf:
+            h = tf - t0
+        nrows = int(u.shape[0])
+        logs = [[] for _ in range(nrows)]
+        if not t0 < tf:
+            return u, logs
+        key = ("independent",) + tuple(u.shape)
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = Engine(self.METHOD, self.lin_op, u.shape, self._rks_config(), fused=self._fused(), independent=True)
+            self._engines = {key: eng}
+            self._cfg_sig = self._config_signature()
+        elif self._cfg_sig != self._config_signature():
+            eng.set_config(self._rks_config())
+            self._cfg_sig = self._config_signature()
+        self._engine = eng
+        eng.begin(t0, tf, h, 0, False, keep_fsal=False)
+        eng.set_u(u)
+        chunk = min(self.CHUNK, _abi.ROW_LOG_CAP)
+        drained = [0] * nrows
+        while True:
+            eng.run_trials(chunk)
+            c = eng.read_ctrl()
+            if keep_log:
+                rows = eng.read_rows()
+                ring = eng.row_logs()
+                for b in range(nrows):
+                    for i in range(drained[b], rows[b].log_count):
+                        r = ring[b, i % _abi.ROW_LOG_CAP]
+                        logs[b].append((float(r["h"]), float(r["s"]), bool(r["accepted"]), float(r["t_after"])))
+                    drained[b] = rows[b].log_count
+            if c.status != _abi.CTRL_RUNNING:
+                break
+        self._raise_on_failure(c.status)
+        self.logger.info("Independent evolution of %d trajectories complete", nrows)
+        return eng.get_u(), logs
 
     # -- evolve() ----------------------------------------------------------------------------
     def evolve(self, u: torch.Tensor, t0: float, tf: float, h_init: Optional[float] = None,

@@ -238,6 +238,7 @@ void hc_ctrl_init(void* blob, double t0, double tf, double h, long long store_fr
     c->epsilon = epsilon; c->incr_f = incr_f; c->decr_f = decr_f; c->safety_f = safety_f; c->minh = minh;
     c->inv_q = 1.0 / (double)q;
     c->h_coeff = NAN;
+    c->log_cap = LOG_CAP;
 }
 // out: {h, h_last, t, s_last, status, accept, numloops, u_sel, n_sel, need_n1, step_count, snap_pending, snap_count}
 void hc_ctrl_advance(void* blob, double sum_u2, double sum_e2, double* out) {

@@ -405,3 +405,62 @@ def test_cfg2b_independent_dt_matches_per_trajectory_reference_runs(rk):
         assert rel(host(uf[b]), uo) < FINAL_TOL
         lengths.add(tuple(round(r.h, 12) for r in ora.log))
     assert len(lengths) > 1                     # the trajectories really take different dt sequences
+
+
+INDEP_CASES = [
+    ("ETD35", "nls", 512), ("ETD34", "ks", 1024), ("IF34", "kdv", 256), ("IF45DP", "nls", 128),
+    ("ETD35", "burgers", 2048), ("ETD34", "nls", 64),        # n < 512: generic shared-memory NL kernel
+]
+
+
+@pytest.mark.parametrize("method,prob,n", INDEP_CASES, ids=[f"{m}-{q}{n}" for m, q, n in INDEP_CASES])
+def test_cfg2b_batched_independent_dt_matches_per_trajectory_oracle(rk, method, prob, n):
+    """cfg 2b in one plan: per-trajectory control blocks, coefficient arrays and buffer roles, stepped by
+    one set of launches, reproduce B separate reference runs (accept/reject sequence, dt, final state)."""
+    B = 6
+    if prob == "nls":
+        p = problems.nls(n, batch=B, seed=3, half_width=20.0)
+        lin, nl = rk.models.nls_ops(dev(p.kx), 2.0)
+        tf = 0.15
+    elif prob == "ks":
+        p = problems.ks(n, batch=B, seed=3)
+        lin, nl = rk.models.ks_ops(dev(p.kx))
+        tf = 2.0
+    elif prob == "kdv":
+        p = problems.kdv(n, batch=B, seed=3)
+        lin, nl = rk.models.kdv_ops(dev(p.kx))
+        tf = 0.2
+    else:
+        p = problems.burgers(n, mu=0.01, batch=B, seed=3)
+        lin, nl = rk.models.burgers_ops(dev(p.kx), 0.01)
+        tf = 0.1
+    # rows of different amplitude so that the controllers really diverge
+    scale = np.linspace(0.6, 1.4, B).reshape(B, 1)
+    u0 = p.u0 * scale
+    eps = 1e-7 if prob == "kdv" else 1e-6
+    sol = getattr(rk, method)(lin, nl, config=rk.SolverConfig(epsilon=eps))
+    uf, logs = sol.evolve_independent(dev(u0), 0.0, tf)
+    seqs = set()
+    for b in range(B):
+        ora = OracleSolver(method, p.lin_op, p.nl_func, Config(epsilon=eps))
+        uo = ora.evolve(u0[b], 0.0, tf)
+        assert [r[2] for r in logs[b]] == [r.accepted for r in ora.log], f"row {b}"
+        hs, ho = np.array([r[0] for r in logs[b]]), np.array([r.h for r in ora.log])
+        np.testing.assert_allclose(hs[:-1], ho[:-1], rtol=DT_TOL)
+        # the last dt is tf - t: a difference that carries the summed absolute deviation of all dts before it
+        np.testing.assert_allclose(hs[-1], ho[-1], rtol=0, atol=DT_TOL * tf)
+        assert rel(host(uf[b]), uo) < FINAL_TOL, f"row {b}"
+        seqs.add(tuple(round(r.h, 12) for r in ora.log))
+    assert len(seqs) > 1
+    # a second evolve on the same plan restarts every row cleanly
+    uf2, logs2 = sol.evolve_independent(dev(u0), 0.0, tf)
+    assert torch.equal(uf, uf2) and logs == logs2
+
+
+def test_cfg2b_batched_independent_failure_status_surfaces(rk):
+    """One trajectory hitting the minimum step makes the whole call raise the reference's exception."""
+    p = problems.nls(256, batch=3, seed=1, half_width=20.0)
+    lin, nl = rk.models.nls_ops(dev(p.kx), 2.0)
+    sol = rk.ETD35(lin, nl, config=rk.SolverConfig(epsilon=1e-12, minh=1e-3))
+    with pytest.raises(sol.MinimumStepReached):
+        sol.evolve_independent(dev(p.u0), 0.0, 1.0, h_init=0.5)
