@@ -204,6 +204,15 @@ struct ArraySource {
     const cplx* in;
     RKS_HD cplx value(long long p) const { return row_ld(in + p); }
 };
+// n = 8192 rows fill 128 KB of shared memory, so only one row is resident per SM and its HBM read
+// cannot overlap another row's arithmetic.  The head of the NEXT row (`nst` elements; all of a half
+// spectrum) is therefore copied by the TMA engine (cp.async.bulk, kernels.cuh) into the spare shared
+// memory while the current row is transformed; the tail still comes from global (L2-prefetched).
+struct StagedRow {
+    const cplx* in; const cplx* stg; int nst;
+    RKS_HD cplx value(long long p) const { return p < nst ? stg[p] : row_ld(in + p); }
+    RKS_HD cplx get(int k) const { return k < nst ? stg[k] : row_ld(in + k); }
+};
 struct StateSink {
     cplx* kout;                     // nullptr: the stage value is not a state
     unsigned long long* mx;         // nullptr: no max tracking; else running max of the bit pattern of |k|^2
@@ -317,11 +326,15 @@ struct SineGordonModel {
 };
 
 // model ids of include/rkstiff_b200.h -> model objects reading/writing plain arrays
+// (make_staged: input row partly staged in shared memory, models 1-3)
 template <int MODEL> struct ModelOf;
 template <> struct ModelOf<1> {
     using type = UuxModel;
     RKS_HD static type make(const cplx* in, cplx* out, const double* kx, double p0, int n, bool on) {
         return type{GlobalHalf{in}, out, kx, p0, n, on};
+    }
+    RKS_HD static UuxModelT<StagedRow> make_staged(StagedRow s, cplx* out, const double* kx, double p0, int n, bool on) {
+        return UuxModelT<StagedRow>{s, out, kx, p0, n, on};
     }
 };
 template <> struct ModelOf<2> {
@@ -329,11 +342,17 @@ template <> struct ModelOf<2> {
     RKS_HD static type make(const cplx* in, cplx* out, const double*, double p0, int n, bool on) {
         return type{ArraySource{in}, StateSink{nullptr, nullptr}, out, p0, n, on};
     }
+    RKS_HD static NlsModelT<StagedRow> make_staged(StagedRow s, cplx* out, const double*, double p0, int n, bool on) {
+        return NlsModelT<StagedRow>{s, StateSink{nullptr, nullptr}, out, p0, n, on};
+    }
 };
 template <> struct ModelOf<3> {
     using type = CubicModel;
     RKS_HD static type make(const cplx* in, cplx* out, const double*, double p0, int n, bool on) {
         return type{GlobalHalf{in}, out, p0, n, on};
+    }
+    RKS_HD static CubicModelT<StagedRow> make_staged(StagedRow s, cplx* out, const double*, double p0, int n, bool on) {
+        return CubicModelT<StagedRow>{s, out, p0, n, on};
     }
 };
 template <> struct ModelOf<4> {

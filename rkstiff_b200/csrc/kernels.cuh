@@ -486,12 +486,16 @@ RKS_D void inner_pingpong_8192(cplx* sm, int T, const fast::Twiddles& ti, const 
     if (tok.g == 0) tok.release();           // group 1 primed one extra arrival: it skips its last release
 }
 
-template <int N, class Model>
+struct NoHook { RKS_D void operator()() const {} };
+
+// `after_first` runs once the first pass has consumed the row's input (staging buffer free again)
+template <int N, class Model, class Hook = NoHook>
 RKS_D void nl_fast_row(cplx* sm, int T, int lrow, int rpc, const fast::Twiddles& ti, const fast::Twiddles& tf,
-                       const Model& m) {
+                       const Model& m, const Hook& after_first = Hook()) {
     constexpr int W = fast::Plan<N>::W, TR = 32 * W;
     fast::phase_first<N>(sm, T, ti, m);
     row_barrier<TR>(lrow, rpc);
+    after_first();
     if (N == 8192 && RKS_PINGPONG) {
         inner_pingpong_8192(sm, T, ti, tf, m);
     } else {
@@ -512,6 +516,44 @@ RKS_D void prefetch_row_l2(const void* row, int lines, int T) {
     const char* base = reinterpret_cast<const char*>(row);
     for (int q = T; q < lines; q += TR) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ((size_t)q << 7)));
 }
+
+// TMA staging of the next input row (n = 8192: one row per SM, see fft_fast.cuh StagedRow).  One
+// mbarrier, one elected thread: arm it with the byte count, issue the bulk copies; every thread
+// waits on the phase parity before the first pass reads the staging buffer.
+constexpr int NL_STAGE_ELEMS = 6144;                 // 96 KB next to the 128 KB row slab
+constexpr int NL_STAGE_BYTES = NL_STAGE_ELEMS * 16 + 16;
+RKS_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+RKS_D void stage_init(unsigned long long* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+RKS_D void stage_issue(cplx* stg, const cplx* src, unsigned bytes, unsigned long long* bar) {
+    const unsigned b = smem_u32(bar);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic reads of stg vs the async writes
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    constexpr unsigned CHUNK = 32768;
+    for (unsigned off = 0; off < bytes; off += CHUNK) {
+        const unsigned sz = bytes - off < CHUNK ? bytes - off : CHUNK;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(stg) + off), "l"(reinterpret_cast<const char*>(src) + off), "r"(sz), "r"(b)
+                     : "memory");
+    }
+}
+RKS_D void stage_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "RKS_STAGE_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra RKS_STAGE_DONE;\n"
+        "bra RKS_STAGE_WAIT;\n"
+        "RKS_STAGE_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+struct StageNext {          // after the first pass: start copying the head of the next row
+    cplx* stg; const cplx* src; unsigned bytes; unsigned long long* bar; bool go;
+    RKS_D void operator()() const { if (go) stage_issue(stg, src, bytes, bar); }
+};
 
 // FK = 0: N_j = N(existing array).  FK = 1 / 2: the stage combine (fuse.cuh, complex / real
 // coefficient arrays) is evaluated in the load prologue, so the stage value k never goes to HBM
@@ -560,6 +602,20 @@ RKS_D void nl_fast_kernel_body(const DevPlan& p, int j, int force, FuseDesc fd) 
         if (fd.write_k) kbase = adapt ? p.U[1 - u_sel] : p.U[0];
     }
 
+    // n = 8192, plain evaluation: input rows arrive through the TMA staging buffer
+    constexpr bool STAGED = W == 16 && FK == 0 && MODEL >= 1 && MODEL <= 3;
+    cplx* stg = reinterpret_cast<cplx*>(smem_raw) + (size_t)RPC * N;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(stg + NL_STAGE_ELEMS);
+    const int nst = p.n_c < NL_STAGE_ELEMS ? (int)p.n_c : NL_STAGE_ELEMS;
+    unsigned parity = 0;
+    if (STAGED) {
+        if (threadIdx.x == 0) {
+            stage_init(bar);
+            if ((long long)blockIdx.x < groups) stage_issue(stg, roles.in + (long long)blockIdx.x * p.n_c, nst * 16u, bar);
+        }
+        __syncthreads();
+    }
+
     for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
         const long long row = g * RPC + lrow;
         const bool on = row < p.batch;
@@ -567,7 +623,18 @@ RKS_D void nl_fast_kernel_body(const DevPlan& p, int j, int force, FuseDesc fd) 
         const long long nrow = row + (long long)gridDim.x * RPC;     // the row this slot handles next
         const int nlines = nrow < p.batch ? lines : 0;
         cplx* out = roles.out + rr * p.n_c;
-        if (FK == 0) {
+        if constexpr (STAGED) {
+            // L2-prefetch only the tail of the next row that does not fit the staging buffer
+            const int head = (nst * 16) >> 7;
+            if (nlines > head)
+                prefetch_row_l2<TR>(reinterpret_cast<const char*>(roles.in + nrow * p.n_c) + ((size_t)head << 7), nlines - head, T);
+            stage_wait(bar, parity);
+            parity ^= 1u;
+            const auto m = fast::ModelOf<MODEL>::make_staged(fast::StagedRow{roles.in + rr * p.n_c, stg, nst}, out, p.kx,
+                                                             p.model_p0, N, on);
+            const StageNext next{stg, roles.in + (nlines ? nrow : rr) * p.n_c, nst * 16u, bar, nlines != 0 && threadIdx.x == 0};
+            nl_fast_row<N>(sm, T, lrow, RPC, ti, tf, m, next);
+        } else if (FK == 0) {
             prefetch_row_l2<TR>(roles.in + (nlines ? nrow : rr) * p.n_c, nlines, T);
             const auto m = fast::ModelOf<MODEL>::make(roles.in + rr * p.n_c, out, p.kx, p.model_p0, N, on);
             nl_fast_row<N>(sm, T, lrow, RPC, ti, tf, m);

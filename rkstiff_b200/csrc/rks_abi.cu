@@ -114,7 +114,10 @@ static size_t nl_fast_smem(int model, int fk) {
     constexpr int RPC = THREADS / (32 * W);
     size_t elems = (size_t)RPC * 512 * W;
     if (fk > 0 && model == RKS_MODEL_UUX_RFFT) elems += (size_t)RPC * (512 * W / 2 + 8);
-    return elems * sizeof(cplx);
+    size_t bytes = elems * sizeof(cplx);
+    // n = 8192 plain evaluation: TMA staging buffer for the next row + its mbarrier (kernels.cuh)
+    if (W == 16 && fk == 0 && model >= RKS_MODEL_UUX_RFFT && model <= RKS_MODEL_CUBIC_RFFT) bytes += NL_STAGE_BYTES;
+    return bytes;
 }
 
 template <int W, int MODEL, int FK>
