@@ -97,7 +97,7 @@ RKS_HD void controller_advance(Ctrl& c, TrialRec* log) {
         rec.accepted = 1; rec.t_after = c.t;
     }
     c.need_n1 = (c.accept && c.n1_refresh) ? 1 : 0;     // ETD35 is not FSAL: etd35.py:317-318
-    log[c.log_count % c.log_cap] = rec;
+    log[c.log_count & (c.log_cap - 1)] = rec;          // ring capacities are powers of two
     c.log_count += 1;
     // reset the reduction scalars for the next trial
     c.red[0] = 0.0; c.red[1] = 0.0; c.red[2] = 0.0;

@@ -237,7 +237,7 @@ RKS_D void coef_kernel_body(const DevPlan& p, int force) {
     }
 }
 template <int FAM, typename LT>
-__global__ void __launch_bounds__(128) coef_kernel(DevPlan p, int force) { coef_kernel_body<FAM, LT>(p, force); }
+__global__ void __launch_bounds__(128) coef_kernel(const __grid_constant__ DevPlan p, int force) { coef_kernel_body<FAM, LT>(p, force); }
 // one plan per blockIdx.z: ensembles whose trajectories keep their own dt (rks_multi_*)
 template <int FAM, typename LT>
 __global__ void __launch_bounds__(128) coef_kernel_multi(const DevPlan* plans, int force) { coef_kernel_body<FAM, LT>(plans[blockIdx.z], force); }
@@ -339,7 +339,7 @@ RKS_D void stage_kernel_body(const DevPlan& p) {
     }
 }
 template <int M, int S, typename CT, bool FULL>
-__global__ void __launch_bounds__(256) stage_kernel(DevPlan p) { stage_kernel_body<M, S, CT, FULL>(p); }
+__global__ void __launch_bounds__(256) stage_kernel(const __grid_constant__ DevPlan p) { stage_kernel_body<M, S, CT, FULL>(p); }
 // one plan per blockIdx.z: ensembles whose trajectories keep their own dt (rks_multi_*)
 template <int M, int S, typename CT, bool FULL>
 __global__ void __launch_bounds__(256) stage_kernel_multi(const DevPlan* plans) { stage_kernel_body<M, S, CT, FULL>(plans[blockIdx.z]); }
@@ -413,7 +413,7 @@ RKS_D void nl_kernel_body(const DevPlan& p, int j, int force, int rows_per_cta) 
         for (int q = tid; q < n; q += tpr) m.store(q, x[q]);
 }
 template <int MODEL>
-__global__ void __launch_bounds__(1024) nl_kernel(DevPlan p, int j, int force, int rows_per_cta) { nl_kernel_body<MODEL>(p, j, force, rows_per_cta); }
+__global__ void __launch_bounds__(1024) nl_kernel(const __grid_constant__ DevPlan p, int j, int force, int rows_per_cta) { nl_kernel_body<MODEL>(p, j, force, rows_per_cta); }
 // one plan per blockIdx.z: ensembles whose trajectories keep their own dt (rks_multi_*)
 template <int MODEL>
 __global__ void __launch_bounds__(1024) nl_kernel_multi(const DevPlan* plans, int j, int force, int rows_per_cta) { nl_kernel_body<MODEL>(plans[blockIdx.z], j, force, rows_per_cta); }
@@ -695,7 +695,7 @@ RKS_D void nl_fast_kernel_body(const DevPlan& p, int j, int force, FuseDesc fd) 
     }
 }
 template <int W, int MODEL, int FK>
-__global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_fast_kernel(DevPlan p, int j, int force, FuseDesc fd) { nl_fast_kernel_body<W, MODEL, FK>(p, j, force, fd); }
+__global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_fast_kernel(const __grid_constant__ DevPlan p, int j, int force, FuseDesc fd) { nl_fast_kernel_body<W, MODEL, FK>(p, j, force, fd); }
 // one plan per blockIdx.z: ensembles whose trajectories keep their own dt (rks_multi_*)
 template <int W, int MODEL, int FK>
 __global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_fast_kernel_multi(const DevPlan* plans, int j, int force, FuseDesc fd) { nl_fast_kernel_body<W, MODEL, FK>(plans[blockIdx.z], j, force, fd); }
@@ -801,7 +801,7 @@ RKS_D void norm_kernel_body(const DevPlan& p, int fuse_controller) {
     }
 }
 template <int M, typename CT, bool FULL>
-__global__ void __launch_bounds__(128) norm_kernel(DevPlan p, int fuse_controller) { norm_kernel_body<M, CT, FULL>(p, fuse_controller); }
+__global__ void __launch_bounds__(128) norm_kernel(const __grid_constant__ DevPlan p, int fuse_controller) { norm_kernel_body<M, CT, FULL>(p, fuse_controller); }
 // one plan per blockIdx.z: ensembles whose trajectories keep their own dt (rks_multi_*)
 template <int M, typename CT, bool FULL>
 __global__ void __launch_bounds__(128) norm_kernel_multi(const DevPlan* plans, int fuse_controller) { norm_kernel_body<M, CT, FULL>(plans[blockIdx.z], fuse_controller); }

@@ -764,7 +764,17 @@ static void launch_norm_t(rks_plan* p, int fuse, cudaStream_t stream) {
     }
     const long long ncols = d.lin_full ? d.batch * d.n_c : d.n_c;
     const long long nrows = d.lin_full ? 1 : d.batch;
-    const long long target = (long long)p->sm_count * 8;          // resident 128-thread CTAs we aim for
+    // one wave of resident 128-thread CTAs (a partial second wave costs as much as a full one)
+    static int per_sm = 0;
+    if (!per_sm) {
+        int full = 0, bcast = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&full, norm_kernel<M, CT, true>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bcast, norm_kernel<M, CT, false>, 128, 0);
+        per_sm = full < bcast ? full : bcast;
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 8) per_sm = 8;
+    }
+    const long long target = (long long)p->sm_count * per_sm;
     long long gx = (ncols + 127) / 128;
     if (gx > target) gx = target;
     long long gy = target / gx;
