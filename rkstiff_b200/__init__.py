@@ -6,7 +6,8 @@ runs in hand-written sm_100a CUDA kernels behind a C ABI (include/rkstiff_b200.h
 fallback: importing the package loads ``librkstiff_b200.so`` and fails loudly if it is missing.
 """
 from . import _abi  # noqa: F401  (loads the CUDA library or raises)
-from . import etd, etd4, etd5, etd34, etd35, grids, if4, if34, if45dp, models, solver, solveras, solvercs  # noqa: F401
+from . import (derivatives, etd, etd4, etd5, etd34, etd35, grids, if4, if34, if45dp, models, solver,  # noqa: F401
+               solveras, solvercs)
 from .etd import ETDConfig
 from .etd4 import ETD4
 from .etd5 import ETD5

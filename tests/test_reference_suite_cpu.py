@@ -95,3 +95,36 @@ def test_matrix_operators_are_rejected_not_emulated():
             rk.IF34(lin, lambda v: v, diagonalize=True)
     with pytest.raises(TypeError):
         rk.ETD4([1.0, 2.0], lambda v: v)
+
+
+def test_device_derivatives_match_reference_semantics():
+    """derivatives.dx_rfft / dx_fft: same results and the same errors as rkstiff/derivatives.py:47-179
+    (its doctests: d/dx sin = cos, d/dx e^{ix} = i e^{ix}); torch tensors, leading batch allowed."""
+    import math
+
+    import numpy as np
+    import torch
+    from rkstiff_b200 import derivatives as d
+    n, length = 128, 2 * math.pi
+    x = torch.arange(n, dtype=torch.float64) * (length / n)
+    kr = torch.from_numpy(np.fft.rfftfreq(n, d=length / n) * 2 * np.pi)
+    kc = torch.from_numpy(np.fft.fftfreq(n, d=length / n) * 2 * np.pi)
+    assert torch.allclose(d.dx_rfft(kr, torch.sin(x)), torch.cos(x), atol=1e-10)
+    assert torch.allclose(d.dx_rfft(kr, torch.sin(x), 2), -torch.sin(x), atol=1e-10)
+    u = torch.exp(1j * x)
+    assert torch.allclose(d.dx_fft(kc, u), 1j * u, atol=1e-10)
+    batch = torch.stack([torch.sin(x), torch.cos(2 * x)])
+    ref = np.fft.irfft((1j * kr.numpy()) ** 3 * np.fft.rfft(batch.numpy(), axis=-1), n=n, axis=-1)
+    np.testing.assert_allclose(d.dx_rfft(kr, batch, 3).numpy(), ref, rtol=0, atol=1e-9)
+    assert d.dx_rfft(kr, batch, 0) is batch and d.dx_fft(kc, u, 0) is u
+    with pytest.raises(TypeError):
+        d.dx_rfft(kr, torch.sin(x), 1.5)
+    with pytest.raises(ValueError):
+        d.dx_rfft(kr, torch.sin(x), -1)
+    with pytest.raises(TypeError):
+        d.dx_rfft(kr, u)
+    with pytest.raises(ValueError):
+        d.dx_rfft(kc, torch.sin(x))
+    with pytest.raises(ValueError):
+        d.dx_fft(kr, u)
+    assert d.dx_rfft(kr, torch.empty(0, dtype=torch.float64)).numel() == 0
