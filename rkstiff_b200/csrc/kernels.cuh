@@ -507,7 +507,8 @@ RKS_D void nl_fast_row(cplx* sm, int T, int lrow, int rpc, const fast::Twiddles&
     }
     row_barrier<TR>(lrow, rpc);
     fast::phase_last<N>(sm, T, tf, m);
-    row_barrier<TR>(lrow, rpc);              // slab reads of the last pass vs the next row's first pass
+    // no barrier here: the last pass reads exactly the slab positions (T + 32 W c + Q1 s) that the same
+    // thread overwrites in the first pass of its next row, so warps run on into the next row's loads
 }
 
 // pull a row that will be needed soon from HBM into L2 (no registers, no smem)
