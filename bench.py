@@ -398,12 +398,24 @@ def run_cfg2b(args):
     rows = sol._engine.read_rows()
     trials = sum(int(r.trial_count) for r in rows)
     steps_max = max(int(r.trial_count) for r in rows)
+    updates = sum(int(r.coeff_updates) for r in rows)
+    secs_local = secs
     if world > 1:
         t = torch.tensor([secs, float(trials), float(steps_max)], dtype=torch.float64, device=device)
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         secs, trials, steps_max = float(tmax[0]), int(t[1]), int(tmax[2])
+    # byte model of a row-trial with per-row coefficients: the 736 B of the shared-dt trial
+    # + 23 coefficient reads in K1 (16 B each) + 21 coefficient writes whenever the row's dt changed
+    local_trials = sum(int(r.trial_count) for r in rows)
+    alg = n * (local_trials * (736 + 23 * 16) + updates * 21 * 16)
+    peak = 6549.8
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak = float(json.load(f).get("hbm_gbs", peak))
+    except OSError:
+        pass
     if rank == 0:
         print(json.dumps({"metric": METRIC, "value": n * trials / secs, "unit": UNIT, "n_gpus": world,
                           "steps": steps_max, "warmup": 0, "ms_per_step": 1e3 * secs / steps_max,
@@ -414,6 +426,9 @@ def run_cfg2b(args):
                                      "method": "ETD35", "n": n, "batch_per_gpu": batch,
                                      "parallelism": f"batch x{world} (no collective)"},
                           "row_trials": trials, "launch_rounds": steps_max,
+                          "roofline": {"bound": "hbm", "kernel": "whole run, rank 0 (per-row coefficient byte model)",
+                                       "achieved": alg / secs_local / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": alg / secs_local / 1e9 / peak, "traffic": None},
                           "gpu_launches": sol._engine.launches()}))
     if world > 1:
         dist.destroy_process_group()

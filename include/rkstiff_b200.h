@@ -211,6 +211,18 @@ int rks_rows_create(rks_rows** out, int model, int64_t n, const double* kx, doub
 int rks_rows_apply(rks_rows* rows, const void* in, void* out, int64_t batch, void* stream);
 void rks_rows_destroy(rks_rows* rows);
 
+/* N-D grids: transform along a STRIDED axis of a contiguous complex128 array viewed as
+ * [outer][n][inner] (n a power of two in 16..4096), the outer-axis part of the reference's
+ * `np.fft.ifft2 / fft2 / ifftn / fftn` calls in N-D nl_func closures (demos/nls.ipynb:500-508).
+ * inverse != 0: unnormalised-by-nothing inverse transform (scaled 1/n), natural order in,
+ * DIGIT-REVERSED order out along the axis; inverse == 0: forward transform taking that
+ * digit-reversed order back to natural order.  A pointwise nonlinearity in between does not
+ * depend on the order, so the pair replaces ifft / fft along the axis.  in == out is allowed. */
+typedef struct rks_axis rks_axis;
+int rks_axis_create(rks_axis** out, int64_t n, void* stream);
+int rks_axis_apply(rks_axis* axis, const void* in, void* out, int64_t outer, int64_t inner, int inverse, void* stream);
+void rks_axis_destroy(rks_axis* axis);
+
 /* the only syncing calls */
 int rks_read_ctrl(rks_plan* plan, rks_ctrl_host* out, void* stream);
 int rks_read_log(rks_plan* plan, rks_trial_rec* out_host, int first, int count, void* stream);

@@ -1,0 +1,126 @@
+// K4 for N-D grids -- FP64 FFT along a STRIDED axis of a contiguous array viewed as
+// [outer][N][inner] (the transforms over every axis but the last one of an N-D spectral model:
+// demos/nls.ipynb:500-508 `fft2`/`ifft2`, SURVEY.md 8a a14 "2-D 4096^2, 3-D 512^3").
+//
+// A CTA owns a tile of C adjacent columns (C consecutive `inner` indices = C*16 contiguous bytes per
+// row) times all N rows, held row-major in shared memory.  Lane -> (column = lane % C, butterfly):
+// the C lanes of a group touch one contiguous C*16-byte segment, both in global memory (coalesced,
+// full sectors) and in shared memory (conflict free), so no transpose is ever materialised.
+// Levels are the in-place radix-8/16 butterflies of fft_fast.cuh.  As for the rows, the inverse
+// transform is decimation-in-frequency (natural order in, digit-reversed order out) and the forward
+// transform the mirrored decimation-in-time: physical-space data stay digit-reversed ALONG THIS
+// AXIS between the two, which a pointwise nonlinearity does not notice.  First level: global ->
+// registers -> tile; last level: tile -> registers -> global; 2 smem round trips for 3 levels.
+#pragma once
+#include "fft_fast.cuh"
+
+namespace rks {
+namespace axis {
+
+// radices, outermost (largest stride) level first; unused levels are 1
+template <int N> struct APlan;
+template <> struct APlan<16>   { static constexpr int R1 = 16, R2 = 1,  R3 = 1;  };
+template <> struct APlan<32>   { static constexpr int R1 = 8,  R2 = 4,  R3 = 1;  };
+template <> struct APlan<64>   { static constexpr int R1 = 8,  R2 = 8,  R3 = 1;  };
+template <> struct APlan<128>  { static constexpr int R1 = 16, R2 = 8,  R3 = 1;  };
+template <> struct APlan<256>  { static constexpr int R1 = 16, R2 = 16, R3 = 1;  };
+template <> struct APlan<512>  { static constexpr int R1 = 8,  R2 = 8,  R3 = 8;  };
+template <> struct APlan<1024> { static constexpr int R1 = 16, R2 = 8,  R3 = 8;  };
+template <> struct APlan<2048> { static constexpr int R1 = 16, R2 = 16, R3 = 8;  };
+template <> struct APlan<4096> { static constexpr int R1 = 16, R2 = 16, R3 = 16; };
+
+// tile geometry: 64 KB tiles (128 KB for N = 4096 so that a row segment is still a full 32-byte sector)
+template <int N> RKS_HD constexpr int tile_cols() { return N <= 512 ? 8 : N == 1024 ? 4 : 2; }
+template <int N> RKS_HD constexpr int tile_threads() { return N == 4096 ? 512 : 256; }
+template <int N> RKS_HD constexpr int last_radix() {
+    return APlan<N>::R3 > 1 ? APlan<N>::R3 : APlan<N>::R2 > 1 ? APlan<N>::R2 : APlan<N>::R1;
+}
+// row swizzle (fft_fast.cuh swz): shift 4 when the stride-1 level is radix 16
+template <int N> RKS_HD constexpr int tile_shift() { return last_radix<N>() == 16 ? 4 : 3; }
+
+struct Col {                 // one thread's column of the tile and of the global array
+    const cplx* gin;         // in  + column offset (row 0)
+    cplx* gout;              // out + column offset
+    long long gstride;       // elements between consecutive rows (= inner)
+    int col;                 // column within the tile
+    bool ok;                 // column exists (inner need not be a multiple of C)
+};
+
+// one decimation-in-frequency level of the inverse transform: rows p0 + Q s, twiddles on the outputs
+template <int N, int R, int Q, bool FIRST, bool LAST>
+RKS_HD void dif_level(cplx* tile, const cplx* tw, const Col& c, int bt, int nbt, double scale) {
+    constexpr int C = tile_cols<N>(), SH = tile_shift<N>();
+#pragma unroll 1
+    for (int u = bt; u < N / R; u += nbt) {
+        const int j = u % Q, p0 = (u / Q) * (R * Q) + j;
+        cplx a[R];
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            if (FIRST) a[s] = c.ok ? fast::row_ld(c.gin + (long long)(p0 + Q * s) * c.gstride) : mk(0.0, 0.0);
+            else a[s] = tile[fast::swz<SH>(p0 + Q * s) * C + c.col];
+        }
+        fast::dftR<R, true>(a);
+        if (Q > 1) fast::twiddle_scale<R, true>(a, tw, 0, j * (N / (R * Q)), fast::SlotPerm<R>());
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const cplx v = a[fast::perm<R>(r)];
+            if (LAST) { if (c.ok) fast::row_st(c.gout + (long long)(p0 + Q * r) * c.gstride, mk(v.x * scale, v.y * scale)); }
+            else tile[fast::swz<SH>(p0 + Q * r) * C + c.col] = v;
+        }
+    }
+}
+
+// one decimation-in-time level of the forward transform: twiddles on the inputs
+template <int N, int R, int Q, bool FIRST, bool LAST>
+RKS_HD void dit_level(cplx* tile, const cplx* tw, const Col& c, int bt, int nbt) {
+    constexpr int C = tile_cols<N>(), SH = tile_shift<N>();
+#pragma unroll 1
+    for (int u = bt; u < N / R; u += nbt) {
+        const int j = u % Q, p0 = (u / Q) * (R * Q) + j;
+        cplx a[R];
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            if (FIRST) a[s] = c.ok ? fast::row_ld(c.gin + (long long)(p0 + Q * s) * c.gstride) : mk(0.0, 0.0);
+            else a[s] = tile[fast::swz<SH>(p0 + Q * s) * C + c.col];
+        }
+        if (Q > 1) fast::twiddle_scale<R, false>(a, tw, 0, j * (N / (R * Q)), fast::SlotId());
+        fast::dftR<R, false>(a);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const cplx v = a[fast::perm<R>(r)];
+            if (LAST) { if (c.ok) fast::row_st(c.gout + (long long)(p0 + Q * r) * c.gstride, v); }
+            else tile[fast::swz<SH>(p0 + Q * r) * C + c.col] = v;
+        }
+    }
+}
+
+struct NoSync { RKS_HD void operator()() const {} };
+
+// all levels of one tile; `sync` separates the levels (__syncthreads on the device, nothing in the
+// serial host emulation, which runs a level for every thread before the next one)
+template <int N, bool INV, int LEVEL>
+RKS_HD void tile_level(cplx* tile, const cplx* tw, const Col& c, int bt, int nbt, double scale) {
+    using P = APlan<N>;
+    constexpr int NL = P::R3 > 1 ? 3 : P::R2 > 1 ? 2 : 1;
+    constexpr int Q1 = N / P::R1, Q2 = Q1 / P::R2;
+    if (LEVEL >= NL) return;
+    if (INV) {
+        if (LEVEL == 0) dif_level<N, P::R1, Q1, true, NL == 1>(tile, tw, c, bt, nbt, scale);
+        else if (LEVEL == 1) dif_level<N, P::R2, Q2, false, NL == 2>(tile, tw, c, bt, nbt, scale);
+        else dif_level<N, P::R3, 1, false, true>(tile, tw, c, bt, nbt, scale);
+    } else {
+        // mirrored order: stride-1 level first, the R1 level last
+        if (NL == 1) { dit_level<N, P::R1, Q1, true, true>(tile, tw, c, bt, nbt); return; }
+        if (NL == 2) {
+            if (LEVEL == 0) dit_level<N, P::R2, Q2, true, false>(tile, tw, c, bt, nbt);
+            else dit_level<N, P::R1, Q1, false, true>(tile, tw, c, bt, nbt);
+            return;
+        }
+        if (LEVEL == 0) dit_level<N, P::R3, 1, true, false>(tile, tw, c, bt, nbt);
+        else if (LEVEL == 1) dit_level<N, P::R2, Q2, false, false>(tile, tw, c, bt, nbt);
+        else dit_level<N, P::R1, Q1, false, true>(tile, tw, c, bt, nbt);
+    }
+}
+
+}  // namespace axis
+}  // namespace rks

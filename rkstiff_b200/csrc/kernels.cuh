@@ -7,6 +7,7 @@
 #include "errctl.cuh"
 #include "fft.cuh"
 #include "fft_fast.cuh"
+#include "fft_axis.cuh"
 #include "fuse.cuh"
 
 namespace rks {
@@ -869,6 +870,32 @@ __global__ void __launch_bounds__(256) copy_u_multi_kernel(const DevPlan* plans,
     for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < p.n_c; e += (long long)gridDim.x * 256) {
         if (to_plan) stg(mine + e, ldcs(row + e));
         else stg(row + e, ldcs(mine + e));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K4, N-D grids: transform along a strided axis of [outer][N][inner] (fft_axis.cuh).  Persistent
+// CTAs loop over (outer, column tile) pairs.  in == out is allowed: a CTA reads its whole tile
+// before it writes any of it.
+// ---------------------------------------------------------------------------------------
+template <int N, bool INV>
+__global__ void __launch_bounds__(axis::tile_threads<N>(), (N == 4096 ? 1 : 2))
+axis_fft_kernel(const cplx* in, cplx* out, long long outer, long long inner, const cplx* tw, double scale) {
+    constexpr int C = axis::tile_cols<N>(), NBT = axis::tile_threads<N>() / C;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    cplx* tile = reinterpret_cast<cplx*>(smem_raw);
+    const int col = threadIdx.x % C, bt = threadIdx.x / C;
+    const long long tpo = (inner + C - 1) / C, tiles = outer * tpo;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const long long o = t / tpo, c0 = (t - o * tpo) * C;
+        const long long off = o * N * inner + c0 + col;
+        const axis::Col c{in + off, out + off, inner, col, c0 + col < inner};
+        axis::tile_level<N, INV, 0>(tile, tw, c, bt, NBT, scale);
+        __syncthreads();
+        axis::tile_level<N, INV, 1>(tile, tw, c, bt, NBT, scale);
+        __syncthreads();
+        axis::tile_level<N, INV, 2>(tile, tw, c, bt, NBT, scale);
+        __syncthreads();
     }
 }
 

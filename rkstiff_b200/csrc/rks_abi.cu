@@ -1051,6 +1051,92 @@ extern "C" void rks_rows_destroy(rks_rows* r) {
 }
 
 // ---------------------------------------------------------------------------------------
+// strided-axis transforms of N-D grids (fft_axis.cuh)
+// ---------------------------------------------------------------------------------------
+struct rks_axis {
+    cplx* tw;
+    long long n;
+    int sm_count;
+};
+
+template <int N>
+static cudaError_t axis_prepare() {
+    const int smem = N * axis::tile_cols<N>() * (int)sizeof(cplx);
+    cudaError_t e = cudaFuncSetAttribute(axis_fft_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(axis_fft_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    return e;
+}
+
+template <int N>
+static void axis_launch(const rks_axis* a, const cplx* in, cplx* out, long long outer, long long inner, int inverse,
+                        cudaStream_t stream) {
+    constexpr int C = axis::tile_cols<N>();
+    const size_t smem = (size_t)N * C * sizeof(cplx);
+    const long long tiles = outer * ((inner + C - 1) / C);
+    const long long cap = (long long)a->sm_count * (N == 4096 ? 1 : 2) * 4;      // persistent CTAs, a few per slot
+    const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
+    if (inverse) axis_fft_kernel<N, true><<<grid, axis::tile_threads<N>(), smem, stream>>>(in, out, outer, inner, a->tw, 1.0 / (double)N);
+    else axis_fft_kernel<N, false><<<grid, axis::tile_threads<N>(), smem, stream>>>(in, out, outer, inner, a->tw, 1.0);
+}
+
+extern "C" int rks_axis_create(rks_axis** out, int64_t n, void* stream_v) {
+    if (!out) return fail(RKS_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (n < 16 || n > 4096 || (n & (n - 1))) return fail(RKS_ERR_UNSUPPORTED, "axis length must be a power of two in [16, 4096]");
+    rks_axis* a = new (std::nothrow) rks_axis();
+    if (!a) return fail(RKS_ERR_ARG, "out of host memory");
+    a->n = n;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&a->sm_count, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(cudaMalloc((void**)&a->tw, sizeof(cplx) * (size_t)n));
+    twiddle_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_v>>>(a->tw, (int)n);
+    cudaError_t e = cudaSuccess;
+    switch (n) {
+        case 16: e = axis_prepare<16>(); break;
+        case 32: e = axis_prepare<32>(); break;
+        case 64: e = axis_prepare<64>(); break;
+        case 128: e = axis_prepare<128>(); break;
+        case 256: e = axis_prepare<256>(); break;
+        case 512: e = axis_prepare<512>(); break;
+        case 1024: e = axis_prepare<1024>(); break;
+        case 2048: e = axis_prepare<2048>(); break;
+        default: e = axis_prepare<4096>(); break;
+    }
+    if (e != cudaSuccess) { cudaFree(a->tw); delete a; return fail(RKS_ERR_CUDA, "axis kernel attributes: %s", cudaGetErrorString(e)); }
+    CUDA_TRY(cudaGetLastError());
+    *out = a;
+    return RKS_OK;
+}
+
+extern "C" int rks_axis_apply(rks_axis* a, const void* in, void* out, int64_t outer, int64_t inner, int inverse, void* stream_v) {
+    if (!a || !in || !out || outer <= 0 || inner <= 0) return fail(RKS_ERR_ARG, "bad axis-transform arguments");
+    if (((uintptr_t)in | (uintptr_t)out) & 15) return fail(RKS_ERR_ARG, "axis arrays must be 16-byte aligned");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    const cplx* i = (const cplx*)in;
+    cplx* o = (cplx*)out;
+    switch (a->n) {
+        case 16: axis_launch<16>(a, i, o, outer, inner, inverse, stream); break;
+        case 32: axis_launch<32>(a, i, o, outer, inner, inverse, stream); break;
+        case 64: axis_launch<64>(a, i, o, outer, inner, inverse, stream); break;
+        case 128: axis_launch<128>(a, i, o, outer, inner, inverse, stream); break;
+        case 256: axis_launch<256>(a, i, o, outer, inner, inverse, stream); break;
+        case 512: axis_launch<512>(a, i, o, outer, inner, inverse, stream); break;
+        case 1024: axis_launch<1024>(a, i, o, outer, inner, inverse, stream); break;
+        case 2048: axis_launch<2048>(a, i, o, outer, inner, inverse, stream); break;
+        default: axis_launch<4096>(a, i, o, outer, inner, inverse, stream); break;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
+extern "C" void rks_axis_destroy(rks_axis* a) {
+    if (!a) return;
+    cudaFree(a->tw);
+    delete a;
+}
+
+// ---------------------------------------------------------------------------------------
 // pointwise nonlinearities for N-D models whose transforms are done by a library FFT
 // ---------------------------------------------------------------------------------------
 extern "C" int rks_pointwise(int model, const void* in, void* out, int64_t count, double p0, void* stream_v) {

@@ -6,8 +6,9 @@ exactly one all-to-all (NCCL over NVLink; gloo in the CPU tests).  ``lin_op``, `
 engine buffer use the spectral layout, which makes the diagonal stepping kernels (K1/K2/K3) purely
 local; only the three error-norm scalars and the transposes cross ranks.
 
-The local 1-D/2-D transforms inside the slabs are library FFTs (``torch.fft`` = cuFFT): the
-hand-written FFT kernels of this package cover the batched 1-D models.
+On CUDA with power-of-two axis lengths the local transforms are the engine's own kernels
+(``fused_nl``: strided-axis transforms of csrc/fft_axis.cuh around the fused last-axis kernel, physical
+data left digit-reversed along the strided axes); other sizes and the CPU/gloo tests use ``torch.fft``.
 """
 from __future__ import annotations
 
@@ -76,6 +77,28 @@ class SlabFFT:
         return torch.fft.ifftn(a, dim=tuple(range(1, nd - 1 if skip_last and nd > 2 else nd)))
 
 
+    def fused_nl(self, s: torch.Tensor, rows, axes, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``F{ N( F^-1{ s } ) }`` with the engine's kernels only: ``axes[d]`` is the ``AxisFFT`` of grid axis d
+        (d < nd-1), ``rows`` the fused last-axis kernel (inverse, pointwise N, forward).  Two all-to-alls."""
+        G, (n0, n1), nd = self.world, self.shape[:2], len(self.shape)
+        tail = tuple(range(3, nd + 1))
+        work = torch.empty_like(s)
+        axes[0].inverse_(s, 0, out=work)                                   # s itself must stay intact
+        a = self._exchange(work.reshape((G, n0 // G, n1 // G) + self.rest))
+        a = a.permute((1, 0, 2) + tail).reshape(self.real_shape)         # a copy only when G > 1
+        if nd > 2:
+            for d in range(1, nd - 1):
+                axes[d].inverse_(a, d)
+            rows(a, out=a)
+            for d in range(nd - 2, 0, -1):
+                axes[d].forward_(a, d)
+        else:
+            rows(a, out=a)                                                  # 2-D: axis 1 is the last axis
+        a = a.reshape((n0 // G, G, n1 // G) + self.rest).permute((1, 0, 2) + tail).contiguous()
+        b = self._exchange(a).reshape(self.spec_shape)
+        return axes[0].forward_(b, 0, out=out)
+
+
 def nls_slab_ops(k_axes: Sequence[torch.Tensor], gamma: float = 2.0, group=None) -> Tuple[torch.Tensor, Callable, SlabFFT]:
     """Slab-decomposed N-D cubic NLS (BASELINE cfg 5): returns this rank's ``lin_op`` block
     (spectral layout), the distributed ``nl_func`` and the transform object.
@@ -95,7 +118,17 @@ def nls_slab_ops(k_axes: Sequence[torch.Tensor], gamma: float = 2.0, group=None)
     lin_global = -1j * k2.to(torch.complex128)
     lin_op = fft.spec_slice(lin_global.expand(shape))
 
-    def nl_func(uf: torch.Tensor) -> torch.Tensor:
+    own = None
+    if lin_op.is_cuda:
+        from . import _abi
+        from .models import AxisFFT, RowNL, _pow2_in_range
+        if _pow2_in_range(shape[-1]) and all(AxisFFT.supported(s) for s in shape[:-1]):
+            cols = {s: AxisFFT(s, lin_op.device) for s in set(shape[:-1])}
+            own = (RowNL(_abi.MODEL_NLS_FFT, shape[-1], None, gamma, lin_op.device), [cols[s] for s in shape[:-1]])
+
+    def nl_func(uf: torch.Tensor, out=None) -> torch.Tensor:
+        if own is not None and uf.is_contiguous():
+            return fft.fused_nl(uf, own[0], own[1], out=out)
         f = fft.inverse(uf).contiguous()
         if f.is_cuda:
             from .models import pointwise_
@@ -104,4 +137,5 @@ def nls_slab_ops(k_axes: Sequence[torch.Tensor], gamma: float = 2.0, group=None)
         f2 = f.real ** 2 + f.imag ** 2                                         # gloo / CPU tests
         return 1j * gamma * fft.forward(f2 * f)
 
+    nl_func.supports_out = True
     return lin_op, nl_func, fft

@@ -171,6 +171,61 @@ class RowNL:
             pass
 
 
+class AxisFFT:
+    """Hand-written FP64 transform along a NON-last axis of a contiguous complex128 array (rks_axis_*,
+    csrc/fft_axis.cuh), in place.  ``inverse_`` leaves the axis in digit-reversed order and ``forward_``
+    expects that order, so the pair brackets a pointwise nonlinearity exactly like ifft / fft do."""
+
+    def __init__(self, n: int, device) -> None:
+        from ctypes import byref, c_void_p
+        self.n = int(n)
+        self.device = torch.device(device)
+        self._h = c_void_p()
+        with torch.cuda.device(self.device):
+            st = c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _abi.check(_abi.lib.rks_axis_create(byref(self._h), self.n, st))
+
+    @staticmethod
+    def supported(n: int) -> bool:
+        return 16 <= n <= 4096 and n & (n - 1) == 0
+
+    def _apply(self, x: torch.Tensor, dim: int, inverse: int, out: Optional[torch.Tensor]) -> torch.Tensor:
+        from ctypes import c_void_p
+        dim = dim % x.dim()
+        if x.dtype != torch.complex128 or not x.is_contiguous() or x.shape[dim] != self.n or dim == x.dim() - 1:
+            raise ValueError(f"AxisFFT needs a contiguous complex128 array with {self.n} points along a non-last axis")
+        if out is None:
+            out = x
+        elif out.dtype != x.dtype or out.shape != x.shape or not out.is_contiguous():
+            raise ValueError("AxisFFT: out must be a contiguous array shaped like the input")
+        outer = 1
+        for d in x.shape[:dim]:
+            outer *= int(d)
+        inner = 1
+        for d in x.shape[dim + 1:]:
+            inner *= int(d)
+        st = c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        _abi.check(_abi.lib.rks_axis_apply(self._h, c_void_p(x.data_ptr()), c_void_p(out.data_ptr()), outer, inner,
+                                           inverse, st))
+        return out
+
+    def inverse_(self, x: torch.Tensor, dim: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """ifft along ``dim`` (scaled 1/n), rows left in digit-reversed order; in place unless ``out`` is given."""
+        return self._apply(x, dim, 1, out)
+
+    def forward_(self, x: torch.Tensor, dim: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """fft along ``dim`` of data in the digit-reversed order ``inverse_`` produces."""
+        return self._apply(x, dim, 0, out)
+
+    def __del__(self):
+        try:
+            if self._h:
+                _abi.lib.rks_axis_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
 def _pow2_in_range(n: int) -> bool:
     return 16 <= n <= 16384 and n & (n - 1) == 0
 
@@ -185,8 +240,16 @@ def allen_cahn_fourier_ops(n: int, eps: float = 0.01, length: float = 2 * 3.1415
     lin_op = 1.0 - eps * (kx[None, :] ** 2 + ky[:, None] ** 2)
 
     rows = RowNL(_abi.MODEL_CUBIC_RFFT, n, None, -1.0, device) if _pow2_in_range(n) else None
+    ycol = AxisFFT(n, device) if rows is not None and AxisFFT.supported(n) else None
 
     def nl_func(uf: torch.Tensor, out=None) -> torch.Tensor:
+        if ycol is not None and uf.is_contiguous():
+            # all three transforms are the engine's kernels: [inverse over y, strided columns] . [c2r, cube,
+            # r2c along x: one fused kernel] . [forward over y]: 3 kernels, 6 passes over the half spectrum
+            work = out if out is not None else torch.empty_like(uf)
+            ycol.inverse_(uf, -2, out=work)
+            rows(work, out=work)
+            return ycol.forward_(work, -2)
         if rows is not None:
             # irfft2 / cube / rfft2 = [ifft over y] . [c2r, cube, r2c along x: ONE fused kernel] . [fft over y]
             a = torch.fft.ifft(uf, dim=-2).contiguous()      # (a transform along a non-last axis may return strided)
@@ -213,10 +276,27 @@ def nls_nd_ops(k_axes: Sequence[torch.Tensor], gamma: float = 2.0):
     n_last = int(k_axes[-1].shape[0])
     # fused innermost axis pays off for 2-D grids; for 3-D the strided outer transforms cost more than
     # one full fftn + the pointwise kernel (measured at 512^3: 98 vs 86 ms per trial)
-    rows = RowNL(_abi.MODEL_NLS_FFT, n_last, None, gamma, k_axes[-1].device) if nd == 2 and _pow2_in_range(n_last) else None
+    device = k_axes[-1].device
+    sizes = [int(k.shape[0]) for k in k_axes]
+    own = _pow2_in_range(n_last) and all(AxisFFT.supported(s) for s in sizes[:-1])
+    rows = RowNL(_abi.MODEL_NLS_FFT, n_last, None, gamma, device) if (own or nd == 2) and _pow2_in_range(n_last) else None
+    cols = {s: AxisFFT(s, device) for s in set(sizes[:-1])} if own else None
     outer = dims[:-1]
 
     def nl_func(uf: torch.Tensor, out=None) -> torch.Tensor:
+        if cols is not None and uf.is_contiguous() and uf.dim() >= nd:
+            # every transform is the engine's: inverse over the strided axes (data stay digit-reversed along
+            # them), then ONE fused kernel for the last axis (inverse, i gamma |f|^2 f, forward), then the
+            # forward transforms over the strided axes: 2 nd - 1 kernels, each one read + one write
+            work = out if out is not None else torch.empty_like(uf)
+            src = uf
+            for d in range(nd - 1):
+                cols[sizes[d]].inverse_(src, d - nd, out=work)
+                src = work
+            rows(work, out=work)
+            for d in range(nd - 2, -1, -1):
+                cols[sizes[d]].forward_(work, d - nd)
+            return work
         if rows is not None:
             # the innermost axis (inverse transform, i gamma |f|^2 f, forward transform) is ONE fused kernel
             a = torch.fft.ifftn(uf, dim=outer).contiguous()

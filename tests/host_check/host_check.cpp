@@ -15,6 +15,7 @@
 #include "../../rkstiff_b200/csrc/errctl.cuh"
 #include "../../rkstiff_b200/csrc/fft.cuh"
 #include "../../rkstiff_b200/csrc/fft_fast.cuh"
+#include "../../rkstiff_b200/csrc/fft_axis.cuh"
 #include "../../rkstiff_b200/csrc/fuse.cuh"
 
 using namespace rks;
@@ -76,6 +77,44 @@ static void generic_row(const Model& m, int n, int nthreads) {
         for (int t = 0; t < nthreads; ++t) fft_dit_pass(x.data(), log2n, q, tw.data(), t, nthreads);
     for (int q = 0; q < n; ++q) m.store(q, x[q]);
 }
+// strided-axis transform of fft_axis.cuh, emulated thread by thread: every level is run for all
+// threads of the CTA before the next one (that is what the __syncthreads between levels gives)
+template <int N, bool INV, int LEVEL>
+static void axis_level_all(cplx* tile, const cplx* tw, const cplx* in, cplx* out, long long inner, long long c0) {
+    constexpr int C = axis::tile_cols<N>(), T = axis::tile_threads<N>(), NBT = T / C;
+    for (int tid = 0; tid < T; ++tid) {
+        const int col = tid % C, bt = tid / C;
+        const axis::Col c{in + c0 + col, out + c0 + col, inner, col, c0 + col < inner};
+        axis::tile_level<N, INV, LEVEL>(tile, tw, c, bt, NBT, INV ? 1.0 / (double)N : 1.0);
+    }
+}
+template <int N, bool INV>
+static void axis_all(const cplx* in, cplx* out, long long inner) {
+    constexpr int C = axis::tile_cols<N>();
+    std::vector<cplx> tw(N), tile((size_t)N * C);
+    for (int j = 0; j < N; ++j) tw[j] = mk(cos(-2.0 * M_PI * j / N), sin(-2.0 * M_PI * j / N));
+    for (long long c0 = 0; c0 < inner; c0 += C) {
+        axis_level_all<N, INV, 0>(tile.data(), tw.data(), in, out, inner, c0);
+        axis_level_all<N, INV, 1>(tile.data(), tw.data(), in, out, inner, c0);
+        axis_level_all<N, INV, 2>(tile.data(), tw.data(), in, out, inner, c0);
+    }
+}
+template <bool INV>
+static int axis_dispatch(int n, const cplx* in, cplx* out, long long inner) {
+    switch (n) {
+        case 16: axis_all<16, INV>(in, out, inner); return 0;
+        case 32: axis_all<32, INV>(in, out, inner); return 0;
+        case 64: axis_all<64, INV>(in, out, inner); return 0;
+        case 128: axis_all<128, INV>(in, out, inner); return 0;
+        case 256: axis_all<256, INV>(in, out, inner); return 0;
+        case 512: axis_all<512, INV>(in, out, inner); return 0;
+        case 1024: axis_all<1024, INV>(in, out, inner); return 0;
+        case 2048: axis_all<2048, INV>(in, out, inner); return 0;
+        case 4096: axis_all<4096, INV>(in, out, inner); return 0;
+        default: return -1;
+    }
+}
+
 extern "C" {
 
 int hc_nl_fast(int model, int n, const double* in, const double* kx, double p0, double* out) {
@@ -228,6 +267,12 @@ int hc_fused_stage(int method, int stage, int n, const double* u, const double* 
 }
 
 // controller: feed (sum_u2, sum_e2) of one trial; state is a caller-held opaque Ctrl blob
+// in / out: [n][inner] complex128 (one `outer` slice); inverse: natural -> digit-reversed rows
+int hc_axis_fft(int n, int inverse, const double* in, double* out, long long inner) {
+    return inverse ? axis_dispatch<true>(n, (const cplx*)in, (cplx*)out, inner)
+                   : axis_dispatch<false>(n, (const cplx*)in, (cplx*)out, inner);
+}
+
 int hc_ctrl_size(void) { return (int)sizeof(Ctrl); }
 void hc_ctrl_init(void* blob, double t0, double tf, double h, long long store_freq, int step_mode, int n1_refresh,
                   double epsilon, double incr_f, double decr_f, double safety_f, double minh, int q) {

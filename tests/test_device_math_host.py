@@ -33,7 +33,7 @@ def hc():
     src = os.path.join(HERE, "host_check", "host_check.cpp")
     lib = os.path.join(HERE, "host_check", "libhostcheck.so")
     deps = [src] + [os.path.join(HERE, "..", "rkstiff_b200", "csrc", f)
-                    for f in ("common.cuh", "coeffs.cuh", "stages.cuh", "errctl.cuh", "fft.cuh", "fft_fast.cuh", "fuse.cuh")]
+                    for f in ("common.cuh", "coeffs.cuh", "stages.cuh", "errctl.cuh", "fft.cuh", "fft_fast.cuh", "fft_axis.cuh", "fuse.cuh")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", lib, src])
     return ctypes.CDLL(lib)
@@ -313,3 +313,33 @@ def test_controller_failure_paths(hc):
         assert int(out[4]) == expect
         if expect == 2:
             assert n == 51      # numloops > MAX_LOOPS on the 51st rejection
+
+
+@pytest.mark.parametrize("n", [16, 32, 64, 128, 256, 512, 1024, 2048, 4096])
+def test_axis_fft_levels_match_numpy(hc, n):
+    """fft_axis.cuh on the host: the inverse (DIF) transform gives ifft in digit-reversed row order, the
+    forward (DIT) transform takes that order back to fft's natural order; inner need not be a tile multiple."""
+    rng = np.random.default_rng(n)
+    inner = 5 if n > 512 else 11
+    x = rng.standard_normal((n, inner)) + 1j * rng.standard_normal((n, inner))
+    # the row permutation, read off a ramp: physical value m sits in the row whose output equals m
+    ramp = np.fft.fft(np.arange(n, dtype=float))[:, None] * np.ones((1, inner))
+    ramp = np.ascontiguousarray(ramp.astype(np.complex128))
+    out = np.empty_like(ramp)
+    assert hc.hc_axis_fft(n, 1, ptr(ramp), ptr(out), ctypes.c_longlong(inner)) == 0
+    perm = np.rint(out[:, 0].real).astype(int)
+    assert sorted(perm) == list(range(n))
+    np.testing.assert_allclose(out, perm[:, None] * np.ones((1, inner)), atol=1e-9 * n)
+    y = np.empty_like(x)
+    assert hc.hc_axis_fft(n, 1, ptr(x), ptr(y), ctypes.c_longlong(inner)) == 0
+    ref = np.fft.ifft(x, axis=0)
+    np.testing.assert_allclose(y, ref[perm], rtol=0, atol=1e-13 * np.abs(ref).max() * np.log2(n))
+    z = np.empty_like(x)
+    assert hc.hc_axis_fft(n, 0, ptr(y), ptr(z), ctypes.c_longlong(inner)) == 0
+    np.testing.assert_allclose(z, x, rtol=0, atol=1e-13 * np.abs(x).max() * np.log2(n))
+    # forward of digit-reversed physical data == numpy fft of the natural-order data
+    phys = rng.standard_normal((n, inner)) + 1j * rng.standard_normal((n, inner))
+    w = np.empty_like(phys)
+    assert hc.hc_axis_fft(n, 0, ptr(np.ascontiguousarray(phys[perm])), ptr(w), ctypes.c_longlong(inner)) == 0
+    reff = np.fft.fft(phys, axis=0)
+    np.testing.assert_allclose(w, reff, rtol=0, atol=1e-13 * np.abs(reff).max() * np.log2(n))

@@ -464,3 +464,34 @@ def test_cfg2b_batched_independent_failure_status_surfaces(rk):
     sol = rk.ETD35(lin, nl, config=rk.SolverConfig(epsilon=1e-12, minh=1e-3))
     with pytest.raises(sol.MinimumStepReached):
         sol.evolve_independent(dev(p.u0), 0.0, 1.0, h_init=0.5)
+
+
+@pytest.mark.parametrize("n", [16, 32, 64, 128, 256, 512, 1024, 2048, 4096])
+def test_axis_fft_kernels_match_torch_fft(rk, n):
+    """rks_axis_*: hand-written transform along a strided axis == torch.fft.ifft / fft along that axis
+    (the inverse leaves the axis digit-reversed; the permutation is read off a ramp)."""
+    ax = rk.models.AxisFFT(n, "cuda")
+    outer, inner = 3, (13 if n <= 512 else 6)
+    g = torch.Generator(device="cpu").manual_seed(n)
+    x = torch.randn(outer, n, inner, 2, generator=g, dtype=torch.float64)
+    x = torch.view_as_complex(x).cuda().contiguous()
+    ramp = torch.fft.fft(torch.arange(n, dtype=torch.float64, device="cuda")).to(torch.complex128)
+    ramp = ramp[None, :, None].expand(1, n, 8).contiguous()
+    perm = torch.round(ax.inverse_(ramp, 1)[0, :, 0].real).long()
+    assert sorted(perm.tolist()) == list(range(n))
+    y = ax.inverse_(x.clone(), 1)
+    ref = torch.fft.ifft(x, dim=1)
+    tol = 1e-13 * float(ref.abs().max()) * np.log2(n)
+    assert float((y - ref[:, perm, :]).abs().max()) < tol
+    out = torch.empty_like(x)
+    assert ax.inverse_(x, 1, out=out) is out and torch.equal(out, y)          # out-of-place variant, input untouched
+    z = ax.forward_(y.clone(), 1)
+    assert float((z - x).abs().max()) < 1e-13 * float(x.abs().max()) * np.log2(n)
+    # 3-D array, middle axis and leading axis
+    if n <= 256:
+        w = torch.view_as_complex(torch.randn(n, n, 24, 2, generator=g, dtype=torch.float64)).cuda().contiguous()
+        v = ax.inverse_(ax.inverse_(w.clone(), 0), 1)
+        refw = torch.fft.ifftn(w, dim=(0, 1))
+        assert float((v - refw[perm][:, perm]).abs().max()) < 1e-13 * float(refw.abs().max()) * 2 * np.log2(n)
+        back = ax.forward_(ax.forward_(v, 1), 0)
+        assert float((back - w).abs().max()) < 1e-12 * float(w.abs().max())
