@@ -221,6 +221,11 @@ void rks_rows_destroy(rks_rows* rows);
 typedef struct rks_axis rks_axis;
 int rks_axis_create(rks_axis** out, int64_t n, void* stream);
 int rks_axis_apply(rks_axis* axis, const void* in, void* out, int64_t outer, int64_t inner, int inverse, void* stream);
+/* same transform when the axis arrives split into `chunks` equal row blocks stored chunk-major,
+ * [chunks][outer][n/chunks][inner] -- what the all-to-all of a slab decomposition delivers -- so the
+ * transposes either side of the exchange never have to be materialised */
+int rks_axis_apply_chunked(rks_axis* axis, const void* in, void* out, int64_t outer, int64_t inner, int64_t chunks,
+                           int inverse, void* stream);
 void rks_axis_destroy(rks_axis* axis);
 
 /* the only syncing calls */

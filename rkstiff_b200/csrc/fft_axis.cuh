@@ -41,9 +41,16 @@ template <int N> RKS_HD constexpr int tile_shift() { return last_radix<N>() == 1
 struct Col {                 // one thread's column of the tile and of the global array
     const cplx* gin;         // in  + column offset (row 0)
     cplx* gout;              // out + column offset
-    long long gstride;       // elements between consecutive rows (= inner)
+    long long gstride;       // elements between consecutive rows inside a row block
+    long long bstride;       // elements between consecutive row blocks
+    int rb_shift;            // rows per block = 1 << rb_shift (31: a single block, plain strided axis)
     int col;                 // column within the tile
     bool ok;                 // column exists (inner need not be a multiple of C)
+    // Row p of the axis.  Blocked rows: the axis is split over G chunks that sit G-major in memory, as an
+    // all-to-all delivers them (dist_fft.py) -- row p = chunk p >> rb_shift, offset p & mask.
+    RKS_HD long long row(int p) const {
+        return (long long)(p >> rb_shift) * bstride + (long long)(p & (int)((1u << rb_shift) - 1u)) * gstride;
+    }
 };
 
 // one decimation-in-frequency level of the inverse transform: rows p0 + Q s, twiddles on the outputs
@@ -56,7 +63,7 @@ RKS_HD void dif_level(cplx* tile, const cplx* tw, const Col& c, int bt, int nbt,
         cplx a[R];
 #pragma unroll
         for (int s = 0; s < R; ++s) {
-            if (FIRST) a[s] = c.ok ? fast::row_ld(c.gin + (long long)(p0 + Q * s) * c.gstride) : mk(0.0, 0.0);
+            if (FIRST) a[s] = c.ok ? fast::row_ld(c.gin + c.row(p0 + Q * s)) : mk(0.0, 0.0);
             else a[s] = tile[fast::swz<SH>(p0 + Q * s) * C + c.col];
         }
         fast::dftR<R, true>(a);
@@ -64,7 +71,7 @@ RKS_HD void dif_level(cplx* tile, const cplx* tw, const Col& c, int bt, int nbt,
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const cplx v = a[fast::perm<R>(r)];
-            if (LAST) { if (c.ok) fast::row_st(c.gout + (long long)(p0 + Q * r) * c.gstride, mk(v.x * scale, v.y * scale)); }
+            if (LAST) { if (c.ok) fast::row_st(c.gout + c.row(p0 + Q * r), mk(v.x * scale, v.y * scale)); }
             else tile[fast::swz<SH>(p0 + Q * r) * C + c.col] = v;
         }
     }
@@ -80,7 +87,7 @@ RKS_HD void dit_level(cplx* tile, const cplx* tw, const Col& c, int bt, int nbt)
         cplx a[R];
 #pragma unroll
         for (int s = 0; s < R; ++s) {
-            if (FIRST) a[s] = c.ok ? fast::row_ld(c.gin + (long long)(p0 + Q * s) * c.gstride) : mk(0.0, 0.0);
+            if (FIRST) a[s] = c.ok ? fast::row_ld(c.gin + c.row(p0 + Q * s)) : mk(0.0, 0.0);
             else a[s] = tile[fast::swz<SH>(p0 + Q * s) * C + c.col];
         }
         if (Q > 1) fast::twiddle_scale<R, false>(a, tw, 0, j * (N / (R * Q)), fast::SlotId());
@@ -88,16 +95,14 @@ RKS_HD void dit_level(cplx* tile, const cplx* tw, const Col& c, int bt, int nbt)
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const cplx v = a[fast::perm<R>(r)];
-            if (LAST) { if (c.ok) fast::row_st(c.gout + (long long)(p0 + Q * r) * c.gstride, v); }
+            if (LAST) { if (c.ok) fast::row_st(c.gout + c.row(p0 + Q * r), v); }
             else tile[fast::swz<SH>(p0 + Q * r) * C + c.col] = v;
         }
     }
 }
 
-struct NoSync { RKS_HD void operator()() const {} };
-
-// all levels of one tile; `sync` separates the levels (__syncthreads on the device, nothing in the
-// serial host emulation, which runs a level for every thread before the next one)
+// level LEVEL of one tile.  The caller separates the levels: __syncthreads on the device; the serial host
+// emulation runs a level for every thread before the next one
 template <int N, bool INV, int LEVEL>
 RKS_HD void tile_level(cplx* tile, const cplx* tw, const Col& c, int bt, int nbt, double scale) {
     using P = APlan<N>;

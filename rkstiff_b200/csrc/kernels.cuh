@@ -880,7 +880,8 @@ __global__ void __launch_bounds__(256) copy_u_multi_kernel(const DevPlan* plans,
 // ---------------------------------------------------------------------------------------
 template <int N, bool INV>
 __global__ void __launch_bounds__(axis::tile_threads<N>(), (N == 4096 ? 1 : 2))
-axis_fft_kernel(const cplx* in, cplx* out, long long outer, long long inner, const cplx* tw, double scale) {
+axis_fft_kernel(const cplx* in, cplx* out, long long outer, long long inner, const cplx* tw, double scale,
+                long long ostride, long long bstride, int rb_shift) {
     constexpr int C = axis::tile_cols<N>(), NBT = axis::tile_threads<N>() / C;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     cplx* tile = reinterpret_cast<cplx*>(smem_raw);
@@ -888,8 +889,8 @@ axis_fft_kernel(const cplx* in, cplx* out, long long outer, long long inner, con
     const long long tpo = (inner + C - 1) / C, tiles = outer * tpo;
     for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
         const long long o = t / tpo, c0 = (t - o * tpo) * C;
-        const long long off = o * N * inner + c0 + col;
-        const axis::Col c{in + off, out + off, inner, col, c0 + col < inner};
+        const long long off = o * ostride + c0 + col;
+        const axis::Col c{in + off, out + off, inner, bstride, rb_shift, col, c0 + col < inner};
         axis::tile_level<N, INV, 0>(tile, tw, c, bt, NBT, scale);
         __syncthreads();
         axis::tile_level<N, INV, 1>(tile, tw, c, bt, NBT, scale);

@@ -1069,14 +1069,14 @@ static cudaError_t axis_prepare() {
 
 template <int N>
 static void axis_launch(const rks_axis* a, const cplx* in, cplx* out, long long outer, long long inner, int inverse,
-                        cudaStream_t stream) {
+                        long long ostride, long long bstride, int rb_shift, cudaStream_t stream) {
     constexpr int C = axis::tile_cols<N>();
     const size_t smem = (size_t)N * C * sizeof(cplx);
     const long long tiles = outer * ((inner + C - 1) / C);
     const long long cap = (long long)a->sm_count * (N == 4096 ? 1 : 2) * 4;      // persistent CTAs, a few per slot
     const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
-    if (inverse) axis_fft_kernel<N, true><<<grid, axis::tile_threads<N>(), smem, stream>>>(in, out, outer, inner, a->tw, 1.0 / (double)N);
-    else axis_fft_kernel<N, false><<<grid, axis::tile_threads<N>(), smem, stream>>>(in, out, outer, inner, a->tw, 1.0);
+    if (inverse) axis_fft_kernel<N, true><<<grid, axis::tile_threads<N>(), smem, stream>>>(in, out, outer, inner, a->tw, 1.0 / (double)N, ostride, bstride, rb_shift);
+    else axis_fft_kernel<N, false><<<grid, axis::tile_threads<N>(), smem, stream>>>(in, out, outer, inner, a->tw, 1.0, ostride, bstride, rb_shift);
 }
 
 extern "C" int rks_axis_create(rks_axis** out, int64_t n, void* stream_v) {
@@ -1109,22 +1109,44 @@ extern "C" int rks_axis_create(rks_axis** out, int64_t n, void* stream_v) {
     return RKS_OK;
 }
 
+static int axis_apply(rks_axis* a, const void* in, void* out, int64_t outer, int64_t inner, int inverse,
+                      long long ostride, long long bstride, int rb_shift, void* stream_v);
+
 extern "C" int rks_axis_apply(rks_axis* a, const void* in, void* out, int64_t outer, int64_t inner, int inverse, void* stream_v) {
-    if (!a || !in || !out || outer <= 0 || inner <= 0) return fail(RKS_ERR_ARG, "bad axis-transform arguments");
+    if (!a) return fail(RKS_ERR_ARG, "axis handle is null");
+    return axis_apply(a, in, out, outer, inner, inverse, a->n * inner, 0, 31, stream_v);
+}
+
+// The axis is split into `chunks` equal row blocks that are stored chunk-major:
+// [chunks][outer][n / chunks][inner] -- the layout an all-to-all of a slab decomposition delivers.
+extern "C" int rks_axis_apply_chunked(rks_axis* a, const void* in, void* out, int64_t outer, int64_t inner, int64_t chunks,
+                                      int inverse, void* stream_v) {
+    if (!a) return fail(RKS_ERR_ARG, "axis handle is null");
+    if (chunks < 1 || (chunks & (chunks - 1)) || chunks > a->n) return fail(RKS_ERR_ARG, "chunks must be a power of two <= n");
+    const long long rb = a->n / chunks;
+    int sh = 0;
+    while ((1ll << sh) < rb) ++sh;
+    if (chunks == 1) sh = 31;
+    return axis_apply(a, in, out, outer, inner, inverse, rb * inner, outer * rb * inner, sh, stream_v);
+}
+
+static int axis_apply(rks_axis* a, const void* in, void* out, int64_t outer, int64_t inner, int inverse,
+                      long long ostride, long long bstride, int rb_shift, void* stream_v) {
+    if (!in || !out || outer <= 0 || inner <= 0) return fail(RKS_ERR_ARG, "bad axis-transform arguments");
     if (((uintptr_t)in | (uintptr_t)out) & 15) return fail(RKS_ERR_ARG, "axis arrays must be 16-byte aligned");
     cudaStream_t stream = (cudaStream_t)stream_v;
     const cplx* i = (const cplx*)in;
     cplx* o = (cplx*)out;
     switch (a->n) {
-        case 16: axis_launch<16>(a, i, o, outer, inner, inverse, stream); break;
-        case 32: axis_launch<32>(a, i, o, outer, inner, inverse, stream); break;
-        case 64: axis_launch<64>(a, i, o, outer, inner, inverse, stream); break;
-        case 128: axis_launch<128>(a, i, o, outer, inner, inverse, stream); break;
-        case 256: axis_launch<256>(a, i, o, outer, inner, inverse, stream); break;
-        case 512: axis_launch<512>(a, i, o, outer, inner, inverse, stream); break;
-        case 1024: axis_launch<1024>(a, i, o, outer, inner, inverse, stream); break;
-        case 2048: axis_launch<2048>(a, i, o, outer, inner, inverse, stream); break;
-        default: axis_launch<4096>(a, i, o, outer, inner, inverse, stream); break;
+        case 16: axis_launch<16>(a, i, o, outer, inner, inverse, ostride, bstride, rb_shift, stream); break;
+        case 32: axis_launch<32>(a, i, o, outer, inner, inverse, ostride, bstride, rb_shift, stream); break;
+        case 64: axis_launch<64>(a, i, o, outer, inner, inverse, ostride, bstride, rb_shift, stream); break;
+        case 128: axis_launch<128>(a, i, o, outer, inner, inverse, ostride, bstride, rb_shift, stream); break;
+        case 256: axis_launch<256>(a, i, o, outer, inner, inverse, ostride, bstride, rb_shift, stream); break;
+        case 512: axis_launch<512>(a, i, o, outer, inner, inverse, ostride, bstride, rb_shift, stream); break;
+        case 1024: axis_launch<1024>(a, i, o, outer, inner, inverse, ostride, bstride, rb_shift, stream); break;
+        case 2048: axis_launch<2048>(a, i, o, outer, inner, inverse, ostride, bstride, rb_shift, stream); break;
+        default: axis_launch<4096>(a, i, o, outer, inner, inverse, ostride, bstride, rb_shift, stream); break;
     }
     CUDA_TRY(cudaGetLastError());
     return RKS_OK;

@@ -81,20 +81,26 @@ class SlabFFT:
         """``F{ N( F^-1{ s } ) }`` with the engine's kernels only: ``axes[d]`` is the ``AxisFFT`` of grid axis d
         (d < nd-1), ``rows`` the fused last-axis kernel (inverse, pointwise N, forward).  Two all-to-alls."""
         G, (n0, n1), nd = self.world, self.shape[:2], len(self.shape)
-        tail = tuple(range(3, nd + 1))
         work = torch.empty_like(s)
         axes[0].inverse_(s, 0, out=work)                                   # s itself must stay intact
         a = self._exchange(work.reshape((G, n0 // G, n1 // G) + self.rest))
-        a = a.permute((1, 0, 2) + tail).reshape(self.real_shape)         # a copy only when G > 1
         if nd > 2:
-            for d in range(1, nd - 1):
-                axes[d].inverse_(a, d)
+            # a = [source rank g][my x planes][g's chunk of axis 1][rest]: axis 1 is transformed in this
+            # chunk-major layout, so neither side of the exchange needs a transposing copy
+            if nd == 3:
+                a = a.reshape((G, n0 // G, n1 // G, self.rest[0]))
+            axes[1].chunked_(a, True)
+            for d in range(2, nd - 1):
+                axes[d].inverse_(a, d + 1)
             rows(a, out=a)
-            for d in range(nd - 2, 0, -1):
-                axes[d].forward_(a, d)
+            for d in range(nd - 2, 1, -1):
+                axes[d].forward_(a, d + 1)
+            axes[1].chunked_(a, False)
         else:
-            rows(a, out=a)                                                  # 2-D: axis 1 is the last axis
-        a = a.reshape((n0 // G, G, n1 // G) + self.rest).permute((1, 0, 2) + tail).contiguous()
+            # 2-D: axis 1 is the last (contiguous) axis and must be whole for the row kernel
+            a = a.permute((1, 0, 2)).reshape(self.real_shape)              # a copy only when G > 1
+            rows(a, out=a)
+            a = a.reshape((n0 // G, G, n1 // G)).permute((1, 0, 2)).contiguous()
         b = self._exchange(a).reshape(self.spec_shape)
         return axes[0].forward_(b, 0, out=out)
 

@@ -209,6 +209,20 @@ class AxisFFT:
                                            inverse, st))
         return out
 
+    def chunked_(self, x: torch.Tensor, inverse: bool) -> torch.Tensor:
+        """In-place transform of an axis that arrives split into G row blocks stored block-major: ``x`` has shape
+        ``(G, outer, n / G, ...)`` (what the all-to-all of a slab decomposition delivers, dist_fft.py)."""
+        from ctypes import c_void_p
+        if x.dtype != torch.complex128 or not x.is_contiguous() or x.dim() < 4 or x.shape[0] * x.shape[2] != self.n:
+            raise ValueError(f"AxisFFT.chunked_ needs a contiguous complex128 array (G, outer, {self.n}/G, inner...)")
+        inner = 1
+        for d in x.shape[3:]:
+            inner *= int(d)
+        st = c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        _abi.check(_abi.lib.rks_axis_apply_chunked(self._h, c_void_p(x.data_ptr()), c_void_p(x.data_ptr()), int(x.shape[1]),
+                                                   inner, int(x.shape[0]), int(bool(inverse)), st))
+        return x
+
     def inverse_(self, x: torch.Tensor, dim: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """ifft along ``dim`` (scaled 1/n), rows left in digit-reversed order; in place unless ``out`` is given."""
         return self._apply(x, dim, 1, out)

@@ -84,7 +84,7 @@ static void axis_level_all(cplx* tile, const cplx* tw, const cplx* in, cplx* out
     constexpr int C = axis::tile_cols<N>(), T = axis::tile_threads<N>(), NBT = T / C;
     for (int tid = 0; tid < T; ++tid) {
         const int col = tid % C, bt = tid / C;
-        const axis::Col c{in + c0 + col, out + c0 + col, inner, col, c0 + col < inner};
+        const axis::Col c{in + c0 + col, out + c0 + col, inner, 0, 31, col, c0 + col < inner};
         axis::tile_level<N, INV, LEVEL>(tile, tw, c, bt, NBT, INV ? 1.0 / (double)N : 1.0);
     }
 }

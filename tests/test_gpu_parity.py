@@ -487,6 +487,13 @@ def test_axis_fft_kernels_match_torch_fft(rk, n):
     assert ax.inverse_(x, 1, out=out) is out and torch.equal(out, y)          # out-of-place variant, input untouched
     z = ax.forward_(y.clone(), 1)
     assert float((z - x).abs().max()) < 1e-13 * float(x.abs().max()) * np.log2(n)
+    # the same axis delivered in G row blocks, block-major (slab-decomposition layout)
+    for G in (2, 8):
+        blocked = x.reshape(outer, G, n // G, inner).permute(1, 0, 2, 3).contiguous()
+        got = ax.chunked_(blocked.clone(), True)
+        want = y.reshape(outer, G, n // G, inner).permute(1, 0, 2, 3)
+        assert torch.equal(got, want.contiguous())
+        assert float((ax.chunked_(got, False) - blocked).abs().max()) < 1e-13 * float(x.abs().max()) * np.log2(n)
     # 3-D array, middle axis and leading axis
     if n <= 256:
         w = torch.view_as_complex(torch.randn(n, n, 24, 2, generator=g, dtype=torch.float64)).cuda().contiguous()
