@@ -237,11 +237,13 @@ RKS_D void coef_kernel_body(const DevPlan& p, int force) {
         }
     }
 }
+// 5 CTAs/SM (96 registers, a few spills): the exp / division chains are latency bound, occupancy pays
+// (256^3 ETD35 coefficient set: 2.09 ms at 3 CTAs/SM, 1.55 ms at 5, 1.76 ms at 6)
 template <int FAM, typename LT>
-__global__ void __launch_bounds__(128) coef_kernel(const __grid_constant__ DevPlan p, int force) { coef_kernel_body<FAM, LT>(p, force); }
+__global__ void __launch_bounds__(128, 5) coef_kernel(const __grid_constant__ DevPlan p, int force) { coef_kernel_body<FAM, LT>(p, force); }
 // one plan per blockIdx.z: ensembles whose trajectories keep their own dt (rks_multi_*)
 template <int FAM, typename LT>
-__global__ void __launch_bounds__(128) coef_kernel_multi(const DevPlan* plans, int force) { coef_kernel_body<FAM, LT>(plans[blockIdx.z], force); }
+__global__ void __launch_bounds__(128, 5) coef_kernel_multi(const DevPlan* plans, int force) { coef_kernel_body<FAM, LT>(plans[blockIdx.z], force); }
 
 
 // ---------------------------------------------------------------------------------------
@@ -879,7 +881,7 @@ __global__ void __launch_bounds__(256) copy_u_multi_kernel(const DevPlan* plans,
 // before it writes any of it.
 // ---------------------------------------------------------------------------------------
 template <int N, bool INV>
-__global__ void __launch_bounds__(axis::tile_threads<N>(), (N == 4096 ? 1 : 2))
+__global__ void __launch_bounds__(axis::tile_threads<N>(), (N == 4096 ? 1 : N == 512 ? 3 : 2))
 axis_fft_kernel(const cplx* in, cplx* out, long long outer, long long inner, const cplx* tw, double scale,
                 long long ostride, long long bstride, int rb_shift) {
     constexpr int C = axis::tile_cols<N>(), NBT = axis::tile_threads<N>() / C;

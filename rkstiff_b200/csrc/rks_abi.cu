@@ -1073,7 +1073,7 @@ static void axis_launch(const rks_axis* a, const cplx* in, cplx* out, long long 
     constexpr int C = axis::tile_cols<N>();
     const size_t smem = (size_t)N * C * sizeof(cplx);
     const long long tiles = outer * ((inner + C - 1) / C);
-    const long long cap = (long long)a->sm_count * (N == 4096 ? 1 : 2) * 4;      // persistent CTAs, a few per slot
+    const long long cap = (long long)a->sm_count * (N == 4096 ? 1 : N == 512 ? 3 : 2) * 4;      // persistent CTAs, a few per slot
     const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
     if (inverse) axis_fft_kernel<N, true><<<grid, axis::tile_threads<N>(), smem, stream>>>(in, out, outer, inner, a->tw, 1.0 / (double)N, ostride, bstride, rb_shift);
     else axis_fft_kernel<N, false><<<grid, axis::tile_threads<N>(), smem, stream>>>(in, out, outer, inner, a->tw, 1.0, ostride, bstride, rb_shift);
