@@ -97,6 +97,11 @@ constexpr int TW_T1 = 0, TW_T2 = 4 * TW_S1, TW_T3 = TW_T2 + 4 * TW_S2, TW_TOTAL 
 
 // static plan of an n-point row
 template <int N> struct Plan;
+// n < 512: a warp's 512-point slab holds 512 / n consecutive rows; only the first / last pass (radix n / 64
+// inside each row) differ from the 512-point plan (phase_first_packed / phase_last_packed)
+template <> struct Plan<64>   { static constexpr int W = 1,  SH = 3, R1 = 1,  R2 = 8,  R3 = 8,  R4 = 1; };
+template <> struct Plan<128>  { static constexpr int W = 1,  SH = 3, R1 = 2,  R2 = 8,  R3 = 8,  R4 = 1; };
+template <> struct Plan<256>  { static constexpr int W = 1,  SH = 3, R1 = 4,  R2 = 8,  R3 = 8,  R4 = 1; };
 template <> struct Plan<512>  { static constexpr int W = 1,  SH = 3, R1 = 8,  R2 = 8,  R3 = 8,  R4 = 1; };
 template <> struct Plan<1024> { static constexpr int W = 2,  SH = 3, R1 = 16, R2 = 8,  R3 = 8,  R4 = 1; };
 template <> struct Plan<2048> { static constexpr int W = 4,  SH = 3, R1 = 16, R2 = 16, R3 = 8,  R4 = 1; };
@@ -136,6 +141,9 @@ RKS_HD cplx twiddle_table_entry_n(int idx) {
 }
 RKS_HD cplx twiddle_table_entry(int idx, int n) {
     switch (n) {
+        case 64: return twiddle_table_entry_n<64>(idx);
+        case 128: return twiddle_table_entry_n<128>(idx);
+        case 256: return twiddle_table_entry_n<256>(idx);
         case 512: return twiddle_table_entry_n<512>(idx);
         case 1024: return twiddle_table_entry_n<1024>(idx);
         case 2048: return twiddle_table_entry_n<2048>(idx);
@@ -362,6 +370,25 @@ template <> struct ModelOf<4> {
     }
 };
 
+// 512 / N consecutive rows of an N-point model packed into one 512-point slab (N = 64, 128, 256):
+// slab position p belongs to row p / N.  Rows past the end of the batch read zeros and store nothing.
+template <int MODEL, int N>
+struct PackedModel {
+    const cplx* in0; cplx* out0; const double* kx; double p0; long long n_c; int nvalid;
+    RKS_HD typename ModelOf<MODEL>::type row(int sub) const {
+        return ModelOf<MODEL>::make(in0 + sub * n_c, out0 + sub * n_c, kx, p0, N, sub < nvalid);
+    }
+    RKS_HD cplx load(int p) const {
+        const int sub = p / N;
+        return sub < nvalid ? row(sub).load(p % N) : mk(0.0, 0.0);
+    }
+    RKS_HD cplx pointwise(cplx z) const { return row(0).pointwise(z); }
+    RKS_HD void store(int p, cplx v) const {
+        const int sub = p / N;
+        if (sub < nvalid) row(sub).store(p % N, v);
+    }
+};
+
 // ---------------------------------------------------------------------------------------
 // generic in-place passes.  A butterfly is identified by the logical position p0 of its first
 // element (elements p0 + Q s) and its twiddle index j (w_L^(r j), L = R Q).  NB butterflies of one
@@ -503,6 +530,26 @@ RKS_HD void phase_core(cplx* sm, int T, const Model& m) {
     int p0[NB], j[NB];
     warp_butterflies<R, 1, NB>((T >> 5) * 512, T & 31, p0, j);
     core_pass<R, P::SH, NB>(sm, p0, m);
+}
+// first / last pass of a packed slab (N < 512): radix N / 64 over stride 64 inside every row; lane l takes
+// the butterflies u = l + 32 c of the slab, u -> (row u / 64, offset u % 64)
+template <int N, class Model>
+RKS_HD void phase_first_packed(cplx* sm, int T, const Twiddles& ti, const Model& m) {
+    using P = Plan<N>;
+    constexpr int NB = (512 / P::R1) / 32;
+    int p0[NB], j[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) { const int u = T + 32 * c; j[c] = u & 63; p0[c] = (u >> 6) * N + j[c]; }
+    dif_pass<P::R1, 64, P::SH, NB, TW_S1, true>(sm, p0, j, ti.t1, m);
+}
+template <int N, class Model>
+RKS_HD void phase_last_packed(cplx* sm, int T, const Twiddles& tf, const Model& m) {
+    using P = Plan<N>;
+    constexpr int NB = (512 / P::R1) / 32;
+    int p0[NB], j[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) { const int u = T + 32 * c; j[c] = u & 63; p0[c] = (u >> 6) * N + j[c]; }
+    dit_pass<P::R1, 64, P::SH, NB, TW_S1, true>(sm, p0, j, tf.t1, m);
 }
 // number of warp-local middle passes per direction
 template <int N> RKS_HD constexpr int middle_passes() { return Plan<N>::R4 > 1 ? 2 : 1; }

@@ -706,6 +706,42 @@ __global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_f
 
 
 // ---------------------------------------------------------------------------------------
+// K4 for short rows (n = 64, 128, 256): every warp is on its own -- it packs 512 / n consecutive rows into
+// its 512-point slab and runs the 512-point pipeline on it (fft_fast.cuh PackedModel); no CTA barrier.
+// ---------------------------------------------------------------------------------------
+constexpr int NL_SMALL_WARPS = 8;
+template <int N, int MODEL>
+RKS_D void nl_small_kernel_body(const DevPlan& p, int j, int force) {
+    constexpr int SUB = 512 / N;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const NlRoles roles = nl_roles(p, j, force);
+    if (!roles.run) return;
+    if (p.ctrl && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&p.ctrl->nl_evals, 1ull);
+    const int w = threadIdx.x >> 5, T = threadIdx.x & 31;
+    cplx* sm = reinterpret_cast<cplx*>(smem_raw) + (size_t)w * 512;
+    const fast::Twiddles ti{p.twf + fast::TW_T1, p.twf + fast::TW_T2, p.twf + fast::TW_T3};
+    const cplx* twf2 = p.twf + fast::TW_TOTAL;
+    const fast::Twiddles tf{twf2 + fast::TW_T1, twf2 + fast::TW_T2, twf2 + fast::TW_T3};
+    const long long slabs = (p.batch + SUB - 1) / SUB;
+    for (long long s = (long long)blockIdx.x * NL_SMALL_WARPS + w; s < slabs; s += (long long)gridDim.x * NL_SMALL_WARPS) {
+        const long long row0 = s * SUB;
+        const long long left = p.batch - row0;
+        const fast::PackedModel<MODEL, N> m{roles.in + row0 * p.n_c, roles.out + row0 * p.n_c, p.kx, p.model_p0, p.n_c,
+                                            (int)(left < SUB ? left : SUB)};
+        fast::phase_first_packed<N>(sm, T, ti, m);        __syncwarp();
+        fast::phase_middle<N, 2, true>(sm, T, ti, m);     __syncwarp();
+        fast::phase_core<N>(sm, T, m);                    __syncwarp();
+        fast::phase_middle<N, 2, false>(sm, T, tf, m);    __syncwarp();
+        fast::phase_last_packed<N>(sm, T, tf, m);
+        // no barrier: the last pass reads the slab positions this thread overwrites in its next first pass
+    }
+}
+template <int N, int MODEL>
+__global__ void __launch_bounds__(32 * NL_SMALL_WARPS, 2) nl_small_kernel(const __grid_constant__ DevPlan p, int j, int force) {
+    nl_small_kernel_body<N, MODEL>(p, j, force);
+}
+
+// ---------------------------------------------------------------------------------------
 // K3: masked norms (solveras.py:451-454) + controller tail.
 // grid (gx, gy): columns grid-stride over x, rows grid-stride over y; 128 threads.
 // ---------------------------------------------------------------------------------------

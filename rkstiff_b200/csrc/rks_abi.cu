@@ -103,6 +103,7 @@ struct rks_plan {
     int roles_u_sel, roles_n_sel;   // host mirror refreshed by rks_read_ctrl
     int nl_rows_per_cta, nl_threads;
     bool nl_fast;                   // n in {512..8192}: register-resident FFT kernel (fft_fast.cuh)
+    bool nl_small;                  // n in {64, 128, 256}: the same pipeline on slabs of packed rows
     bool no_fuse;                   // default: K1 and K4 as separate kernels (north_star decomposition); RKS_FUSE=1 fuses
     size_t nl_smem;
 };
@@ -171,6 +172,18 @@ static cudaError_t prepare_nl_fast(int model) {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel_multi<W, 4, 0>, attr, (int)nl_fast_smem<W>(model, 0));
     }
     return e;
+}
+
+template <int N>
+static cudaError_t prepare_nl_small(int model) {
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    const int smem = NL_SMALL_WARPS * 512 * (int)sizeof(cplx);
+    switch (model) {
+        case RKS_MODEL_UUX_RFFT: return cudaFuncSetAttribute(nl_small_kernel<N, 1>, attr, smem);
+        case RKS_MODEL_NLS_FFT: return cudaFuncSetAttribute(nl_small_kernel<N, 2>, attr, smem);
+        case RKS_MODEL_CUBIC_RFFT: return cudaFuncSetAttribute(nl_small_kernel<N, 3>, attr, smem);
+        default: return cudaFuncSetAttribute(nl_small_kernel<N, 4>, attr, smem);
+    }
 }
 
 extern "C" int rks_abi_version(void) { return RKS_ABI_VERSION; }
@@ -351,6 +364,7 @@ extern "C" int rks_plan_create_independent(rks_plan** out, int method, int64_t b
     p->use_graph = getenv("RKS_NO_GRAPH") == nullptr;
     p->no_fuse = true;
     p->nl_fast = false;
+    p->nl_small = false;
     CUDA_TRY(cudaGetDevice(&p->device));
     CUDA_TRY(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device));
     CUDA_TRY(cudaMallocHost((void**)&p->pinned_raw, sizeof(Ctrl)));
@@ -437,11 +451,15 @@ static int prepare_nl_launch(rks_plan* p, int model, long long n, cplx* twf_dev,
     DevPlan& d = p->d;
     p->nl_fast = (n >= 512 && n <= 8192) && !getenv("RKS_NL_GENERIC");
     p->no_fuse = getenv("RKS_FUSE") == nullptr;       // fused K1+K4 is opt-in (RKS_FUSE=1): see DESIGN.md 4
+    p->nl_small = (n == 64 || n == 128 || n == 256) && !getenv("RKS_NL_GENERIC");
     if (p->nl_fast) {
         cudaError_t e = n == 512 ? prepare_nl_fast<1>(model) : n == 1024 ? prepare_nl_fast<2>(model)
                       : n == 2048 ? prepare_nl_fast<4>(model) : n == 4096 ? prepare_nl_fast<8>(model)
                       : prepare_nl_fast<16>(model);
         CUDA_TRY(e);
+    }
+    if (p->nl_small) CUDA_TRY(n == 64 ? prepare_nl_small<64>(model) : n == 128 ? prepare_nl_small<128>(model) : prepare_nl_small<256>(model));
+    if (p->nl_fast || p->nl_small) {
         fast_twiddle_kernel<<<(2 * fast::TW_TOTAL + 255) / 256, 256, 0, stream>>>(twf_dev, (int)n);
         p->launches += 1;
     }
@@ -663,8 +681,31 @@ static void dispatch_nl_fast(rks_plan* p, int j, int force, const FuseDesc& fd, 
     p->launches += 1;
 }
 
+template <int N, int MODEL>
+static void launch_nl_small_t(rks_plan* p, int j, int force, cudaStream_t stream) {
+    const long long slabs = (p->d.batch + 512 / N - 1) / (512 / N);
+    const long long ctas = (slabs + NL_SMALL_WARPS - 1) / NL_SMALL_WARPS;
+    const long long cap = (long long)p->sm_count * 3;
+    nl_small_kernel<N, MODEL><<<(unsigned)(ctas < cap ? ctas : cap), 32 * NL_SMALL_WARPS, NL_SMALL_WARPS * 512 * sizeof(cplx), stream>>>(p->d, j, force);
+}
+template <int N>
+static void launch_nl_small(rks_plan* p, int j, int force, cudaStream_t stream) {
+    switch (p->d.model) {
+        case RKS_MODEL_UUX_RFFT: launch_nl_small_t<N, 1>(p, j, force, stream); break;
+        case RKS_MODEL_NLS_FFT: launch_nl_small_t<N, 2>(p, j, force, stream); break;
+        case RKS_MODEL_CUBIC_RFFT: launch_nl_small_t<N, 3>(p, j, force, stream); break;
+        default: launch_nl_small_t<N, 4>(p, j, force, stream); break;
+    }
+}
 static int launch_nl(rks_plan* p, int j, int force, cudaStream_t stream) {
     const DevPlan& d = p->d;
+    if (p->nl_small && !p->multi_n) {
+        if (d.n == 64) launch_nl_small<64>(p, j, force, stream);
+        else if (d.n == 128) launch_nl_small<128>(p, j, force, stream);
+        else launch_nl_small<256>(p, j, force, stream);
+        p->launches += 1;
+        return RKS_OK;
+    }
     if (p->nl_fast) {
         FuseDesc none;
         memset(&none, 0, sizeof(none));

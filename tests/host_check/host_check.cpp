@@ -60,6 +60,33 @@ static int fast_dispatch(int n, const Model& m, const fast::Twiddles& tw) {
     return -1;
 }
 
+// serial emulation of the packed short-row kernel (nl_small_kernel): one warp, 512 / N rows per slab
+template <int N, int MODEL>
+static void packed_rows(int rows, long long n_c, const cplx* in, cplx* out, const double* kx, double p0,
+                        const fast::Twiddles& tw) {
+    constexpr int SUB = 512 / N;
+    std::vector<cplx> sm(512);
+    for (int row0 = 0; row0 < rows; row0 += SUB) {
+        const int left = rows - row0;
+        const fast::PackedModel<MODEL, N> m{in + row0 * n_c, out + row0 * n_c, kx, p0, n_c, left < SUB ? left : SUB};
+        for (int T = 0; T < 32; ++T) fast::phase_first_packed<N>(sm.data(), T, tw, m);
+        for (int T = 0; T < 32; ++T) fast::phase_middle<N, 2, true>(sm.data(), T, tw, m);
+        for (int T = 0; T < 32; ++T) fast::phase_core<N>(sm.data(), T, m);
+        for (int T = 0; T < 32; ++T) fast::phase_middle<N, 2, false>(sm.data(), T, tw, m);
+        for (int T = 0; T < 32; ++T) fast::phase_last_packed<N>(sm.data(), T, tw, m);
+    }
+}
+template <int MODEL>
+static int packed_dispatch(int n, int rows, long long n_c, const cplx* in, cplx* out, const double* kx, double p0,
+                           const fast::Twiddles& tw) {
+    switch (n) {
+        case 64: packed_rows<64, MODEL>(rows, n_c, in, out, kx, p0, tw); return 0;
+        case 128: packed_rows<128, MODEL>(rows, n_c, in, out, kx, p0, tw); return 0;
+        case 256: packed_rows<256, MODEL>(rows, n_c, in, out, kx, p0, tw); return 0;
+    }
+    return -1;
+}
+
 // fused NL of one row through the generic radix-4 passes (fft.cuh), emulating `nthreads` threads
 template <class Model>
 static void generic_row(const Model& m, int n, int nthreads) {
@@ -127,6 +154,20 @@ int hc_nl_fast(int model, int n, const double* in, const double* kx, double p0, 
     if (model == 2) return fast_dispatch(n, fast::ModelOf<2>::make(cin, co, kx, p0, n, true), tw);
     if (model == 3) return fast_dispatch(n, fast::ModelOf<3>::make(cin, co, kx, p0, n, true), tw);
     return fast_dispatch(n, fast::ModelOf<4>::make(cin, co, kx, p0, n, true), tw);
+}
+
+// `rows` consecutive rows of n_c elements through the packed short-row pipeline (n = 64, 128, 256)
+int hc_nl_packed(int model, int n, int rows, const double* in, const double* kx, double p0, double* out) {
+    std::vector<cplx> tab(fast::TW_TOTAL);
+    for (int j = 0; j < fast::TW_TOTAL; ++j) tab[j] = fast::twiddle_table_entry(j, n);
+    const fast::Twiddles tw{tab.data() + fast::TW_T1, tab.data() + fast::TW_T2, tab.data() + fast::TW_T3};
+    const cplx* cin = reinterpret_cast<const cplx*>(in);
+    cplx* co = reinterpret_cast<cplx*>(out);
+    const long long n_c = (model == 1 || model == 3) ? n / 2 + 1 : n;
+    if (model == 1) return packed_dispatch<1>(n, rows, n_c, cin, co, kx, p0, tw);
+    if (model == 2) return packed_dispatch<2>(n, rows, n_c, cin, co, kx, p0, tw);
+    if (model == 3) return packed_dispatch<3>(n, rows, n_c, cin, co, kx, p0, tw);
+    return packed_dispatch<4>(n, rows, n_c, cin, co, kx, p0, tw);
 }
 
 void hc_nl(int model, int n, const double* in, const double* kx, double p0, double* out, int nthreads) {

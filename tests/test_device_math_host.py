@@ -343,3 +343,30 @@ def test_axis_fft_levels_match_numpy(hc, n):
     assert hc.hc_axis_fft(n, 0, ptr(np.ascontiguousarray(phys[perm])), ptr(w), ctypes.c_longlong(inner)) == 0
     reff = np.fft.fft(phys, axis=0)
     np.testing.assert_allclose(w, reff, rtol=0, atol=1e-13 * np.abs(reff).max() * np.log2(n))
+
+
+@pytest.mark.parametrize("n", [64, 128, 256])
+@pytest.mark.parametrize("model", [1, 2, 3, 4])
+def test_packed_short_row_pipeline_matches_generic_rows(hc, n, model):
+    """nl_small_kernel on the host: 512/n rows packed per slab, ragged last slab, all four models == the
+    generic per-row pipeline (which the other tests pin to NumPy)."""
+    rng = np.random.default_rng(100 * n + model)
+    rows = 2 * (512 // n) + 1                       # two full slabs and a ragged one
+    n_c = n // 2 + 1 if model in (1, 3) else n
+    x = rng.standard_normal((rows, n_c)) + 1j * rng.standard_normal((rows, n_c))
+    if model in (1, 3):
+        x[:, 0] = x[:, 0].real
+        x[:, -1] = x[:, -1].real
+    x = np.ascontiguousarray(x)
+    kx = np.ascontiguousarray(np.sqrt(1.0 + np.arange(n, dtype=float) ** 2) if model == 4 else np.arange(n_c, dtype=float) * 0.37)
+    p0 = {1: 6.0, 2: 2.0, 3: -1.0, 4: 0.0}[model]
+    got = np.full_like(x, np.nan)
+    assert hc.hc_nl_packed(model, n, rows, ptr(x), ptr(kx), ctypes.c_double(p0), ptr(got)) == 0
+    want = np.empty_like(x)
+    for r in range(rows):
+        row_out = np.empty(n_c, dtype=np.complex128)
+        hc.hc_nl(model, n, ptr(np.ascontiguousarray(x[r])), ptr(kx), ctypes.c_double(p0), ptr(row_out), 32)
+        want[r] = row_out
+    assert np.isfinite(got).all()
+    scale = np.abs(want).max()
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-13 * scale)

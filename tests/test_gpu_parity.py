@@ -213,7 +213,10 @@ def test_adaptive_dt_sequence_and_final_state(rk, golden, tag, method, path):
     ref_h, ref_acc = g[pre + "trial_h"], g[pre + "trial_accepted"]
     assert len(hs) == len(ref_h), f"{len(hs)} trials vs {len(ref_h)} in the reference"
     np.testing.assert_array_equal(acc, ref_acc)
-    np.testing.assert_allclose(hs, ref_h, rtol=DT_TOL, atol=0)
+    np.testing.assert_allclose(hs[:-1], ref_h[:-1], rtol=DT_TOL, atol=0)
+    # the last dt is the clamp tf - t (solveras.py:637): it carries the summed absolute deviation of every dt
+    # before it, each within DT_TOL relative, so its own bound is DT_TOL * tf absolute
+    np.testing.assert_allclose(hs[-1], ref_h[-1], rtol=0, atol=DT_TOL * float(g[pre + "tf"]))
     np.testing.assert_allclose(np.array(sol.t), g[pre + "t"], rtol=DT_TOL, atol=0)
     assert len(sol.u) == int(g[pre + "n_snap"])
     assert rel(host(uf), g[pre + "u_final"]) < FINAL_TOL
