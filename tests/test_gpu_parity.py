@@ -68,7 +68,7 @@ def make(rk, method, prob, nl, epsilon=None):
 # --------------------------------------------------------------------------------------------
 # K4: fused nonlinearity
 # --------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n", [16, 64, 256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("n", [16, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
 @pytest.mark.parametrize("batch", [1, 3, 40, 301])
 def test_fused_uux_matches_numpy(rk, n, batch):
     p = problems.ks(n, batch=batch, seed=n) if n >= 64 else problems.kdv(n, batch=batch, seed=n)
@@ -81,7 +81,7 @@ def test_fused_uux_matches_numpy(rk, n, batch):
     assert rel(got, p.nl_func(p.u0)) < 2e-14 * np.log2(n)
 
 
-@pytest.mark.parametrize("n", [16, 128, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("n", [16, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
 @pytest.mark.parametrize("batch", [1, 5, 150])
 def test_fused_nls_matches_numpy(rk, n, batch):
     p = problems.nls(n, batch=batch, seed=n, half_width=20.0)
@@ -352,10 +352,10 @@ def test_batched_2d_grid_shares_one_dt(rk):
 # fused Allen-Cahn (cubic) and sine-Gordon models: oracle = the reference's solver
 # logic driven by a NumPy nl_func of the same model
 # --------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n", [64, 512, 2048])
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096, 8192])      # packed, fast and TMA-staged kernels
 @pytest.mark.parametrize("name", ["allen_cahn_1d", "sine_gordon"])
 def test_fused_new_models_match_numpy(rk, name, n):
-    p = getattr(problems, name)(n, batch=5)
+    p = getattr(problems, name)(n, batch=5 if n < 8192 else 300)              # 8192: several rows per persistent CTA
     sol = rk.ETD4(dev(p.lin_op), fused_for(rk, p))
     u = dev(p.u0)
     eng = sol._get_engine(u)
