@@ -184,6 +184,11 @@ void* rks_nl_input(rks_plan* plan, int j);
 void* rks_nl_output(rks_plan* plan, int j);
 /* K3: masked norms -> s -> accept/reject -> new h, t, roles, status, log record */
 int rks_error_control(rks_plan* plan, void* stream);
+/* diagonalize=True (dense lin_op diagonalised on the host, the plan stepping the eigenbasis state): the next
+ * rks_error_control takes max|u+|, the mask and the tolerance from `u_phys` = S u+ (device array of the plan's
+ * state shape) and the error norm from the plan's own eigenbasis estimate -- the mix the reference's
+ * _compute_s sees (etd35.py:495, solveras.py:451-454).  One-shot: cleared by that rks_error_control. */
+int rks_norm_override(rks_plan* plan, const void* u_phys, void* stream);
 /* K3 split for multi-GPU shared-dt ensembles: local partial results live in three doubles
  * (max|u+|^2, sum|u+|^2, sum|err|^2) the caller all-reduces between the calls. */
 int rks_error_sums(rks_plan* plan, void* stream);

@@ -165,6 +165,22 @@ def main():
                 ad[f"{tag}_{m}_{k}"] = v
     np.savez_compressed(os.path.join(GOLD, "adaptive_runs.npz"), **ad)
 
+    # ---- 4b. diagonalize=True on a dense operator --------------------------
+    dg = {}
+    prob = problems.dense_advection_diffusion()
+    for m, eps, tf in (("IF34", 1e-6, 1.0), ("ETD34", 1e-6, 1.0), ("ETD35", 1e-6, 1.0), ("ETD35", 1e-9, 0.5)):
+        cls = getattr(getattr(ref, m.lower()), m)
+        sol = cls(prob.lin_op, prob.nl_func, config=ref.solveras.SolverConfig(epsilon=eps), diagonalize=True)
+        log = instrument(sol)
+        uf = sol.evolve(prob.u0.copy(), 0.0, tf, store_data=True, store_freq=3)
+        s = np.array(log["s"])
+        pre = f"{m}_{eps:g}_"
+        dg.update({pre + "u_final": uf, pre + "trial_h": np.array(log["h"]), pre + "trial_s": s,
+                   pre + "trial_accepted": ~(np.isinf(s) | np.isnan(s) | (s < 1.0)), pre + "t": np.array(sol.t),
+                   pre + "u_snap_last": np.asarray(sol.u[-1]), pre + "n_snap": len(sol.u), pre + "tf": tf})
+    dg["lin_op"], dg["u0"] = prob.lin_op, prob.u0
+    np.savez_compressed(os.path.join(GOLD, "diagonalized_runs.npz"), **dg)
+
     # ---- 5. README quickstart (cfg 1) summary -------------------------------------------
     p = problems.ks(1024)
     r = run_adaptive(ref, "IF34", p, 50.0, None if False else 1e-4, 20, None)

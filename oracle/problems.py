@@ -228,3 +228,23 @@ def sine_gordon(n: int = 256, batch: int = 0, half_width: float = 20.0, seed: in
         phi0 = breather(0.5, 0.0)
     psi0 = 1j * omega * np.fft.fft(phi0, axis=-1)            # phi_t = 0
     return Problem("sine_gordon", lin, nl, psi0, "sine_gordon", n, omega, {}, x)
+
+
+def dense_advection_diffusion(n: int = 16, nu: float = 0.05, c: float = 0.5, omega: float = 3.0) -> Problem:
+    """A small DENSE-operator problem for ``diagonalize=True``: two fields (p, q) on (0, 1), homogeneous
+    Dirichlet ends, centred differences, each with A = nu d_xx - c d_x (non-symmetric: the eigenvector
+    matrix is not orthogonal, cond(S) ~ 1e2) and rotating into each other at rate omega (complex
+    eigenvalue pairs lambda_k +- i omega):  L = [[A, omega I], [-omega I, A]],  N(u) = u - u^3."""
+    dx = 1.0 / (n + 1)
+    x = np.arange(1, n + 1) * dx
+    lo = nu / dx ** 2 + c / (2 * dx)
+    hi = nu / dx ** 2 - c / (2 * dx)
+    amat = np.diag(np.full(n, -2 * nu / dx ** 2)) + np.diag(np.full(n - 1, lo), -1) + np.diag(np.full(n - 1, hi), 1)
+    eye = np.eye(n)
+    lin = np.block([[amat, omega * eye], [-omega * eye, amat]])
+
+    def nl(u):
+        return u - u ** 3
+
+    u0 = np.concatenate([0.8 * np.sin(np.pi * x) + 0.3 * np.sin(3 * np.pi * x), 0.5 * np.sin(2 * np.pi * x)])
+    return Problem("dense_advdiff", lin, nl, u0.astype(np.complex128), "none", 2 * n, x, {"nu": nu, "c": c, "omega": omega}, x)

@@ -450,3 +450,58 @@ class OracleSolver:
                 self.t.append(tc)
                 self.u.append(u)
         return u
+
+
+class OracleDiagonalized(OracleSolver):
+    """``diagonalize=True`` for a dense ``lin_op`` (etd35.py:348-495, etd34.py:194-300, if34.py:137-200):
+    L = S diag(w) S^-1 once on the host, stages in the eigenbasis v = S^-1 u with N'(k) = S^-1 N(S k); the
+    trial returns the PHYSICAL u+ = S k next to the EIGENSPACE error estimate, and the controller takes its
+    mask and tolerance from the former and the error norm from the latter (solveras.py:451-454)."""
+
+    def __init__(self, method, lin_op, nl_func, cfg=None):
+        if method not in ("IF34", "ETD34", "ETD35"):
+            raise ValueError("the reference diagonalizes IF34, ETD34 and ETD35 only")
+        lin_op = np.asarray(lin_op)
+        if lin_op.ndim != 2 or lin_op.shape[0] != lin_op.shape[1]:
+            raise ValueError("Cannot diagonalize a 1D system")
+        if np.linalg.cond(lin_op) > 1e16:
+            raise ValueError("Linear operator is non-invertible")
+        self.matrix = lin_op
+        self.eig_vals, self.S = np.linalg.eig(lin_op)
+        self.Sinv = np.linalg.inv(self.S)
+        self.phys_nl = nl_func
+        super().__init__(method, self.eig_vals, nl_func, cfg if cfg is not None else Config())
+        self._v = None
+
+    def _nl_eig(self, k):
+        self.nl_calls += 1
+        return self.Sinv.dot(self.phys_nl(self.S.dot(k)))
+
+    def _n1_init(self, u):
+        self.nl_calls += 1
+        self._N[1] = self.Sinv.dot(self.phys_nl(u))
+        self._v = self.Sinv.dot(u)
+
+    def trial(self, u, h):
+        self._update_coeffs(h)
+        c, N, m = self._coef, self._N, self.method
+        if not self._n1_ready:
+            self._n1_init(u)
+            self._n1_ready = True
+        if m == "ETD35":
+            if self._accept:
+                self._n1_init(u)                    # etd35.py:459-460: stage_init(u) again
+            k = _stages_etd5(c, self._nl_eig, self._v, N)
+            err = c["a75"] * (-N[1] + 4 * N[3] - 6 * N[4] + 4 * N[5] - N[6])
+            return self.S.dot(k), err
+        if self._accept:                            # FSAL: etd34.py:283-285, if34.py:180-182
+            N[1] = N[5].copy()
+            self._v = self.Sinv.dot(u)
+        if m == "ETD34":
+            k = _stages_krogstad(c, self._nl_eig, self._v, N)
+            N[5] = self._nl_eig(k)
+            return self.S.dot(k), c["a54"] * (N[4] - N[5])
+        k = _stages_if4(c, self._nl_eig, self._v, N, h)
+        N[5] = self._nl_eig(k)
+        return self.S.dot(k), h * (N[4] - N[5]) / 6.0
+

@@ -76,6 +76,7 @@ def _load():
         "rks_nl_input": (P, [P, c_int]),
         "rks_nl_output": (P, [P, c_int]),
         "rks_error_control": (c_int, [P, P]),
+        "rks_norm_override": (c_int, [P, P, P]),
         "rks_error_sums": (c_int, [P, P]),
         "rks_controller": (c_int, [P, P]),
         "rks_reduction_scalars": (P, [P]),

@@ -92,6 +92,10 @@ class Engine:
         self._h_set: Optional[float] = None
         self._n1_ready = False
         self._red = None
+        #: diagonalize=True: maps the plan's (eigenbasis) u+ to the physical array whose magnitudes drive the
+        #: error controller (rks_norm_override); None for diagonal operators
+        self.norm_map: Optional[Callable] = None
+        self._norm_keep = None
 
     def __del__(self):
         try:
@@ -198,6 +202,10 @@ class Engine:
         return self._red
 
     def error_control(self) -> None:
+        if self.norm_map is not None:
+            uplus = self._view(lib.rks_nl_input(self.plan, self.stages + 1))       # U[1 - u_sel]
+            self._norm_keep = self.norm_map(uplus).contiguous()
+            check(lib.rks_norm_override(self.plan, c_void_p(self._norm_keep.data_ptr()), self.st))
         if self.group is None:
             check(lib.rks_error_control(self.plan, self.st))
             return

@@ -151,6 +151,8 @@ struct DevPlan {
     const cplx* tw;    // twiddles exp(-2 pi i j / n), j < n (generic NL kernel)
     const cplx* twf;   // fast-path twiddle tables (fft_fast.cuh: o | a | b)
     const double* kx;  // wavenumbers of the fused model
+    const cplx* norm_u; // nullptr, or the array whose magnitudes drive the error controller (diagonalize=True:
+                        // the physical S u+ while the estimate stays in the eigenbasis, etd35.py:495)
     long long batch, n_c, lin_elems, n;
     double model_p0;   // c (u u_x models) or gamma (NLS)
     int method, lin_complex, lin_full, model, log2n;

@@ -772,7 +772,7 @@ RKS_D void norm_kernel_body(const DevPlan& p, int fuse_controller) {
     const double h = c->h;
     const double m = sqrt(c->red[0]);                       // max |u+|
     const double cutoff = c->adapt_cutoff;
-    const cplx* __restrict__ un = p.U[1 - u_sel];
+    const cplx* __restrict__ un = p.norm_u ? p.norm_u : p.U[1 - u_sel];
     const CT* __restrict__ coef = (const CT*)p.coef;
     const long long cstride = p.lin_elems;
     const long long ncols = FULL ? p.batch * p.n_c : p.n_c;
@@ -846,6 +846,32 @@ __global__ void __launch_bounds__(128) norm_kernel(const __grid_constant__ DevPl
 template <int M, typename CT, bool FULL>
 __global__ void __launch_bounds__(128) norm_kernel_multi(const DevPlan* plans, int fuse_controller) { norm_kernel_body<M, CT, FULL>(plans[blockIdx.z], fuse_controller); }
 
+
+// max |x|^2 over an array -> ctrl.red[0], REPLACING what the last stage kernel accumulated there
+// (diagonalize=True: the mask and tolerance of the controller come from the physical S u+)
+__global__ void __launch_bounds__(1024) max_abs2_kernel(DevPlan p, const cplx* x, long long count) {
+    Ctrl* c = p.ctrl;
+    if (c->status != ST_RUNNING) return;
+    unsigned long long best = 0ull;
+    for (long long e = threadIdx.x; e < count; e += 1024) {
+        const cplx v = x[e];
+        const double a = v.x * v.x + v.y * v.y;
+        const unsigned long long bits = (a != a) ? 0x7ff8000000000000ull : (unsigned long long)__double_as_longlong(a);
+        best = bits > best ? bits : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+        best = t > best ? t : best;
+    }
+    __shared__ unsigned long long sh[32];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w) best = sh[w] > best ? sh[w] : best;
+        c->red[0] = __longlong_as_double((long long)best);
+    }
+}
 
 __global__ void controller_kernel(DevPlan p) {
     Ctrl* c = p.ctrl;

@@ -841,7 +841,23 @@ static int launch_norm(rks_plan* p, int fuse, cudaStream_t stream) {
 
 extern "C" int rks_error_control(rks_plan* p, void* stream) {
     if (!p) return fail(RKS_ERR_ARG, "plan is null");
-    if (int rc = launch_norm(p, 1, (cudaStream_t)stream)) return rc;
+    const int rc = launch_norm(p, 1, (cudaStream_t)stream);
+    p->d.norm_u = nullptr;                                 // an override lasts for one trial
+    if (rc) return rc;
+    CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
+// The NEXT rks_error_control takes |u+| (max, mask, tolerance) from `u_phys` instead of the plan's own u+,
+// while the error estimate stays the plan's: the reference's diagonalize=True strategies return the physical
+// S k next to the eigenbasis estimate (etd35.py:495, etd34.py:300, if34.py:200) and _compute_s mixes the two.
+extern "C" int rks_norm_override(rks_plan* p, const void* u_phys, void* stream) {
+    if (!p || !u_phys) return fail(RKS_ERR_ARG, "null argument");
+    if (!method_adaptive(p->method) || p->multi_n) return fail(RKS_ERR_UNSUPPORTED, "norm override needs a shared-dt adaptive plan");
+    if (((uintptr_t)u_phys) & 15) return fail(RKS_ERR_ARG, "u_phys must be 16-byte aligned");
+    max_abs2_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p->d, (const cplx*)u_phys, p->d.batch * p->d.n_c);
+    p->launches += 1;
+    p->d.norm_u = (const cplx*)u_phys;
     CUDA_TRY(cudaGetLastError());
     return RKS_OK;
 }

@@ -11,7 +11,11 @@ class IF34(BaseSolverAS):
 
     def __init__(self, lin_op, nl_func, config: Optional[SolverConfig] = None, diagonalize: bool = False,
                  loglevel: Union[str, int] = "WARNING", group=None) -> None:
-        if diagonalize:
-            raise NotImplementedError("diagonalize=True (dense lin_op) is outside the diagonal hot path")
         super().__init__(lin_op, nl_func, config=config, loglevel=loglevel, group=group)
+        # diagonalize=True: a 2-D lin_op is a DENSE matrix, diagonalised once on the host; a 1-D lin_op is
+        # already diagonal and the flag is ignored, as in the reference (tests/test_etd35.py:202-205)
+        if diagonalize and lin_op.dim() >= 2:
+            if group is not None:
+                raise ValueError("diagonalize=True is a single-process mode")
+            self._init_diagonalized(lin_op)
         self._h_coeff = None

@@ -2,10 +2,10 @@
 
 Differences from the reference, all extensions:
   * ``lin_op`` and ``u`` are CUDA tensors (complex128 state, float64 or complex128 operator);
-  * ``lin_op`` is always a *diagonal* operator: it may be ``(n,)`` broadcast over leading batch
-    dimensions of ``u`` or have any rank matching the trailing dimensions of ``u`` (N-D grids).
-    Dense-matrix operators (the reference's 2-D ``lin_op``) are out of scope and rejected via
-    ``diagonalize=True`` / ``matrix=True`` -> NotImplementedError;
+  * ``lin_op`` is a *diagonal* operator: it may be ``(n,)`` broadcast over leading batch dimensions of
+    ``u`` or have any rank matching the trailing dimensions of ``u`` (N-D grids).  A dense square matrix
+    is accepted by IF34 / ETD34 / ETD35 with ``diagonalize=True`` (eigen-decomposition on the host, the
+    engine steps the eigenbasis state); the reference's matrix-exponential strategies are out of scope;
   * ``nl_func`` is a torch callable or a fused-kernel handle from :mod:`rkstiff_b200.models`.
 """
 from __future__ import annotations
@@ -44,6 +44,10 @@ class BaseSolver(ABC):
         self.snapshot_device = "cuda"
         self._snap_stream = None
         self._diag = True
+        # diagonalize=True (dense lin_op): eigen-decomposition done once on the host; the engine steps the
+        # eigenbasis state with lin_op = eigenvalues (solveras.py:_init_diagonalized)
+        self._S = self._Sinv = self._eig = None
+        self._nl_eig = None
         self._group = group
         self._engines: Dict[tuple, Engine] = {}
         self._engine: Optional[Engine] = None
@@ -63,18 +67,33 @@ class BaseSolver(ABC):
 
     def _fused(self):
         from .models import FusedNL
+        if self._S is not None:
+            return None
         return self.nl_func if isinstance(self.nl_func, FusedNL) else None
 
     def _callable(self):
         """None when the fused CUDA nonlinearity is used, else the torch callable."""
+        if self._S is not None:
+            if self._nl_eig is None:
+                # N'(k) = S^-1 N(S k)  (etd35.py:463): two dense matrix-vector products around the user's callable
+                self._nl_eig = lambda k: torch.matmul(self._Sinv, self.nl_func(torch.matmul(self._S, k)).to(torch.complex128))
+            return self._nl_eig
         return None if self._fused() is not None else self.nl_func
+
+    def _to_eig(self, u: torch.Tensor) -> torch.Tensor:
+        return u if self._S is None else torch.matmul(self._Sinv, u.to(torch.complex128))
+
+    def _to_phys(self, v: torch.Tensor) -> torch.Tensor:
+        return v if self._S is None else torch.matmul(self._S, v)
 
     def _get_engine(self, u: torch.Tensor) -> Engine:
         key = tuple(u.shape)
         eng = self._engines.get(key)
         if eng is None:
-            eng = Engine(self.METHOD, self.lin_op, u.shape, self._rks_config(), fused=self._fused(),
-                         group=self._group)
+            eng = Engine(self.METHOD, self.lin_op if self._eig is None else self._eig, u.shape, self._rks_config(),
+                         fused=self._fused(), group=self._group)
+            if self._S is not None:
+                eng.norm_map = self._to_phys          # the controller's |u+| is the physical one (etd35.py:495)
             self._engines = {key: eng}           # one live plan per solver: a new shape replaces the old
             self._cfg_sig = self._config_signature()
         elif self._cfg_sig != self._config_signature():

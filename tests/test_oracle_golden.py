@@ -119,3 +119,26 @@ def test_cfg1_readme_quickstart(golden):
     assert sol.t[-1] == pytest.approx(49.65786485353072, rel=1e-15)
     np.testing.assert_array_equal(np.array([r.h for r in sol.log]), g["trial_h"])
     assert np.linalg.norm(uf) == pytest.approx(float(g["u_final_norm"]), rel=1e-12)
+
+
+DIAG_CASES = [("IF34", 1e-6), ("ETD34", 1e-6), ("ETD35", 1e-6), ("ETD35", 1e-9)]
+
+
+@pytest.mark.parametrize("method,eps", DIAG_CASES)
+def test_diagonalized_runs_match_reference(golden, method, eps):
+    """diagonalize=True (dense lin_op, etd35.py:348-495): the oracle's eigenbasis strategy reproduces the
+    reference's trial sequence and states bit for bit (same LAPACK eig / inv on the host)."""
+    from oracle.rk_oracle import OracleDiagonalized
+    g = golden("diagonalized_runs.npz")
+    p = problems.dense_advection_diffusion()
+    np.testing.assert_array_equal(p.lin_op, g["lin_op"])
+    np.testing.assert_array_equal(p.u0, g["u0"])
+    pre = f"{method}_{eps:g}_"
+    sol = OracleDiagonalized(method, p.lin_op, p.nl_func, Config(epsilon=eps))
+    uf = sol.evolve(p.u0.copy(), 0.0, float(g[pre + "tf"]), store_freq=3)
+    np.testing.assert_array_equal(np.array([r.h for r in sol.log]), g[pre + "trial_h"])
+    np.testing.assert_array_equal(np.array([r.accepted for r in sol.log]), g[pre + "trial_accepted"])
+    np.testing.assert_array_equal(uf, g[pre + "u_final"])
+    np.testing.assert_array_equal(np.array(sol.t), g[pre + "t"])
+    assert len(sol.u) == int(g[pre + "n_snap"])
+

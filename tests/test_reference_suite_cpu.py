@@ -88,11 +88,12 @@ def test_module_surface_matches_reference_imports():
 def test_matrix_operators_are_rejected_not_emulated():
     torch = pytest.importorskip("torch")
     if torch.cuda.is_available():
+        # a 1-D operator is already diagonal: the flag is ignored (reference tests/test_etd35.py:202-205)
         lin = torch.zeros(8, dtype=torch.float64, device="cuda")
-        with pytest.raises(NotImplementedError):
-            rk.ETD35(lin, lambda v: v, diagonalize=True)
-        with pytest.raises(NotImplementedError):
-            rk.IF34(lin, lambda v: v, diagonalize=True)
+        assert rk.ETD35(lin, lambda v: v, diagonalize=True)._S is None
+        # a dense matrix is diagonalised; a singular one is refused (tests/test_etd35.py:255-262)
+        with pytest.raises(ValueError):
+            rk.IF34(torch.tensor([[1.0, 2.0], [2.0, 4.0]], dtype=torch.float64, device="cuda"), lambda v: v, diagonalize=True)
     with pytest.raises(TypeError):
         rk.ETD4([1.0, 2.0], lambda v: v)
 
