@@ -555,12 +555,21 @@ def run_ours(args):
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
     # ncu --set full captures under profiles/ (same geometry); None when that kernel/geometry was not captured
     traffic = None
+    co_bounds = None
     if top.startswith("nl") and batch * n_c == 4096 * 8192:
-        traffic = 536.98e6 + 478.76e6           # profiles/r01_v4_nl_fast_ncu_raw.csv
+        traffic = 537.16e6 + 480.97e6           # profiles/r01_final2_ncu_full_nl_fast_8192_tma.csv
+        # the FFT pair is not HBM-bound: ncu counts, per SM and launch, 424 k LSU wavefront cycles and ~370 k FP64
+        # pipe cycles against 234 k cycles of its HBM share (673 k elapsed) -- DESIGN.md section 4
+        co_bounds = {"source": "profiles/r01_final2_ncu_full_nl_fast_8192_tma.csv", "lsu_wavefronts_pct": 63.1,
+                     "fp64_pipe_pct": 55.0, "dram_pct": 34.8,
+                     "note": "FP64 butterflies and shared-memory passes bound this kernel, not HBM"}
     elif top.startswith("nl") and batch * n_c == 65536 * 513:
         traffic = 540.44e6 + 480.53e6           # profiles/r01_v4_nl_fast_cfg3_ncu_raw.csv
+        co_bounds = {"source": "profiles/r01_v4_nl_fast_cfg3_ncu_raw.csv", "lsu_wavefronts_pct": 93.0,
+                     "note": "rfft models run full-length complex transforms: shared-memory (LSU) bound"}
     roofline = {"bound": "hbm", "kernel": top, "achieved": b_top / t_top / 1e9, "peak": peak_gbs, "unit": "GB/s",
                 "frac": b_top / t_top / 1e9 / peak_gbs, "traffic": traffic, "peak_source": peak_src,
+                "co_bounds": co_bounds,
                 "share_of_step": shares[top] / sum(shares.values()),
                 "whole_step": {"algorithmic_bytes_per_elem": BYTES_PER_ELEM[method],
                                "achieved": BYTES_PER_ELEM[method] * elems * K / secs / 1e9,
