@@ -118,8 +118,9 @@ def kdv_multi_soliton(x: torch.Tensor, ampl: Sequence[float], x0: Sequence[float
 # ----------------------------------------------------------------------------------------------
 # N-D Fourier-diagonal models.  lin_op has the shape of the spectral grid and u
 # that shape (plus optional leading batch dims): the engine's "lin_op shaped like u" path.  The
-# nonlinear term is a torch callable here (library FFT for the N-D transform; K1/K2/K3 are the
-# engine's kernels) -- the hand-written fused kernels cover the 1-D models above.
+# nonlinear term is a Python callable that composes the engine's own kernels: AxisFFT over the strided
+# axes (csrc/fft_axis.cuh) around RowNL, the fused last-axis kernel.  Grids whose axis lengths are not
+# powers of two (16..4096 strided, 16..16384 last axis) fall back to torch.fft + the pointwise kernel.
 # ----------------------------------------------------------------------------------------------
 def pointwise_(model_id: int, x: torch.Tensor, p0: float) -> torch.Tensor:
     """In-place pointwise nonlinearity of an N-D model in one CUDA kernel (rks_pointwise):
@@ -135,7 +136,7 @@ def pointwise_(model_id: int, x: torch.Tensor, p0: float) -> torch.Tensor:
 class RowNL:
     """Fused ``F{ N( F^-1{ . } ) }`` along the LAST axis of any contiguous array (rks_rows_*): the
     innermost-axis part of an N-D nonlinear term, done by the engine's hand-written FFT kernel in one
-    read + one write.  The outer axes are transformed by the caller (library FFT)."""
+    read + one write.  The outer axes are transformed by the caller (AxisFFT)."""
 
     def __init__(self, model_id: int, n: int, kx: Optional[torch.Tensor], p0: float, device) -> None:
         from ctypes import byref, c_void_p
