@@ -248,3 +248,23 @@ def dense_advection_diffusion(n: int = 16, nu: float = 0.05, c: float = 0.5, ome
 
     u0 = np.concatenate([0.8 * np.sin(np.pi * x) + 0.3 * np.sin(3 * np.pi * x), 0.5 * np.sin(2 * np.pi * x)])
     return Problem("dense_advdiff", lin, nl, u0.astype(np.complex128), "none", 2 * n, x, {"nu": nu, "c": c, "omega": omega}, x)
+
+
+def allen_cahn_cheb(n: int = 20, eps: float = 0.01) -> Problem:
+    """The reference's own dense-operator test problem (tests/testing_util.py:12-25, models.py:202-262):
+    Allen-Cahn on n + 1 Chebyshev points, w = u - x on the interior, lin_op = eps D^2 + I (dense)."""
+    j = np.arange(n + 1)
+    x = np.polynomial.chebyshev.chebpts2(n + 1)
+    c = np.r_[2, np.ones(n - 1), 2] * np.power(-1.0, j)
+    dmat = np.outer(c, 1.0 / c) / ((x[:, None] - x[None, :]) + np.eye(n + 1))
+    dmat = dmat - np.diag(dmat.sum(axis=1))
+    lin = (eps * dmat.dot(dmat) + np.eye(n + 1))[1:-1, 1:-1]
+    xi = x[1:-1]
+
+    def nl(w):
+        return np.asarray(xi - np.power(w + xi, 3), dtype=np.complex128).ravel()
+
+    u0 = 0.53 * x + 0.47 * np.sin(-1.5 * np.pi * x)
+    return Problem("allen_cahn_cheb", lin, nl, (u0 - x)[1:-1].astype(np.complex128), "none", n - 1, xi,
+                   {"eps": eps, "u0int": u0[1:-1]}, xi)
+

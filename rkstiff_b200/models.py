@@ -115,6 +115,20 @@ def kdv_multi_soliton(x: torch.Tensor, ampl: Sequence[float], x0: Sequence[float
     return out
 
 
+def allen_cahn_ops(x: torch.Tensor, d_cheb_matrix: torch.Tensor, epsilon: float = 0.01):
+    """Allen-Cahn on a Chebyshev grid with the ends pinned to u(+-1) = +-1, written for w = u - x
+    (rkstiff/models.py:202-262): DENSE ``lin_op = eps D^2 + I`` without its boundary rows/columns and
+    ``nl_func(w) = x - (w + x)^3`` on the interior points.  Use with ``diagonalize=True``."""
+    d2 = d_cheb_matrix @ d_cheb_matrix
+    lin_op = (epsilon * d2 + torch.eye(d2.shape[0], dtype=d2.dtype, device=d2.device))[1:-1, 1:-1].contiguous()
+    xi = x[1:-1]
+
+    def nl_func(w: torch.Tensor) -> torch.Tensor:
+        return (xi - (w + xi) ** 3).to(torch.complex128)
+
+    return lin_op, nl_func
+
+
 # ----------------------------------------------------------------------------------------------
 # N-D Fourier-diagonal models (SURVEY.md 8f-1).  lin_op has the shape of the spectral grid and u
 # that shape (plus optional leading batch dims): the engine's "lin_op shaped like u" path.  The

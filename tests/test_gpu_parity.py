@@ -560,3 +560,28 @@ def test_diagonalized_step_api_and_errors(rk, caplog):
         rk.ETD35(dev(ill), lambda v: v, diagonalize=True)
     assert any("condition number" in r.getMessage() for r in caplog.records)
 
+
+def test_reference_allen_cahn_chebyshev_test_through_diagonalize(rk):
+    """The reference's dense-operator test (tests/test_etd35.py:36-48, its matrix-exponential path) run through
+    diagonalize=True: same physical assertions, and the run equals the oracle's diagonalized strategy."""
+    from oracle.rk_oracle import OracleDiagonalized
+    p = problems.allen_cahn_cheb(20)
+    x, d = rk.grids.construct_x_dx_cheb(20, -1.0, 1.0)
+    lin_dev, nl = rk.models.allen_cahn_ops(x, d, 0.01)
+    assert float((lin_dev - dev(p.lin_op)).abs().max()) < 1e-10
+    sol = rk.ETD35(dev(p.lin_op), nl, config=rk.SolverConfig(epsilon=1e-4),
+                   etd_config=rk.ETDConfig(contour_points=32, contour_radius=10), diagonalize=True)
+    wf = sol.evolve(dev(p.u0), 0.0, 60.0, store_data=False)
+    uf = host(wf).real + p.kx
+    u0int = p.params["u0int"]
+    assert abs(u0int[0] - uf[0]) < 0.01 and abs(u0int[7] - uf[7]) > 1
+    ora = OracleDiagonalized("ETD35", p.lin_op, p.nl_func, Config(epsilon=1e-4, contour_points=32, contour_radius=10.0))
+    wo = ora.evolve(p.u0.copy(), 0.0, 60.0, store_data=False)
+    assert [r[2] for r in sol.trial_log] == [r.accepted for r in ora.log]
+    # t = 60 of metastable front dynamics amplifies roundoff along the way (the reference's own test only checks
+    # two grid values): dt is compared tightly over the first 40 trials, loosely over the whole run
+    hs, ho = np.array([r[0] for r in sol.trial_log]), np.array([r.h for r in ora.log])
+    np.testing.assert_allclose(hs[:40], ho[:40], rtol=1e-8)
+    np.testing.assert_allclose(hs[:-1], ho[:-1], rtol=1e-4)
+    assert rel(host(wf), wo) < 1e-5
+

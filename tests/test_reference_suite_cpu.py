@@ -129,3 +129,28 @@ def test_device_derivatives_match_reference_semantics():
     with pytest.raises(ValueError):
         d.dx_fft(kr, u)
     assert d.dx_rfft(kr, torch.empty(0, dtype=torch.float64)).numel() == 0
+
+
+def test_chebyshev_grid_and_dense_allen_cahn_operator():
+    """grids.construct_x_dx_cheb / models.allen_cahn_ops (rkstiff/grids.py:134-220, models.py:202-262) on the
+    CPU device: points of chebpts2, D 1 = 0, D x = 1, D x^2 = 2x, and the interior operator eps D^2 + I."""
+    import numpy as np
+    import torch
+    from oracle import problems
+    from rkstiff_b200 import grids, models
+    n = 20
+    x, d = grids.construct_x_dx_cheb(n, -1.0, 1.0, device="cpu")
+    np.testing.assert_allclose(x.numpy(), np.polynomial.chebyshev.chebpts2(n + 1), rtol=0, atol=1e-15)
+    assert float((d @ torch.ones_like(x)).abs().max()) < 1e-12
+    assert float((d @ x - 1.0).abs().max()) < 1e-12
+    assert float((d @ x ** 2 - 2 * x).abs().max()) < 1e-11
+    lin, nl = models.allen_cahn_ops(x, d, 0.01)
+    p = problems.allen_cahn_cheb(n)
+    np.testing.assert_allclose(lin.numpy(), p.lin_op, rtol=0, atol=1e-11)
+    w = torch.from_numpy(p.u0)
+    np.testing.assert_allclose(nl(w).numpy(), p.nl_func(p.u0), rtol=0, atol=1e-15)
+    with pytest.raises(ValueError):
+        grids.construct_x_cheb(1, device="cpu")
+    with pytest.raises(TypeError):
+        grids.construct_x_cheb(4.0, device="cpu")
+
