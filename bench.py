@@ -40,6 +40,9 @@ STAGE_PASSES = {"IF4": [3, 3, 3, 6], "IF34": [3, 3, 3, 6], "ETD4": [3, 4, 4, 6],
                 "ETD5": [3, 4, 4, 6, 7, 7], "ETD35": [3, 4, 4, 6, 7, 8], "IF45DP": [3, 4, 5, 6, 7, 7]}
 NORM_PASSES = {"IF34": 3, "ETD34": 3, "ETD35": 2, "IF45DP": 7}
 ADAPTIVE = ("IF34", "ETD34", "ETD35", "IF45DP")
+# dram bytes / pipe utilisation of one nl_fast_pre_kernel<16> launch at 4096 x 8192 (profiles/, ncu --set full); None = not captured
+NL_PRE_TRAFFIC = None
+NL_PRE_CO_BOUNDS = None
 
 
 # ------------------------------------------------------------------------------------------
@@ -125,7 +128,9 @@ class ClockSampler:
 # CPU baseline: the oracle (NumPy port of the reference path), bounded sample
 # ------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    workload, rows, seed, steps, warmup, method = args
+    """`steps` trial steps of the oracle on `rows` trajectories; with min_secs > 0 it keeps stepping until that
+    much time has passed (the cpu_baseline leg: a sample of 10-30 s whatever the host's speed)."""
+    workload, rows, seed, steps, warmup, method, min_secs = args
     import numpy as np
     from oracle import problems
     from oracle.rk_oracle import Config, OracleSolver
@@ -142,26 +147,29 @@ def _cpu_worker(args):
             u, _, h = sol.step(u, h)
         sol.log.clear()
         t0 = time.perf_counter()
-        for _ in range(steps):
+        done = 0
+        while done < steps or time.perf_counter() - t0 < min_secs:
             u, _, h = sol.step(u, h)
+            done += 1
         dt = time.perf_counter() - t0
         trials = len(sol.log)
     else:
         for _ in range(warmup):
             u = sol.step(u, h)
         t0 = time.perf_counter()
-        for _ in range(steps):
+        trials = 0
+        while trials < steps or time.perf_counter() - t0 < min_secs:
             u = sol.step(u, h)
+            trials += 1
         dt = time.perf_counter() - t0
-        trials = steps
     assert np.isfinite(u).all()
     return trials * rows * n, dt
 
 
-def cpu_baseline(workload, cores, steps, warmup, rows, method):
+def cpu_baseline(workload, cores, steps, warmup, rows, method, min_secs=0.0):
     """gp*steps/s of the oracle on `cores` processes, each stepping its own `rows`-trajectory shard."""
     import multiprocessing as mp
-    jobs = [(workload, rows, 100 + i, steps, warmup, method) for i in range(cores)]
+    jobs = [(workload, rows, 100 + i, steps, warmup, method, min_secs) for i in range(cores)]
     if cores == 1:
         res = [_cpu_worker(jobs[0])]
     else:
@@ -169,7 +177,7 @@ def cpu_baseline(workload, cores, steps, warmup, rows, method):
             res = pool.map(_cpu_worker, jobs)
     work = sum(r[0] for r in res)
     wall = max(r[1] for r in res)
-    return work / wall, wall
+    return work / wall, wall, work
 
 
 def run_reference(args):
@@ -180,11 +188,12 @@ def run_reference(args):
         return
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     cores = os.cpu_count() or 1
-    rows = 16 if args.workload == "cfg2" else 256
-    steps = max(1, min(args.steps, 12 if args.workload == "cfg2" else 40))
-    warm = max(1, min(args.warmup, 2))
+    # a step = one trial step of a bounded sample of the workload: `rows` trajectories per process; K and W are
+    # honoured as given (K = 40: ~4 s per process for cfg2, ~2 s for cfg3)
+    rows = 64 if args.workload == "cfg2" else 1024
+    steps, warm = max(1, args.steps), max(0, args.warmup)
     method = args.method or ("ETD35" if args.workload == "cfg2" else "ETD4")
-    value, wall = cpu_baseline(args.workload, cores, steps, warm, rows, method)
+    value, wall, _ = cpu_baseline(args.workload, cores, steps, warm, rows, method)
     sample = (f"{cores} processes x {rows} trajectories x {steps} steps of the oracle "
               f"({'NLS n=8192' if args.workload == 'cfg2' else 'KS n=1024'} {method})")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -539,13 +548,22 @@ def run_ours(args):
     n_nl = S if (not adaptive or method in ("IF34", "ETD34", "IF45DP")) else S - 1
     if method == "ETD35":
         n_nl = S                                   # 5 stage NLs + N1 = N(u) after an accept
+    # the kernels of the timed region, one at a time: rks_stage_nl_part launches exactly what rks_stage_nl(s) does
+    # (for the NLS workload the intermediate stages use the pre-transforming pair; RKS_PT=0: plain)
+    part = lambda s, which: rk._abi.check(rk._abi.lib.rks_stage_nl_part(eng.plan, s, which, eng.st))
+    pt = args.workload == "cfg2" and os.environ.get("RKS_PT", "1")[:1] != "0"
+    n_pre = S - 1 if pt else 0
     t_nl = time_kernel(torch, lambda: eng.nl(2), reps)
-    kern["nl (K4 fused spectral nonlinearity)"] = (t_nl, 2 * 16 * elems, n_nl)
+    kern["nl (K4 fused spectral nonlinearity)"] = (t_nl, 2 * 16 * elems, n_nl - n_pre)
+    if pt:
+        t_pre = time_kernel(torch, lambda: part(1, 2), reps)
+        kern["nl-pre (K4 on rows K1 pre-transformed)"] = (t_pre, 2 * 16 * elems, n_pre)
     for s in range(1, S + 1):
         if not adaptive and s == S:
             continue            # in place: timing it alone would advance u repeatedly
-        t = time_kernel(torch, lambda s=s: eng.stage(s), reps)
-        kern[f"stage{s} (K1 combine)"] = (t, STAGE_PASSES[method][s - 1] * 16 * elems, 1)
+        t = time_kernel(torch, lambda s=s: part(s, 1), reps)
+        name = f"stage{s} (K1 combine + first inverse FFT pass)" if pt and s < S else f"stage{s} (K1 combine)"
+        kern[name] = (t, STAGE_PASSES[method][s - 1] * 16 * elems, 1)
     if adaptive:
         t = time_kernel(torch, lambda: rk._abi.check(rk._abi.lib.rks_error_sums(eng.plan, eng.st)), reps)
         kern["norm (K3 masked norms)"] = (t, NORM_PASSES[method] * 16 * elems, 1)
@@ -556,7 +574,10 @@ def run_ours(args):
     # ncu --set full captures under profiles/ (same geometry); None when that kernel/geometry was not captured
     traffic = None
     co_bounds = None
-    if top.startswith("nl") and batch * n_c == 4096 * 8192:
+    if top.startswith("nl-pre"):
+        traffic = NL_PRE_TRAFFIC              # from this round's ncu --set full capture, when there is one
+        co_bounds = NL_PRE_CO_BOUNDS
+    elif top.startswith("nl") and batch * n_c == 4096 * 8192:
         traffic = 537.16e6 + 480.97e6           # profiles/r01_final2_ncu_full_nl_fast_8192_tma.csv
         # the FFT pair is not HBM-bound: ncu counts, per SM and launch, 424 k LSU wavefront cycles and ~370 k FP64
         # pipe cycles against 234 k cycles of its HBM share (673 k elapsed) -- DESIGN.md section 4
@@ -618,9 +639,10 @@ def run_ours(args):
     # ---- CPU baseline on rank 0, N = 1 only (the oracle also serves as the checker of a small sample) --
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # ~10-20 s of single-core NumPy work (cfg 2 at B=64, cfg 3 at B=1024)
+        # 12 s of single-core NumPy work (cfg 2 at B=64, cfg 3 at B=1024), at least 24 / 60 steps
         rows, cs, cw = (64, 24, 1) if args.workload == "cfg2" else (1024, 60, 2)
-        v, wall = cpu_baseline(args.workload, 1, cs, cw, rows, method)
+        v, wall, work = cpu_baseline(args.workload, 1, cs, cw, rows, method, min_secs=12.0)
+        cs = work // (rows * n)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"oracle (NumPy port of the reference path), 1 process, {rows} trajectories x {cs} steps, "
                          f"{wall:.1f} s",

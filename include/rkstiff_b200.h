@@ -179,6 +179,12 @@ int rks_nl(rks_plan* plan, int j, void* stream);
  * has a fused model with n in 512..8192: the stage value k is formed in the load prologue of the
  * FFT kernel and never written to HBM unless it is the new state. */
 int rks_stage_nl(rks_plan* plan, int stage, void* stream);
+/* The two kernels rks_stage_nl(plan, stage) launches, separately: part 1 = the stage kernel, part 2 = the
+ * evaluation.  For intermediate stages of a complex-field (NLS) plan with n in 512..8192 these are the
+ * pre-transforming pair: the stage kernel also applies the first inverse FFT pass and the evaluation starts
+ * one pass later (RKS_PT=0 in the environment selects the plain pair).  Results equal
+ * rks_stage + rks_nl; the stage value left in K by part 1 is in that intermediate layout. */
+int rks_stage_nl_part(rks_plan* plan, int stage, int part, void* stream);
 /* for caller-supplied nl_func: device pointers valid for the roles last read by rks_read_ctrl */
 void* rks_nl_input(rks_plan* plan, int j);
 void* rks_nl_output(rks_plan* plan, int j);

@@ -73,6 +73,7 @@ def _load():
         "rks_stage": (c_int, [P, c_int, P]),
         "rks_nl": (c_int, [P, c_int, P]),
         "rks_stage_nl": (c_int, [P, c_int, P]),
+        "rks_stage_nl_part": (c_int, [P, c_int, c_int, P]),
         "rks_nl_input": (P, [P, c_int]),
         "rks_nl_output": (P, [P, c_int]),
         "rks_error_control": (c_int, [P, P]),

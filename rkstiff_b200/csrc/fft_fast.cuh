@@ -522,6 +522,28 @@ RKS_HD void phase_middle(cplx* sm, int T, const Twiddles& tw, const Model& m) {
     if (DIF) dif_pass<R, Q, P::SH, NB, TS, false>(sm, p0, j, tab, m);
     else dit_pass<R, Q, P::SH, NB, TS, false>(sm, p0, j, tab, m);
 }
+// ---- pre-transformed rows (complex-field models) ----
+// The stage kernel K1 is HBM bound and leaves the FP64 pipe idle, K4 is FP64/LSU bound and leaves HBM idle.
+// For an intermediate stage value k (consumed by N(.) only) K1 therefore applies the FIRST inverse pass --
+// the radix-R1 butterflies over stride Q1 = n / R1 with their twiddles -- while the 16 values of a butterfly
+// are still in its registers (pre_butterfly) and stores the result at the logical positions phase_first
+// would have written.  K4 then starts at the first warp-local pass, reading global memory (phase_pre):
+// one shared-memory round trip, the largest twiddle pass and R1's butterflies leave the bound kernel.
+// The arithmetic is the same operations in the same order: both routes agree to the last bit.
+template <int R1>
+RKS_HD void pre_butterfly(cplx* a, const cplx* t1, int j) {     // a[s] = k[j + Q1 s] -> a[perm(r)] = row[j + Q1 r]
+    dftR<R1, true>(a);
+    twiddle_scale<R1, true>(a, t1, TW_S1, j, SlotPerm<R1>());
+}
+// first pass of K4 on a pre-transformed row: middle pass 2 of the inverse transform, input from the model
+template <int N, class Model>
+RKS_HD void phase_pre(cplx* sm, int T, const Twiddles& ti, const Model& m) {
+    using P = Plan<N>;
+    constexpr int Q1 = N / P::R1, R = P::R2, Q = Q1 / P::R2, NB = 16 / R;
+    int p0[NB], j[NB];
+    warp_butterflies<R, Q, NB>((T >> 5) * 512, T & 31, p0, j);
+    dif_pass<R, Q, P::SH, NB, TW_S2, true>(sm, p0, j, ti.t2, m);
+}
 template <int N, class Model>
 RKS_HD void phase_core(cplx* sm, int T, const Model& m) {
     using P = Plan<N>;

@@ -348,6 +348,65 @@ template <int M, int S, typename CT, bool FULL>
 __global__ void __launch_bounds__(256) stage_kernel_multi(const DevPlan* plans) { stage_kernel_body<M, S, CT, FULL>(plans[blockIdx.z]); }
 
 
+// K1 for an intermediate stage whose value only feeds the fused NLS-type nonlinearity (fft_fast.cuh, "pre-
+// transformed rows"): block (32, 8), thread = one first-pass butterfly of one row, i.e. the R1 modes
+// j + Q1 s of the row.  The stage value of each mode is combined exactly as in stage_kernel, the radix-R1
+// inverse butterfly and its twiddles are applied in registers (FP64 work this HBM-bound kernel has room for)
+// and the result goes to K in the layout the first pass of K4 would have produced.  Same byte model as
+// stage_kernel (reads_s + 1 passes); coefficients are shared by the batch (lin_elems == n_c) and come from L1/L2.
+template <int M, int S, typename CT, int R1>
+__global__ void __launch_bounds__(256, 2) stage_pre_kernel(const __grid_constant__ DevPlan p) {
+    constexpr bool ADAPT = method_adaptive(M);
+    constexpr unsigned NMASK = stage_nl_mask(M, S);
+    constexpr unsigned CMASK = stage_coef_mask(M, S);
+    constexpr int NC = method_ncoef(M);
+    constexpr int NIN = 1 + __builtin_popcount(NMASK);
+    constexpr int CH = NIN <= 3 ? 4 : 2;                 // modes whose loads are in flight together
+    static_assert(S < method_stages(M), "the last stage value is a state: it stays in natural order");
+    const Ctrl* c = p.ctrl;
+    int u_sel = 0, n_sel = 0;
+    if (ADAPT) {
+        if (c->status != ST_RUNNING) return;
+        u_sel = c->u_sel; n_sel = c->n_sel;
+    }
+    const double h = c->h;
+    const int q1 = (int)(p.n_c / R1);
+    const int col = blockIdx.x * 32 + threadIdx.x;
+    const long long row = (long long)blockIdx.y * 8 + threadIdx.y;
+    if (col >= q1 || row >= p.batch) return;
+    const long long base = row * p.n_c + col;
+    const cplx* u = p.U[u_sel] + base;
+    const CT* __restrict__ coef = (const CT*)p.coef + col;
+    const long long cstride = p.lin_elems;
+    const cplx* nl[8];
+#pragma unroll
+    for (int j = 1; j <= 7; ++j) nl[j] = (NMASK & (1u << j)) ? p.NL[nl_phys(M, j, n_sel)] + base : nullptr;
+
+    cplx a[R1];
+#pragma unroll
+    for (int s0 = 0; s0 < R1; s0 += CH) {
+        CT cv[CH][NC];
+        cplx uv[CH], nv[CH][8];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {               // all loads of CH modes first
+            const int off = (s0 + i) * q1;
+#pragma unroll
+            for (int k = 0; k < NC; ++k)
+                if (CMASK & (1u << k)) cv[i][k] = ldcoef(coef + k * cstride + off);
+            uv[i] = ldcs(u + off);
+#pragma unroll
+            for (int j = 1; j <= 7; ++j)
+                if (NMASK & (1u << j)) nv[i][j] = ldcs(nl[j] + off);
+        }
+#pragma unroll
+        for (int i = 0; i < CH; ++i) a[s0 + i] = stage_combine<M, S, CT>(uv[i], nv[i], cv[i], h);
+    }
+    fast::pre_butterfly<R1>(a, p.twf + fast::TW_T1, col);
+    cplx* out = p.K + base;
+#pragma unroll
+    for (int r = 0; r < R1; ++r) stg(out + r * q1, a[fast::perm<R1>(r)]);
+}
+
 // ---------------------------------------------------------------------------------------
 // K4: fused spectral nonlinearity, one trajectory row per CTA slot, row resident in smem.
 // j selects input/output roles; predicated on device so that no host sync is needed.
@@ -491,18 +550,27 @@ RKS_D void inner_pingpong_8192(cplx* sm, int T, const fast::Twiddles& ti, const 
 
 struct NoHook { RKS_D void operator()() const {} };
 
-// `after_first` runs once the first pass has consumed the row's input (staging buffer free again)
-template <int N, class Model, class Hook = NoHook>
+// `after_first` runs once the first pass has consumed the row's input (staging buffer free again).
+// PT: the row is pre-transformed (fft_fast.cuh pre_butterfly: K1 already applied the first inverse pass), so
+// the first pass here is the warp-local middle pass reading global memory / the staging buffer.
+template <int N, bool PT = false, class Model, class Hook = NoHook>
 RKS_D void nl_fast_row(cplx* sm, int T, int lrow, int rpc, const fast::Twiddles& ti, const fast::Twiddles& tf,
                        const Model& m, const Hook& after_first = Hook()) {
     constexpr int W = fast::Plan<N>::W, TR = 32 * W;
-    fast::phase_first<N>(sm, T, ti, m);
-    row_barrier<TR>(lrow, rpc);
-    after_first();
-    if (N == 8192 && RKS_PINGPONG) {
+    if (PT) {
+        fast::phase_pre<N>(sm, T, ti, m);
+        // warp-local pass: the barrier is only needed before the staging buffer is refilled
+        if (!std::is_same<Hook, NoHook>::value) row_barrier<TR>(lrow, rpc); else __syncwarp();
+        after_first();
+    } else {
+        fast::phase_first<N>(sm, T, ti, m);
+        row_barrier<TR>(lrow, rpc);
+        after_first();
+    }
+    if (N == 8192 && RKS_PINGPONG && !PT) {
         inner_pingpong_8192(sm, T, ti, tf, m);
     } else {
-        fast::phase_middle<N, 2, true>(sm, T, ti, m);   __syncwarp();
+        if (!PT) { fast::phase_middle<N, 2, true>(sm, T, ti, m);   __syncwarp(); }
         if (fast::middle_passes<N>() == 2) { fast::phase_middle<N, 3, true>(sm, T, ti, m);   __syncwarp(); }
         fast::phase_core<N>(sm, T, m);                  __syncwarp();
         if (fast::middle_passes<N>() == 2) { fast::phase_middle<N, 3, false>(sm, T, tf, m);  __syncwarp(); }
@@ -510,8 +578,10 @@ RKS_D void nl_fast_row(cplx* sm, int T, int lrow, int rpc, const fast::Twiddles&
     }
     row_barrier<TR>(lrow, rpc);
     fast::phase_last<N>(sm, T, tf, m);
-    // no barrier here: the last pass reads exactly the slab positions (T + 32 W c + Q1 s) that the same
-    // thread overwrites in the first pass of its next row, so warps run on into the next row's loads
+    // !PT: no barrier here -- the last pass reads exactly the slab positions (T + 32 W c + Q1 s) that the same
+    // thread overwrites in the first pass of its next row, so warps run on into the next row's loads.
+    // PT: the next row's first pass writes the warp's own 512-point slice, which other warps are still reading.
+    if (PT) row_barrier<TR>(lrow, rpc);
 }
 
 // pull a row that will be needed soon from HBM into L2 (no registers, no smem)
@@ -562,8 +632,10 @@ struct StageNext {          // after the first pass: start copying the head of t
 // FK = 0: N_j = N(existing array).  FK = 1 / 2: the stage combine (fuse.cuh, complex / real
 // coefficient arrays) is evaluated in the load prologue, so the stage value k never goes to HBM
 // unless it is a state (fd.write_k: final stage of fixed-step and FSAL methods).
-template <int W, int MODEL, int FK>
+// PT: the input row is a pre-transformed stage value (stage_pre_kernel below; complex-field models, FK = 0).
+template <int W, int MODEL, int FK, bool PT = false>
 RKS_D void nl_fast_kernel_body(const DevPlan& p, int j, int force, FuseDesc fd) {
+    static_assert(!PT || (FK == 0 && MODEL == 2), "pre-transformed rows: plain evaluation of the NLS model only");
     using CT = typename std::conditional<FK == 2, double, cplx>::type;
     constexpr int N = 512 * W;
     constexpr int TR = 32 * W;                       // threads per row
@@ -637,11 +709,11 @@ RKS_D void nl_fast_kernel_body(const DevPlan& p, int j, int force, FuseDesc fd) 
             const auto m = fast::ModelOf<MODEL>::make_staged(fast::StagedRow{roles.in + rr * p.n_c, stg, nst}, out, p.kx,
                                                              p.model_p0, N, on);
             const StageNext next{stg, roles.in + (nlines ? nrow : rr) * p.n_c, nst * 16u, bar, nlines != 0 && threadIdx.x == 0};
-            nl_fast_row<N>(sm, T, lrow, RPC, ti, tf, m, next);
+            nl_fast_row<N, PT>(sm, T, lrow, RPC, ti, tf, m, next);
         } else if (FK == 0) {
             prefetch_row_l2<TR>(roles.in + (nlines ? nrow : rr) * p.n_c, nlines, T);
             const auto m = fast::ModelOf<MODEL>::make(roles.in + rr * p.n_c, out, p.kx, p.model_p0, N, on);
-            nl_fast_row<N>(sm, T, lrow, RPC, ti, tf, m);
+            nl_fast_row<N, PT>(sm, T, lrow, RPC, ti, tf, m);
         } else {
             FuseSource<CT> src;
             src.nterms = fd.nterms;
@@ -700,6 +772,9 @@ RKS_D void nl_fast_kernel_body(const DevPlan& p, int j, int force, FuseDesc fd) 
 }
 template <int W, int MODEL, int FK>
 __global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_fast_kernel(const __grid_constant__ DevPlan p, int j, int force, FuseDesc fd) { nl_fast_kernel_body<W, MODEL, FK>(p, j, force, fd); }
+// the same evaluation of a row K1 has pre-transformed (NLS model)
+template <int W>
+__global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_fast_pre_kernel(const __grid_constant__ DevPlan p, int j, int force, FuseDesc fd) { nl_fast_kernel_body<W, 2, 0, true>(p, j, force, fd); }
 // one plan per blockIdx.z: ensembles whose trajectories keep their own dt (rks_multi_*)
 template <int W, int MODEL, int FK>
 __global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_fast_kernel_multi(const DevPlan* plans, int j, int force, FuseDesc fd) { nl_fast_kernel_body<W, MODEL, FK>(plans[blockIdx.z], j, force, fd); }

@@ -105,6 +105,7 @@ struct rks_plan {
     bool nl_fast;                   // n in {512..8192}: register-resident FFT kernel (fft_fast.cuh)
     bool nl_small;                  // n in {64, 128, 256}: the same pipeline on slabs of packed rows
     bool no_fuse;                   // default: K1 and K4 as separate kernels (north_star decomposition); RKS_FUSE=1 fuses
+    bool pretransform;              // intermediate NLS stages: K1 applies the first inverse FFT pass (RKS_PT=0 disables)
     size_t nl_smem;
 };
 
@@ -161,6 +162,7 @@ static cudaError_t prepare_nl_fast(int model) {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 1, 2>, attr, (int)nl_fast_smem<W>(model, 2));
     } else if (model == RKS_MODEL_NLS_FFT) {
         e = cudaFuncSetAttribute(nl_fast_kernel<W, 2, 0>, attr, (int)nl_fast_smem<W>(model, 0));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_pre_kernel<W>, attr, (int)nl_fast_smem<W>(model, 0));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel_multi<W, 2, 0>, attr, (int)nl_fast_smem<W>(model, 0));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 2, 1>, attr, (int)nl_fast_smem<W>(model, 1));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 2, 2>, attr, (int)nl_fast_smem<W>(model, 2));
@@ -451,6 +453,8 @@ static int prepare_nl_launch(rks_plan* p, int model, long long n, cplx* twf_dev,
     DevPlan& d = p->d;
     p->nl_fast = (n >= 512 && n <= 8192) && !getenv("RKS_NL_GENERIC");
     p->no_fuse = getenv("RKS_FUSE") == nullptr;       // fused K1+K4 is opt-in (RKS_FUSE=1): see DESIGN.md 4
+    const char* pt = getenv("RKS_PT");
+    p->pretransform = !(pt && pt[0] == '0');           // pre-transformed intermediate stages
     p->nl_small = (n == 64 || n == 128 || n == 256) && !getenv("RKS_NL_GENERIC");
     if (p->nl_fast) {
         cudaError_t e = n == 512 ? prepare_nl_fast<1>(model) : n == 1024 ? prepare_nl_fast<2>(model)
@@ -647,6 +651,41 @@ static int launch_stage_m(rks_plan* p, int s, cudaStream_t stream) {
     return RKS_OK;
 }
 
+// K1 for a pre-transformed intermediate stage (stage_pre_kernel): R1 = radix of the first FFT pass of the row
+template <int M, int S, typename CT>
+static void launch_stage_pre_t(rks_plan* p, cudaStream_t stream) {
+    const DevPlan& d = p->d;
+    const int r1 = d.n == 512 ? 8 : 16;                      // fft_fast.cuh Plan<N>::R1
+    const unsigned gx = (unsigned)((d.n / r1 + 31) / 32), gy = (unsigned)((d.batch + 7) / 8);
+    if (r1 == 8) stage_pre_kernel<M, S, CT, 8><<<dim3(gx, gy), dim3(32, 8), 0, stream>>>(d);
+    else stage_pre_kernel<M, S, CT, 16><<<dim3(gx, gy), dim3(32, 8), 0, stream>>>(d);
+}
+template <int M, typename CT>
+static void launch_stage_pre_m(rks_plan* p, int s, cudaStream_t stream) {
+    constexpr int SMAX = method_stages(M);
+    switch (s) {
+        case 1: launch_stage_pre_t<M, 1, CT>(p, stream); break;
+        case 2: launch_stage_pre_t<M, 2, CT>(p, stream); break;
+        case 3: launch_stage_pre_t<M, 3, CT>(p, stream); break;
+        case 4: if (SMAX > 4) launch_stage_pre_t<M, (SMAX > 4 ? 4 : 1), CT>(p, stream); break;
+        case 5: if (SMAX > 5) launch_stage_pre_t<M, (SMAX > 5 ? 5 : 1), CT>(p, stream); break;
+        default: break;
+    }
+}
+static void launch_stage_pre(rks_plan* p, int s, cudaStream_t stream) {
+    const bool cx = p->d.lin_complex != 0;
+    switch (p->method) {
+        case M_IF4: cx ? launch_stage_pre_m<M_IF4, cplx>(p, s, stream) : launch_stage_pre_m<M_IF4, double>(p, s, stream); break;
+        case M_IF34: cx ? launch_stage_pre_m<M_IF34, cplx>(p, s, stream) : launch_stage_pre_m<M_IF34, double>(p, s, stream); break;
+        case M_IF45DP: cx ? launch_stage_pre_m<M_IF45DP, cplx>(p, s, stream) : launch_stage_pre_m<M_IF45DP, double>(p, s, stream); break;
+        case M_ETD4: launch_stage_pre_m<M_ETD4, cplx>(p, s, stream); break;
+        case M_ETD34: launch_stage_pre_m<M_ETD34, cplx>(p, s, stream); break;
+        case M_ETD5: launch_stage_pre_m<M_ETD5, cplx>(p, s, stream); break;
+        case M_ETD35: launch_stage_pre_m<M_ETD35, cplx>(p, s, stream); break;
+    }
+    p->launches += 1;
+}
+
 extern "C" int rks_stage(rks_plan* p, int s, void* stream_v) {
     if (!p) return fail(RKS_ERR_ARG, "plan is null");
     if (s < 1 || s > method_stages(p->method)) return fail(RKS_ERR_ARG, "stage out of range");
@@ -677,6 +716,29 @@ static void dispatch_nl_fast(rks_plan* p, int j, int force, const FuseDesc& fd, 
         case 2048: launch_nl_fast<4>(p, j, force, fd, fk, stream); break;
         case 4096: launch_nl_fast<8>(p, j, force, fd, fk, stream); break;
         default: launch_nl_fast<16>(p, j, force, fd, fk, stream); break;
+    }
+    p->launches += 1;
+}
+
+// K4 on a row stage_pre_kernel has pre-transformed (NLS model, plain evaluation)
+template <int W>
+static void launch_nl_fast_pre_t(rks_plan* p, int j, int force, cudaStream_t stream) {
+    constexpr int THREADS = W == 16 ? 512 : 256;
+    constexpr int RPC = THREADS / (32 * W);
+    FuseDesc none;
+    memset(&none, 0, sizeof(none));
+    const long long groups = (p->d.batch + RPC - 1) / RPC;
+    const long long resident = (long long)p->sm_count * (W == 16 ? 1 : 2);
+    const unsigned grid = (unsigned)(groups < resident ? groups : resident);
+    nl_fast_pre_kernel<W><<<grid, THREADS, nl_fast_smem<W>(RKS_MODEL_NLS_FFT, 0), stream>>>(p->d, j, force, none);
+}
+static void dispatch_nl_fast_pre(rks_plan* p, int j, int force, cudaStream_t stream) {
+    switch (p->d.n) {
+        case 512: launch_nl_fast_pre_t<1>(p, j, force, stream); break;
+        case 1024: launch_nl_fast_pre_t<2>(p, j, force, stream); break;
+        case 2048: launch_nl_fast_pre_t<4>(p, j, force, stream); break;
+        case 4096: launch_nl_fast_pre_t<8>(p, j, force, stream); break;
+        default: launch_nl_fast_pre_t<16>(p, j, force, stream); break;
     }
     p->launches += 1;
 }
@@ -753,7 +815,16 @@ static bool can_fuse_stage(const rks_plan* p, int s) {
     return true;
 }
 
-extern "C" int rks_stage_nl(rks_plan* p, int s, void* stream_v) {
+// Intermediate stage of a fast NLS-type plan: its value only feeds N(.), so K1 may hand it over pre-transformed
+// (stage_pre_kernel -> nl_fast_pre_kernel).  The last stage is a state and keeps the natural layout.
+static bool can_pretransform(const rks_plan* p, int s) {
+    return p->pretransform && p->nl_fast && !p->multi_n && p->d.lin_elems == p->d.n_c && !p->d.lin_full
+        && p->d.model == RKS_MODEL_NLS_FFT && s < method_stages(p->method);
+}
+
+// part: 0 = stage s and the evaluation it feeds, 1 = the stage kernel only, 2 = the evaluation only (the
+// kernels of part 0, separately: per-kernel timing in bench.py)
+static int stage_nl_parts(rks_plan* p, int s, int part, void* stream_v) {
     if (!p) return fail(RKS_ERR_ARG, "plan is null");
     if (p->d.model == RKS_MODEL_NONE) return fail(RKS_ERR_UNSUPPORTED, "no fused model set (rks_set_model)");
     const int m = p->method, S = method_stages(m);
@@ -763,9 +834,17 @@ extern "C" int rks_stage_nl(rks_plan* p, int s, void* stream_v) {
     // etd4.py:174) or N_last (FSAL methods, if34.py:129); none for ETD35
     const int j = s < S ? s + 1 : (adapt ? (method_fsal(m) ? S + 1 : 0) : 1);
     cudaStream_t stream = (cudaStream_t)stream_v;
-    if (!can_fuse_stage(p, s)) {
-        if (int rc = rks_stage(p, s, stream_v)) return rc;
-        return j ? rks_nl(p, j, stream_v) : RKS_OK;
+    if (can_pretransform(p, s) && (part != 0 || !can_fuse_stage(p, s))) {
+        if (p->d.batch > 65535ll * 8) return fail(RKS_ERR_UNSUPPORTED, "batch too large for one launch");
+        if (part != 2) launch_stage_pre(p, s, stream);
+        if (part != 1) dispatch_nl_fast_pre(p, j, adapt ? 0 : 1, stream);
+        CUDA_TRY(cudaGetLastError());
+        return RKS_OK;
+    }
+    if (part != 0 || !can_fuse_stage(p, s)) {
+        if (part != 2)
+            if (int rc = rks_stage(p, s, stream_v)) return rc;
+        return (j && part != 1) ? rks_nl(p, j, stream_v) : RKS_OK;
     }
     FuseDesc fd = fuse_desc(m, s);
     fd.write_k = (s == S) ? 1 : 0;
@@ -774,6 +853,11 @@ extern "C" int rks_stage_nl(rks_plan* p, int s, void* stream_v) {
     dispatch_nl_fast(p, j, adapt ? 0 : 1, fd, fk, stream);
     CUDA_TRY(cudaGetLastError());
     return RKS_OK;
+}
+extern "C" int rks_stage_nl(rks_plan* p, int s, void* stream) { return stage_nl_parts(p, s, 0, stream); }
+extern "C" int rks_stage_nl_part(rks_plan* p, int s, int part, void* stream) {
+    if (part < 1 || part > 2) return fail(RKS_ERR_ARG, "part must be 1 (stage) or 2 (evaluation)");
+    return stage_nl_parts(p, s, part, stream);
 }
 
 extern "C" void* rks_nl_input(rks_plan* p, int j) {

@@ -48,6 +48,30 @@ static void fast_row(const Model& m, const fast::Twiddles& tw) {
     for (int T = 0; T < TR; ++T) fast::phase_middle<N, 2, false>(sm.data(), T, tw, m);
     for (int T = 0; T < TR; ++T) fast::phase_last<N>(sm.data(), T, tw, m);
 }
+// serial emulation of the pre-transformed route: stage_pre_kernel's butterflies on the row `k` (the stage value),
+// then nl_fast_pre_kernel's phase sequence on the result
+template <int N>
+static void pre_row(const cplx* k, cplx* out, double gamma, const fast::Twiddles& tw) {
+    using P = fast::Plan<N>;
+    constexpr int TR = 32 * P::W, R1 = P::R1, Q1 = N / R1;
+    std::vector<cplx> kt(N), sm(N);
+    for (int col = 0; col < Q1; ++col) {                    // one K1 thread per first-pass butterfly
+        cplx a[R1];
+        for (int s = 0; s < R1; ++s) a[s] = k[col + s * Q1];
+        fast::pre_butterfly<R1>(a, tw.t1, col);
+        for (int r = 0; r < R1; ++r) kt[col + r * Q1] = a[fast::perm<R1>(r)];
+    }
+    const auto m = fast::ModelOf<2>::make(kt.data(), out, nullptr, gamma, N, true);
+    for (int T = 0; T < TR; ++T) fast::phase_pre<N>(sm.data(), T, tw, m);
+    if (fast::middle_passes<N>() == 2)
+        for (int T = 0; T < TR; ++T) fast::phase_middle<N, 3, true>(sm.data(), T, tw, m);
+    for (int T = 0; T < TR; ++T) fast::phase_core<N>(sm.data(), T, m);
+    if (fast::middle_passes<N>() == 2)
+        for (int T = 0; T < TR; ++T) fast::phase_middle<N, 3, false>(sm.data(), T, tw, m);
+    for (int T = 0; T < TR; ++T) fast::phase_middle<N, 2, false>(sm.data(), T, tw, m);
+    for (int T = 0; T < TR; ++T) fast::phase_last<N>(sm.data(), T, tw, m);
+}
+
 template <class Model>
 static int fast_dispatch(int n, const Model& m, const fast::Twiddles& tw) {
     switch (n) {
@@ -154,6 +178,23 @@ int hc_nl_fast(int model, int n, const double* in, const double* kx, double p0, 
     if (model == 2) return fast_dispatch(n, fast::ModelOf<2>::make(cin, co, kx, p0, n, true), tw);
     if (model == 3) return fast_dispatch(n, fast::ModelOf<3>::make(cin, co, kx, p0, n, true), tw);
     return fast_dispatch(n, fast::ModelOf<4>::make(cin, co, kx, p0, n, true), tw);
+}
+
+// NLS evaluation of one row through the pre-transformed route (K1 applies the first inverse pass)
+int hc_nl_pre(int n, const double* in, double gamma, double* out) {
+    std::vector<cplx> tab(fast::TW_TOTAL);
+    for (int j = 0; j < fast::TW_TOTAL; ++j) tab[j] = fast::twiddle_table_entry(j, n);
+    const fast::Twiddles tw{tab.data() + fast::TW_T1, tab.data() + fast::TW_T2, tab.data() + fast::TW_T3};
+    const cplx* cin = reinterpret_cast<const cplx*>(in);
+    cplx* co = reinterpret_cast<cplx*>(out);
+    switch (n) {
+        case 512: pre_row<512>(cin, co, gamma, tw); return 0;
+        case 1024: pre_row<1024>(cin, co, gamma, tw); return 0;
+        case 2048: pre_row<2048>(cin, co, gamma, tw); return 0;
+        case 4096: pre_row<4096>(cin, co, gamma, tw); return 0;
+        case 8192: pre_row<8192>(cin, co, gamma, tw); return 0;
+    }
+    return -1;
 }
 
 // `rows` consecutive rows of n_c elements through the packed short-row pipeline (n = 64, 128, 256)

@@ -80,6 +80,21 @@ def test_nl_nls_matches_numpy(hc, n):
 
 
 @pytest.mark.parametrize("n", [512, 1024, 2048, 4096, 8192])
+def test_pretransformed_route_is_bit_identical(hc, n):
+    """fft_fast.cuh pre_butterfly/phase_pre: K1 applying the first inverse pass and K4 starting one pass later
+    perform the same operations in the same order as the plain K4, so the two routes agree to the last bit."""
+    p = problems.nls(n, batch=3, half_width=20.0, seed=n)
+    rng = np.random.default_rng(n)
+    for row in p.u0:
+        row = np.ascontiguousarray(row + 1e-3 * (rng.standard_normal(n) + 1j * rng.standard_normal(n)))
+        plain, pre = np.empty_like(row), np.empty_like(row)
+        assert hc.hc_nl_fast(2, n, ptr(row), None, ctypes.c_double(2.0), ptr(plain)) == 0
+        assert hc.hc_nl_pre(n, ptr(row), ctypes.c_double(2.0), ptr(pre)) == 0
+        np.testing.assert_array_equal(pre, plain)
+        assert rel(pre, p.nl_func(row)) < 2e-15 * np.log2(n)
+
+
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096, 8192])
 def test_fast_register_fft_nl_matches_numpy(hc, n):
     """fft_fast.cuh: the register-resident W x 8 x 8 x 8 pipeline, emulated thread by thread."""
     p = problems.nls(n, batch=2, half_width=20.0)

@@ -585,3 +585,83 @@ def test_reference_allen_cahn_chebyshev_test_through_diagonalize(rk):
     np.testing.assert_allclose(hs[:-1], ho[:-1], rtol=1e-4)
     assert rel(host(wf), wo) < 1e-5
 
+
+
+# --------------------------------------------------------------------------------------------
+# pre-transformed intermediate stages (complex-field fused model, n = 512 ... 8192): K1 applies the first inverse
+# FFT pass (stage_pre_kernel), K4 starts one pass later (nl_fast_pre_kernel).  DESIGN.md section 4.
+# --------------------------------------------------------------------------------------------
+PT_SIZES = [512, 1024, 2048, 4096, 8192]
+
+
+def _stage_outputs(rk, method, p, monkeypatch, pt):
+    """N_2 ... N_S of one trial at h = 0.004 through rks_stage_nl, with the pre-transforming pair on or off."""
+    monkeypatch.setenv("RKS_PT", "1" if pt else "0")
+    sol = make(rk, method, p, fused_for(rk, p))
+    u = dev(p.u0)
+    eng = sol._get_engine(u)
+    adaptive = method in ADAPTIVE
+    eng.begin(0.0, 1.0, 0.004, 0, not adaptive)
+    if not adaptive:
+        eng.ensure_fixed_coeffs(0.004)
+    eng.set_u(u)
+    eng.update_coeffs()
+    eng.nl(1)
+    outs = []
+    for s in range(1, eng.stages):
+        rk._abi.check(rk._abi.lib.rks_stage_nl(eng.plan, s, eng.st))
+        outs.append(host(eng.state_view(f"N{s + 1}")).copy())
+    return outs, sol
+
+
+@pytest.mark.parametrize("n", PT_SIZES)
+@pytest.mark.parametrize("method", METHODS)
+def test_pretransformed_pair_equals_plain_pair(rk, method, n, monkeypatch):
+    """Every intermediate N of every method, batch 5 (a ragged last CTA for every rows-per-CTA): same operations
+    in the same order, so only the compiler's FMA contraction may differ between the two routes."""
+    p = problems.nls(n, batch=5, seed=n, half_width=20.0)
+    plain, _ = _stage_outputs(rk, method, p, monkeypatch, pt=False)
+    pre, sol = _stage_outputs(rk, method, p, monkeypatch, pt=True)
+    assert len(pre) == len(plain) > 0
+    for a, b in zip(pre, plain):
+        assert rel(a, b) < 1e-14
+    # the two kernels rks_stage_nl launches, separately
+    eng = sol._engine
+    for which in (1, 2):
+        rk._abi.check(rk._abi.lib.rks_stage_nl_part(eng.plan, 1, which, eng.st))
+    assert rel(host(eng.state_view("N2")), plain[0]) < 1e-14
+    assert rk._abi.lib.rks_stage_nl_part(eng.plan, 1, 0, eng.st) != 0          # part must be 1 or 2
+
+
+@pytest.mark.parametrize("n", PT_SIZES)
+@pytest.mark.parametrize("method", FIXED)
+def test_pretransformed_fixed_step_parity(rk, method, n):
+    p = problems.nls(n, batch=5, seed=n + 1, half_width=20.0)
+    sol = make(rk, method, p, fused_for(rk, p))
+    u, h = dev(p.u0), 0.004
+    for _ in range(3):
+        ref = OracleSolver(method, p.lin_op, p.nl_func).step(host(u), h)
+        sol.reset()
+        u = sol.step(u, h)
+        assert rel(host(u), ref) < STEP_TOL
+    # and a run of consecutive steps through the captured graph (FSAL / N1 carried over)
+    uf = sol.evolve(dev(p.u0), 0.0, 0.02, h, store_data=False)
+    ora = OracleSolver(method, p.lin_op, p.nl_func)
+    assert rel(host(uf), ora.evolve(p.u0, 0.0, 0.02, h, store_data=False)) < 10 * STEP_TOL
+
+
+@pytest.mark.parametrize("n", [512, 2048, 8192])
+@pytest.mark.parametrize("method", ADAPTIVE)
+def test_pretransformed_adaptive_parity(rk, method, n):
+    p = problems.nls(n, batch=3, seed=n + 2, half_width=20.0)
+    eps, tf = 1e-6, (0.004 if method == "IF45DP" else 0.08)
+    sol = make(rk, method, p, fused_for(rk, p), eps)
+    uf = sol.evolve(dev(p.u0), 0.0, tf, store_data=False)
+    ora = OracleSolver(method, p.lin_op, p.nl_func, Config(epsilon=eps))
+    uo = ora.evolve(p.u0, 0.0, tf, store_data=False)
+    hs, acc = np.array([r[0] for r in sol.trial_log]), [r[2] for r in sol.trial_log]
+    ho = np.array([r.h for r in ora.log])
+    assert acc == [r.accepted for r in ora.log]
+    np.testing.assert_allclose(hs[:-1], ho[:-1], rtol=DT_TOL, atol=0)
+    np.testing.assert_allclose(hs[-1], ho[-1], rtol=0, atol=DT_TOL * tf)
+    assert rel(host(uf), uo) < FINAL_TOL
