@@ -148,6 +148,7 @@ struct DevPlan {
     void* coef;        // ncoef arrays of lin_elems entries (double or cplx)
     const void* lin;   // lin_op copy (double or cplx)
     double* partials;  // per-block partial sums of the norm kernel (2 per block)
+    int* pre_cnt;      // stage_pre_kernel work counters: {next row, finished warps} per column block (zero between launches)
     const cplx* tw;    // twiddles exp(-2 pi i j / n), j < n (generic NL kernel)
     const cplx* twf;   // fast-path twiddle tables (fft_fast.cuh: o | a | b)
     const double* kx;  // wavenumbers of the fused model

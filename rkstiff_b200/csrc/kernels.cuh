@@ -349,20 +349,52 @@ __global__ void __launch_bounds__(256) stage_kernel_multi(const DevPlan* plans) 
 
 
 // K1 for an intermediate stage whose value only feeds the fused NLS-type nonlinearity (fft_fast.cuh, "pre-
-// transformed rows"): block (32, 8), thread = one first-pass butterfly of one row, i.e. the R1 modes
-// j + Q1 s of the row.  The stage value of each mode is combined exactly as in stage_kernel, the radix-R1
-// inverse butterfly and its twiddles are applied in registers (FP64 work this HBM-bound kernel has room for)
-// and the result goes to K in the layout the first pass of K4 would have produced.  Same byte model as
-// stage_kernel (reads_s + 1 passes); coefficients are shared by the batch (lin_elems == n_c) and come from L1/L2.
+// transformed rows").  Thread = one first-pass butterfly of one row, i.e. the R1 modes j + Q1 s of the row: the
+// stage value of each mode is combined exactly as in stage_kernel, the radix-R1 inverse butterfly and its
+// twiddles are applied in registers (FP64 work this HBM-bound kernel has room for) and the result goes to K in
+// the layout the first pass of K4 would have produced.  Same byte model as stage_kernel (reads_s + 1 passes).
+//
+// A thread that keeps 16 accumulators cannot also keep enough loads in flight from registers (the first version
+// did: 14 warps/SM, 15-22 warps stalled on the long scoreboard per issue, 0.88-0.97 of the HBM roofline), so the
+// state loads go through shared memory with cp.async: persistent CTAs of 128 threads = 32 columns x 4 rows that
+// walk down the batch, every thread streaming CHM modes x NIN arrays per commit group into its own slots of an
+// NBUF-deep ring (no barrier: a thread only reads what it copied).  The copies of the next chunks -- of the next
+// row, while the butterfly runs -- are always in flight: ~100-190 KB per SM.  The coefficients of the CTA's 32 x R1
+// modes are shared by all rows (lin_elems == n_c): loaded into shared memory once.
+RKS_D void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+RKS_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING> RKS_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
+#ifndef RKS_PRE_DESC
+#define RKS_PRE_DESC 1
+#endif
+constexpr int PRE_THREADS = 128;
 template <int M, int S, typename CT, int R1>
-__global__ void __launch_bounds__(256, 2) stage_pre_kernel(const __grid_constant__ DevPlan p) {
+struct PreCfg {
+    static constexpr unsigned NMASK = stage_nl_mask(M, S);
+    static constexpr unsigned CMASK = stage_coef_mask(M, S);
+    static constexpr int NIN = 1 + __builtin_popcount(NMASK);      // u and the N_j the stage reads
+    static constexpr int NCU = __builtin_popcount(CMASK);          // coefficient arrays the stage reads
+    static constexpr int CHM = NIN <= 3 ? 4 : 2;                   // modes per commit group
+    static constexpr int NCH = R1 / CHM;                           // groups per row
+    static constexpr int NBUF = (NIN >= 6 ? 2 : 3) < NCH ? (NIN >= 6 ? 2 : 3) : NCH;
+    static constexpr size_t COEF_BYTES = (size_t)NCU * R1 * 32 * sizeof(CT);
+    static constexpr size_t RING_BYTES = (size_t)NBUF * CHM * NIN * PRE_THREADS * sizeof(cplx);
+    static constexpr size_t SMEM = COEF_BYTES + RING_BYTES;
+};
+
+template <int M, int S, typename CT, int R1>
+__global__ void __launch_bounds__(PRE_THREADS) stage_pre_kernel(const __grid_constant__ DevPlan p) {
+    using C = PreCfg<M, S, CT, R1>;
     constexpr bool ADAPT = method_adaptive(M);
-    constexpr unsigned NMASK = stage_nl_mask(M, S);
-    constexpr unsigned CMASK = stage_coef_mask(M, S);
-    constexpr int NC = method_ncoef(M);
-    constexpr int NIN = 1 + __builtin_popcount(NMASK);
-    constexpr int CH = NIN <= 3 ? 4 : 2;                 // modes whose loads are in flight together
+    constexpr unsigned NMASK = C::NMASK, CMASK = C::CMASK;
+    constexpr int NC = method_ncoef(M), NIN = C::NIN, CHM = C::CHM, NCH = C::NCH, NBUF = C::NBUF;
     static_assert(S < method_stages(M), "the last stage value is a state: it stays in natural order");
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    CT* csm = reinterpret_cast<CT*>(smem_raw);                                   // [NCU][R1][32]
+    cplx* ring = reinterpret_cast<cplx*>(smem_raw + C::COEF_BYTES);              // [NBUF][CHM][NIN][PRE_THREADS]
     const Ctrl* c = p.ctrl;
     int u_sel = 0, n_sel = 0;
     if (ADAPT) {
@@ -371,40 +403,111 @@ __global__ void __launch_bounds__(256, 2) stage_pre_kernel(const __grid_constant
     }
     const double h = c->h;
     const int q1 = (int)(p.n_c / R1);
-    const int col = blockIdx.x * 32 + threadIdx.x;
-    const long long row = (long long)blockIdx.y * 8 + threadIdx.y;
-    if (col >= q1 || row >= p.batch) return;
-    const long long base = row * p.n_c + col;
-    const cplx* u = p.U[u_sel] + base;
-    const CT* __restrict__ coef = (const CT*)p.coef + col;
-    const long long cstride = p.lin_elems;
-    const cplx* nl[8];
-#pragma unroll
-    for (int j = 1; j <= 7; ++j) nl[j] = (NMASK & (1u << j)) ? p.NL[nl_phys(M, j, n_sel)] + base : nullptr;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int col0 = blockIdx.x * 32, col = col0 + lane;
 
-    cplx a[R1];
+    // coefficients of this column block, compacted to the slots the stage uses
+    {
+        const CT* __restrict__ coef = (const CT*)p.coef;
+        int ci = 0;
 #pragma unroll
-    for (int s0 = 0; s0 < R1; s0 += CH) {
-        CT cv[CH][NC];
-        cplx uv[CH], nv[CH][8];
-#pragma unroll
-        for (int i = 0; i < CH; ++i) {               // all loads of CH modes first
-            const int off = (s0 + i) * q1;
-#pragma unroll
-            for (int k = 0; k < NC; ++k)
-                if (CMASK & (1u << k)) cv[i][k] = ldcoef(coef + k * cstride + off);
-            uv[i] = ldcs(u + off);
-#pragma unroll
-            for (int j = 1; j <= 7; ++j)
-                if (NMASK & (1u << j)) nv[i][j] = ldcs(nl[j] + off);
+        for (int k = 0; k < NC; ++k) {
+            if (!(CMASK & (1u << k))) continue;
+            for (int e = tid; e < R1 * 32; e += PRE_THREADS)
+                csm[ci * R1 * 32 + e] = ldcoef(coef + (long long)k * p.lin_elems + col0 + (e >> 5) * q1 + (e & 31));
+            ++ci;
         }
-#pragma unroll
-        for (int i = 0; i < CH; ++i) a[s0 + i] = stage_combine<M, S, CT>(uv[i], nv[i], cv[i], h);
     }
-    fast::pre_butterfly<R1>(a, p.twf + fast::TW_T1, col);
-    cplx* out = p.K + base;
+    __syncthreads();
+
+    // the arrays the stage reads: u, then N_j in ascending j
+    const cplx* src[NIN];
+    src[0] = p.U[u_sel] + col;
+    {
+        int a = 1;
 #pragma unroll
-    for (int r = 0; r < R1; ++r) stg(out + r * q1, a[fast::perm<R1>(r)]);
+        for (int j = 1; j <= 7; ++j)
+            if (NMASK & (1u << j)) src[a++] = p.NL[nl_phys(M, j, n_sel)] + col;
+    }
+    // Rows are handed out dynamically, one at a time per warp (atomic counter per column block): every CTA does
+    // the same amount of work, but SMs do not get the same share of HBM and a static split left 4-13 % of the
+    // SM time idle at the end (ncu: smsp__cycles_active / sm__cycles_elapsed).  The warp whose grab ends the
+    // column block last re-arms the counters for the next launch.
+    int* cnt = p.pre_cnt + 2 * blockIdx.x;
+    const int total_warps = (int)gridDim.y * (PRE_THREADS / 32);
+    bool drained = false;
+    auto grab = [&]() -> long long {
+        if (drained) return p.batch;
+        int r = 0;
+        if (lane == 0) r = atomicAdd(cnt, 1);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        // K4 wrote the N this stage reads in ascending row order: walk down from the last row, whose lines are
+        // the ones still in L2; K is then written towards row 0, where K4 starts reading
+        if (r < p.batch) return RKS_PRE_DESC ? p.batch - 1 - r : r;
+        drained = true;
+        if (lane == 0 && atomicAdd(cnt + 1, 1) == total_warps - 1) {
+            cnt[0] = 0; cnt[1] = 0;
+            __threadfence();
+        }
+        return p.batch;
+    };
+    cplx* my = ring + tid;
+
+    // commit group = CHM modes of the row the producer side is on; it runs NBUF groups ahead of the consumer,
+    // so it moves on to the next row (prow) while the consumer is still on the current one
+    long long prow = 0;
+    int ichunk = 0, ibuf = 0;
+    auto issue = [&]() {
+        if (ichunk == 0) prow = grab();
+        if (prow < p.batch) {
+            const long long base = prow * p.n_c + (long long)(ichunk * CHM) * q1;
+#pragma unroll
+            for (int i = 0; i < CHM; ++i)
+#pragma unroll
+                for (int a = 0; a < NIN; ++a)
+                    cp_async16(my + ((ibuf * CHM + i) * NIN + a) * PRE_THREADS, src[a] + base + (long long)i * q1);
+            ibuf = ibuf + 1 == NBUF ? 0 : ibuf + 1;
+        }
+        ichunk = ichunk + 1 == NCH ? 0 : ichunk + 1;
+        cp_async_commit();
+    };
+    issue();
+    long long row = prow;                       // the row whose groups are consumed
+#pragma unroll
+    for (int g = 1; g < NBUF; ++g) issue();
+
+    int rbuf = 0;
+    while (row < p.batch) {
+        cplx a[R1];
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            cp_async_wait<NBUF - 1>();
+#pragma unroll
+            for (int i = 0; i < CHM; ++i) {
+                const int s = ch * CHM + i;
+                const cplx* slot = my + (rbuf * CHM + i) * NIN * PRE_THREADS;
+                cplx nv[8];
+                CT cv[NC];
+                const cplx uv = slot[0];
+                int ai = 1, ci = 0;
+#pragma unroll
+                for (int j = 1; j <= 7; ++j)
+                    if (NMASK & (1u << j)) nv[j] = slot[(ai++) * PRE_THREADS];
+#pragma unroll
+                for (int kk = 0; kk < NC; ++kk)
+                    if (CMASK & (1u << kk)) cv[kk] = csm[((ci++) * R1 + s) * 32 + lane];
+                a[s] = stage_combine<M, S, CT>(uv, nv, cv, h);
+            }
+            rbuf = rbuf + 1 == NBUF ? 0 : rbuf + 1;
+            issue();                     // refill the buffer just consumed (values are in registers)
+        }
+        fast::pre_butterfly<R1>(a, p.twf + fast::TW_T1, col);
+        cplx* out = p.K + row * p.n_c + col;
+#pragma unroll
+        for (int r = 0; r < R1; ++r) stg(out + r * q1, a[fast::perm<R1>(r)]);
+        row = prow;                      // the producer is on the next row by now (NBUF <= NCH groups ahead)
+    }
+    cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------

@@ -32,6 +32,7 @@ static_assert(RKS_LOG_CAP == LOG_CAP, "log capacity");
 // ---------------------------------------------------------------------------------------
 constexpr size_t ALIGN = 256;
 constexpr int NORM_MAX_BLOCKS = 4096;
+constexpr size_t PRE_CNT_BYTES = 256;       // stage_pre_kernel: {next row, finished warps} per column block (<= 16)
 constexpr int MULTI_NORM_BLOCKS = 16;       // norm-kernel blocks per row in independent-dt mode
 constexpr int MULTI_LOG_CAP = RKS_ROW_LOG_CAP;          // trial records kept per row in independent-dt mode
 constexpr long long MODEL_MAX_N = 16384;        // longest row the smem-resident FFT handles
@@ -52,7 +53,7 @@ static Layout make_layout(int method, long long batch, long long n_c, long long 
     const size_t coef_elem = (is_if && !lin_is_complex) ? sizeof(double) : sizeof(cplx);
     L.ctrl = take(sizeof(Ctrl));
     L.log = take(sizeof(TrialRec) * LOG_CAP);
-    L.partials = take(sizeof(double) * 2 * NORM_MAX_BLOCKS);
+    L.partials = take(sizeof(double) * 2 * NORM_MAX_BLOCKS + PRE_CNT_BYTES);    // + row counters of stage_pre_kernel
     const long long nmax = n_c <= MODEL_MAX_N ? 2 * n_c : 0;
     L.tw = take(sizeof(cplx) * (size_t)nmax);
     L.twf = take(sizeof(cplx) * (size_t)(n_c <= MODEL_MAX_N ? 2 * fast::TW_TOTAL : 0));
@@ -259,6 +260,7 @@ extern "C" int rks_plan_create(rks_plan** out, int method, int64_t batch, int64_
     d.ctrl = (Ctrl*)(w + L.ctrl);
     d.log = (TrialRec*)(w + L.log);
     d.partials = (double*)(w + L.partials);
+    d.pre_cnt = (int*)(d.partials + 2 * NORM_MAX_BLOCKS);
     d.tw = (const cplx*)(w + L.tw);
     d.twf = (const cplx*)(w + L.twf);
     d.kx = (const double*)(w + L.kx);
@@ -273,7 +275,7 @@ extern "C" int rks_plan_create(rks_plan** out, int method, int64_t batch, int64_
     d.method = method; d.lin_complex = lin_is_complex; d.lin_full = (lin_elems == batch * n_c) ? 1 : 0;   // also true for batch == 1: linear kernels
     d.model = RKS_MODEL_NONE; d.log2n = 0; d.model_p0 = 0.0;
 
-    CUDA_TRY(cudaMemsetAsync(w + L.ctrl, 0, L.partials + sizeof(double) * 2 * NORM_MAX_BLOCKS - L.ctrl, stream));
+    CUDA_TRY(cudaMemsetAsync(w + L.ctrl, 0, L.partials + sizeof(double) * 2 * NORM_MAX_BLOCKS + PRE_CNT_BYTES - L.ctrl, stream));
     CUDA_TRY(cudaMemcpyAsync(w + L.lin, lin_op, (lin_is_complex ? sizeof(cplx) : sizeof(double)) * (size_t)lin_elems,
                              cudaMemcpyDeviceToDevice, stream));
     set_config_kernel<<<1, 1, 0, stream>>>(d.ctrl, cfg_args(*cfg, method));
@@ -652,13 +654,29 @@ static int launch_stage_m(rks_plan* p, int s, cudaStream_t stream) {
 }
 
 // K1 for a pre-transformed intermediate stage (stage_pre_kernel): R1 = radix of the first FFT pass of the row
+template <int M, int S, typename CT, int R1>
+static void launch_stage_pre_r(rks_plan* p, cudaStream_t stream) {
+    using C = PreCfg<M, S, CT, R1>;
+    // once per instantiation: opt in to the dynamic shared memory and ask how many CTAs an SM holds
+    static int resident = 0;
+    if (!resident) {
+        cudaFuncSetAttribute(stage_pre_kernel<M, S, CT, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, stage_pre_kernel<M, S, CT, R1>, PRE_THREADS, C::SMEM);
+        resident = nb > 0 ? nb : 1;
+    }
+    const DevPlan& d = p->d;
+    // persistent: column blocks x row groups fill the resident slots once; every CTA walks down the batch
+    const long long gx = d.n / R1 / 32, slots = (long long)p->sm_count * resident;
+    long long gy = slots / gx, need = (d.batch + 3) / 4;
+    if (gy < 1) gy = 1;
+    if (gy > need) gy = need;
+    stage_pre_kernel<M, S, CT, R1><<<dim3((unsigned)gx, (unsigned)gy), PRE_THREADS, C::SMEM, stream>>>(d);
+}
 template <int M, int S, typename CT>
 static void launch_stage_pre_t(rks_plan* p, cudaStream_t stream) {
-    const DevPlan& d = p->d;
-    const int r1 = d.n == 512 ? 8 : 16;                      // fft_fast.cuh Plan<N>::R1
-    const unsigned gx = (unsigned)((d.n / r1 + 31) / 32), gy = (unsigned)((d.batch + 7) / 8);
-    if (r1 == 8) stage_pre_kernel<M, S, CT, 8><<<dim3(gx, gy), dim3(32, 8), 0, stream>>>(d);
-    else stage_pre_kernel<M, S, CT, 16><<<dim3(gx, gy), dim3(32, 8), 0, stream>>>(d);
+    if (p->d.n == 512) launch_stage_pre_r<M, S, CT, 8>(p, stream);       // fft_fast.cuh Plan<N>::R1
+    else launch_stage_pre_r<M, S, CT, 16>(p, stream);
 }
 template <int M, typename CT>
 static void launch_stage_pre_m(rks_plan* p, int s, cudaStream_t stream) {
@@ -835,7 +853,6 @@ static int stage_nl_parts(rks_plan* p, int s, int part, void* stream_v) {
     const int j = s < S ? s + 1 : (adapt ? (method_fsal(m) ? S + 1 : 0) : 1);
     cudaStream_t stream = (cudaStream_t)stream_v;
     if (can_pretransform(p, s) && (part != 0 || !can_fuse_stage(p, s))) {
-        if (p->d.batch > 65535ll * 8) return fail(RKS_ERR_UNSUPPORTED, "batch too large for one launch");
         if (part != 2) launch_stage_pre(p, s, stream);
         if (part != 1) dispatch_nl_fast_pre(p, j, adapt ? 0 : 1, stream);
         CUDA_TRY(cudaGetLastError());
