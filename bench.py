@@ -41,8 +41,11 @@ STAGE_PASSES = {"IF4": [3, 3, 3, 6], "IF34": [3, 3, 3, 6], "ETD4": [3, 4, 4, 6],
 NORM_PASSES = {"IF34": 3, "ETD34": 3, "ETD35": 2, "IF45DP": 7}
 ADAPTIVE = ("IF34", "ETD34", "ETD35", "IF45DP")
 # dram bytes / pipe utilisation of one nl_fast_pre_kernel<16> launch at 4096 x 8192 (profiles/, ncu --set full); None = not captured
-NL_PRE_TRAFFIC = None
-NL_PRE_CO_BOUNDS = None
+NL_PRE_TRAFFIC = 536.95e6 + 480.89e6        # profiles/r01_v8_ncu_full_nl_fast_pre_8192.csv
+NL_PRE_CO_BOUNDS = {"source": "profiles/r01_v8_ncu_full_nl_fast_pre_8192.csv", "lsu_wavefronts_pct": 62.3,
+                    "fp64_pipe_pct": 53.3, "dram_pct": 39.9,
+                    "note": "FP64 butterflies and shared-memory passes bound this kernel, not HBM; the first inverse "
+                            "pass runs in the HBM-bound stage kernel instead"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -574,8 +577,8 @@ def run_ours(args):
     # ncu --set full captures under profiles/ (same geometry); None when that kernel/geometry was not captured
     traffic = None
     co_bounds = None
-    if top.startswith("nl-pre"):
-        traffic = NL_PRE_TRAFFIC              # from this round's ncu --set full capture, when there is one
+    if top.startswith("nl-pre") and batch * n_c == 4096 * 8192:
+        traffic = NL_PRE_TRAFFIC
         co_bounds = NL_PRE_CO_BOUNDS
     elif top.startswith("nl") and batch * n_c == 4096 * 8192:
         traffic = 537.16e6 + 480.97e6           # profiles/r01_final2_ncu_full_nl_fast_8192_tma.csv
