@@ -367,6 +367,10 @@ RKS_D void cp_async16(void* dst_smem, const void* src) {
 RKS_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int PENDING> RKS_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
 
+#ifndef RKS_PRE_CHM2
+#define RKS_PRE_CHM2 4       // ring geometry of the two-array stages (stage 1 of every method)
+#define RKS_PRE_NBUF2 3
+#endif
 #ifndef RKS_PRE_DESC
 #define RKS_PRE_DESC 1
 #endif
@@ -377,9 +381,10 @@ struct PreCfg {
     static constexpr unsigned CMASK = stage_coef_mask(M, S);
     static constexpr int NIN = 1 + __builtin_popcount(NMASK);      // u and the N_j the stage reads
     static constexpr int NCU = __builtin_popcount(CMASK);          // coefficient arrays the stage reads
-    static constexpr int CHM = NIN <= 3 ? 4 : 2;                   // modes per commit group
+    static constexpr int CHM = NIN == 2 ? RKS_PRE_CHM2 : NIN <= 3 ? 4 : 2;     // modes per commit group
     static constexpr int NCH = R1 / CHM;                           // groups per row
-    static constexpr int NBUF = (NIN >= 6 ? 2 : 3) < NCH ? (NIN >= 6 ? 2 : 3) : NCH;
+    static constexpr int NBUF0 = NIN == 2 ? RKS_PRE_NBUF2 : NIN >= 6 ? 2 : 3;
+    static constexpr int NBUF = NBUF0 < NCH ? NBUF0 : NCH;
     static constexpr size_t COEF_BYTES = (size_t)NCU * R1 * 32 * sizeof(CT);
     static constexpr size_t RING_BYTES = (size_t)NBUF * CHM * NIN * PRE_THREADS * sizeof(cplx);
     static constexpr size_t SMEM = COEF_BYTES + RING_BYTES;
@@ -684,6 +689,8 @@ RKS_D void nl_fast_row(cplx* sm, int T, int lrow, int rpc, const fast::Twiddles&
     // !PT: no barrier here -- the last pass reads exactly the slab positions (T + 32 W c + Q1 s) that the same
     // thread overwrites in the first pass of its next row, so warps run on into the next row's loads.
     // PT: the next row's first pass writes the warp's own 512-point slice, which other warps are still reading.
+    // (Merging this barrier with the one after the first pass -- loads + butterflies, barrier, stores -- was
+    // measured slower: 309 vs 298 us per launch at 4096 x 8192.)
     if (PT) row_barrier<TR>(lrow, rpc);
 }
 
