@@ -180,7 +180,7 @@ int rks_nl(rks_plan* plan, int j, void* stream);
  * FFT kernel and never written to HBM unless it is the new state. */
 int rks_stage_nl(rks_plan* plan, int stage, void* stream);
 /* The two kernels rks_stage_nl(plan, stage) launches, separately: part 1 = the stage kernel, part 2 = the
- * evaluation.  For intermediate stages of a complex-field (NLS) plan with n in 512..8192 these are the
+ * evaluation.  For intermediate stages of a complex-field (NLS) plan with n in 1024..8192 these are the
  * pre-transforming pair: the stage kernel also applies the first inverse FFT pass and the evaluation starts
  * one pass later (RKS_PT=0 in the environment selects the plain pair).  Results equal
  * rks_stage + rks_nl; the stage value left in K by part 1 is in that intermediate layout. */

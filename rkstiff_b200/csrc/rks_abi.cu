@@ -163,7 +163,7 @@ static cudaError_t prepare_nl_fast(int model) {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 1, 2>, attr, (int)nl_fast_smem<W>(model, 2));
     } else if (model == RKS_MODEL_NLS_FFT) {
         e = cudaFuncSetAttribute(nl_fast_kernel<W, 2, 0>, attr, (int)nl_fast_smem<W>(model, 0));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_pre_kernel<W>, attr, (int)nl_fast_smem<W>(model, 0));
+        if (W > 1 && e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_pre_kernel<(W > 1 ? W : 2)>, attr, (int)nl_fast_smem<W>(model, 0));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel_multi<W, 2, 0>, attr, (int)nl_fast_smem<W>(model, 0));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 2, 1>, attr, (int)nl_fast_smem<W>(model, 1));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 2, 2>, attr, (int)nl_fast_smem<W>(model, 2));
@@ -675,8 +675,7 @@ static void launch_stage_pre_r(rks_plan* p, cudaStream_t stream) {
 }
 template <int M, int S, typename CT>
 static void launch_stage_pre_t(rks_plan* p, cudaStream_t stream) {
-    if (p->d.n == 512) launch_stage_pre_r<M, S, CT, 8>(p, stream);       // fft_fast.cuh Plan<N>::R1
-    else launch_stage_pre_r<M, S, CT, 16>(p, stream);
+    launch_stage_pre_r<M, S, CT, 16>(p, stream);       // fft_fast.cuh Plan<N>::R1 for n = 1024 ... 8192
 }
 template <int M, typename CT>
 static void launch_stage_pre_m(rks_plan* p, int s, cudaStream_t stream) {
@@ -752,7 +751,6 @@ static void launch_nl_fast_pre_t(rks_plan* p, int j, int force, cudaStream_t str
 }
 static void dispatch_nl_fast_pre(rks_plan* p, int j, int force, cudaStream_t stream) {
     switch (p->d.n) {
-        case 512: launch_nl_fast_pre_t<1>(p, j, force, stream); break;
         case 1024: launch_nl_fast_pre_t<2>(p, j, force, stream); break;
         case 2048: launch_nl_fast_pre_t<4>(p, j, force, stream); break;
         case 4096: launch_nl_fast_pre_t<8>(p, j, force, stream); break;
@@ -836,7 +834,8 @@ static bool can_fuse_stage(const rks_plan* p, int s) {
 // Intermediate stage of a fast NLS-type plan: its value only feeds N(.), so K1 may hand it over pre-transformed
 // (stage_pre_kernel -> nl_fast_pre_kernel).  The last stage is a state and keeps the natural layout.
 static bool can_pretransform(const rks_plan* p, int s) {
-    return p->pretransform && p->nl_fast && !p->multi_n && p->d.lin_elems == p->d.n_c && !p->d.lin_full
+    // n = 512: a row is one warp's slice, K4 is already warp-local there and the pair measured 5-16 % slower
+    return p->pretransform && p->nl_fast && p->d.n >= 1024 && !p->multi_n && p->d.lin_elems == p->d.n_c && !p->d.lin_full
         && p->d.model == RKS_MODEL_NLS_FFT && s < method_stages(p->method);
 }
 
