@@ -633,6 +633,23 @@ def test_pretransformed_pair_equals_plain_pair(rk, method, n, monkeypatch):
     assert rk._abi.lib.rks_stage_nl_part(eng.plan, 1, 0, eng.st) != 0          # part must be 1 or 2
 
 
+@pytest.mark.parametrize("method,n,batch", [("ETD35", 8192, 301), ("ETD4", 8192, 301), ("IF45DP", 4096, 700),
+                                            ("ETD35", 2048, 1), ("IF34", 1024, 2)])
+def test_pretransformed_pair_ragged_batches(rk, method, n, batch, monkeypatch):
+    """Batches the persistent stage kernel walks through several rows per warp (its row counters are re-armed by the
+    last warp of every launch: stages 1..S-1 run back to back here), and batches smaller than one CTA."""
+    p = problems.nls(n, batch=batch, seed=batch, half_width=20.0)
+    plain, _ = _stage_outputs(rk, method, p, monkeypatch, pt=False)
+    pre, sol = _stage_outputs(rk, method, p, monkeypatch, pt=True)
+    for a, b in zip(pre, plain):
+        assert rel(a, b) < 1e-14
+        assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max()          # no row skipped or taken twice
+    eng = sol._engine
+    for _ in range(3):                                                  # the same launch again: counters back at zero
+        rk._abi.check(rk._abi.lib.rks_stage_nl(eng.plan, 1, eng.st))
+    assert rel(host(eng.state_view("N2")), plain[0]) < 1e-14
+
+
 @pytest.mark.parametrize("n", PT_SIZES)
 @pytest.mark.parametrize("method", FIXED)
 def test_pretransformed_fixed_step_parity(rk, method, n):
