@@ -62,8 +62,8 @@ RKS_HD cplx stage_combine(cplx u, const cplx* nv, const CT* cv, double h) {
         if (S == 2) return cmul(cv[ifc::E2], u) + (h * nv[2]) / 2.0;
         if (S == 3) return cmul(cv[ifc::E], u) + cmul(scale(h, cv[ifc::E2]), nv[3]);
         return cmul(cv[ifc::E], u)
-             + h * (cmul(cv[ifc::E], nv[1]) / 6.0 + cmul(cv[ifc::E2], nv[2]) / 3.0
-                    + cmul(cv[ifc::E2], nv[3]) / 3.0 + nv[4] / 6.0);
+             + h * (div_const<6>(cmul(cv[ifc::E], nv[1])) + div_const<3>(cmul(cv[ifc::E2], nv[2]))
+                    + div_const<3>(cmul(cv[ifc::E2], nv[3])) + div_const<6>(nv[4]));
     }
     if (M == M_ETD4 || M == M_ETD34) {
         if (S == 1) return cmul(cv[kro::E2], u) + cmul(cv[kro::a21], nv[1]);
@@ -112,7 +112,7 @@ RKS_HD cplx etd35_err(const cplx* nv, const CT* cv) {
 // (if34.py:130, etd34.py:190, if45dp.py:172-179)
 template <int M, typename CT>
 RKS_HD cplx embedded_err(const cplx* nv, const CT* cv, double h) {
-    if (M == M_IF34) return (h * (nv[4] - nv[5])) / 6.0;
+    if (M == M_IF34) return div_const<6>(h * (nv[4] - nv[5]));
     if (M == M_ETD34) return cmul(cv[kro::a54], nv[4] - nv[5]);
     return cmul(cv[dp::r1], nv[1]) + cmul(cv[dp::r3], nv[3]) + cmul(cv[dp::r4], nv[4])
          + cmul(cv[dp::r5], nv[5]) + dp_r6(h) * nv[6] + dp_r7(h) * nv[7];
