@@ -161,8 +161,10 @@ RKS_HD void tableau_if45dp(T z, double h, int r4_fix, T* out) {
     out[dp::r5] = scale(-17253.0 * h, E19) / 339200.0;
 }
 // IF45DP scalars (if45dp.py:231,236,237)
-RKS_HD double dp_a76(double h) { return (11.0 * h) / 84.0; }
-RKS_HD double dp_r6(double h) { return (22.0 * h) / 525.0; }
-RKS_HD double dp_r7(double h) { return -h / 40.0; }
+// (evaluated by every thread of the last stage / the norm kernel: div_const, common.cuh, is the same correctly
+// rounded quotient without the reciprocal iteration and its slow-path call)
+RKS_HD double dp_a76(double h) { return div_const<84>(11.0 * h); }
+RKS_HD double dp_r6(double h) { return div_const<525>(22.0 * h); }
+RKS_HD double dp_r7(double h) { return div_const<40>(-h); }
 
 }  // namespace rks
