@@ -341,8 +341,11 @@ RKS_D void stage_kernel_body(const DevPlan& p) {
         }
     }
 }
+// Coefficients shared by the batch: three CTAs per SM (<= 85 registers; the six-stage methods' last stages otherwise
+// sit at 86-90 registers = two CTAs, where the IF45DP one ran at 0.90 of the roofline: 638 -> 563 us with three).
+// Full-size coefficient arrays need the registers (they would spill 100-150 bytes).
 template <int M, int S, typename CT, bool FULL>
-__global__ void __launch_bounds__(256) stage_kernel(const __grid_constant__ DevPlan p) { stage_kernel_body<M, S, CT, FULL>(p); }
+__global__ void __launch_bounds__(256, (FULL ? 1 : 3)) stage_kernel(const __grid_constant__ DevPlan p) { stage_kernel_body<M, S, CT, FULL>(p); }
 // one plan per blockIdx.z: ensembles whose trajectories keep their own dt (rks_multi_*)
 template <int M, int S, typename CT, bool FULL>
 __global__ void __launch_bounds__(256) stage_kernel_multi(const DevPlan* plans) { stage_kernel_body<M, S, CT, FULL>(plans[blockIdx.z]); }
