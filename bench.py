@@ -657,6 +657,8 @@ def run_ours(args):
                 "dtype": "f64", "data": "synthetic", "config": workload_config(args.workload, world, method),
                 "accepted_steps": accepted, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clocks}
+        line["config"]["kernel_pair"] = ("pre-transforming K1/K4 pair on the intermediate stages (DESIGN.md 4)" if pt
+                                         else "plain K1 + K4")
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

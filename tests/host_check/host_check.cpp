@@ -180,6 +180,21 @@ int hc_nl_fast(int model, int n, const double* in, const double* kx, double p0, 
     return fast_dispatch(n, fast::ModelOf<4>::make(cin, co, kx, p0, n, true), tw);
 }
 
+// x / d through div_const<d> (common.cuh) for the divisors the kernels use
+int hc_div_const(int d, int n, const double* x, double* out) {
+    for (int i = 0; i < n; ++i) {
+        switch (d) {
+            case 3: out[i] = div_const<3>(x[i]); break;
+            case 6: out[i] = div_const<6>(x[i]); break;
+            case 40: out[i] = div_const<40>(x[i]); break;
+            case 84: out[i] = div_const<84>(x[i]); break;
+            case 525: out[i] = div_const<525>(x[i]); break;
+            default: return -1;
+        }
+    }
+    return 0;
+}
+
 // NLS evaluation of one row through the pre-transformed route (K1 applies the first inverse pass)
 int hc_nl_pre(int n, const double* in, double gamma, double* out) {
     std::vector<cplx> tab(fast::TW_TOTAL);

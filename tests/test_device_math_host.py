@@ -385,3 +385,26 @@ def test_packed_short_row_pipeline_matches_generic_rows(hc, n, model):
     assert np.isfinite(got).all()
     scale = np.abs(want).max()
     np.testing.assert_allclose(got, want, rtol=0, atol=2e-13 * scale)
+
+
+@pytest.mark.parametrize("d", [3, 6, 40, 84, 525])
+def test_div_const_is_the_correctly_rounded_quotient(hc, d):
+    """common.cuh div_const<D>: q = x RN(1/D), r = fma(-D, q, x), q + r RN(1/D) must equal x / D bit for bit
+    (NumPy's division, which the reference's `/ 6`, `/ 3`, `/ 84` ... are) over the normal range; inf and NaN pass through."""
+    rng = np.random.default_rng(d)
+    bits = rng.integers(0, 1 << 52, size=2_000_000, dtype=np.uint64)
+    expo = rng.integers(1023 - 900, 1023 + 900, size=bits.size, dtype=np.uint64)
+    sign = rng.integers(0, 2, size=bits.size, dtype=np.uint64) << np.uint64(63)
+    x = (bits | (expo << np.uint64(52)) | sign).view(np.float64)
+    # adversarial mantissas: small odd integers, all-ones tails, exact multiples of D
+    extra = np.concatenate([np.arange(1, 200001, 2, dtype=np.float64), np.arange(0, 100000, dtype=np.float64) * d,
+                            (np.uint64(0x3ff0000000000000) | (np.uint64(0xfffffffffffff) - np.arange(100000, dtype=np.uint64))).view(np.float64),
+                            np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-300, -1e300, 5e-324])])
+    x = np.ascontiguousarray(np.concatenate([x, extra]))
+    out = np.empty_like(x)
+    assert hc.hc_div_const(d, x.size, ptr(x), ptr(out)) == 0
+    with np.errstate(invalid="ignore"):
+        ref = x / float(d)
+    normal = ~(np.abs(ref) < 2.3e-308) | (ref == 0)          # subnormal quotients may differ by one subnormal ulp
+    np.testing.assert_array_equal(out[normal], ref[normal])
+    assert np.all(np.abs(out[~normal] - ref[~normal]) <= 5e-324)
