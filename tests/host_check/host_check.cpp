@@ -15,6 +15,7 @@
 #include "../../rkstiff_b200/csrc/errctl.cuh"
 #include "../../rkstiff_b200/csrc/fft.cuh"
 #include "../../rkstiff_b200/csrc/fft_fast.cuh"
+#include "../../rkstiff_b200/csrc/fft_real.cuh"
 #include "../../rkstiff_b200/csrc/fft_axis.cuh"
 #include "../../rkstiff_b200/csrc/fuse.cuh"
 
@@ -70,6 +71,33 @@ static void pre_row(const cplx* k, cplx* out, double gamma, const fast::Twiddles
         for (int T = 0; T < TR; ++T) fast::phase_middle<N, 3, false>(sm.data(), T, tw, m);
     for (int T = 0; T < TR; ++T) fast::phase_middle<N, 2, false>(sm.data(), T, tw, m);
     for (int T = 0; T < TR; ++T) fast::phase_last<N>(sm.data(), T, tw, m);
+}
+
+// serial emulation of the real-field variant (fft_real.cuh): inverse passes as in fast_row, then the paired core
+// pass, the forward middle pass on the even blocks and the half-length last pass with its exchange
+template <int N, class Model>
+static void fast_row_real(const Model& m, const fast::Twiddles& tw) {
+    using P = fast::Plan<N>;
+    constexpr int TR = 32 * P::W, H = P::R1 / 2, NB = (N / P::R1) / TR;
+    std::vector<cplx> sm(N);
+    for (int T = 0; T < TR; ++T) fast::phase_first<N>(sm.data(), T, tw, m);
+    for (int T = 0; T < TR; ++T) fast::phase_middle<N, 2, true>(sm.data(), T, tw, m);
+    for (int T = 0; T < TR; ++T) fast::phase_core_pair<N>(sm.data(), T, m);
+    for (int T = 0; T < TR; ++T) fast::phase_middle_even<N>(sm.data(), T, tw);
+    std::vector<cplx> regs((size_t)TR * NB * H);
+    for (int T = 0; T < TR; ++T) fast::phase_last_half_load<N>(sm.data(), T, tw, regs.data() + (size_t)T * NB * H);
+    for (int T = 0; T < TR; ++T) fast::phase_last_half_exchange<N>(sm.data(), T, regs.data() + (size_t)T * NB * H);
+    for (int T = 0; T < TR; ++T) fast::phase_last_half_split<N>(sm.data(), T, tw, regs.data() + (size_t)T * NB * H, m);
+}
+template <class Model>
+static int fast_real_dispatch(int n, const Model& m, const fast::Twiddles& tw) {
+    switch (n) {
+        case 512: fast_row_real<512>(m, tw); return 0;
+        case 1024: fast_row_real<1024>(m, tw); return 0;
+        case 2048: fast_row_real<2048>(m, tw); return 0;
+        case 4096: fast_row_real<4096>(m, tw); return 0;
+    }
+    return -1;
 }
 
 template <class Model>
@@ -178,6 +206,18 @@ int hc_nl_fast(int model, int n, const double* in, const double* kx, double p0, 
     if (model == 2) return fast_dispatch(n, fast::ModelOf<2>::make(cin, co, kx, p0, n, true), tw);
     if (model == 3) return fast_dispatch(n, fast::ModelOf<3>::make(cin, co, kx, p0, n, true), tw);
     return fast_dispatch(n, fast::ModelOf<4>::make(cin, co, kx, p0, n, true), tw);
+}
+
+// real-field models (1 = u u_x, 3 = cubic) through the half-length forward transform of fft_real.cuh
+int hc_nl_fast_real(int model, int n, const double* in, const double* kx, double p0, double* out) {
+    std::vector<cplx> tab(fast::TW_TOTAL);
+    for (int j = 0; j < fast::TW_TOTAL; ++j) tab[j] = fast::twiddle_table_entry(j, n);
+    const fast::Twiddles tw{tab.data() + fast::TW_T1, tab.data() + fast::TW_T2, tab.data() + fast::TW_T3};
+    const cplx* cin = reinterpret_cast<const cplx*>(in);
+    cplx* co = reinterpret_cast<cplx*>(out);
+    if (model == 1) return fast_real_dispatch(n, fast::ModelOf<1>::make(cin, co, kx, p0, n, true), tw);
+    if (model == 3) return fast_real_dispatch(n, fast::ModelOf<3>::make(cin, co, kx, p0, n, true), tw);
+    return -1;
 }
 
 // x / d through div_const<d> (common.cuh) for the divisors the kernels use

@@ -408,3 +408,28 @@ def test_div_const_is_the_correctly_rounded_quotient(hc, d):
     normal = ~(np.abs(ref) < 2.3e-308) | (ref == 0)          # subnormal quotients may differ by one subnormal ulp
     np.testing.assert_array_equal(out[normal], ref[normal])
     assert np.all(np.abs(out[~normal] - ref[~normal]) <= 5e-324)
+
+
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096])
+def test_real_field_half_length_forward_matches_numpy(hc, n):
+    """fft_real.cuh (not wired into a kernel yet): the forward transform of the real pointwise product as a half-length
+    complex transform on the digit-reversed in-place layout -- paired core pass, even-block middle pass, radix-R1/2 last
+    pass with the C[k] / conj C[n/2-k] exchange -- for the u u_x model (incl. a Nyquist mode with an imaginary part)
+    and the cubic model, against NumPy and against the full-length route."""
+    p = problems.ks(n)
+    rng = np.random.default_rng(n)
+    uf = p.u0 + 1e-3 * (rng.standard_normal(p.u0.shape) + 1j * rng.standard_normal(p.u0.shape))
+    uf[-1] += 0.3j
+    out, full = np.empty_like(uf), np.empty_like(uf)
+    assert hc.hc_nl_fast_real(1, n, ptr(uf), ptr(p.kx), ctypes.c_double(6.0), ptr(out)) == 0
+    assert hc.hc_nl_fast(1, n, ptr(uf), ptr(p.kx), ctypes.c_double(6.0), ptr(full)) == 0
+    ref = -6 * np.fft.rfft(np.fft.irfft(uf) * np.fft.irfft(1j * p.kx * uf))
+    assert rel(out, ref) < 1e-14 * np.log2(n)
+    assert rel(out, full) < 1e-14 * np.log2(n)
+    # cubic model: N = -rfft(irfft(u)^3)
+    uf = uf / np.abs(uf).max()
+    out = np.empty_like(uf)
+    assert hc.hc_nl_fast_real(3, n, ptr(uf), None, ctypes.c_double(-1.0), ptr(out)) == 0
+    ref = -np.fft.rfft(np.fft.irfft(uf) ** 3)
+    assert rel(out, ref) < 1e-14 * np.log2(n)
+    assert hc.hc_nl_fast_real(2, n, ptr(uf), None, ctypes.c_double(1.0), ptr(out)) != 0     # complex-field model: not applicable
