@@ -7,6 +7,7 @@
 #include "errctl.cuh"
 #include "fft.cuh"
 #include "fft_fast.cuh"
+#include "fft_real.cuh"
 #include "fft_axis.cuh"
 #include "fuse.cuh"
 
@@ -892,6 +893,58 @@ __global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_f
 template <int W, int MODEL, int FK>
 __global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_fast_kernel_multi(const DevPlan* plans, int j, int force, FuseDesc fd) { nl_fast_kernel_body<W, MODEL, FK>(plans[blockIdx.z], j, force, fd); }
 
+
+// ---------------------------------------------------------------------------------------
+// EXPERIMENT, opt-in (RKS_RFFT_HALF=1), not measured yet: K4 for the real-field models (1 = u u_x, 3 = cubic) with the
+// forward transform of the real product as a half-length complex transform (fft_real.cuh; CPU-pinned against NumPy
+// in tests/test_device_math_host.py).  n = 512 ... 4096, plain evaluation only.  Half the forward butterflies, but
+// three more row barriers per row (the E/O split needs C[n/2 - k] from another thread).
+// ---------------------------------------------------------------------------------------
+template <int N, class Model>
+RKS_D void nl_fast_row_real(cplx* sm, int T, int lrow, int rpc, const fast::Twiddles& ti, const fast::Twiddles& tf,
+                            const Model& m) {
+    using P = fast::Plan<N>;
+    constexpr int TR = 32 * P::W, H = P::R1 / 2, NB = (N / P::R1) / TR;
+    fast::phase_first<N>(sm, T, ti, m);
+    row_barrier<TR>(lrow, rpc);
+    fast::phase_middle<N, 2, true>(sm, T, ti, m);   __syncwarp();
+    fast::phase_core_pair<N>(sm, T, m);             __syncwarp();
+    fast::phase_middle_even<N>(sm, T, tf);
+    row_barrier<TR>(lrow, rpc);
+    cplx x[NB * H];
+    fast::phase_last_half_load<N>(sm, T, tf, x);
+    row_barrier<TR>(lrow, rpc);                      // every thread has read its G values: the slab may take C
+    fast::phase_last_half_exchange<N>(sm, T, x);
+    row_barrier<TR>(lrow, rpc);
+    fast::phase_last_half_split<N>(sm, T, tf, x, m);
+    row_barrier<TR>(lrow, rpc);                      // partners' C values are read before the next row overwrites them
+}
+template <int W, int MODEL>
+__global__ void __launch_bounds__(256, 2) nl_fast_real_kernel(const __grid_constant__ DevPlan p, int j, int force) {
+    static_assert(W <= 8 && (MODEL == 1 || MODEL == 3), "real-field models, rows of 512 ... 4096 points");
+    constexpr int N = 512 * W, TR = 32 * W, THREADS = 256, RPC = THREADS / TR;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const NlRoles roles = nl_roles(p, j, force);
+    if (!roles.run) return;
+    if (p.ctrl && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&p.ctrl->nl_evals, 1ull);
+    const int lrow = threadIdx.x / TR, T = threadIdx.x - lrow * TR;
+    cplx* sm = reinterpret_cast<cplx*>(smem_raw) + (size_t)lrow * N;
+    const fast::Twiddles ti{p.twf + fast::TW_T1, p.twf + fast::TW_T2, p.twf + fast::TW_T3};
+    const cplx* twf2 = p.twf + fast::TW_TOTAL;
+    const fast::Twiddles tf{twf2 + fast::TW_T1, twf2 + fast::TW_T2, twf2 + fast::TW_T3};
+    const int lines = (int)((p.n_c * 16 + 127) >> 7);
+    const long long groups = (p.batch + RPC - 1) / RPC;
+    for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
+        const long long row = g * RPC + lrow;
+        const bool on = row < p.batch;
+        const long long rr = on ? row : p.batch - 1;
+        const long long nrow = row + (long long)gridDim.x * RPC;
+        const int nlines = nrow < p.batch ? lines : 0;
+        prefetch_row_l2<TR>(roles.in + (nlines ? nrow : rr) * p.n_c, nlines, T);
+        const auto m = fast::ModelOf<MODEL>::make(roles.in + rr * p.n_c, roles.out + rr * p.n_c, p.kx, p.model_p0, N, on);
+        nl_fast_row_real<N>(sm, T, lrow, RPC, ti, tf, m);
+    }
+}
 
 // ---------------------------------------------------------------------------------------
 // K4 for short rows (n = 64, 128, 256): every warp is on its own -- it packs 512 / n consecutive rows into

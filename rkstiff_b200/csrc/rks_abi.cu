@@ -107,6 +107,7 @@ struct rks_plan {
     bool nl_small;                  // n in {64, 128, 256}: the same pipeline on slabs of packed rows
     bool no_fuse;                   // default: K1 and K4 as separate kernels (north_star decomposition); RKS_FUSE=1 fuses
     bool pretransform;              // intermediate NLS stages: K1 applies the first inverse FFT pass (RKS_PT=0 disables)
+    bool rfft_half;                 // EXPERIMENT (RKS_RFFT_HALF=1): half-length forward transform for the real-field models
     size_t nl_smem;
 };
 
@@ -455,6 +456,18 @@ static int prepare_nl_launch(rks_plan* p, int model, long long n, cplx* twf_dev,
     DevPlan& d = p->d;
     p->nl_fast = (n >= 512 && n <= 8192) && !getenv("RKS_NL_GENERIC");
     p->no_fuse = getenv("RKS_FUSE") == nullptr;       // fused K1+K4 is opt-in (RKS_FUSE=1): see DESIGN.md 4
+    p->rfft_half = getenv("RKS_RFFT_HALF") != nullptr && p->nl_fast && n <= 4096
+                   && (model == RKS_MODEL_UUX_RFFT || model == RKS_MODEL_CUBIC_RFFT);
+    if (p->rfft_half) {
+        const auto a = cudaFuncAttributeMaxDynamicSharedMemorySize;
+        const int sm = 256 / 32 * 512 * (int)sizeof(cplx);          // rows per CTA x n x 16 B = 64 KB for every n
+        const bool uux = model == RKS_MODEL_UUX_RFFT;
+        cudaError_t e = n == 512 ? (uux ? cudaFuncSetAttribute(nl_fast_real_kernel<1, 1>, a, sm) : cudaFuncSetAttribute(nl_fast_real_kernel<1, 3>, a, sm))
+                      : n == 1024 ? (uux ? cudaFuncSetAttribute(nl_fast_real_kernel<2, 1>, a, sm) : cudaFuncSetAttribute(nl_fast_real_kernel<2, 3>, a, sm))
+                      : n == 2048 ? (uux ? cudaFuncSetAttribute(nl_fast_real_kernel<4, 1>, a, sm) : cudaFuncSetAttribute(nl_fast_real_kernel<4, 3>, a, sm))
+                                  : (uux ? cudaFuncSetAttribute(nl_fast_real_kernel<8, 1>, a, sm) : cudaFuncSetAttribute(nl_fast_real_kernel<8, 3>, a, sm));
+        CUDA_TRY(e);
+    }
     const char* pt = getenv("RKS_PT");
     p->pretransform = !(pt && pt[0] == '0');           // pre-transformed intermediate stages
     p->nl_small = (n == 64 || n == 128 || n == 256) && !getenv("RKS_NL_GENERIC");
@@ -775,6 +788,25 @@ static void launch_nl_small(rks_plan* p, int j, int force, cudaStream_t stream) 
         default: launch_nl_small_t<N, 4>(p, j, force, stream); break;
     }
 }
+// EXPERIMENT (RKS_RFFT_HALF=1): real-field models through the half-length forward transform
+template <int W, int MODEL>
+static void launch_nl_fast_real_t(rks_plan* p, int j, int force, cudaStream_t stream) {
+    constexpr int RPC = 256 / (32 * W);
+    const long long groups = (p->d.batch + RPC - 1) / RPC, resident = (long long)p->sm_count * 2;
+    const unsigned grid = (unsigned)(groups < resident ? groups : resident);
+    nl_fast_real_kernel<W, MODEL><<<grid, 256, (size_t)RPC * 512 * W * sizeof(cplx), stream>>>(p->d, j, force);
+}
+static void launch_nl_fast_real(rks_plan* p, int j, int force, cudaStream_t stream) {
+    const bool uux = p->d.model == RKS_MODEL_UUX_RFFT;
+    switch (p->d.n) {
+        case 512: uux ? launch_nl_fast_real_t<1, 1>(p, j, force, stream) : launch_nl_fast_real_t<1, 3>(p, j, force, stream); break;
+        case 1024: uux ? launch_nl_fast_real_t<2, 1>(p, j, force, stream) : launch_nl_fast_real_t<2, 3>(p, j, force, stream); break;
+        case 2048: uux ? launch_nl_fast_real_t<4, 1>(p, j, force, stream) : launch_nl_fast_real_t<4, 3>(p, j, force, stream); break;
+        default: uux ? launch_nl_fast_real_t<8, 1>(p, j, force, stream) : launch_nl_fast_real_t<8, 3>(p, j, force, stream); break;
+    }
+    p->launches += 1;
+}
+
 static int launch_nl(rks_plan* p, int j, int force, cudaStream_t stream) {
     const DevPlan& d = p->d;
     if (p->nl_small && !p->multi_n) {
@@ -782,6 +814,10 @@ static int launch_nl(rks_plan* p, int j, int force, cudaStream_t stream) {
         else if (d.n == 128) launch_nl_small<128>(p, j, force, stream);
         else launch_nl_small<256>(p, j, force, stream);
         p->launches += 1;
+        return RKS_OK;
+    }
+    if (p->nl_fast && p->rfft_half && !p->multi_n) {
+        launch_nl_fast_real(p, j, force, stream);
         return RKS_OK;
     }
     if (p->nl_fast) {

@@ -682,3 +682,23 @@ def test_pretransformed_adaptive_parity(rk, method, n):
     np.testing.assert_allclose(hs[:-1], ho[:-1], rtol=DT_TOL, atol=0)
     np.testing.assert_allclose(hs[-1], ho[-1], rtol=0, atol=DT_TOL * tf)
     assert rel(host(uf), uo) < FINAL_TOL
+
+
+# --------------------------------------------------------------------------------------------
+# EXPERIMENT (opt-in, RKS_RFFT_HALF=1; csrc/fft_real.cuh): half-length forward transform for the real-field models.
+# Pinned on the CPU (tests/test_device_math_host.py); this GPU check runs only when asked for, so that the default
+# suite covers exactly the default kernels:  RKS_TEST_RFFT_HALF=1 python -m pytest tests -m gpu -k rfft_half
+# --------------------------------------------------------------------------------------------
+@pytest.mark.skipif(__import__("os").environ.get("RKS_TEST_RFFT_HALF") is None, reason="opt-in experiment (RKS_TEST_RFFT_HALF=1)")
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096])
+@pytest.mark.parametrize("batch", [1, 5, 150])
+@pytest.mark.parametrize("name", ["ks", "allen_cahn_1d"])
+def test_rfft_half_length_forward_matches_full_length(rk, name, n, batch, monkeypatch):
+    monkeypatch.setenv("RKS_RFFT_HALF", "1")
+    p = problems.ks(n, batch=batch, seed=n) if name == "ks" else problems.allen_cahn_1d(n, batch=batch, seed=n)
+    sol = rk.ETD4(dev(p.lin_op), fused_for(rk, p))
+    u = dev(p.u0)
+    eng = sol._get_engine(u)
+    eng.set_u(u)
+    eng.nl(1)
+    assert rel(host(eng.state_view("N1")), p.nl_func(p.u0)) < 2e-14 * np.log2(n)
