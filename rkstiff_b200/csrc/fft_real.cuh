@@ -1,7 +1,7 @@
 // K4 for the real-field (rfft) models: forward transform of the REAL pointwise product as a half-length complex
-// transform.  NOT wired into a kernel yet (round-2 item, DESIGN.md section 6 "what comes next"): this header holds
-// the per-thread phase functions, tests/host_check runs them serially and tests/test_device_math_host.py pins them
-// to NumPy.  Nothing in rks_abi.cu includes it.
+// transform.  EXPERIMENT (DESIGN.md section 6 "what comes next"): this header holds the per-thread phase functions,
+// tests/host_check runs them serially and tests/test_device_math_host.py pins them to NumPy; the only kernel that uses
+// them is the opt-in, not yet measured nl_fast_real_kernel (kernels.cuh, RKS_RFFT_HALF=1).  The default kernels do not.
 //
 // Why: the u u_x / cubic models run a full-length complex inverse transform (it carries two real fields, or one with
 // half the butterflies idle) and then a full-length complex FORWARD transform of a real signal w -- half of that

@@ -412,7 +412,7 @@ def test_div_const_is_the_correctly_rounded_quotient(hc, d):
 
 @pytest.mark.parametrize("n", [512, 1024, 2048, 4096])
 def test_real_field_half_length_forward_matches_numpy(hc, n):
-    """fft_real.cuh (not wired into a kernel yet): the forward transform of the real pointwise product as a half-length
+    """fft_real.cuh (used by the opt-in nl_fast_real_kernel only): the forward transform of the real pointwise product as a half-length
     complex transform on the digit-reversed in-place layout -- paired core pass, even-block middle pass, radix-R1/2 last
     pass with the C[k] / conj C[n/2-k] exchange -- for the u u_x model (incl. a Nyquist mode with an imaginary part)
     and the cubic model, against NumPy and against the full-length route."""
