@@ -8,6 +8,7 @@
 #include "fft.cuh"
 #include "fft_fast.cuh"
 #include "fft_real.cuh"
+#include "fft_fast_x2.cuh"
 #include "fft_axis.cuh"
 #include "fuse.cuh"
 
@@ -893,6 +894,76 @@ __global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_f
 template <int W, int MODEL, int FK>
 __global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_fast_kernel_multi(const DevPlan* plans, int j, int force, FuseDesc fd) { nl_fast_kernel_body<W, MODEL, FK>(plans[blockIdx.z], j, force, fd); }
 
+
+// ---------------------------------------------------------------------------------------
+// EXPERIMENT, opt-in (RKS_K4_X2=1), not measured yet: the n = 8192 NLS evaluation of pre-transformed rows (the plain
+// one spills at 255 registers and is not dispatched) with 8 warps x 255 registers, two
+// logical threads per physical thread and every pass written loads / butterflies / stores (fft_fast_x2.cuh; results
+// bit-identical to nl_fast_kernel / nl_fast_pre_kernel on the CPU harness).  Same TMA staging of the next row.
+// ---------------------------------------------------------------------------------------
+template <bool PT, class Model, class Hook>
+RKS_D void nl_fast_row_x2(cplx* sm, int t, const fast::Twiddles& ti, const fast::Twiddles& tf, const Model& m,
+                          const Hook& after_first) {
+    constexpr int N = 8192;
+    if (PT) {
+        fast::phase_pre_x2<N>(sm, t, ti, m);
+        __syncthreads();                                  // staging buffer consumed by every warp
+        after_first();
+    } else {
+        // radix-16 passes: one logical thread after the other (two 16-point butterflies + twiddles at once spill)
+        fast::phase_first<N>(sm, fast::x2_first(t), ti, m);
+        fast::phase_first<N>(sm, fast::x2_second(t), ti, m);
+        __syncthreads();
+        after_first();
+        fast::phase_middle_x2<N, 2, true>(sm, t, ti, m);    __syncwarp();
+    }
+    fast::phase_middle_x2<N, 3, true>(sm, t, ti, m);        __syncwarp();
+    fast::phase_core_x2<N>(sm, t, m);                       __syncwarp();
+    fast::phase_middle_x2<N, 3, false>(sm, t, tf, m);       __syncwarp();
+    fast::phase_middle_x2<N, 2, false>(sm, t, tf, m);
+    __syncthreads();
+    fast::phase_last<N>(sm, fast::x2_first(t), tf, m);
+    fast::phase_last<N>(sm, fast::x2_second(t), tf, m);
+    // !PT: the last pass reads the slab positions the same thread overwrites in the first pass of its next row (both
+    // logical threads are this thread's); PT: the next first pass writes the warp's slices, which others still read
+    if (PT) __syncthreads();
+}
+template <bool PT>
+__global__ void __launch_bounds__(256, 1) nl_fast_x2_kernel(const __grid_constant__ DevPlan p, int j, int force) {
+    constexpr int N = 8192, THREADS = 256;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const NlRoles roles = nl_roles(p, j, force);
+    if (!roles.run) return;
+    if (p.ctrl && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&p.ctrl->nl_evals, 1ull);
+    const int t = threadIdx.x;
+    cplx* sm = reinterpret_cast<cplx*>(smem_raw);
+    const fast::Twiddles ti{p.twf + fast::TW_T1, p.twf + fast::TW_T2, p.twf + fast::TW_T3};
+    const cplx* twf2 = p.twf + fast::TW_TOTAL;
+    const fast::Twiddles tf{twf2 + fast::TW_T1, twf2 + fast::TW_T2, twf2 + fast::TW_T3};
+    const int lines = (int)((p.n_c * 16 + 127) >> 7);
+    cplx* stg = sm + N;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(stg + NL_STAGE_ELEMS);
+    const int nst = NL_STAGE_ELEMS;
+    unsigned parity = 0;
+    if (t == 0) {
+        stage_init(bar);
+        if ((long long)blockIdx.x < p.batch) stage_issue(stg, roles.in + (long long)blockIdx.x * p.n_c, nst * 16u, bar);
+    }
+    __syncthreads();
+    for (long long row = blockIdx.x; row < p.batch; row += gridDim.x) {
+        const long long nrow = row + gridDim.x;
+        const int nlines = nrow < p.batch ? lines : 0;
+        const int head = (nst * 16) >> 7;
+        if (nlines > head)
+            prefetch_row_l2<THREADS>(reinterpret_cast<const char*>(roles.in + nrow * p.n_c) + ((size_t)head << 7), nlines - head, t);
+        stage_wait(bar, parity);
+        parity ^= 1u;
+        const auto m = fast::ModelOf<2>::make_staged(fast::StagedRow{roles.in + row * p.n_c, stg, nst}, roles.out + row * p.n_c,
+                                                     p.kx, p.model_p0, N, true);
+        const StageNext next{stg, roles.in + (nlines ? nrow : row) * p.n_c, nst * 16u, bar, nlines != 0 && t == 0};
+        nl_fast_row_x2<PT>(sm, t, ti, tf, m, next);
+    }
+}
 
 // ---------------------------------------------------------------------------------------
 // EXPERIMENT, opt-in (RKS_RFFT_HALF=1), not measured yet: K4 for the real-field models (1 = u u_x, 3 = cubic) with the

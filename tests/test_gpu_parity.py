@@ -702,3 +702,17 @@ def test_rfft_half_length_forward_matches_full_length(rk, name, n, batch, monkey
     eng.set_u(u)
     eng.nl(1)
     assert rel(host(eng.state_view("N1")), p.nl_func(p.u0)) < 2e-14 * np.log2(n)
+
+
+# EXPERIMENT (opt-in, RKS_K4_X2=1; csrc/fft_fast_x2.cuh): n = 8192 pre-transformed NLS evaluation with 8 warps x 255
+# registers.  CPU-pinned (bit-identical passes); the GPU check runs on request only:
+#   RKS_TEST_K4_X2=1 python -m pytest tests -m gpu -k k4_x2
+@pytest.mark.skipif(__import__("os").environ.get("RKS_TEST_K4_X2") is None, reason="opt-in experiment (RKS_TEST_K4_X2=1)")
+@pytest.mark.parametrize("method,batch", [("ETD35", 5), ("ETD4", 301), ("IF45DP", 2)])
+def test_k4_x2_pair_equals_plain_pair(rk, method, batch, monkeypatch):
+    p = problems.nls(8192, batch=batch, seed=batch, half_width=20.0)
+    plain, _ = _stage_outputs(rk, method, p, monkeypatch, pt=False)
+    monkeypatch.setenv("RKS_K4_X2", "1")
+    x2, _ = _stage_outputs(rk, method, p, monkeypatch, pt=True)
+    for a, b in zip(x2, plain):
+        assert rel(a, b) < 1e-14
