@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -13,6 +14,9 @@
 using namespace rks;
 
 static thread_local char g_err[512] = "";
+// per-device caches of function attributes / occupancy answers (a process may drive several GPUs)
+constexpr int MAX_DEVICES = 64;
+static std::mutex g_attr_mutex;
 
 static int fail(int code, const char* fmt, const char* detail = "") {
     snprintf(g_err, sizeof(g_err), fmt, detail);
@@ -191,6 +195,14 @@ static cudaError_t prepare_nl_small(int model) {
     }
 }
 
+// frees a partially built handle when a creation function returns early (CUDA_TRY)
+template <class T, void (*DESTROY)(T*)>
+struct HandleGuard {
+    T* h;
+    ~HandleGuard() { if (h) DESTROY(h); }
+    void release() { h = nullptr; }
+};
+
 extern "C" int rks_abi_version(void) { return RKS_ABI_VERSION; }
 extern "C" const char* rks_last_error(void) { return g_err; }
 
@@ -243,6 +255,7 @@ extern "C" int rks_plan_create(rks_plan** out, int method, int64_t batch, int64_
 
     rks_plan* p = new (std::nothrow) rks_plan();
     if (!p) return fail(RKS_ERR_ARG, "out of host memory");
+    HandleGuard<rks_plan, rks_plan_destroy> guard{p};
     memset(&p->d, 0, sizeof(DevPlan));
     p->lay = L;
     p->ws = (unsigned char*)workspace;
@@ -287,6 +300,7 @@ extern "C" int rks_plan_create(rks_plan** out, int method, int64_t batch, int64_
     begin_kernel<<<1, 1, 0, stream>>>(d.ctrl, b);
     p->launches += 2;
     CUDA_TRY(cudaGetLastError());
+    guard.release();
     *out = p;
     return RKS_OK;
 }
@@ -359,6 +373,7 @@ extern "C" int rks_plan_create_independent(rks_plan** out, int method, int64_t b
     if (workspace_bytes < L.total) return fail(RKS_ERR_WORKSPACE, "workspace too small");
     rks_plan* p = new (std::nothrow) rks_plan();
     if (!p) return fail(RKS_ERR_ARG, "out of host memory");
+    HandleGuard<rks_plan, rks_plan_destroy> guard{p};
     memset(&p->d, 0, sizeof(DevPlan));
     memset(&p->lay, 0, sizeof(Layout));
     p->ws = (unsigned char*)workspace;
@@ -421,6 +436,7 @@ extern "C" int rks_plan_create_independent(rks_plan** out, int method, int64_t b
     begin_multi_kernel<<<g, 128, 0, stream>>>(p->multi_dev, (int)batch, b);
     p->launches += 2;
     CUDA_TRY(cudaGetLastError());
+    guard.release();
     *out = p;
     return RKS_OK;
 }
@@ -676,13 +692,20 @@ static int launch_stage_m(rks_plan* p, int s, cudaStream_t stream) {
 template <int M, int S, typename CT, int R1>
 static void launch_stage_pre_r(rks_plan* p, cudaStream_t stream) {
     using C = PreCfg<M, S, CT, R1>;
-    // once per instantiation: opt in to the dynamic shared memory and ask how many CTAs an SM holds
-    static int resident = 0;
-    if (!resident) {
-        cudaFuncSetAttribute(stage_pre_kernel<M, S, CT, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, stage_pre_kernel<M, S, CT, R1>, PRE_THREADS, C::SMEM);
-        resident = nb > 0 ? nb : 1;
+    // once per instantiation AND device (function attributes are per device): opt in to the dynamic shared
+    // memory and ask how many CTAs an SM holds
+    static int resident_dev[MAX_DEVICES] = {0};
+    int resident;
+    {
+        std::lock_guard<std::mutex> lock(g_attr_mutex);
+        int& slot = resident_dev[p->device % MAX_DEVICES];
+        if (!slot) {
+            cudaFuncSetAttribute(stage_pre_kernel<M, S, CT, R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, stage_pre_kernel<M, S, CT, R1>, PRE_THREADS, C::SMEM);
+            slot = nb > 0 ? nb : 1;
+        }
+        resident = slot;
     }
     const DevPlan& d = p->d;
     // persistent: column blocks x row groups fill the resident slots once; every CTA walks down the batch
@@ -955,14 +978,20 @@ static void launch_norm_t(rks_plan* p, int fuse, cudaStream_t stream) {
     const long long ncols = d.lin_full ? d.batch * d.n_c : d.n_c;
     const long long nrows = d.lin_full ? 1 : d.batch;
     // one wave of resident 128-thread CTAs (a partial second wave costs as much as a full one)
-    static int per_sm = 0;
-    if (!per_sm) {
-        int full = 0, bcast = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&full, norm_kernel<M, CT, true>, 128, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bcast, norm_kernel<M, CT, false>, 128, 0);
-        per_sm = full < bcast ? full : bcast;
-        if (per_sm < 1) per_sm = 1;
-        if (per_sm > 8) per_sm = 8;
+    static int per_sm_dev[MAX_DEVICES] = {0};
+    int per_sm;
+    {
+        std::lock_guard<std::mutex> lock(g_attr_mutex);
+        int& slot = per_sm_dev[p->device % MAX_DEVICES];
+        if (!slot) {
+            int full = 0, bcast = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&full, norm_kernel<M, CT, true>, 128, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bcast, norm_kernel<M, CT, false>, 128, 0);
+            slot = full < bcast ? full : bcast;
+            if (slot < 1) slot = 1;
+            if (slot > 8) slot = 8;
+        }
+        per_sm = slot;
     }
     const long long target = (long long)p->sm_count * per_sm;
     long long gx = (ncols + 127) / 128;
@@ -1194,7 +1223,7 @@ extern "C" int rks_read_log(rks_plan* p, rks_trial_rec* out, int first, int coun
 // ---------------------------------------------------------------------------------------
 struct rks_rows {
     rks_plan plan;            // only d (model fields), sm_count and the launch shape are used
-    void* dev_mem;
+    void* dev_mem = nullptr;
 };
 
 extern "C" int rks_rows_create(rks_rows** out, int model, int64_t n, const double* kx, double p0, void* stream_v) {
@@ -1206,6 +1235,7 @@ extern "C" int rks_rows_create(rks_rows** out, int model, int64_t n, const doubl
     cudaStream_t stream = (cudaStream_t)stream_v;
     rks_rows* r = new (std::nothrow) rks_rows();
     if (!r) return fail(RKS_ERR_ARG, "out of host memory");
+    HandleGuard<rks_rows, rks_rows_destroy> guard{r};
     rks_plan* p = &r->plan;
     memset(&p->d, 0, sizeof(DevPlan));
     p->launches = 0; p->no_fuse = true; p->use_graph = false; p->pinned_raw = nullptr; p->pinned_log = nullptr;
@@ -1227,8 +1257,9 @@ extern "C" int rks_rows_create(rks_rows** out, int model, int64_t n, const doubl
     d.log2n = log2n;
     twiddle_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((cplx*)w, (int)n);
     if (kx) CUDA_TRY(cudaMemcpyAsync(w + tw_b + twf_b, kx, sizeof(double) * (size_t)n_c, cudaMemcpyDeviceToDevice, stream));
-    if (int rc = prepare_nl_launch(p, model, n, (cplx*)(w + tw_b), stream)) { cudaFree(r->dev_mem); delete r; return rc; }
+    if (int rc = prepare_nl_launch(p, model, n, (cplx*)(w + tw_b), stream)) return rc;
     CUDA_TRY(cudaGetLastError());
+    guard.release();
     *out = r;
     return RKS_OK;
 }
@@ -1239,13 +1270,16 @@ extern "C" int rks_rows_apply(rks_rows* r, const void* in, void* out, int64_t ba
     p->d.batch = batch;
     p->d.U[0] = (cplx*)in;
     p->d.NL[1] = (cplx*)out;
-    // generic kernel: rows per CTA must not exceed the batch
+    // generic kernel: rows per CTA must not exceed THIS batch (the handle keeps its full launch shape)
+    const int rpc0 = p->nl_rows_per_cta, thr0 = p->nl_threads;
+    const size_t sm0 = p->nl_smem;
     if (!p->nl_fast) {
         while (p->nl_rows_per_cta > 1 && p->nl_rows_per_cta > batch) {
             p->nl_rows_per_cta >>= 1; p->nl_threads >>= 1; p->nl_smem >>= 1;
         }
     }
     launch_nl(p, 1, 1, (cudaStream_t)stream);
+    p->nl_rows_per_cta = rpc0; p->nl_threads = thr0; p->nl_smem = sm0;
     CUDA_TRY(cudaGetLastError());
     return RKS_OK;
 }
@@ -1260,9 +1294,9 @@ extern "C" void rks_rows_destroy(rks_rows* r) {
 // strided-axis transforms of N-D grids (fft_axis.cuh)
 // ---------------------------------------------------------------------------------------
 struct rks_axis {
-    cplx* tw;
-    long long n;
-    int sm_count;
+    cplx* tw = nullptr;
+    long long n = 0;
+    int sm_count = 0;
 };
 
 template <int N>
@@ -1291,6 +1325,7 @@ extern "C" int rks_axis_create(rks_axis** out, int64_t n, void* stream_v) {
     if (n < 16 || n > 4096 || (n & (n - 1))) return fail(RKS_ERR_UNSUPPORTED, "axis length must be a power of two in [16, 4096]");
     rks_axis* a = new (std::nothrow) rks_axis();
     if (!a) return fail(RKS_ERR_ARG, "out of host memory");
+    HandleGuard<rks_axis, rks_axis_destroy> guard{a};
     a->n = n;
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -1309,8 +1344,9 @@ extern "C" int rks_axis_create(rks_axis** out, int64_t n, void* stream_v) {
         case 2048: e = axis_prepare<2048>(); break;
         default: e = axis_prepare<4096>(); break;
     }
-    if (e != cudaSuccess) { cudaFree(a->tw); delete a; return fail(RKS_ERR_CUDA, "axis kernel attributes: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) return fail(RKS_ERR_CUDA, "axis kernel attributes: %s", cudaGetErrorString(e));
     CUDA_TRY(cudaGetLastError());
+    guard.release();
     *out = a;
     return RKS_OK;
 }

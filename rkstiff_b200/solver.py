@@ -89,6 +89,13 @@ class BaseSolver(ABC):
     def _get_engine(self, u: torch.Tensor) -> Engine:
         key = tuple(u.shape)
         eng = self._engines.get(key)
+        if (eng is None and self._S is None and self.lin_op.dim() == 2 and u.dim() == 1
+                and self.lin_op.shape[0] == self.lin_op.shape[1] == u.shape[0]):
+            # the reference reads ANY 2-D lin_op as a dense matrix (solver.py:129-135); here a 2-D lin_op is a
+            # diagonal operator on a 2-D grid unless diagonalize=True was given
+            raise ValueError("lin_op is a square matrix and u a vector: dense operators need diagonalize=True "
+                             "(IF34 / ETD34 / ETD35 only); without it a 2-D lin_op is an elementwise operator "
+                             "on a 2-D grid and u must have the same trailing shape")
         if eng is None:
             eng = Engine(self.METHOD, self.lin_op if self._eig is None else self._eig, u.shape, self._rks_config(),
                          fused=self._fused(), group=self._group)

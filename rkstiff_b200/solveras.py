@@ -10,6 +10,7 @@ once per chunk of trials, not once per trial; with a torch ``nl_func`` it syncs 
 from __future__ import annotations
 
 import math
+import weakref
 from typing import Callable, List, Optional, Tuple, Union
 
 import torch
@@ -201,7 +202,8 @@ class BaseSolverAS(BaseSolver):
         else:
             eng.set_h(h)
             tag = self._last_out
-            if not (tag is not None and tag[0] is eng and tag[1] == u.data_ptr() and tag[2] == u._version):
+            # identity of the tensor object (a weak reference: a recycled address can never match), unmodified since
+            if not (tag is not None and tag[0] is eng and tag[1]() is u and tag[2] == u._version):
                 eng.set_u(self._to_eig(u))
         nl = self._callable()
         while True:
@@ -214,7 +216,7 @@ class BaseSolverAS(BaseSolver):
         self._accept = True
         self._h_coeff = c.h_coeff
         out = self._to_phys(eng.get_u())
-        self._last_out = (eng, out.data_ptr(), out._version)
+        self._last_out = (eng, weakref.ref(out), out._version)
         self.logger.debug("Step accepted, returning h=%s, h_suggest=%s", c.h_last, c.h)
         return out, c.h_last, c.h
 

@@ -1,6 +1,7 @@
 """BaseSolverCS: constant-step driver (rkstiff/solvercs.py:31-279) on the CUDA engine."""
 from __future__ import annotations
 
+import weakref
 from typing import Callable, Union
 
 import torch
@@ -36,12 +37,12 @@ class BaseSolverCS(BaseSolver):
     def _load_state(self, eng, u: torch.Tensor) -> None:
         """Copy u into the plan unless it is the (unmodified) tensor the last step returned."""
         tag = self._last_out
-        if tag is not None and tag[0] is eng and tag[1] == u.data_ptr() and tag[2] == u._version:
+        if tag is not None and tag[0] is eng and tag[1]() is u and tag[2] == u._version:
             return
         eng.set_u(u)
 
     def _remember(self, eng, out: torch.Tensor) -> None:
-        self._last_out = (eng, out.data_ptr(), out._version)
+        self._last_out = (eng, weakref.ref(out), out._version)
 
     def _update_stages(self, u: torch.Tensor, h: float) -> torch.Tensor:
         eng = self._get_engine(u)

@@ -1,0 +1,12 @@
+#!/bin/bash
+# round 2, call 1: measure the two opt-in K4 variants that round 1 left unmeasured, A/B against the defaults
+mkdir -p gpurun_out; O=gpurun_out; T=r02a
+echo "== opt-in tests"; RKS_TEST_RFFT_HALF=1 RKS_TEST_K4_X2=1 timeout 400 python -m pytest tests -m gpu -q -k "rfft_half or k4_x2" > $O/${T}_optin_tests.log 2>&1; echo "rc=$?"; tail -5 $O/${T}_optin_tests.log
+echo "== bench_nl default"; timeout 200 python tools/bench_nl.py > $O/${T}_bench_nl_default.txt 2>&1; cat $O/${T}_bench_nl_default.txt
+echo "== bench_nl RFFT_HALF"; RKS_RFFT_HALF=1 timeout 200 python tools/bench_nl.py > $O/${T}_bench_nl_rffthalf.txt 2>&1; cat $O/${T}_bench_nl_rffthalf.txt
+echo "== cfg3 default"; timeout 200 python bench.py --workload cfg3 --no-cpu-baseline > $O/${T}_bench_cfg3.json 2> $O/${T}_bench_cfg3.err; echo "rc=$?"
+echo "== cfg3 RFFT_HALF"; RKS_RFFT_HALF=1 timeout 200 python bench.py --workload cfg3 --no-cpu-baseline > $O/${T}_bench_cfg3_rffthalf.json 2> $O/${T}_bench_cfg3_rffthalf.err; echo "rc=$?"
+echo "== cfg2 default"; timeout 200 python bench.py --no-cpu-baseline > $O/${T}_bench_cfg2.json 2> $O/${T}_bench_cfg2.err; echo "rc=$?"
+echo "== cfg2 K4_X2"; RKS_K4_X2=1 timeout 200 python bench.py --no-cpu-baseline > $O/${T}_bench_cfg2_x2.json 2> $O/${T}_bench_cfg2_x2.err; echo "rc=$?"
+python tools/show_bench.py $O/${T}_bench_cfg3.json $O/${T}_bench_cfg3_rffthalf.json $O/${T}_bench_cfg2.json $O/${T}_bench_cfg2_x2.json 2>/dev/null
+tail -3 $O/${T}_*.err
