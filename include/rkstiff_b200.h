@@ -136,6 +136,27 @@ int rks_plan_create(rks_plan** out, int method, int64_t batch, int64_t n_c, cons
                     size_t workspace_bytes, void* stream);
 void rks_plan_destroy(rks_plan* plan);
 
+/* Large grids ("lin_op shaped like u" on 2-D/3-D spectral grids, demos/nls.ipynb:496-511): a Fourier grid has far
+ * fewer DISTINCT lin_op values than modes (|k|^2 takes <= 3 (n/2)^2 values on n^3 points), and the reference's
+ * update_coeffs (etd35.py:157-288, if45dp.py:183-238) is a pure function of z = h * lin_op.  These two plan
+ * flavours therefore never build full-size coefficient arrays; every other call takes them unchanged.
+ *
+ * indexed: `values` = the n_values distinct lin_op entries (device), `index` = n_c int32 (device) mapping each
+ *   mode to its entry.  K2 builds one coefficient record per distinct value, K1/K3 gather it through L2.
+ *   Any method; batch <= 65535 trajectories share lin_op. */
+size_t rks_workspace_bytes_indexed(int method, int64_t batch, int64_t n_c, int64_t n_values, int lin_is_complex);
+int rks_plan_create_indexed(rks_plan** out, int method, int64_t batch, int64_t n_c, const void* values,
+                            int lin_is_complex, int64_t n_values, const int32_t* index, const rks_config* cfg,
+                            void* workspace, size_t workspace_bytes, void* stream);
+/* separable (IF4 / IF34 / IF45DP): lin_op[i0, i1(, i2)] = sum_d a_d[i_d] on a grid of `dims` (nd = 2 or 3, last
+ *   axis contiguous).  Every IF coefficient is rational * h * exp(q z) (if4.py:72-83, if45dp.py:204-237), so
+ *   K2 builds the per-axis tables exp(q h a_d) (sum(dims) entries per exponent) and K1/K3 multiply them.
+ *   `axis_terms` = a_0 | a_1 (| a_2) concatenated (device), the constant term folded into a_0. */
+size_t rks_workspace_bytes_separable(int method, int64_t batch, int nd, const int64_t* dims, int lin_is_complex);
+int rks_plan_create_separable(rks_plan** out, int method, int64_t batch, int nd, const int64_t* dims,
+                              const void* axis_terms, int lin_is_complex, const rks_config* cfg, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 /* Independent-dt ensemble (BASELINE cfg 2b): `batch` trajectories of one 1-D problem, each with its
  * own controller, dt, coefficient arrays and buffer roles -- B separate reference solvers
  * (solveras.py:279-325 run once per trajectory) stepped by one set of launches (gridDim.z = row).

@@ -60,6 +60,12 @@ def _load():
         "rks_plan_create": (c_int, [POINTER(P), c_int, c_int64, c_int64, P, c_int, c_int64, POINTER(RksConfig), P,
                                     c_size_t, P]),
         "rks_plan_destroy": (None, [P]),
+        "rks_workspace_bytes_indexed": (c_size_t, [c_int, c_int64, c_int64, c_int64, c_int]),
+        "rks_plan_create_indexed": (c_int, [POINTER(P), c_int, c_int64, c_int64, P, c_int, c_int64, P,
+                                            POINTER(RksConfig), P, c_size_t, P]),
+        "rks_workspace_bytes_separable": (c_size_t, [c_int, c_int64, c_int, POINTER(c_int64), c_int]),
+        "rks_plan_create_separable": (c_int, [POINTER(P), c_int, c_int64, c_int, POINTER(c_int64), P, c_int,
+                                              POINTER(RksConfig), P, c_size_t, P]),
         "rks_workspace_bytes_independent": (c_size_t, [c_int, c_int64, c_int64, c_int]),
         "rks_plan_create_independent": (c_int, [POINTER(P), c_int, c_int64, c_int64, P, c_int, POINTER(RksConfig), P,
                                                 c_size_t, P]),

@@ -20,12 +20,61 @@ def _stream(device) -> c_void_p:
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _bits(x: torch.Tensor) -> torch.Tensor:
+    return x.contiguous().view(torch.int64)
+
+
+def distinct_values(lin: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The distinct entries of ``lin`` (by bit pattern) and, per element, the int32 index of its entry.
+    A Fourier-grid operator has few of them (|k|^2 takes <= 3 (n/2)^2 values on n^3 points)."""
+    flat = lin.reshape(-1)
+    if flat.dtype == torch.complex128:
+        ur, ir = torch.unique(_bits(flat.real), return_inverse=True)
+        ui, ii = torch.unique(_bits(flat.imag), return_inverse=True)
+        key, inv = torch.unique(ir * ui.numel() + ii, return_inverse=True)
+        del ir, ii
+        vals = torch.complex(ur[key // ui.numel()].view(torch.float64), ui[key % ui.numel()].view(torch.float64))
+    else:
+        ub, inv = torch.unique(_bits(flat), return_inverse=True)
+        vals = ub.view(torch.float64)
+    return vals.contiguous(), inv.to(torch.int32).contiguous()
+
+
+def separable_terms(lin: torch.Tensor) -> Optional[torch.Tensor]:
+    """``lin[i0, i1(, i2)] == a_0[i0] + a_1[i1] (+ a_2[i2])`` up to rounding?  Returns the concatenated per-axis
+    terms (the constant folded into a_0) or None.  Fourier-grid operators are of this form: c - eps |k|^2."""
+    nd = lin.dim()
+    if nd not in (2, 3):
+        return None
+    origin = lin[(0,) * nd]
+    terms, recon, mag = [], None, None
+    for d in range(nd):
+        idx = [0] * nd
+        idx[d] = slice(None)
+        a = lin[tuple(idx)].clone()
+        if d > 0:
+            a = a - origin
+        shape = [1] * nd
+        shape[d] = lin.shape[d]
+        recon = a.reshape(shape) if recon is None else recon + a.reshape(shape)
+        mag = a.abs().reshape(shape) if mag is None else mag + a.abs().reshape(shape)
+        terms.append(a)
+    eps = torch.finfo(torch.float64).eps
+    ok = bool(((recon - lin).abs() <= 4 * eps * (mag + lin.abs())).all())
+    del recon, mag
+    return torch.cat(terms).contiguous() if ok else None
+
+
 class Engine:
     """One plan: owns the workspace tensor and exposes the strategy-object operations
     (update_coeffs / n1_init / update_stages of the reference) plus the device controller."""
 
+    #: grids with at least this many modes per trajectory get their coefficients by distinct value / per axis
+    #: instead of as full-size arrays (coef_storage="auto")
+    DEDUPE_MIN_MODES = 1 << 16
+
     def __init__(self, method: str, lin_op: torch.Tensor, u_shape: torch.Size, cfg: RksConfig,
-                 fused=None, group=None, independent: bool = False):
+                 fused=None, group=None, independent: bool = False, coef_storage: str = "auto"):
         if not lin_op.is_cuda:
             raise ValueError("lin_op must be a CUDA tensor: rkstiff_b200 has no CPU path")
         if lin_op.dtype not in (torch.float64, torch.complex128):
@@ -68,10 +117,30 @@ class Engine:
                 nbytes = lib.rks_workspace_bytes(self.mid, self.batch, self.n_c, self.n_c, int(is_cx))
             if nbytes == 0:
                 raise ValueError("invalid plan geometry")
+            self.coef_storage = "arrays"
+            extra = self._coef_strategy(lin, coef_storage) if not self.independent else None
+            if extra is not None and extra[0] == "separable":
+                dims = (ctypes.c_int64 * nd)(*[int(d) for d in lin.shape])
+                nbytes = lib.rks_workspace_bytes_separable(self.mid, self.batch, nd, dims, int(is_cx))
+            elif extra is not None:
+                nbytes = lib.rks_workspace_bytes_indexed(self.mid, self.batch, self.n_c, extra[1].numel(), int(is_cx))
+            if nbytes == 0:
+                raise ValueError("invalid plan geometry")
             self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             self.plan = c_void_p()
             self._cfg = cfg
-            if self.independent:
+            if extra is not None and extra[0] == "separable":
+                check(lib.rks_plan_create_separable(byref(self.plan), self.mid, self.batch, nd, dims,
+                                                    c_void_p(extra[1].data_ptr()), int(is_cx), byref(cfg),
+                                                    c_void_p(self.ws.data_ptr()), nbytes, _stream(self.device)))
+                self.coef_storage = "separable"
+            elif extra is not None:
+                check(lib.rks_plan_create_indexed(byref(self.plan), self.mid, self.batch, self.n_c,
+                                                  c_void_p(extra[1].data_ptr()), int(is_cx), extra[1].numel(),
+                                                  c_void_p(extra[2].data_ptr()), byref(cfg),
+                                                  c_void_p(self.ws.data_ptr()), nbytes, _stream(self.device)))
+                self.coef_storage = "indexed"
+            elif self.independent:
                 check(lib.rks_plan_create_independent(byref(self.plan), self.mid, self.batch, self.n_c,
                                                       c_void_p(lin.data_ptr()), int(is_cx), byref(cfg),
                                                       c_void_p(self.ws.data_ptr()), nbytes, _stream(self.device)))
@@ -96,6 +165,29 @@ class Engine:
         #: error controller (rks_norm_override); None for diagonal operators
         self.norm_map: Optional[Callable] = None
         self._norm_keep = None
+
+    def _coef_strategy(self, lin: torch.Tensor, want: str):
+        """How the coefficient arrays of this plan are stored: None = one entry per mode (1-D rows:
+        shared by the batch, a few KB), ("separable", terms) for IF methods whose N-D lin_op is a sum of per-axis
+        terms, ("indexed", values, index) when lin_op has few distinct values."""
+        if want not in ("auto", "arrays", "indexed", "separable"):
+            raise ValueError("coef_storage must be 'auto', 'arrays', 'indexed' or 'separable'")
+        if want == "arrays" or (want == "auto" and (lin.dim() < 2 or self.n_c < self.DEDUPE_MIN_MODES)):
+            return None
+        if want in ("auto", "separable") and self.method in ("IF4", "IF34", "IF45DP") and lin.dim() in (2, 3):
+            terms = separable_terms(lin)
+            if terms is not None:
+                return ("separable", terms)
+            if want == "separable":
+                raise ValueError("lin_op is not a sum of per-axis terms")
+        elif want == "separable":
+            raise ValueError("separable coefficient tables need an IF method and a 2-D or 3-D lin_op")
+        if self.batch > 65535:
+            return None
+        values, index = distinct_values(lin)
+        if want == "auto" and values.numel() * 4 > self.n_c:
+            return None                                   # too few repeats to pay for the gather
+        return ("indexed", values, index)
 
     def __del__(self):
         try:

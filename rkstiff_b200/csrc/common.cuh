@@ -80,6 +80,8 @@ RKS_HD double cexp_t(double z) { return exp(z); }
 RKS_HD cplx cexp_t(cplx z) { return cexp(z); }
 RKS_HD cplx cmul(double a, cplx b) { return mk(a * b.x, a * b.y); }
 RKS_HD cplx cmul(cplx a, cplx b) { return a * b; }
+RKS_HD double cmul1(double a, double b) { return a * b; }
+RKS_HD cplx cmul1(cplx a, cplx b) { return a * b; }
 RKS_HD double scale(double s, double a) { return s * a; }
 RKS_HD cplx scale(double s, cplx a) { return mk(s * a.x, s * a.y); }
 
@@ -170,7 +172,16 @@ struct DevPlan {
     long long batch, n_c, lin_elems, n;
     double model_p0;   // c (u u_x models) or gamma (NLS)
     int method, lin_complex, lin_full, model, log2n;
+    // --- coefficient storage of large grids ("lin_op shaped like u" with many modes)
+    int coef_mode;     // CM_COLUMN / CM_FLAT: `coef` = ncoef arrays of lin_elems entries (set by lin_full);
+                       // CM_INDEXED: `coef` = one grouped record per DISTINCT lin_op value, `cidx` maps a mode to it;
+                       // CM_SEPARABLE (IF methods, lin_op = sum of per-axis terms): `coef` = per-axis exponential
+                       // tables [nq][sep_ntab], coefficient = cscale[slot] * prod_d table[q][off_d + i_d]
+    const int* cidx;   // CM_INDEXED: n_c indices into the table of distinct values
+    const double* cscale;   // CM_SEPARABLE: the rational * h factor of every coefficient slot
+    int sep_nd, sep_dims[3], sep_ntab;   // CM_SEPARABLE: spectral grid dims (last = contiguous axis), sum of them
 };
+enum : int { CM_COLUMN = 0, CM_FLAT = 1, CM_INDEXED = 2, CM_SEPARABLE = 3 };
 
 // select the physical N buffer for logical index j under the FSAL role swap
 RKS_HD int nl_phys(int method, int j, int n_sel) {

@@ -152,8 +152,29 @@ RKS_D cplx warp_sum(cplx v) {
     return v;
 }
 
-template <int FAM, typename LT>
+// where a mode's coefficients go: ncoef arrays of lin_elems entries (GROUPED = false), or one grouped record
+// per distinct lin_op value (CM_INDEXED, stages.cuh group_*)
+template <int M, typename CT, bool GROUPED>
+RKS_D void emit_coefs(const DevPlan& p, long long i, const CT* arr) {
+    constexpr int NC = method_ncoef(M), S = method_stages(M);
+    CT* out = (CT*)p.coef;
+    if (!GROUPED) {
+#pragma unroll
+        for (int s = 0; s < NC; ++s) out[s * p.lin_elems + i] = arr[s];
+        return;
+    }
+    CT* rec = out + i * record_elems<CT>(M);
+#pragma unroll
+    for (int g = 1; g <= S + 1; ++g) {
+#pragma unroll
+        for (int s = 0; s < NC; ++s)
+            if (group_mask(M, g) & (1u << s)) rec[group_off<CT>(M, g) + group_pos(group_mask(M, g), s)] = arr[s];
+    }
+}
+
+template <int M, typename LT, bool GROUPED>
 RKS_D void coef_kernel_body(const DevPlan& p, int force) {
+    constexpr int FAM = (M == M_IF4 || M == M_IF34) ? 0 : (M == M_ETD4 || M == M_ETD34) ? 1 : (M == M_ETD5 || M == M_ETD35) ? 2 : 3;
     Ctrl* c = p.ctrl;
     const double h = c->h;
     if (!force) {
@@ -162,30 +183,27 @@ RKS_D void coef_kernel_body(const DevPlan& p, int force) {
     }
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < p.lin_elems;
-    const long long stride = p.lin_elems;
     if (i == 0) atomicAdd((unsigned long long*)&c->coeff_updates, 1ull);
 
     if (FAM == 0) {
         if (!valid) return;
-        LT* out = (LT*)p.coef;
+        LT arr[ifc::COUNT];
         const LT z = scale(h, load_lin<LT>(p.lin, i));
-        out[ifc::E * stride + i] = cexp_t(z);
-        out[ifc::E2 * stride + i] = cexp_t(z / 2.0);
+        arr[ifc::E] = cexp_t(z);
+        arr[ifc::E2] = cexp_t(z / 2.0);
+        emit_coefs<M, LT, GROUPED>(p, i, arr);
         return;
     }
     if (FAM == 3) {
         if (!valid) return;
-        LT* out = (LT*)p.coef;
         LT arr[dp::COUNT];
         tableau_if45dp<LT>(scale(h, load_lin<LT>(p.lin, i)), h, c->r4_fix, arr);
-#pragma unroll
-        for (int s = 0; s < dp::COUNT; ++s) out[s * stride + i] = arr[s];
+        emit_coefs<M, LT, GROUPED>(p, i, arr);
         return;
     }
     if (FAM == 1 || FAM == 2) {
         // ETD strategies cast lin_op to complex128 (etd35.py:124)
         constexpr bool FIVE = (FAM == 2);
-        cplx* out = (cplx*)p.coef;
         cplx z = mk(0.0, 0.0);
         if (valid) {
             if (p.lin_complex) z = scale(h, ldg((const cplx*)p.lin + i));
@@ -227,26 +245,48 @@ RKS_D void coef_kernel_body(const DevPlan& p, int force) {
             arr[e5::E34] = ez.t;
             arr[e5::E] = ez.f;
             tableau_etd5(ps, arr);
-#pragma unroll
-            for (int s = 0; s < e5::COUNT; ++s) stg(out + s * stride + i, arr[s]);
+            emit_coefs<M, cplx, GROUPED>(p, i, arr);
         } else {
             cplx arr[kro::COUNT];
             arr[kro::E] = ez.f;
             arr[kro::E2] = ez.h;
             tableau_krogstad(ps, arr);
-#pragma unroll
-            for (int s = 0; s < kro::COUNT; ++s) stg(out + s * stride + i, arr[s]);
+            emit_coefs<M, cplx, GROUPED>(p, i, arr);
         }
     }
 }
 // 5 CTAs/SM (96 registers, a few spills): the exp / division chains are latency bound, occupancy pays
 // (256^3 ETD35 coefficient set: 2.09 ms at 3 CTAs/SM, 1.55 ms at 5, 1.76 ms at 6)
-template <int FAM, typename LT>
-__global__ void __launch_bounds__(128, 5) coef_kernel(const __grid_constant__ DevPlan p, int force) { coef_kernel_body<FAM, LT>(p, force); }
+template <int M, typename LT, bool GROUPED>
+__global__ void __launch_bounds__(128, 5) coef_kernel(const __grid_constant__ DevPlan p, int force) { coef_kernel_body<M, LT, GROUPED>(p, force); }
 // one plan per blockIdx.z: ensembles whose trajectories keep their own dt (rks_multi_*)
-template <int FAM, typename LT>
-__global__ void __launch_bounds__(128, 5) coef_kernel_multi(const DevPlan* plans, int force) { coef_kernel_body<FAM, LT>(plans[blockIdx.z], force); }
+template <int M, typename LT>
+__global__ void __launch_bounds__(128, 5) coef_kernel_multi(const DevPlan* plans, int force) { coef_kernel_body<M, LT, false>(plans[blockIdx.z], force); }
 
+// K2 for CM_SEPARABLE plans (IF methods, lin_op = sum of per-axis terms a_d): the per-axis tables
+// exp(q h a_d[i]) for every exponent id q of the method, and the rational * h factor of every slot.
+// `lin` holds the concatenated axis terms (sep_ntab values); p.coef = [nq][sep_ntab].
+template <int M, typename LT>
+__global__ void __launch_bounds__(128) coef_sep_kernel(const __grid_constant__ DevPlan p, int force) {
+    constexpr int NQ = sep_nq(M), NC = method_ncoef(M);
+    Ctrl* c = p.ctrl;
+    const double h = c->h;
+    if (!force) {
+        if (c->status != ST_RUNNING) return;
+        if (h == c->h_coeff) return;
+    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        atomicAdd((unsigned long long*)&c->coeff_updates, 1ull);
+        double* cs = const_cast<double*>(p.cscale);
+        for (int s = 0; s < NC; ++s) cs[s] = sep_scale(M, s, h, c->r4_fix);
+    }
+    if (i >= p.sep_ntab) return;
+    LT* out = (LT*)p.coef;
+    const LT z = scale(h, load_lin<LT>(p.lin, i));
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) out[q * p.sep_ntab + i] = sep_exp<LT>(M, q, z);
+}
 
 // ---------------------------------------------------------------------------------------
 // K1: stage combine.  !FULL: block (32, 8), thread = one mode column x R batch rows, the
@@ -255,7 +295,42 @@ __global__ void __launch_bounds__(128, 5) coef_kernel_multi(const DevPlan* plans
 // ---------------------------------------------------------------------------------------
 constexpr int STAGE_R = 2;
 
-template <int M, int S, typename CT, bool FULL>
+// row index of a separable plan (rows = batch x the outer grid axes) -> product over the outer axes of the
+// exponential tables, for every exponent id in QMASK
+template <int M, typename CT, unsigned QMASK>
+RKS_D void sep_row_factors(const DevPlan& p, long long row, CT* aq) {
+    constexpr int NQ = sep_nq(M);
+    const CT* __restrict__ tab = (const CT*)p.coef;
+    const int ntab = p.sep_ntab;
+    int i0, i1 = 0;
+    if (p.sep_nd == 2) {
+        i0 = (int)(row % p.sep_dims[0]);
+    } else {
+        i1 = (int)(row % p.sep_dims[1]);
+        i0 = (int)((row / p.sep_dims[1]) % p.sep_dims[0]);
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        if (!(QMASK & (1u << q))) continue;
+        CT v = ldcoef(tab + q * ntab + i0);
+        if (p.sep_nd == 3) v = cmul1(v, ldcoef(tab + q * ntab + p.sep_dims[0] + i1));
+        aq[q] = v;
+    }
+}
+// the coefficient slots in CMASK from the row factors aq and the column factors bq
+template <int M, typename CT, unsigned CMASK>
+RKS_D void sep_coefs(const DevPlan& p, const CT* aq, const CT* bq, CT* cv) {
+    constexpr int NC = method_ncoef(M);
+#pragma unroll
+    for (int s = 0; s < NC; ++s) {
+        if (!(CMASK & (1u << s))) continue;
+        const CT e = cmul1(aq[sep_q(M, s)], bq[sep_q(M, s)]);
+        const bool pure = M != M_IF45DP || s <= dp::E;                 // the stage exponentials themselves
+        cv[s] = pure ? e : scale(__ldg(p.cscale + s), e);
+    }
+}
+
+template <int M, int S, typename CT, int CM>
 RKS_D void stage_kernel_body(const DevPlan& p) {
     constexpr int R = STAGE_R;
     constexpr bool ADAPT = method_adaptive(M);
@@ -263,7 +338,9 @@ RKS_D void stage_kernel_body(const DevPlan& p) {
     constexpr bool LAST = (S == SMAX);
     constexpr unsigned NMASK = stage_nl_mask(M, S);
     constexpr unsigned CMASK = stage_coef_mask(M, S);
-    constexpr int NC = method_ncoef(M);
+    constexpr unsigned QMASK = CM == CM_SEPARABLE ? sep_qmask(M, S) : 0u;
+    constexpr int NC = method_ncoef(M), NQ = sep_nq(M);
+    constexpr bool PER_ELEM = CM == CM_FLAT || CM == CM_INDEXED || CM == CM_SEPARABLE;   // coefficients differ per element of a thread
     const Ctrl* c = p.ctrl;
     int u_sel = 0, n_sel = 0;
     if (ADAPT) {
@@ -276,31 +353,59 @@ RKS_D void stage_kernel_body(const DevPlan& p) {
     const CT* __restrict__ coef = (const CT*)p.coef;
     const long long cstride = p.lin_elems;
 
-    long long didx[R], cidx[R];
+    long long didx[R], cidx[R], rowi[R];
     bool ok[R];
-    if (FULL) {
+    if (CM == CM_FLAT) {
         const long long total = p.batch * p.n_c;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const long long e = ((long long)blockIdx.x * R + r) * 256 + threadIdx.y * 32 + threadIdx.x;
             didx[r] = e; cidx[r] = e; ok[r] = e < total;
         }
+    } else if (CM == CM_INDEXED) {
+        // x: modes of one trajectory, y: trajectory; the mode's index selects the record of its lin_op value
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const long long e = ((long long)blockIdx.x * R + r) * 256 + threadIdx.y * 32 + threadIdx.x;
+            ok[r] = e < p.n_c;
+            didx[r] = (long long)blockIdx.y * p.n_c + e;
+            cidx[r] = ok[r] ? (long long)__ldg(p.cidx + e) : 0;
+        }
     } else {
+        // CM_COLUMN: (batch, n_c); CM_SEPARABLE: the same picture with rows = batch x outer grid axes, columns = last axis
+        const long long ncol = CM == CM_SEPARABLE ? p.sep_dims[p.sep_nd - 1] : p.n_c;
+        const long long nrow = CM == CM_SEPARABLE ? p.batch * (p.n_c / ncol) : p.batch;
         const long long col = (long long)blockIdx.x * 32 + threadIdx.x;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const long long row = ((long long)blockIdx.y * 8 + threadIdx.y) * R + r;
-            didx[r] = row * p.n_c + col; cidx[r] = col; ok[r] = (col < p.n_c) && (row < p.batch);
+            didx[r] = row * ncol + col; cidx[r] = col; rowi[r] = row; ok[r] = (col < ncol) && (row < nrow);
         }
     }
 
     // ---- loads (all issued before any use)
     CT cv[R][NC];
+    CT bq[NQ];
     cplx uv[R], nv[R][8];
+    if (CM == CM_SEPARABLE && ok[0]) {
+        const CT* __restrict__ tab = coef + (p.sep_ntab - p.sep_dims[p.sep_nd - 1]) + cidx[0];      // last axis' block of the table
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+            if (QMASK & (1u << q)) bq[q] = ldcoef(tab + q * p.sep_ntab);
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         if (!ok[r]) continue;
-        if (FULL || r == 0) {
+        if (CM == CM_SEPARABLE) {
+            CT aq[NQ];
+            sep_row_factors<M, CT, QMASK>(p, rowi[r], aq);
+            sep_coefs<M, CT, CMASK>(p, aq, bq, cv[r]);
+        } else if (CM == CM_INDEXED) {
+            const CT* __restrict__ rec = coef + cidx[r] * record_elems<CT>(M) + group_off<CT>(M, S);
+#pragma unroll
+            for (int s = 0; s < NC; ++s)
+                if (CMASK & (1u << s)) cv[r][s] = ldcoef(rec + group_pos(CMASK, s));
+        } else if (CM == CM_FLAT || r == 0) {
 #pragma unroll
             for (int s = 0; s < NC; ++s)
                 if (CMASK & (1u << s)) cv[r][s] = ldcoef(coef + s * cstride + cidx[r]);
@@ -315,7 +420,7 @@ RKS_D void stage_kernel_body(const DevPlan& p) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         if (!ok[r]) continue;
-        const CT* cr = FULL ? cv[r] : cv[0];
+        const CT* cr = PER_ELEM ? cv[r] : cv[0];
         const cplx k = stage_combine<M, S, CT>(uv[r], nv[r], cr, h);
         stg(out + didx[r], k);
         if (LAST && ADAPT) {
@@ -345,12 +450,12 @@ RKS_D void stage_kernel_body(const DevPlan& p) {
 }
 // Coefficients shared by the batch: three CTAs per SM (<= 85 registers; the six-stage methods' last stages otherwise
 // sit at 86-90 registers = two CTAs, where the IF45DP one ran at 0.90 of the roofline: 638 -> 563 us with three).
-// Full-size coefficient arrays need the registers (they would spill 100-150 bytes).
-template <int M, int S, typename CT, bool FULL>
-__global__ void __launch_bounds__(256, (FULL ? 1 : 3)) stage_kernel(const __grid_constant__ DevPlan p) { stage_kernel_body<M, S, CT, FULL>(p); }
+// Per-element coefficients (full-size arrays, gathered records, separable tables) need the registers.
+template <int M, int S, typename CT, int CM>
+__global__ void __launch_bounds__(256, (CM == CM_COLUMN ? 3 : 1)) stage_kernel(const __grid_constant__ DevPlan p) { stage_kernel_body<M, S, CT, CM>(p); }
 // one plan per blockIdx.z: ensembles whose trajectories keep their own dt (rks_multi_*)
-template <int M, int S, typename CT, bool FULL>
-__global__ void __launch_bounds__(256) stage_kernel_multi(const DevPlan* plans) { stage_kernel_body<M, S, CT, FULL>(plans[blockIdx.z]); }
+template <int M, int S, typename CT, int CM>
+__global__ void __launch_bounds__(256) stage_kernel_multi(const DevPlan* plans) { stage_kernel_body<M, S, CT, CM>(plans[blockIdx.z]); }
 
 
 // K1 for an intermediate stage whose value only feeds the fused NLS-type nonlinearity (fft_fast.cuh, "pre-
@@ -1073,11 +1178,13 @@ RKS_D double block_sum(double v, double* sh) {
     return t;     // valid in thread 0
 }
 
-template <int M, typename CT, bool FULL>
+template <int M, typename CT, int CM>
 RKS_D void norm_kernel_body(const DevPlan& p, int fuse_controller) {
     constexpr unsigned NMASK = err_nl_mask(M);
     constexpr unsigned CMASK = err_coef_mask(M);
-    constexpr int NC = method_ncoef(M);
+    constexpr unsigned QMASK = CM == CM_SEPARABLE ? sep_qmask(M, method_stages(M) + 1) : 0u;
+    constexpr int NC = method_ncoef(M), NQ = sep_nq(M);
+    constexpr bool FULL = CM == CM_FLAT;
     Ctrl* c = p.ctrl;
     if (c->status != ST_RUNNING) return;
     const int u_sel = c->u_sel, n_sel = c->n_sel;
@@ -1087,11 +1194,12 @@ RKS_D void norm_kernel_body(const DevPlan& p, int fuse_controller) {
     const cplx* __restrict__ un = p.norm_u ? p.norm_u : p.U[1 - u_sel];
     const CT* __restrict__ coef = (const CT*)p.coef;
     const long long cstride = p.lin_elems;
-    const long long ncols = FULL ? p.batch * p.n_c : p.n_c;
-    const long long nrows = FULL ? 1 : p.batch;
+    // columns x rows: (n_c, batch); flat: one long row; separable: (last grid axis, batch x outer axes)
+    const long long ncols = FULL ? p.batch * p.n_c : CM == CM_SEPARABLE ? p.sep_dims[p.sep_nd - 1] : p.n_c;
+    const long long nrows = FULL ? 1 : CM == CM_SEPARABLE ? p.batch * (p.n_c / ncols) : p.batch;
 
     constexpr int NLOADS = 1 + (M == M_ETD35 ? 1 : __builtin_popcount(NMASK));
-    constexpr int UN = FULL ? 1 : NLOADS <= 2 ? 4 : NLOADS <= 3 ? 2 : 1;       // FULL: one "row", the column loop is the long one
+    constexpr int UN = (FULL || CM == CM_INDEXED) ? 1 : NLOADS <= 2 ? 4 : NLOADS <= 3 ? 2 : 1;   // flat / indexed: the column loop is the long one
     const double thr2 = (cutoff * m) * (cutoff * m);
     const bool band_ok = thr2 > 1e-290 && thr2 < 1e290;                         // else: always the exact test
     const double band_hi = band_ok ? thr2 * (1.0 + 1e-9) : __longlong_as_double(0x7ff0000000000000ll);
@@ -1100,9 +1208,24 @@ RKS_D void norm_kernel_body(const DevPlan& p, int fuse_controller) {
     double su = 0.0, se = 0.0;
     for (long long col = (long long)blockIdx.x * 128 + threadIdx.x; col < ncols; col += (long long)gridDim.x * 128) {
         CT cv[NC];
+        CT bq[NQ];
+        if (CM == CM_SEPARABLE) {
+            const CT* __restrict__ tab = coef + (p.sep_ntab - ncols) + col;
 #pragma unroll
-        for (int s = 0; s < NC; ++s)
-            if (CMASK & (1u << s)) cv[s] = ldcoef(coef + s * cstride + col);
+            for (int q = 0; q < NQ; ++q)
+                if (QMASK & (1u << q)) bq[q] = ldcoef(tab + q * p.sep_ntab);
+        } else if (CM == CM_INDEXED) {
+            if (CMASK) {
+                const CT* __restrict__ rec = coef + (long long)__ldg(p.cidx + col) * record_elems<CT>(M) + group_off<CT>(M, method_stages(M) + 1);
+#pragma unroll
+                for (int s = 0; s < NC; ++s)
+                    if (CMASK & (1u << s)) cv[s] = ldcoef(rec + group_pos(CMASK, s));
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < NC; ++s)
+                if (CMASK & (1u << s)) cv[s] = ldcoef(coef + s * cstride + col);
+        }
         // UN rows per iteration, all loads issued first (a thread with one row in flight keeps ~32 KB per SM on
         // the wire: 5.2 TB/s; with four it is the HBM roofline)
         for (long long row0 = blockIdx.y; row0 < nrows; row0 += (long long)UN * gridDim.y) {
@@ -1124,6 +1247,12 @@ RKS_D void norm_kernel_body(const DevPlan& p, int fuse_controller) {
             }
 #pragma unroll
             for (int q = 0; q < UN; ++q) {
+                if (CM == CM_SEPARABLE && CMASK) {
+                    CT aq[NQ];
+                    const long long row = row0 + (long long)q * gridDim.y;
+                    sep_row_factors<M, CT, QMASK>(p, ok[q] ? row : row0, aq);
+                    sep_coefs<M, CT, CMASK>(p, aq, bq, cv);
+                }
                 if (M != M_ETD35) ev[q] = embedded_err<M, CT>(nv[q], cv, h);
                 const double u2 = abs2(uv[q]);
                 // idx = magu / magu.max() > adapt_cutoff   (solveras.py:452).  The square root and the division
@@ -1172,11 +1301,11 @@ RKS_D void norm_kernel_body(const DevPlan& p, int fuse_controller) {
         }
     }
 }
-template <int M, typename CT, bool FULL>
-__global__ void __launch_bounds__(128) norm_kernel(const __grid_constant__ DevPlan p, int fuse_controller) { norm_kernel_body<M, CT, FULL>(p, fuse_controller); }
+template <int M, typename CT, int CM>
+__global__ void __launch_bounds__(128) norm_kernel(const __grid_constant__ DevPlan p, int fuse_controller) { norm_kernel_body<M, CT, CM>(p, fuse_controller); }
 // one plan per blockIdx.z: ensembles whose trajectories keep their own dt (rks_multi_*)
-template <int M, typename CT, bool FULL>
-__global__ void __launch_bounds__(128) norm_kernel_multi(const DevPlan* plans, int fuse_controller) { norm_kernel_body<M, CT, FULL>(plans[blockIdx.z], fuse_controller); }
+template <int M, typename CT, int CM>
+__global__ void __launch_bounds__(128) norm_kernel_multi(const DevPlan* plans, int fuse_controller) { norm_kernel_body<M, CT, CM>(plans[blockIdx.z], fuse_controller); }
 
 
 // max |x|^2 over an array -> ctrl.red[0], REPLACING what the last stage kernel accumulated there

@@ -44,10 +44,26 @@ constexpr long long MODEL_MAX_N = 16384;        // longest row the smem-resident
 static size_t align_up(size_t v) { return (v + ALIGN - 1) / ALIGN * ALIGN; }
 
 struct Layout {
-    size_t ctrl, log, partials, tw, twf, kx, lin, coef, U[2], K, ERR, NL[8], total;
+    size_t ctrl, log, partials, tw, twf, kx, lin, coef, cidx, cscale, U[2], K, ERR, NL[8], total;
 };
 
-static Layout make_layout(int method, long long batch, long long n_c, long long lin_elems, int lin_is_complex) {
+// CT elements of one grouped coefficient record (stages.cuh record_elems, runtime method id)
+static size_t record_elems_rt(int m, bool real_coef) {
+    switch (m) {
+        case M_IF4: return real_coef ? record_elems<double>(M_IF4) : record_elems<cplx>(M_IF4);
+        case M_IF34: return real_coef ? record_elems<double>(M_IF34) : record_elems<cplx>(M_IF34);
+        case M_IF45DP: return real_coef ? record_elems<double>(M_IF45DP) : record_elems<cplx>(M_IF45DP);
+        case M_ETD4: return record_elems<cplx>(M_ETD4);
+        case M_ETD34: return record_elems<cplx>(M_ETD34);
+        case M_ETD5: return record_elems<cplx>(M_ETD5);
+        default: return record_elems<cplx>(M_ETD35);
+    }
+}
+
+// mode CM_COLUMN / CM_FLAT: lin_elems = n_c or batch * n_c coefficient entries per array;
+// CM_INDEXED: lin_elems = number of distinct lin_op values; CM_SEPARABLE: lin_elems = sum of the grid dims
+static Layout make_layout(int method, long long batch, long long n_c, long long lin_elems, int lin_is_complex,
+                          int mode = CM_COLUMN) {
     Layout L;
     memset(&L, 0, sizeof(L));
     size_t off = 0;
@@ -55,6 +71,8 @@ static Layout make_layout(int method, long long batch, long long n_c, long long 
     const size_t state = (size_t)batch * (size_t)n_c * sizeof(cplx);
     const bool is_if = method_is_if(method);
     const size_t coef_elem = (is_if && !lin_is_complex) ? sizeof(double) : sizeof(cplx);
+    const size_t coef_per_entry = mode == CM_INDEXED ? record_elems_rt(method, coef_elem == sizeof(double))
+                                : mode == CM_SEPARABLE ? (size_t)sep_nq(method) : (size_t)method_ncoef(method);
     L.ctrl = take(sizeof(Ctrl));
     L.log = take(sizeof(TrialRec) * LOG_CAP);
     L.partials = take(sizeof(double) * 2 * NORM_MAX_BLOCKS + PRE_CNT_BYTES);    // + row counters of stage_pre_kernel
@@ -63,7 +81,9 @@ static Layout make_layout(int method, long long batch, long long n_c, long long 
     L.twf = take(sizeof(cplx) * (size_t)(n_c <= MODEL_MAX_N ? 2 * fast::TW_TOTAL : 0));
     L.kx = take(sizeof(double) * (size_t)(n_c <= MODEL_MAX_N ? n_c : 0));
     L.lin = take((lin_is_complex ? sizeof(cplx) : sizeof(double)) * (size_t)lin_elems);
-    L.coef = take(coef_elem * (size_t)lin_elems * method_ncoef(method));
+    L.coef = take(coef_elem * (size_t)lin_elems * coef_per_entry);
+    L.cidx = take(mode == CM_INDEXED ? sizeof(int) * (size_t)n_c : 0);
+    L.cscale = take(mode == CM_SEPARABLE ? sizeof(double) * 32 : 0);
     L.U[0] = take(state);
     L.U[1] = method_adaptive(method) ? take(state) : L.U[0];
     L.K = take(state);
@@ -237,20 +257,21 @@ static int check_cfg(const rks_config* c) {
     return RKS_OK;
 }
 
-extern "C" int rks_plan_create(rks_plan** out, int method, int64_t batch, int64_t n_c, const void* lin_op,
-                               int lin_is_complex, int64_t lin_elems, const rks_config* cfg, void* workspace,
-                               size_t workspace_bytes, void* stream_v) {
+// mode CM_COLUMN / CM_FLAT (chosen from lin_elems), CM_INDEXED (lin_op = the distinct values, `index` maps the
+// n_c modes to them) or CM_SEPARABLE (lin_op = the concatenated per-axis terms of an nd-dimensional grid `dims`)
+static int plan_create_impl(rks_plan** out, int method, int64_t batch, int64_t n_c, const void* lin_op,
+                            int lin_is_complex, int64_t lin_elems, int mode, const int32_t* index, int nd,
+                            const int64_t* dims, const rks_config* cfg, void* workspace, size_t workspace_bytes,
+                            void* stream_v) {
     if (!out) return fail(RKS_ERR_ARG, "out is null");
     *out = nullptr;
     if (!valid_method(method)) return fail(RKS_ERR_ARG, "unknown method id");
-    if (batch <= 0 || n_c <= 0) return fail(RKS_ERR_ARG, "batch and n_c must be positive");
-    if (lin_elems != n_c && lin_elems != batch * n_c)
-        return fail(RKS_ERR_ARG, "lin_op must have n_c or batch*n_c elements");
+    if (batch <= 0 || n_c <= 0 || lin_elems <= 0) return fail(RKS_ERR_ARG, "batch, n_c and the lin_op length must be positive");
     if (!lin_op || !workspace) return fail(RKS_ERR_ARG, "null device pointer");
     if (((uintptr_t)workspace) % ALIGN) return fail(RKS_ERR_WORKSPACE, "workspace must be 256-byte aligned");
     if (int rc = check_cfg(cfg)) return rc;
     cudaStream_t stream = (cudaStream_t)stream_v;
-    Layout L = make_layout(method, batch, n_c, lin_elems, lin_is_complex);
+    Layout L = make_layout(method, batch, n_c, lin_elems, lin_is_complex, mode);
     if (workspace_bytes < L.total) return fail(RKS_ERR_WORKSPACE, "workspace too small");
 
     rks_plan* p = new (std::nothrow) rks_plan();
@@ -287,8 +308,20 @@ extern "C" int rks_plan_create(rks_plan** out, int method, int64_t batch, int64_
     d.ERR = method == M_ETD35 ? (cplx*)(w + L.ERR) : nullptr;
     for (int j = 1; j <= method_nl_buffers(method); ++j) d.NL[j] = (cplx*)(w + L.NL[j]);
     d.batch = batch; d.n_c = n_c; d.lin_elems = lin_elems; d.n = 0;
-    d.method = method; d.lin_complex = lin_is_complex; d.lin_full = (lin_elems == batch * n_c) ? 1 : 0;   // also true for batch == 1: linear kernels
+    d.method = method; d.lin_complex = lin_is_complex;
+    d.coef_mode = mode;
+    d.lin_full = mode == CM_FLAT ? 1 : 0;
     d.model = RKS_MODEL_NONE; d.log2n = 0; d.model_p0 = 0.0;
+    if (mode == CM_INDEXED) {
+        d.cidx = (const int*)(w + L.cidx);
+        CUDA_TRY(cudaMemcpyAsync(w + L.cidx, index, sizeof(int) * (size_t)n_c, cudaMemcpyDeviceToDevice, stream));
+    }
+    if (mode == CM_SEPARABLE) {
+        d.cscale = (const double*)(w + L.cscale);
+        d.sep_nd = nd;
+        for (int k = 0; k < nd; ++k) d.sep_dims[k] = (int)dims[k];
+        d.sep_ntab = (int)lin_elems;
+    }
 
     CUDA_TRY(cudaMemsetAsync(w + L.ctrl, 0, L.partials + sizeof(double) * 2 * NORM_MAX_BLOCKS + PRE_CNT_BYTES - L.ctrl, stream));
     CUDA_TRY(cudaMemcpyAsync(w + L.lin, lin_op, (lin_is_complex ? sizeof(cplx) : sizeof(double)) * (size_t)lin_elems,
@@ -303,6 +336,66 @@ extern "C" int rks_plan_create(rks_plan** out, int method, int64_t batch, int64_
     guard.release();
     *out = p;
     return RKS_OK;
+}
+
+extern "C" int rks_plan_create(rks_plan** out, int method, int64_t batch, int64_t n_c, const void* lin_op,
+                               int lin_is_complex, int64_t lin_elems, const rks_config* cfg, void* workspace,
+                               size_t workspace_bytes, void* stream_v) {
+    if (out) *out = nullptr;
+    if (lin_elems != n_c && lin_elems != batch * n_c)
+        return fail(RKS_ERR_ARG, "lin_op must have n_c or batch*n_c elements");
+    // lin_elems == batch * n_c also for batch == 1: the flat kernels
+    const int mode = (lin_elems == batch * n_c) ? CM_FLAT : CM_COLUMN;
+    return plan_create_impl(out, method, batch, n_c, lin_op, lin_is_complex, lin_elems, mode, nullptr, 0, nullptr, cfg,
+                            workspace, workspace_bytes, stream_v);
+}
+
+// Grids with many modes but few distinct lin_op values: coefficient records per distinct value
+extern "C" size_t rks_workspace_bytes_indexed(int method, int64_t batch, int64_t n_c, int64_t n_values, int lin_is_complex) {
+    if (!valid_method(method) || batch <= 0 || batch > 65535 || n_c <= 0 || n_values <= 0 || n_values > n_c) return 0;
+    return make_layout(method, batch, n_c, n_values, lin_is_complex, CM_INDEXED).total;
+}
+extern "C" int rks_plan_create_indexed(rks_plan** out, int method, int64_t batch, int64_t n_c, const void* values,
+                                       int lin_is_complex, int64_t n_values, const int32_t* index, const rks_config* cfg,
+                                       void* workspace, size_t workspace_bytes, void* stream_v) {
+    if (out) *out = nullptr;
+    if (!index) return fail(RKS_ERR_ARG, "index is null");
+    if (n_values <= 0 || n_values > n_c) return fail(RKS_ERR_ARG, "n_values must be in 1..n_c");
+    if (batch > 65535) return fail(RKS_ERR_UNSUPPORTED, "indexed plans take at most 65535 trajectories");
+    return plan_create_impl(out, method, batch, n_c, values, lin_is_complex, n_values, CM_INDEXED, index, 0, nullptr, cfg,
+                            workspace, workspace_bytes, stream_v);
+}
+
+// IF methods on an nd-dimensional grid whose lin_op is a sum of per-axis terms: per-axis exponential tables
+static int64_t sep_total(int nd, const int64_t* dims, int64_t* modes) {
+    if (nd < 2 || nd > 3 || !dims) return 0;
+    int64_t sum = 0, prod = 1;
+    for (int k = 0; k < nd; ++k) {
+        if (dims[k] <= 0 || dims[k] > (1ll << 24)) return 0;
+        sum += dims[k]; prod *= dims[k];
+    }
+    if (modes) *modes = prod;
+    return sum;
+}
+extern "C" size_t rks_workspace_bytes_separable(int method, int64_t batch, int nd, const int64_t* dims, int lin_is_complex) {
+    int64_t n_c = 0;
+    const int64_t ntab = sep_total(nd, dims, &n_c);
+    if (!valid_method(method) || !method_is_if(method) || batch <= 0 || !ntab) return 0;
+    return make_layout(method, batch, n_c, ntab, lin_is_complex, CM_SEPARABLE).total;
+}
+extern "C" int rks_plan_create_separable(rks_plan** out, int method, int64_t batch, int nd, const int64_t* dims,
+                                         const void* axis_terms, int lin_is_complex, const rks_config* cfg,
+                                         void* workspace, size_t workspace_bytes, void* stream_v) {
+    if (out) *out = nullptr;
+    if (!valid_method(method) || !method_is_if(method))
+        return fail(RKS_ERR_UNSUPPORTED, "separable coefficient tables exist for the IF methods only");
+    int64_t n_c = 0;
+    const int64_t ntab = sep_total(nd, dims, &n_c);
+    if (!ntab) return fail(RKS_ERR_ARG, "separable plans take 2 or 3 positive grid dimensions");
+    const int64_t rows = batch * (n_c / dims[nd - 1]);
+    if (rows > 65535ll * 8 * STAGE_R) return fail(RKS_ERR_UNSUPPORTED, "too many grid rows for one launch");
+    return plan_create_impl(out, method, batch, n_c, axis_terms, lin_is_complex, ntab, CM_SEPARABLE, nullptr, nd, dims, cfg,
+                            workspace, workspace_bytes, stream_v);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -420,7 +513,7 @@ extern "C" int rks_plan_create_independent(rks_plan** out, int method, int64_t b
         d.ERR = method == M_ETD35 ? (cplx*)(w + L.ERR) + ro : nullptr;
         for (int j = 1; j <= method_nl_buffers(method); ++j) d.NL[j] = (cplx*)(w + L.NL[j]) + ro;
         d.batch = 1; d.n_c = n_c; d.lin_elems = n_c; d.n = 0;
-        d.method = method; d.lin_complex = lin_is_complex; d.lin_full = 1;
+        d.method = method; d.lin_complex = lin_is_complex; d.lin_full = 1; d.coef_mode = CM_FLAT;
         d.model = RKS_MODEL_NONE;
     }
     p->d = p->multi_host[0];
@@ -617,27 +710,27 @@ extern "C" int rks_get_u(rks_plan* p, void* u_out, void* stream) {
 // ---------------------------------------------------------------------------------------
 // K2 dispatch
 // ---------------------------------------------------------------------------------------
-template <int FAM, typename LT>
+template <int M, typename LT>
 static void launch_coef_t(rks_plan* p, int force, cudaStream_t stream) {
     const DevPlan& d = p->d;
     const unsigned grid = (unsigned)((d.lin_elems + 127) / 128);
-    if (p->multi_n) coef_kernel_multi<FAM, LT><<<dim3(grid, 1, (unsigned)p->multi_n), 128, 0, stream>>>(p->multi_dev, force);
-    else coef_kernel<FAM, LT><<<grid, 128, 0, stream>>>(d, force);
+    if (p->multi_n) coef_kernel_multi<M, LT><<<dim3(grid, 1, (unsigned)p->multi_n), 128, 0, stream>>>(p->multi_dev, force);
+    else if (d.coef_mode == CM_INDEXED) coef_kernel<M, LT, true><<<grid, 128, 0, stream>>>(d, force);
+    else if (d.coef_mode == CM_SEPARABLE) {
+        if constexpr (method_is_if(M)) coef_sep_kernel<M, LT><<<(unsigned)((d.sep_ntab + 127) / 128), 128, 0, stream>>>(d, force);
+    } else coef_kernel<M, LT, false><<<grid, 128, 0, stream>>>(d, force);
 }
 
 static int launch_coeffs(rks_plan* p, int force, cudaStream_t stream) {
-    const int m = p->method;
     const bool cx = p->d.lin_complex != 0;
-    if (m == M_IF4 || m == M_IF34) {
-        if (cx) launch_coef_t<0, cplx>(p, force, stream);
-        else launch_coef_t<0, double>(p, force, stream);
-    } else if (m == M_ETD4 || m == M_ETD34) {
-        launch_coef_t<1, cplx>(p, force, stream);
-    } else if (m == M_ETD5 || m == M_ETD35) {
-        launch_coef_t<2, cplx>(p, force, stream);
-    } else {
-        if (cx) launch_coef_t<3, cplx>(p, force, stream);
-        else launch_coef_t<3, double>(p, force, stream);
+    switch (p->method) {
+        case M_IF4: cx ? launch_coef_t<M_IF4, cplx>(p, force, stream) : launch_coef_t<M_IF4, double>(p, force, stream); break;
+        case M_IF34: cx ? launch_coef_t<M_IF34, cplx>(p, force, stream) : launch_coef_t<M_IF34, double>(p, force, stream); break;
+        case M_IF45DP: cx ? launch_coef_t<M_IF45DP, cplx>(p, force, stream) : launch_coef_t<M_IF45DP, double>(p, force, stream); break;
+        case M_ETD4: launch_coef_t<M_ETD4, cplx>(p, force, stream); break;
+        case M_ETD34: launch_coef_t<M_ETD34, cplx>(p, force, stream); break;
+        case M_ETD5: launch_coef_t<M_ETD5, cplx>(p, force, stream); break;
+        default: launch_coef_t<M_ETD35, cplx>(p, force, stream); break;
     }
     p->launches += 1;
     return RKS_OK;
@@ -661,15 +754,25 @@ static void launch_stage_t(rks_plan* p, cudaStream_t stream) {
     const dim3 block(32, 8);
     if (p->multi_n) {
         const unsigned gx = (unsigned)((d.n_c + 256 * STAGE_R - 1) / (256 * STAGE_R));
-        stage_kernel_multi<M, S, CT, true><<<dim3(gx, 1, (unsigned)p->multi_n), block, 0, stream>>>(p->multi_dev);
-    } else if (d.lin_full) {
+        stage_kernel_multi<M, S, CT, CM_FLAT><<<dim3(gx, 1, (unsigned)p->multi_n), block, 0, stream>>>(p->multi_dev);
+    } else if (d.coef_mode == CM_FLAT) {
         const long long total = d.batch * d.n_c;
         const unsigned gx = (unsigned)((total + 256 * STAGE_R - 1) / (256 * STAGE_R));
-        stage_kernel<M, S, CT, true><<<dim3(gx), block, 0, stream>>>(d);
+        stage_kernel<M, S, CT, CM_FLAT><<<dim3(gx), block, 0, stream>>>(d);
+    } else if (d.coef_mode == CM_INDEXED) {
+        const unsigned gx = (unsigned)((d.n_c + 256 * STAGE_R - 1) / (256 * STAGE_R));
+        stage_kernel<M, S, CT, CM_INDEXED><<<dim3(gx, (unsigned)d.batch), block, 0, stream>>>(d);
+    } else if (d.coef_mode == CM_SEPARABLE) {
+        if constexpr (method_is_if(M)) {
+            const long long ncol = d.sep_dims[d.sep_nd - 1], nrow = d.batch * (d.n_c / ncol);
+            const unsigned gx = (unsigned)((ncol + 31) / 32);
+            const unsigned gy = (unsigned)((nrow + 8 * STAGE_R - 1) / (8 * STAGE_R));
+            stage_kernel<M, S, CT, CM_SEPARABLE><<<dim3(gx, gy), block, 0, stream>>>(d);
+        }
     } else {
         const unsigned gx = (unsigned)((d.n_c + 31) / 32);
         const unsigned gy = (unsigned)((d.batch + 8 * STAGE_R - 1) / (8 * STAGE_R));
-        stage_kernel<M, S, CT, false><<<dim3(gx, gy), block, 0, stream>>>(d);
+        stage_kernel<M, S, CT, CM_COLUMN><<<dim3(gx, gy), block, 0, stream>>>(d);
     }
 }
 
@@ -748,7 +851,7 @@ static void launch_stage_pre(rks_plan* p, int s, cudaStream_t stream) {
 extern "C" int rks_stage(rks_plan* p, int s, void* stream_v) {
     if (!p) return fail(RKS_ERR_ARG, "plan is null");
     if (s < 1 || s > method_stages(p->method)) return fail(RKS_ERR_ARG, "stage out of range");
-    if (p->d.batch > 65535ll * 8 * STAGE_R && !p->d.lin_full) return fail(RKS_ERR_UNSUPPORTED, "batch too large for one launch");
+    if (p->d.batch > 65535ll * 8 * STAGE_R && p->d.coef_mode == CM_COLUMN) return fail(RKS_ERR_UNSUPPORTED, "batch too large for one launch");
     cudaStream_t stream = (cudaStream_t)stream_v;
     const bool cx = p->d.lin_complex != 0;
     switch (p->method) {
@@ -907,7 +1010,7 @@ static bool can_fuse_stage(const rks_plan* p, int s) {
 // (stage_pre_kernel -> nl_fast_pre_kernel).  The last stage is a state and keeps the natural layout.
 static bool can_pretransform(const rks_plan* p, int s) {
     // n = 512: a row is one warp's slice, K4 is already warp-local there and the pair measured 5-16 % slower
-    return p->pretransform && p->nl_fast && p->d.n >= 1024 && !p->multi_n && p->d.lin_elems == p->d.n_c && !p->d.lin_full
+    return p->pretransform && p->nl_fast && p->d.n >= 1024 && !p->multi_n && p->d.lin_elems == p->d.n_c && p->d.coef_mode == CM_COLUMN
         && p->d.model == RKS_MODEL_NLS_FFT && s < method_stages(p->method);
 }
 
@@ -972,11 +1075,13 @@ static void launch_norm_t(rks_plan* p, int fuse, cudaStream_t stream) {
     if (p->multi_n) {
         long long gx = (d.n_c + 127) / 128;
         if (gx > MULTI_NORM_BLOCKS) gx = MULTI_NORM_BLOCKS;
-        norm_kernel_multi<M, CT, true><<<dim3((unsigned)gx, 1, (unsigned)p->multi_n), 128, 0, stream>>>(p->multi_dev, fuse);
+        norm_kernel_multi<M, CT, CM_FLAT><<<dim3((unsigned)gx, 1, (unsigned)p->multi_n), 128, 0, stream>>>(p->multi_dev, fuse);
         return;
     }
-    const long long ncols = d.lin_full ? d.batch * d.n_c : d.n_c;
-    const long long nrows = d.lin_full ? 1 : d.batch;
+    const int mode = d.coef_mode;
+    const long long sep_cols = mode == CM_SEPARABLE ? d.sep_dims[d.sep_nd - 1] : 1;
+    const long long ncols = mode == CM_FLAT ? d.batch * d.n_c : mode == CM_SEPARABLE ? sep_cols : d.n_c;
+    const long long nrows = mode == CM_FLAT ? 1 : mode == CM_SEPARABLE ? d.batch * (d.n_c / sep_cols) : d.batch;
     // one wave of resident 128-thread CTAs (a partial second wave costs as much as a full one)
     static int per_sm_dev[MAX_DEVICES] = {0};
     int per_sm;
@@ -985,8 +1090,8 @@ static void launch_norm_t(rks_plan* p, int fuse, cudaStream_t stream) {
         int& slot = per_sm_dev[p->device % MAX_DEVICES];
         if (!slot) {
             int full = 0, bcast = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&full, norm_kernel<M, CT, true>, 128, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bcast, norm_kernel<M, CT, false>, 128, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&full, norm_kernel<M, CT, CM_FLAT>, 128, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bcast, norm_kernel<M, CT, CM_COLUMN>, 128, 0);
             slot = full < bcast ? full : bcast;
             if (slot < 1) slot = 1;
             if (slot > 8) slot = 8;
@@ -1000,8 +1105,12 @@ static void launch_norm_t(rks_plan* p, int fuse, cudaStream_t stream) {
     if (gy < 1) gy = 1;
     if (gy > nrows) gy = nrows;
     while (gx * gy > NORM_MAX_BLOCKS) { if (gy > 1) --gy; else --gx; }
-    if (d.lin_full) norm_kernel<M, CT, true><<<dim3((unsigned)gx, (unsigned)gy), 128, 0, stream>>>(d, fuse);
-    else norm_kernel<M, CT, false><<<dim3((unsigned)gx, (unsigned)gy), 128, 0, stream>>>(d, fuse);
+    const dim3 grid((unsigned)gx, (unsigned)gy);
+    if (mode == CM_FLAT) norm_kernel<M, CT, CM_FLAT><<<grid, 128, 0, stream>>>(d, fuse);
+    else if (mode == CM_INDEXED) norm_kernel<M, CT, CM_INDEXED><<<grid, 128, 0, stream>>>(d, fuse);
+    else if (mode == CM_SEPARABLE) {
+        if constexpr (method_is_if(M)) norm_kernel<M, CT, CM_SEPARABLE><<<grid, 128, 0, stream>>>(d, fuse);
+    } else norm_kernel<M, CT, CM_COLUMN><<<grid, 128, 0, stream>>>(d, fuse);
 }
 
 static int launch_norm(rks_plan* p, int fuse, cudaStream_t stream) {
@@ -1453,7 +1562,7 @@ extern "C" void* rks_array(rks_plan* p, const char* name) {
         return j <= method_nl_buffers(p->method) ? d.NL[j] : nullptr;
     }
     const int slot = coef_slot(p->method, s);
-    if (slot < 0) return nullptr;
+    if (slot < 0 || d.coef_mode == CM_INDEXED || d.coef_mode == CM_SEPARABLE) return nullptr;    // no per-slot arrays there
     const bool real_coef = method_is_if(p->method) && !d.lin_complex;
     const size_t elem = real_coef ? sizeof(double) : sizeof(cplx);
     return (unsigned char*)d.coef + elem * (size_t)d.lin_elems * slot;

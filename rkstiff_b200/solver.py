@@ -10,6 +10,7 @@ Differences from the reference, all extensions:
 """
 from __future__ import annotations
 
+import os
 from abc import ABC, abstractmethod
 from typing import Callable, Dict, Optional, Union
 
@@ -42,6 +43,10 @@ class BaseSolver(ABC):
         #: tensors filled by asynchronous device-to-host copies on a side stream, so that storing multi-GB
         #: states neither stalls the stepping stream nor fills HBM; call solver.sync_snapshots() before use)
         self.snapshot_device = "cuda"
+        #: coefficient storage of N-D grids: "auto" (grids of >= Engine.DEDUPE_MIN_MODES modes: per-axis exponential
+        #: tables for IF methods with a sum-separable lin_op, else one record per DISTINCT lin_op value), "arrays"
+        #: (one entry per mode), "indexed", "separable".  Read when the plan is built.
+        self.coef_storage = os.environ.get("RKS_COEF_STORAGE", "auto")
         self._snap_stream = None
         self._diag = True
         # diagonalize=True (dense lin_op): eigen-decomposition done once on the host; the engine steps the
@@ -98,7 +103,7 @@ class BaseSolver(ABC):
                              "on a 2-D grid and u must have the same trailing shape")
         if eng is None:
             eng = Engine(self.METHOD, self.lin_op if self._eig is None else self._eig, u.shape, self._rks_config(),
-                         fused=self._fused(), group=self._group)
+                         fused=self._fused(), group=self._group, coef_storage=self.coef_storage)
             if self._S is not None:
                 eng.norm_map = self._to_phys          # the controller's |u+| is the physical one (etd35.py:495)
             self._engines = {key: eng}           # one live plan per solver: a new shape replaces the old

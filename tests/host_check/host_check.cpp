@@ -400,6 +400,49 @@ int hc_coeffs(int method, int n, const double* lin, int lin_complex, double h, d
     return nc;
 }
 
+// CM_SEPARABLE: coefficient slots of an IF method on an (n0, n1) grid from the per-axis exponential tables,
+// exactly as K2 (coef_sep_kernel) and K1 (sep_coefs) form them; out is [ncoef][n0*n1] complex
+int hc_sep_coeffs(int method, int n0, int n1, const double* a0, const double* a1, int lin_complex, double h, int r4_fix,
+                  double* out) {
+    if (!method_is_if(method)) return -1;
+    cplx* o = reinterpret_cast<cplx*>(out);
+    const int nc = method_ncoef(method), nq = sep_nq(method);
+    const long long n = (long long)n0 * n1;
+    std::vector<cplx> t0((size_t)nq * n0), t1((size_t)nq * n1);
+    for (int q = 0; q < nq; ++q) {
+        for (int i = 0; i < n0; ++i)
+            t0[(size_t)q * n0 + i] = lin_complex ? sep_exp<cplx>(method, q, scale(h, mk(a0[2 * i], a0[2 * i + 1])))
+                                                 : mk(sep_exp<double>(method, q, h * a0[i]), 0.0);
+        for (int j = 0; j < n1; ++j)
+            t1[(size_t)q * n1 + j] = lin_complex ? sep_exp<cplx>(method, q, scale(h, mk(a1[2 * j], a1[2 * j + 1])))
+                                                 : mk(sep_exp<double>(method, q, h * a1[j]), 0.0);
+    }
+    for (int s = 0; s < nc; ++s) {
+        const int q = sep_q(method, s);
+        const double sc = sep_scale(method, s, h, r4_fix);
+        const bool pure = method != M_IF45DP || s <= dp::E;
+        for (int i = 0; i < n0; ++i)
+            for (int j = 0; j < n1; ++j) {
+                const cplx e = t0[(size_t)q * n0 + i] * t1[(size_t)q * n1 + j];
+                o[(long long)s * n + (long long)i * n1 + j] = pure ? e : scale(sc, e);
+            }
+    }
+    return nc;
+}
+
+// CM_INDEXED record layout of a method: out[g] = offset of group g = 1..S+1, out[0] = record length (CT elements);
+// masks[g] = the slots the group holds
+int hc_record_layout(int method, int real_coef, int* out, unsigned* masks) {
+    const int S = method_stages(method);
+#define HC_LAYOUT(M) if (method == M) { \
+        out[0] = real_coef ? record_elems<double>(M) : record_elems<cplx>(M); \
+        for (int g = 1; g <= S + 1; ++g) { out[g] = real_coef ? group_off<double>(M, g) : group_off<cplx>(M, g); masks[g] = group_mask(M, g); } \
+        return S + 1; }
+    HC_LAYOUT(M_IF4) HC_LAYOUT(M_ETD4) HC_LAYOUT(M_ETD5) HC_LAYOUT(M_IF34) HC_LAYOUT(M_ETD34) HC_LAYOUT(M_ETD35) HC_LAYOUT(M_IF45DP)
+#undef HC_LAYOUT
+    return -1;
+}
+
 #define HC_STAGE(M, S) if (method == M && stage == S) { stage_all<M, S>(n, cu, Np, cc, h, co, ce); return 0; }
 // one stage combine with complex coefficients; N is 8 pointers (index 1..7, may be null)
 int hc_stage(int method, int stage, int n, const double* u, const double* const* N, const double* coef, double h,

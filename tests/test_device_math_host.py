@@ -449,3 +449,47 @@ def test_two_logical_threads_per_thread_passes_are_bit_identical(hc, n):
             out[:] = 0
             assert hc.hc_nl_x2(n, ptr(row), ctypes.c_double(2.0), ptr(out), pre) == 0
             np.testing.assert_array_equal(out, plain)
+
+
+# ------------------------------------------------------------------------------------------------
+# coefficient storage of large grids: per-axis exponential tables, grouped records
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("method", ["IF4", "IF34", "IF45DP"])
+@pytest.mark.parametrize("cx", [False, True])
+def test_separable_if_coefficients_match_the_direct_ones(hc, method, cx):
+    """exp(q h (a_i + b_j)) = exp(q h a_i) exp(q h b_j): the per-axis tables reproduce every coefficient slot of the
+    reference formulas (if4.py:72-83, if45dp.py:204-237) on the flattened grid to rounding."""
+    rng = np.random.default_rng(5)
+    n0, n1, h = 12, 9, 0.037
+    ky, kx = np.fft.fftfreq(n0, 1.0 / n0), np.fft.rfftfreq(2 * (n1 - 1), 1.0 / (2 * (n1 - 1)))
+    if cx:
+        a0, a1 = (0.3 - 1j * ky ** 2).astype(np.complex128), (-1j * kx ** 2 + 0.01 * rng.standard_normal(n1)).astype(np.complex128)
+    else:
+        a0, a1 = 1.0 - 0.05 * ky ** 2, -0.05 * kx ** 2
+    lin = np.ascontiguousarray((a0[:, None] + a1[None, :]).ravel())
+    direct, _ = device_coeffs(hc, method, lin, h)
+    names = SLOTS[FAMILY[method]]
+    out = np.zeros((len(names), n0 * n1), dtype=np.complex128)
+    nc = hc.hc_sep_coeffs(MID[method], n0, n1, ptr(np.ascontiguousarray(a0)), ptr(np.ascontiguousarray(a1)), int(cx),
+                          ctypes.c_double(h), 0, ptr(out))
+    assert nc == len(names)
+    for name, arr in zip(names, out):
+        np.testing.assert_allclose(arr, direct[name], rtol=2e-15 * (1 + np.abs(h * lin).max()), atol=0, err_msg=f"{method}.{name}")
+
+
+@pytest.mark.parametrize("method", METHODS)
+@pytest.mark.parametrize("real", [False, True])
+def test_grouped_record_layout(hc, method, real):
+    """every stage's slots are contiguous, start on a 32-byte sector and do not overlap another group"""
+    if real and method not in ("IF4", "IF34", "IF45DP"):
+        pytest.skip("real coefficient arrays exist for the IF methods only")
+    out = (ctypes.c_int * 9)()
+    masks = (ctypes.c_uint * 9)()
+    ng = hc.hc_record_layout(MID[method], int(real), out, masks)
+    assert ng == {"IF4": 5, "ETD4": 5, "IF34": 5, "ETD34": 5}.get(method, 7)
+    elem = 8 if real else 16
+    end = 0
+    for g in range(1, ng + 1):
+        assert out[g] * elem % 32 == 0 and out[g] >= end
+        end = out[g] + bin(masks[g]).count("1")
+    assert out[0] >= end and out[0] * elem % 32 == 0

@@ -716,3 +716,111 @@ def test_k4_x2_pair_equals_plain_pair(rk, method, batch, monkeypatch):
     x2, _ = _stage_outputs(rk, method, p, monkeypatch, pt=True)
     for a, b in zip(x2, plain):
         assert rel(a, b) < 1e-14
+
+
+# --------------------------------------------------------------------------------------------
+# coefficient storage of large grids: records per distinct lin_op value ("indexed") and per-axis
+# exponential tables ("separable") against full-size arrays and against the flattened oracle
+# --------------------------------------------------------------------------------------------
+def _grid_case(rk, kind, n):
+    if kind == "allen_cahn_2d":
+        p = problems.allen_cahn_2d(n)
+        lin, nl = rk.models.allen_cahn_fourier_ops(n, eps=0.01)
+        return p, lin, nl, p.params["shape"]
+    p = problems.nls_3d(n)
+    k = dev(p.kx)
+    lin, nl = rk.models.nls_nd_ops([k, k, k], gamma=2.0)
+    return p, lin, nl, (n, n, n)
+
+
+GRID_CASES = [("IF45DP", "allen_cahn_2d", 64, "separable", 0.05, 1e-4), ("IF34", "allen_cahn_2d", 64, "separable", 0.5, 1e-5),
+              ("IF45DP", "allen_cahn_2d", 32, "indexed", 0.05, 1e-4), ("ETD34", "allen_cahn_2d", 64, "indexed", 0.5, 1e-5),
+              ("ETD35", "nls_3d", 16, "indexed", 0.2, 1e-5), ("IF34", "nls_3d", 16, "separable", 0.1, 1e-5),
+              ("IF45DP", "nls_3d", 16, "separable", 0.02, 1e-5), ("IF34", "nls_3d", 16, "indexed", 0.1, 1e-5)]
+
+
+@pytest.mark.parametrize("method,kind,n,storage,tf,eps", GRID_CASES, ids=[f"{c[0]}-{c[1]}{c[2]}-{c[3]}" for c in GRID_CASES])
+def test_grid_coefficient_storage_matches_flattened_oracle(rk, method, kind, n, storage, tf, eps):
+    p, lin, nl, shape = _grid_case(rk, kind, n)
+    sol = getattr(rk, method)(lin, nl, config=rk.SolverConfig(epsilon=eps))
+    sol.coef_storage = storage
+    uf = sol.evolve(dev(p.u0.reshape(shape)), 0.0, tf, store_freq=3)
+    assert sol._engine.coef_storage == storage
+    ora = OracleSolver(method, p.lin_op, p.nl_func, Config(epsilon=eps))
+    uo = ora.evolve(p.u0, 0.0, tf, store_freq=3)
+    assert [r[2] for r in sol.trial_log] == [r.accepted for r in ora.log]
+    np.testing.assert_allclose([r[0] for r in sol.trial_log], [r.h for r in ora.log], rtol=DT_TOL)
+    np.testing.assert_allclose(sol.t, ora.t, rtol=DT_TOL)
+    assert rel(host(uf).ravel(), uo) < FINAL_TOL
+
+
+@pytest.mark.parametrize("method", ["ETD4", "ETD5", "IF4", "ETD34", "ETD35", "IF34", "IF45DP"])
+def test_indexed_records_are_bit_identical_to_full_arrays(rk, method):
+    """K2 evaluates the same formulas on the same z: gathering a record must give the bits of the full-size arrays."""
+    p, lin, nl, shape = _grid_case(rk, "allen_cahn_2d", 32)
+    lin = lin.to(torch.complex128) * (1.0 + 0.3j) if method.startswith("ETD") else lin
+    u0 = dev(np.stack([p.u0.reshape(shape), 0.7 * p.u0.reshape(shape), -0.4 * p.u0.reshape(shape)]))
+    outs = {}
+    for storage in ("arrays", "indexed"):
+        sol = getattr(rk, method)(lin, nl)
+        sol.coef_storage = storage
+        if method in ADAPTIVE:
+            outs[storage] = (host(sol.evolve(u0, 0.0, 0.05, store_data=False)), [r[:3] for r in sol.trial_log])
+        else:
+            u = u0
+            for _ in range(3):
+                u = sol.step(u, 0.01)
+            outs[storage] = (host(u), None)
+        assert sol._engine.coef_storage == storage
+    np.testing.assert_array_equal(outs["arrays"][0], outs["indexed"][0])
+    assert outs["arrays"][1] == outs["indexed"][1]
+
+
+@pytest.mark.parametrize("method", ["IF4", "IF34", "IF45DP"])
+@pytest.mark.parametrize("kind,n", [("allen_cahn_2d", 32), ("nls_3d", 16)])
+def test_separable_tables_agree_with_full_arrays(rk, method, kind, n):
+    """products of per-axis exponentials vs exp of the summed exponent: one rounding per factor"""
+    p, lin, nl, shape = _grid_case(rk, kind, n)
+    u0 = dev(np.stack([p.u0.reshape(shape), 0.5 * p.u0.reshape(shape)]))
+    outs = {}
+    for storage in ("arrays", "separable"):
+        sol = getattr(rk, method)(lin, nl)
+        sol.coef_storage = storage
+        if method in ADAPTIVE:
+            outs[storage] = host(sol.evolve(u0, 0.0, 0.02, store_data=False))
+            outs[storage + "_log"] = [r[2] for r in sol.trial_log]
+        else:
+            outs[storage] = host(sol.step(u0, 0.01))
+        assert sol._engine.coef_storage == storage
+    assert rel(outs["separable"], outs["arrays"]) < 1e-13
+    assert outs.get("separable_log") == outs.get("arrays_log")
+
+
+def test_non_separable_operator_is_detected(rk):
+    from rkstiff_b200._engine import distinct_values, separable_terms
+    a = torch.linspace(0, 1, 7, dtype=torch.float64, device="cuda")
+    sep = 1.0 - a[:, None] ** 2 - 3 * a[None, :5]
+    assert separable_terms(sep) is not None
+    assert separable_terms(sep * (1 + a[:, None] * a[None, :5])) is None
+    vals, idx = distinct_values((a[:, None] ** 2 + a[None, :] ** 2).to(torch.complex128) * 1j)
+    assert vals.numel() < 49 and idx.dtype == torch.int32
+    np.testing.assert_array_equal(host(vals)[host(idx)].reshape(7, 7), host((a[:, None] ** 2 + a[None, :] ** 2) * 1j))
+    sol = rk.IF34(sep * (1 + a[:, None] * a[None, :5]), lambda v: v)
+    sol.coef_storage = "separable"
+    with pytest.raises(ValueError):
+        sol.step(torch.zeros(7, 5, dtype=torch.complex128, device="cuda"), 0.1)
+
+
+def test_step_recognises_only_the_tensor_it_returned(rk):
+    """a new tensor at a recycled address must be copied in, not mistaken for the previous output."""
+    p = problems.ks(256, batch=2)
+    sol = rk.ETD4(dev(p.lin_op), fused_for(rk, p))
+    u1 = sol.step(dev(p.u0), 0.05)
+    ref = OracleSolver("ETD4", p.lin_op, p.nl_func).step(0.5 * host(u1), 0.05)
+    ptr = u1.data_ptr()
+    u_new = (0.5 * u1).clone()
+    del u1
+    again = torch.empty_like(u_new)          # the caching allocator hands the freed block out again
+    again.copy_(u_new)
+    got = sol.step(again, 0.05)
+    assert rel(host(got), ref) < STEP_TOL, (ptr, again.data_ptr())
