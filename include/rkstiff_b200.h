@@ -178,6 +178,15 @@ int rks_set_config(rks_plan* plan, const rks_config* cfg, void* stream);
 int rks_set_model(rks_plan* plan, int model, int64_t n, const double* kx, const double* params_host,
                   int nparams, void* stream);
 
+/* Fused nonlinearity of a 2-D / 3-D spectral grid (the fft2 / fftn closures of demos/nls.ipynb:496-511 that the
+ * reference is given on flattened arrays): `grid` = real-space points per axis (nd = 2 or 3, powers of two,
+ * 16..4096, last axis 16..16384), last axis contiguous.  RKS_MODEL_NLS_FFT: N = i p0 fftn(|f|^2 f), f = ifftn(u^),
+ * spectral dims = grid;  RKS_MODEL_CUBIC_RFFT: N = p0 rfftn(irfftn(u^)^3), last spectral dim grid[nd-1]/2+1.
+ * Evaluated by the engine's own kernels -- inverse transforms over the strided axes, the fused last-axis kernel,
+ * forward transforms over the strided axes -- all predicated on the device, so rks_nl / rks_stage_nl /
+ * rks_run_trials / rks_run_fixed work as for 1-D rows (no host sync per trial, graph replay). */
+int rks_set_model_nd(rks_plan* plan, int model, int nd, const int64_t* grid, double p0, void* stream);
+
 /* (re)start: clears FSAL state / cached h (BaseSolver*.reset + _reset, solveras.py:306-312,
  * etd35.py:836-840) and arms the controller.  step_mode != 0: stop after the first accepted
  * trial (step()); otherwise integrate until t >= tf (evolve(), solveras.py:605-650). */

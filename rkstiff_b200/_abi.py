@@ -71,6 +71,7 @@ def _load():
                                                 c_size_t, P]),
         "rks_set_config": (c_int, [P, POINTER(RksConfig), P]),
         "rks_set_model": (c_int, [P, c_int, c_int64, P, POINTER(c_double), c_int, P]),
+        "rks_set_model_nd": (c_int, [P, c_int, c_int, POINTER(c_int64), c_double, P]),
         "rks_begin": (c_int, [P, c_double, c_double, c_double, c_int64, c_int, c_int, P]),
         "rks_set_h": (c_int, [P, c_double, P]),
         "rks_set_u": (c_int, [P, P, P]),

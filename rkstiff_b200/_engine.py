@@ -7,6 +7,7 @@ stepping path runs in the CUDA library.
 from __future__ import annotations
 
 import ctypes
+import math
 from ctypes import byref, c_double, c_void_p
 from typing import Callable, List, Optional, Tuple
 
@@ -148,7 +149,13 @@ class Engine:
                 check(lib.rks_plan_create(byref(self.plan), self.mid, self.batch, self.n_c, c_void_p(lin.data_ptr()),
                                           int(is_cx), self.n_c, byref(cfg), c_void_p(self.ws.data_ptr()), nbytes,
                                           _stream(self.device)))
-            if fused is not None:
+            if fused is not None and hasattr(fused, "grid"):
+                if tuple(lin.shape) != tuple(fused.grid[:-1]) + (self.n_c // max(1, math.prod(fused.grid[:-1])),):
+                    raise ValueError(f"lin_op shape {tuple(lin.shape)} does not match the model's grid {fused.grid}")
+                grid = (ctypes.c_int64 * len(fused.grid))(*fused.grid)
+                check(lib.rks_set_model_nd(self.plan, fused.model_id, len(fused.grid), grid, float(fused.param),
+                                           _stream(self.device)))
+            elif fused is not None:
                 kx = fused.kx.to(device=self.device, dtype=torch.float64).contiguous() if fused.kx is not None else None
                 params = (c_double * 1)(float(fused.param))
                 check(lib.rks_set_model(self.plan, fused.model_id, fused.n,

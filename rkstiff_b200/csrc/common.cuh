@@ -180,6 +180,7 @@ struct DevPlan {
     const int* cidx;   // CM_INDEXED: n_c indices into the table of distinct values
     const double* cscale;   // CM_SEPARABLE: the rational * h factor of every coefficient slot
     int sep_nd, sep_dims[3], sep_ntab;   // CM_SEPARABLE: spectral grid dims (last = contiguous axis), sum of them
+    int nd_inplace;    // row kernel of an N-D grid model: the rows of N_j are transformed in place (kernels.cuh nl_roles)
 };
 enum : int { CM_COLUMN = 0, CM_FLAT = 1, CM_INDEXED = 2, CM_SEPARABLE = 3 };
 

@@ -652,6 +652,7 @@ RKS_D NlRoles nl_roles(const DevPlan& p, int j, int force) {
     else if (j <= S) r.in = p.K;
     else r.in = p.U[1 - u_sel];                      // FSAL: N(u+)
     r.out = p.NL[nl_phys(m, j, n_sel)];
+    if (p.nd_inplace) r.in = r.out;                  // N-D grid: the strided-axis kernels already moved the input into N_j
     return r;
 }
 
@@ -1404,9 +1405,8 @@ __global__ void __launch_bounds__(256) copy_u_multi_kernel(const DevPlan* plans,
 // before it writes any of it.
 // ---------------------------------------------------------------------------------------
 template <int N, bool INV>
-__global__ void __launch_bounds__(axis::tile_threads<N>(), (N == 4096 ? 1 : N == 512 ? 3 : 2))
-axis_fft_kernel(const cplx* in, cplx* out, long long outer, long long inner, const cplx* tw, double scale,
-                long long ostride, long long bstride, int rb_shift) {
+RKS_D void axis_fft_body(const cplx* in, cplx* out, long long outer, long long inner, const cplx* tw, double scale,
+                         long long ostride, long long bstride, int rb_shift) {
     constexpr int C = axis::tile_cols<N>(), NBT = axis::tile_threads<N>() / C;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     cplx* tile = reinterpret_cast<cplx*>(smem_raw);
@@ -1423,6 +1423,23 @@ axis_fft_kernel(const cplx* in, cplx* out, long long outer, long long inner, con
         axis::tile_level<N, INV, 2>(tile, tw, c, bt, NBT, scale);
         __syncthreads();
     }
+}
+template <int N, bool INV>
+__global__ void __launch_bounds__(axis::tile_threads<N>(), (N == 4096 ? 1 : N == 512 ? 3 : 2))
+axis_fft_kernel(const cplx* in, cplx* out, long long outer, long long inner, const cplx* tw, double scale,
+                long long ostride, long long bstride, int rb_shift) {
+    axis_fft_body<N, INV>(in, out, outer, inner, tw, scale, ostride, bstride, rb_shift);
+}
+// the same transform as one step of the nonlinear term N_j of an N-D grid model (rks_set_model_nd): arrays and
+// the run predicate come from the control block (no host sync, graph replay); the first step of an evaluation
+// reads the stage value and writes N_j, the others work on N_j in place
+template <int N, bool INV>
+__global__ void __launch_bounds__(axis::tile_threads<N>(), (N == 4096 ? 1 : N == 512 ? 3 : 2))
+axis_fft_plan_kernel(const __grid_constant__ DevPlan p, int j, int force, int first, long long outer, long long inner,
+                     const cplx* tw, double scale) {
+    const NlRoles r = nl_roles(p, j, force);
+    if (!r.run) return;
+    axis_fft_body<N, INV>(first ? r.in : r.out, r.out, outer, inner, tw, scale, (long long)N * inner, 0, 31);
 }
 
 }  // namespace rks

@@ -134,6 +134,11 @@ struct rks_plan {
     bool rfft_half;                 // EXPERIMENT (RKS_RFFT_HALF=1): half-length forward transform for the real-field models
     bool k4_x2;                     // EXPERIMENT (RKS_K4_X2=1): n = 8192 pre-transformed NLS evaluation with 8 warps x 255 registers
     size_t nl_smem;
+    // N-D grid model (rks_set_model_nd): strided-axis handles, the fused last-axis kernel, spectral grid dims
+    struct rks_axis* nd_axes[2] = {nullptr, nullptr};
+    struct rks_rows* nd_rows = nullptr;
+    int nd = 0;
+    long long nd_spec[3] = {0, 0, 0};
 };
 
 // smem of a fast NL launch: the row slabs plus, for the fused u u_x models, one staging row each
@@ -536,6 +541,9 @@ extern "C" int rks_plan_create_independent(rks_plan** out, int method, int64_t b
 
 extern "C" void rks_plan_destroy(rks_plan* p) {
     if (!p) return;
+    if (p->nd_axes[1] && p->nd_axes[1] != p->nd_axes[0]) rks_axis_destroy(p->nd_axes[1]);
+    if (p->nd_axes[0]) rks_axis_destroy(p->nd_axes[0]);
+    if (p->nd_rows) rks_rows_destroy(p->nd_rows);
     if (p->graph.exec) cudaGraphExecDestroy(p->graph.exec);
     if (p->graph.stream) cudaStreamDestroy(p->graph.stream);
     cudaFreeHost(p->pinned_raw);
@@ -945,8 +953,11 @@ static void launch_nl_fast_real(rks_plan* p, int j, int force, cudaStream_t stre
     p->launches += 1;
 }
 
+static int launch_nl_nd(rks_plan* p, int j, int force, cudaStream_t stream);
+
 static int launch_nl(rks_plan* p, int j, int force, cudaStream_t stream) {
     const DevPlan& d = p->d;
+    if (p->nd_rows) return launch_nl_nd(p, j, force, stream);
     if (p->nl_small && !p->multi_n) {
         if (d.n == 64) launch_nl_small<64>(p, j, force, stream);
         else if (d.n == 128) launch_nl_small<128>(p, j, force, stream);
@@ -1000,7 +1011,7 @@ extern "C" int rks_nl(rks_plan* p, int j, void* stream) {
 // unless it is a state); otherwise this is rks_stage + rks_nl.
 static bool can_fuse_stage(const rks_plan* p, int s) {
     const int m = p->method, S = method_stages(m);
-    if (!p->nl_fast || p->no_fuse || p->multi_n || p->d.lin_elems != p->d.n_c) return false;
+    if (!p->nl_fast || p->no_fuse || p->multi_n || p->nd_rows || p->d.lin_elems != p->d.n_c) return false;
     if (p->d.model != RKS_MODEL_UUX_RFFT && p->d.model != RKS_MODEL_NLS_FFT) return false;
     if (s == S && m == M_ETD35) return false;              // last ETD35 stage emits err and feeds no N
     return true;
@@ -1010,7 +1021,7 @@ static bool can_fuse_stage(const rks_plan* p, int s) {
 // (stage_pre_kernel -> nl_fast_pre_kernel).  The last stage is a state and keeps the natural layout.
 static bool can_pretransform(const rks_plan* p, int s) {
     // n = 512: a row is one warp's slice, K4 is already warp-local there and the pair measured 5-16 % slower
-    return p->pretransform && p->nl_fast && p->d.n >= 1024 && !p->multi_n && p->d.lin_elems == p->d.n_c && p->d.coef_mode == CM_COLUMN
+    return p->pretransform && p->nl_fast && !p->nd_rows && p->d.n >= 1024 && !p->multi_n && p->d.lin_elems == p->d.n_c && p->d.coef_mode == CM_COLUMN
         && p->d.model == RKS_MODEL_NLS_FFT && s < method_stages(p->method);
 }
 
@@ -1500,6 +1511,110 @@ static int axis_apply(rks_axis* a, const void* in, void* out, int64_t outer, int
         default: axis_launch<4096>(a, i, o, outer, inner, inverse, ostride, bstride, rb_shift, stream); break;
     }
     CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// N-D grid models as engine models: N_j of a 2-D / 3-D spectral grid = inverse transforms over the strided axes
+// (stage value -> N_j, then in place), the fused last-axis kernel on the rows of N_j, forward transforms over the
+// strided axes.  Every kernel resolves its arrays and its run predicate from the control block, so whole trials
+// are enqueued (and graph-replayed) without a host sync: rks_run_trials works for cfg 4 / cfg 5 like for 1-D rows.
+// Replaces the N-D nl_func closures of demos/nls.ipynb:496-511 inside the trial loop solveras.py:379-410.
+// ---------------------------------------------------------------------------------------
+template <int N>
+static void axis_launch_plan(const rks_axis* a, const DevPlan& d, int j, int force, int first, long long outer, long long inner,
+                             int inverse, cudaStream_t stream) {
+    constexpr int C = axis::tile_cols<N>();
+    const size_t smem = (size_t)N * C * sizeof(cplx);
+    const long long tiles = outer * ((inner + C - 1) / C);
+    const long long cap = (long long)a->sm_count * (N == 4096 ? 1 : N == 512 ? 3 : 2) * 4;
+    const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
+    if (inverse) axis_fft_plan_kernel<N, true><<<grid, axis::tile_threads<N>(), smem, stream>>>(d, j, force, first, outer, inner, a->tw, 1.0 / (double)N);
+    else axis_fft_plan_kernel<N, false><<<grid, axis::tile_threads<N>(), smem, stream>>>(d, j, force, first, outer, inner, a->tw, 1.0);
+}
+template <int N>
+static cudaError_t axis_plan_prepare() {
+    const int smem = N * axis::tile_cols<N>() * (int)sizeof(cplx);
+    cudaError_t e = cudaFuncSetAttribute(axis_fft_plan_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(axis_fft_plan_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    return e;
+}
+#define RKS_AXIS_SWITCH(n, CALL) \
+    switch (n) { \
+        case 16: CALL(16); break; case 32: CALL(32); break; case 64: CALL(64); break; case 128: CALL(128); break; \
+        case 256: CALL(256); break; case 512: CALL(512); break; case 1024: CALL(1024); break; \
+        case 2048: CALL(2048); break; default: CALL(4096); break; }
+
+static void axis_step(rks_plan* p, int which, int j, int force, int first, long long outer, long long inner, int inverse,
+                      cudaStream_t stream) {
+    const rks_axis* a = p->nd_axes[which];
+#define RKS_CALL(N) axis_launch_plan<N>(a, p->d, j, force, first, outer, inner, inverse, stream)
+    RKS_AXIS_SWITCH(a->n, RKS_CALL)
+#undef RKS_CALL
+    p->launches += 1;
+}
+
+static int launch_nl_nd(rks_plan* p, int j, int force, cudaStream_t stream) {
+    const DevPlan& d = p->d;
+    const long long s0 = p->nd_spec[0], s1 = p->nd_spec[1], s2 = p->nd_spec[2];
+    const long long slast = p->nd == 2 ? s1 : s2;
+    axis_step(p, 0, j, force, 1, d.batch, d.n_c / s0, 1, stream);
+    if (p->nd == 3) axis_step(p, 1, j, force, 0, d.batch * s0, s2, 1, stream);
+    // rows of N_j, in place: the row kernels take the plan's arrays, control block and roles
+    rks_plan* rp = &p->nd_rows->plan;
+    DevPlan& r = rp->d;
+    r.ctrl = d.ctrl; r.log = d.log; r.K = d.K; r.ERR = d.ERR;
+    r.U[0] = d.U[0]; r.U[1] = d.U[1];
+    for (int q = 0; q < 8; ++q) r.NL[q] = d.NL[q];
+    r.method = d.method; r.batch = d.batch * (d.n_c / slast); r.nd_inplace = 1;
+    const long long before = rp->launches;
+    if (int rc = launch_nl(rp, j, force, stream)) return rc;
+    p->launches += rp->launches - before;
+    if (p->nd == 3) axis_step(p, 1, j, force, 0, d.batch * s0, s2, 0, stream);
+    axis_step(p, 0, j, force, 0, d.batch, d.n_c / s0, 0, stream);
+    return RKS_OK;
+}
+
+extern "C" int rks_set_model_nd(rks_plan* p, int model, int nd, const int64_t* grid, double p0, void* stream_v) {
+    if (!p || !grid) return fail(RKS_ERR_ARG, "null argument");
+    if (p->multi_n) return fail(RKS_ERR_UNSUPPORTED, "N-D models need a shared-dt plan");
+    if (nd != 2 && nd != 3) return fail(RKS_ERR_UNSUPPORTED, "N-D models take 2 or 3 grid dimensions");
+    if (model != RKS_MODEL_NLS_FFT && model != RKS_MODEL_CUBIC_RFFT)
+        return fail(RKS_ERR_UNSUPPORTED, "N-D models: RKS_MODEL_NLS_FFT (complex field) or RKS_MODEL_CUBIC_RFFT (real field)");
+    const bool half = model == RKS_MODEL_CUBIC_RFFT;
+    long long spec[3] = {0, 0, 0}, modes = 1;
+    for (int k = 0; k < nd; ++k) {
+        const long long n = grid[k];
+        const bool last = k == nd - 1;
+        if (n < 16 || (n & (n - 1)) || n > (last ? MODEL_MAX_N : 4096))
+            return fail(RKS_ERR_UNSUPPORTED, "grid axes must be powers of two: 16..4096, last axis 16..16384");
+        spec[k] = last && half ? n / 2 + 1 : n;
+        modes *= spec[k];
+    }
+    if (modes != p->d.n_c) return fail(RKS_ERR_ARG, "grid does not match the plan's modes per trajectory");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    if (p->graph.exec) { cudaGraphExecDestroy(p->graph.exec); p->graph.exec = nullptr; }
+    if (p->nd_rows) return fail(RKS_ERR_UNSUPPORTED, "the plan already has an N-D model");
+    if (int rc = rks_axis_create(&p->nd_axes[0], grid[0], stream_v)) return rc;
+    if (nd == 3) {
+        if (grid[1] == grid[0]) p->nd_axes[1] = p->nd_axes[0];
+        else if (int rc = rks_axis_create(&p->nd_axes[1], grid[1], stream_v)) return rc;
+    }
+    for (int k = 0; k < nd - 1; ++k) {
+        cudaError_t e = cudaSuccess;
+#define RKS_CALL(N) e = axis_plan_prepare<N>()
+        RKS_AXIS_SWITCH(grid[k], RKS_CALL)
+#undef RKS_CALL
+        if (e != cudaSuccess) return fail(RKS_ERR_CUDA, "axis kernel attributes: %s", cudaGetErrorString(e));
+    }
+    if (int rc = rks_rows_create(&p->nd_rows, model, grid[nd - 1], nullptr, p0, stream_v)) return rc;
+    p->nd = nd;
+    for (int k = 0; k < 3; ++k) p->nd_spec[k] = spec[k];
+    p->d.model = model; p->d.model_p0 = p0; p->d.n = grid[nd - 1];
+    p->nl_fast = false; p->nl_small = false; p->no_fuse = true; p->pretransform = false;
+    p->rfft_half = false; p->k4_x2 = false;
+    CUDA_TRY(cudaGetLastError());
+    (void)stream;
     return RKS_OK;
 }
 

@@ -55,6 +55,29 @@ class FusedNL:
         return f"FusedNL({self.name}, n={self.n}, param={self.param})"
 
 
+class FusedGridNL(FusedNL):
+    """Handle of a fused nonlinearity on a 2-D / 3-D spectral grid (``rks_set_model_nd``): passed as ``nl_func`` the
+    engine launches the strided-axis and row FFT kernels itself, predicated on the device, so whole adaptive trials
+    are enqueued and graph-replayed without a host sync (the N-D closures of demos/nls.ipynb:496-511 inside the
+    trial loop solveras.py:379-410).  Called like a function it runs the same kernels from Python."""
+
+    def __init__(self, model_id: int, grid: Sequence[int], param: float, name: str, compose) -> None:
+        self.model_id = model_id
+        self.grid = tuple(int(g) for g in grid)
+        self.n = self.grid[-1]
+        self.kx = None
+        self.param = float(param)
+        self.name = name
+        self._compose = compose
+        self.supports_out = True
+
+    def __call__(self, uf: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self._compose(uf, out=out)
+
+    def __repr__(self) -> str:
+        return f"FusedGridNL({self.name}, grid={self.grid}, param={self.param})"
+
+
 def _n_from_rfft_kx(kx: torch.Tensor) -> int:
     return 2 * (kx.shape[-1] - 1)
 
@@ -287,6 +310,8 @@ def allen_cahn_fourier_ops(n: int, eps: float = 0.01, length: float = 2 * 3.1415
         return torch.fft.rfft2(pointwise_(_abi.MODEL_CUBIC_RFFT, u, -1.0), out=out)      # -(u^3), one kernel
 
     nl_func.supports_out = True          # the engine lets the transform write N_j in place (no copy pass)
+    if ycol is not None:
+        return lin_op, FusedGridNL(_abi.MODEL_CUBIC_RFFT, (n, n), -1.0, "allen_cahn_2d", nl_func)
     return lin_op, nl_func
 
 
@@ -303,8 +328,9 @@ def nls_nd_ops(k_axes: Sequence[torch.Tensor], gamma: float = 2.0):
     dims = tuple(range(-nd, 0))
 
     n_last = int(k_axes[-1].shape[0])
-    # fused innermost axis pays off for 2-D grids; for 3-D the strided outer transforms cost more than
-    # one full fftn + the pointwise kernel (measured at 512^3: 98 vs 86 ms per trial)
+    # power-of-two grids: every transform is the engine's own (10 passes per 3-D evaluation where ifftn + pointwise
+    # + fftn cost 14; 512^3 ETD35: 85 -> 53 ms per trial); other sizes: torch.fft around the fused last axis (2-D)
+    # or around the pointwise kernel
     device = k_axes[-1].device
     sizes = [int(k.shape[0]) for k in k_axes]
     own = _pow2_in_range(n_last) and all(AxisFFT.supported(s) for s in sizes[:-1])
@@ -334,4 +360,6 @@ def nls_nd_ops(k_axes: Sequence[torch.Tensor], gamma: float = 2.0):
         return torch.fft.fftn(pointwise_(_abi.MODEL_NLS_FFT, f, gamma), dim=dims, out=out)   # F{i gamma |f|^2 f}
 
     nl_func.supports_out = True
+    if cols is not None and nd in (2, 3):
+        return lin_op, FusedGridNL(_abi.MODEL_NLS_FFT, sizes, gamma, f"nls_{nd}d", nl_func)
     return lin_op, nl_func

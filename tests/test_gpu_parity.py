@@ -824,3 +824,63 @@ def test_step_recognises_only_the_tensor_it_returned(rk):
     again.copy_(u_new)
     got = sol.step(again, 0.05)
     assert rel(host(got), ref) < STEP_TOL, (ptr, again.data_ptr())
+
+
+# --------------------------------------------------------------------------------------------
+# N-D grid models as engine models (rks_set_model_nd): the trial loop runs without a host sync per trial
+# --------------------------------------------------------------------------------------------
+def _grid_handles(rk, kind, n):
+    if kind == "nls_2d":
+        p = problems.nls(n, half_width=6.0)
+        k = dev(p.kx)
+        lin, nl = rk.models.nls_nd_ops([k, k], gamma=2.0)
+        x = p.x
+        u0 = np.fft.fft2(np.exp(-(x[:, None] ** 2 + x[None, :] ** 2)) * (1.0 + 0.0j))
+        return lin, nl, dev(u0)
+    p, lin, nl, shape = _grid_case(rk, kind, n)
+    return lin, nl, dev(p.u0.reshape(shape))
+
+
+@pytest.mark.parametrize("method,kind,n,tf", [("IF45DP", "allen_cahn_2d", 64, 0.05), ("ETD35", "nls_3d", 16, 0.2),
+                                              ("ETD35", "nls_2d", 64, 0.1), ("IF34", "allen_cahn_2d", 128, 0.5),
+                                              ("ETD34", "nls_3d", 32, 0.05)])
+def test_grid_model_in_engine_equals_python_composition(rk, method, kind, n, tf):
+    """the engine launching the axis / row kernels itself (32-trial graph-replayed chunks) == the same kernels
+    composed from Python with one control-block read per trial: identical decisions, identical bits"""
+    lin, nl, u0 = _grid_handles(rk, kind, n)
+    assert isinstance(nl, rk.models.FusedGridNL)
+    a = getattr(rk, method)(lin, nl, config=rk.SolverConfig(epsilon=1e-5))
+    ua = a.evolve(u0, 0.0, tf, store_freq=2)
+    b = getattr(rk, method)(lin, lambda v, out=None: nl(v), config=rk.SolverConfig(epsilon=1e-5))
+    ub = b.evolve(u0, 0.0, tf, store_freq=2)
+    assert len(a.trial_log) > 3 and a.trial_log == b.trial_log
+    assert a.t == b.t
+    np.testing.assert_array_equal(host(ua), host(ub))
+    for x, y in zip(a.u[1:], b.u[1:]):
+        np.testing.assert_array_equal(host(x), host(y))
+    # far fewer host syncs: launches per trial are the same, but the fused run reads the control block per chunk
+    assert a._engine.fused is not None and b._engine.fused is None
+
+
+def test_grid_model_fixed_step_and_batch(rk):
+    lin, nl, u0 = _grid_handles(rk, "allen_cahn_2d", 32)
+    u0 = torch.stack([u0, 0.5 * u0])
+    a = rk.ETD4(lin, nl)
+    ua = a.evolve(u0, 0.0, 0.1, 0.01, store_freq=5)
+    b = rk.ETD4(lin, lambda v, out=None: nl(v))
+    ub = b.evolve(u0, 0.0, 0.1, 0.01, store_freq=5)
+    np.testing.assert_array_equal(host(ua), host(ub))
+    assert a.t == b.t and len(a.u) == len(b.u)
+
+
+def test_non_power_of_two_grid_falls_back_to_a_callable(rk):
+    n = 24
+    p = problems.allen_cahn_2d(n)
+    lin, nl = rk.models.allen_cahn_fourier_ops(n, eps=0.01)
+    assert not isinstance(nl, rk.models.FusedGridNL)
+    sol = rk.IF34(lin, nl)
+    uf = sol.evolve(dev(p.u0.reshape(p.params["shape"])), 0.0, 0.3)
+    ora = OracleSolver("IF34", p.lin_op, p.nl_func)
+    uo = ora.evolve(p.u0, 0.0, 0.3)
+    assert [r[2] for r in sol.trial_log] == [r.accepted for r in ora.log]
+    assert rel(host(uf).ravel(), uo) < FINAL_TOL

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, call 1: measure the two opt-in K4 variants that round 1 left unmeasured, A/B against the defaults
 mkdir -p gpurun_out; O=gpurun_out; T=r02a
-echo "== new tests (coefficient storage)"; timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "grid_coefficient or indexed_records or separable_tables or non_separable or recognises" > $O/${T}_new_tests.log 2>&1; echo "rc=$?"; tail -15 $O/${T}_new_tests.log
+echo "== new tests (coefficient storage)"; timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "grid_coefficient or indexed_records or separable_tables or non_separable or recognises or grid_model or non_power or cfg4 or cfg5 or batched_2d" > $O/${T}_new_tests.log 2>&1; echo "rc=$?"; tail -15 $O/${T}_new_tests.log
 echo "== opt-in tests"; RKS_TEST_RFFT_HALF=1 RKS_TEST_K4_X2=1 timeout 400 python -m pytest tests -m gpu -q -k "rfft_half or k4_x2" > $O/${T}_optin_tests.log 2>&1; echo "rc=$?"; tail -5 $O/${T}_optin_tests.log
 echo "== bench_nl default"; timeout 200 python tools/bench_nl.py > $O/${T}_bench_nl_default.txt 2>&1; cat $O/${T}_bench_nl_default.txt
 echo "== bench_nl RFFT_HALF"; RKS_RFFT_HALF=1 timeout 200 python tools/bench_nl.py > $O/${T}_bench_nl_rffthalf.txt 2>&1; cat $O/${T}_bench_nl_rffthalf.txt
