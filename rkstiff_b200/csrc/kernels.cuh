@@ -8,7 +8,6 @@
 #include "fft.cuh"
 #include "fft_fast.cuh"
 #include "fft_real.cuh"
-#include "fft_fast_x2.cuh"
 #include "fft_axis.cuh"
 #include "fuse.cuh"
 
@@ -712,97 +711,60 @@ RKS_D void row_barrier(int lrow, int rpc) {
     asm volatile("bar.sync %0, %1;" ::"r"(lrow + 1), "r"(TR) : "memory");
 }
 
-#ifndef RKS_PINGPONG
-#define RKS_PINGPONG 0
-#endif
-
-// EXPERIMENT, off by default (measured slower: 459 us vs 370 us per launch at 4096 x 8192).
-// n = 8192 runs one CTA per SM and ncu shows FP64 ~50 % and LSU ~63 % busy with little overlap.  Here
-// the warp-local part of the transform is run by two groups of 8 warps (two per scheduler each) that
-// hand an "LSU token" back and forth through two named barriers: while one group moves data between
-// registers and shared memory, the other computes.  Strict alternation loses more (two warps per
-// scheduler cannot fill the FP64 pipe, barrier bubbles) than the overlap wins.
-struct LsuToken {
-    int g;
-    RKS_D void acquire() const { asm volatile("bar.sync %0, 512;" ::"r"(1 + g) : "memory"); }
-    RKS_D void release() const { asm volatile("bar.arrive %0, 512;" ::"r"(2 - g) : "memory"); }
-    RKS_D void prime() const { if (g == 1) asm volatile("bar.arrive 1, 512;" ::: "memory"); }   // group 0 starts
-};
-
-template <class Model>
-RKS_D void inner_pingpong_8192(cplx* sm, int T, const fast::Twiddles& ti, const fast::Twiddles& tf, const Model& m) {
-    using namespace fast;
-    constexpr int SH = 3;
-    const int w = T >> 5, l = T & 31;
-    const LsuToken tok{(w >> 2) & 1};
-    const int c0 = w * 512;
-    // first elements / twiddle indices of this lane's two butterflies in each pass
-    const int u0 = l, u1 = l + 32;
-    const int a0 = c0 + u0, a1 = c0 + u1;                                        // pass 2: R 8, Q 64
-    const int b0 = c0 + (u0 >> 3) * 64 + (u0 & 7), b1 = c0 + (u1 >> 3) * 64 + (u1 & 7);   // pass 3: R 8, Q 8
-    const int k0 = c0 + u0 * 8, k1 = c0 + u1 * 8;                                // core:   R 8, Q 1
-    cplx a[8];
-    tok.prime();
-    tok.acquire(); bf_load<8, 64, SH>(sm, a0, a); tok.release();
-    bf_dif<8, 64, TW_S2>(a, ti.t2, u0);
-    tok.acquire(); bf_store<8, 64, SH>(sm, a0, a); bf_load<8, 64, SH>(sm, a1, a); tok.release();
-    bf_dif<8, 64, TW_S2>(a, ti.t2, u1);
-    tok.acquire(); bf_store<8, 64, SH>(sm, a1, a); __syncwarp(); bf_load<8, 8, SH>(sm, b0, a); tok.release();
-    bf_dif<8, 8, TW_S3>(a, ti.t3, u0 & 7);
-    tok.acquire(); bf_store<8, 8, SH>(sm, b0, a); bf_load<8, 8, SH>(sm, b1, a); tok.release();
-    bf_dif<8, 8, TW_S3>(a, ti.t3, u1 & 7);
-    tok.acquire(); bf_store<8, 8, SH>(sm, b1, a); __syncwarp(); bf_load<8, 1, SH>(sm, k0, a); tok.release();
-    bf_core<8>(a, m);
-    tok.acquire(); bf_store<8, 1, SH>(sm, k0, a); bf_load<8, 1, SH>(sm, k1, a); tok.release();
-    bf_core<8>(a, m);
-    tok.acquire(); bf_store<8, 1, SH>(sm, k1, a); __syncwarp(); bf_load<8, 8, SH>(sm, b0, a); tok.release();
-    bf_dit<8, 8, TW_S3>(a, tf.t3, u0 & 7);
-    tok.acquire(); bf_store<8, 8, SH>(sm, b0, a); bf_load<8, 8, SH>(sm, b1, a); tok.release();
-    bf_dit<8, 8, TW_S3>(a, tf.t3, u1 & 7);
-    tok.acquire(); bf_store<8, 8, SH>(sm, b1, a); __syncwarp(); bf_load<8, 64, SH>(sm, a0, a); tok.release();
-    bf_dit<8, 64, TW_S2>(a, tf.t2, u0);
-    tok.acquire(); bf_store<8, 64, SH>(sm, a0, a); bf_load<8, 64, SH>(sm, a1, a); tok.release();
-    bf_dit<8, 64, TW_S2>(a, tf.t2, u1);
-    tok.acquire(); bf_store<8, 64, SH>(sm, a1, a);
-    if (tok.g == 0) tok.release();           // group 1 primed one extra arrival: it skips its last release
-}
-
 struct NoHook { RKS_D void operator()() const {} };
 
 // `after_first` runs once the first pass has consumed the row's input (staging buffer free again).
 // PT: the row is pre-transformed (fft_fast.cuh pre_butterfly: K1 already applied the first inverse pass), so
-// the first pass here is the warp-local middle pass reading global memory / the staging buffer.
+// the first pass here is the warp-local middle pass reading global memory / the staging buffer.  `arrived`
+// (PT with a staging buffer): shared counter of the warps that have consumed the buffer.
 template <int N, bool PT = false, class Model, class Hook = NoHook>
 RKS_D void nl_fast_row(cplx* sm, int T, int lrow, int rpc, const fast::Twiddles& ti, const fast::Twiddles& tf,
-                       const Model& m, const Hook& after_first = Hook()) {
-    constexpr int W = fast::Plan<N>::W, TR = 32 * W;
+                       const Model& m, const Hook& after_first = Hook(), int* arrived = nullptr) {
+    using P = fast::Plan<N>;
+    constexpr int W = P::W, TR = 32 * W;
     if (PT) {
         fast::phase_pre<N>(sm, T, ti, m);
-        // warp-local pass: the barrier is only needed before the staging buffer is refilled
-        if (!std::is_same<Hook, NoHook>::value) row_barrier<TR>(lrow, rpc); else __syncwarp();
-        after_first();
+        __syncwarp();
+        if (!std::is_same<Hook, NoHook>::value) {
+            // No CTA barrier: the warp that consumes the staging buffer LAST refills it (the other warps run on into
+            // their warp-local passes).  Release/acquire through the shared counter orders every warp's reads of
+            // the buffer before the bulk copy that overwrites it.
+            if ((T & 31) == 0) {
+                __threadfence_block();
+                if (atomicAdd(arrived, 1) == W - 1) {
+                    atomicExch(arrived, 0);          // re-armed long before any warp gets here again (row barrier below)
+                    __threadfence_block();
+                    after_first();
+                }
+            }
+        }
     } else {
         fast::phase_first<N>(sm, T, ti, m);
         row_barrier<TR>(lrow, rpc);
         after_first();
     }
-    if (N == 8192 && RKS_PINGPONG && !PT) {
-        inner_pingpong_8192(sm, T, ti, tf, m);
-    } else {
-        if (!PT) { fast::phase_middle<N, 2, true>(sm, T, ti, m);   __syncwarp(); }
-        if (fast::middle_passes<N>() == 2) { fast::phase_middle<N, 3, true>(sm, T, ti, m);   __syncwarp(); }
-        fast::phase_core<N>(sm, T, m);                  __syncwarp();
-        if (fast::middle_passes<N>() == 2) { fast::phase_middle<N, 3, false>(sm, T, tf, m);  __syncwarp(); }
-        fast::phase_middle<N, 2, false>(sm, T, tf, m);
-    }
+    if (!PT) { fast::phase_middle<N, 2, true>(sm, T, ti, m);   __syncwarp(); }
+    if (fast::middle_passes<N>() == 2) { fast::phase_middle<N, 3, true>(sm, T, ti, m);   __syncwarp(); }
+    fast::phase_core<N>(sm, T, m);                  __syncwarp();
+    if (fast::middle_passes<N>() == 2) { fast::phase_middle<N, 3, false>(sm, T, tf, m);  __syncwarp(); }
+    fast::phase_middle<N, 2, false>(sm, T, tf, m);
     row_barrier<TR>(lrow, rpc);
-    fast::phase_last<N>(sm, T, tf, m);
-    // !PT: no barrier here -- the last pass reads exactly the slab positions (T + 32 W c + Q1 s) that the same
-    // thread overwrites in the first pass of its next row, so warps run on into the next row's loads.
-    // PT: the next row's first pass writes the warp's own 512-point slice, which other warps are still reading.
-    // (Merging this barrier with the one after the first pass -- loads + butterflies, barrier, stores -- was
-    // measured slower: 309 vs 298 us per launch at 4096 x 8192.)
-    if (PT) row_barrier<TR>(lrow, rpc);
+    if constexpr (!PT) {
+        fast::phase_last<N>(sm, T, tf, m);
+        // no barrier here -- the last pass reads exactly the slab positions (T + 32 W c + Q1 s) that the same
+        // thread overwrites in the first pass of its next row, so warps run on into the next row's loads.
+    } else {
+        // PT: the next row's first pass writes the warp's own 512-point slice, which other warps read in this pass.
+        // The barrier sits right after the slab loads of the (single) last-pass butterfly of a thread, so the
+        // butterfly, its 16 global stores and the next row's first pass are not held up by the slowest warp.
+        constexpr int R1 = P::R1, Q1 = N / R1;
+        static_assert(Q1 == 32 * W, "pre-transformed rows: one last-pass butterfly per thread");
+        cplx a[R1];
+        fast::bf_load<R1, Q1, P::SH>(sm, T, a);
+        row_barrier<TR>(lrow, rpc);
+        fast::bf_dit<R1, Q1, fast::TW_S1>(a, tf.t1, T);
+        fast::bf_store_global<R1, Q1>(m, T, a);
+    }
 }
 
 // pull a row that will be needed soon from HBM into L2 (no registers, no smem)
@@ -903,10 +865,12 @@ RKS_D void nl_fast_kernel_body(const DevPlan& p, int j, int force, FuseDesc fd) 
     constexpr bool STAGED = W == 16 && FK == 0 && MODEL >= 1 && MODEL <= 3;
     cplx* stg = reinterpret_cast<cplx*>(smem_raw) + (size_t)RPC * N;
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(stg + NL_STAGE_ELEMS);
+    int* arrived = reinterpret_cast<int*>(bar + 1);          // PT: warps that have consumed the staging buffer
     const int nst = p.n_c < NL_STAGE_ELEMS ? (int)p.n_c : NL_STAGE_ELEMS;
     unsigned parity = 0;
     if (STAGED) {
         if (threadIdx.x == 0) {
+            *arrived = 0;
             stage_init(bar);
             if ((long long)blockIdx.x < groups) stage_issue(stg, roles.in + (long long)blockIdx.x * p.n_c, nst * 16u, bar);
         }
@@ -929,8 +893,9 @@ RKS_D void nl_fast_kernel_body(const DevPlan& p, int j, int force, FuseDesc fd) 
             parity ^= 1u;
             const auto m = fast::ModelOf<MODEL>::make_staged(fast::StagedRow{roles.in + rr * p.n_c, stg, nst}, out, p.kx,
                                                              p.model_p0, N, on);
-            const StageNext next{stg, roles.in + (nlines ? nrow : rr) * p.n_c, nst * 16u, bar, nlines != 0 && threadIdx.x == 0};
-            nl_fast_row<N, PT>(sm, T, lrow, RPC, ti, tf, m, next);
+            // !PT: thread 0 issues the copy after the row barrier; PT: the lane the counter elects
+            const StageNext next{stg, roles.in + (nlines ? nrow : rr) * p.n_c, nst * 16u, bar, nlines != 0 && (PT || threadIdx.x == 0)};
+            nl_fast_row<N, PT>(sm, T, lrow, RPC, ti, tf, m, next, arrived);
         } else if (FK == 0) {
             prefetch_row_l2<TR>(roles.in + (nlines ? nrow : rr) * p.n_c, nlines, T);
             const auto m = fast::ModelOf<MODEL>::make(roles.in + rr * p.n_c, out, p.kx, p.model_p0, N, on);
@@ -1000,76 +965,6 @@ __global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_f
 template <int W, int MODEL, int FK>
 __global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_fast_kernel_multi(const DevPlan* plans, int j, int force, FuseDesc fd) { nl_fast_kernel_body<W, MODEL, FK>(plans[blockIdx.z], j, force, fd); }
 
-
-// ---------------------------------------------------------------------------------------
-// EXPERIMENT, opt-in (RKS_K4_X2=1), not measured yet: the n = 8192 NLS evaluation of pre-transformed rows (the plain
-// one spills at 255 registers and is not dispatched) with 8 warps x 255 registers, two
-// logical threads per physical thread and every pass written loads / butterflies / stores (fft_fast_x2.cuh; results
-// bit-identical to nl_fast_kernel / nl_fast_pre_kernel on the CPU harness).  Same TMA staging of the next row.
-// ---------------------------------------------------------------------------------------
-template <bool PT, class Model, class Hook>
-RKS_D void nl_fast_row_x2(cplx* sm, int t, const fast::Twiddles& ti, const fast::Twiddles& tf, const Model& m,
-                          const Hook& after_first) {
-    constexpr int N = 8192;
-    if (PT) {
-        fast::phase_pre_x2<N>(sm, t, ti, m);
-        __syncthreads();                                  // staging buffer consumed by every warp
-        after_first();
-    } else {
-        // radix-16 passes: one logical thread after the other (two 16-point butterflies + twiddles at once spill)
-        fast::phase_first<N>(sm, fast::x2_first(t), ti, m);
-        fast::phase_first<N>(sm, fast::x2_second(t), ti, m);
-        __syncthreads();
-        after_first();
-        fast::phase_middle_x2<N, 2, true>(sm, t, ti, m);    __syncwarp();
-    }
-    fast::phase_middle_x2<N, 3, true>(sm, t, ti, m);        __syncwarp();
-    fast::phase_core_x2<N>(sm, t, m);                       __syncwarp();
-    fast::phase_middle_x2<N, 3, false>(sm, t, tf, m);       __syncwarp();
-    fast::phase_middle_x2<N, 2, false>(sm, t, tf, m);
-    __syncthreads();
-    fast::phase_last<N>(sm, fast::x2_first(t), tf, m);
-    fast::phase_last<N>(sm, fast::x2_second(t), tf, m);
-    // !PT: the last pass reads the slab positions the same thread overwrites in the first pass of its next row (both
-    // logical threads are this thread's); PT: the next first pass writes the warp's slices, which others still read
-    if (PT) __syncthreads();
-}
-template <bool PT>
-__global__ void __launch_bounds__(256, 1) nl_fast_x2_kernel(const __grid_constant__ DevPlan p, int j, int force) {
-    constexpr int N = 8192, THREADS = 256;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const NlRoles roles = nl_roles(p, j, force);
-    if (!roles.run) return;
-    if (p.ctrl && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&p.ctrl->nl_evals, 1ull);
-    const int t = threadIdx.x;
-    cplx* sm = reinterpret_cast<cplx*>(smem_raw);
-    const fast::Twiddles ti{p.twf + fast::TW_T1, p.twf + fast::TW_T2, p.twf + fast::TW_T3};
-    const cplx* twf2 = p.twf + fast::TW_TOTAL;
-    const fast::Twiddles tf{twf2 + fast::TW_T1, twf2 + fast::TW_T2, twf2 + fast::TW_T3};
-    const int lines = (int)((p.n_c * 16 + 127) >> 7);
-    cplx* stg = sm + N;
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(stg + NL_STAGE_ELEMS);
-    const int nst = NL_STAGE_ELEMS;
-    unsigned parity = 0;
-    if (t == 0) {
-        stage_init(bar);
-        if ((long long)blockIdx.x < p.batch) stage_issue(stg, roles.in + (long long)blockIdx.x * p.n_c, nst * 16u, bar);
-    }
-    __syncthreads();
-    for (long long row = blockIdx.x; row < p.batch; row += gridDim.x) {
-        const long long nrow = row + gridDim.x;
-        const int nlines = nrow < p.batch ? lines : 0;
-        const int head = (nst * 16) >> 7;
-        if (nlines > head)
-            prefetch_row_l2<THREADS>(reinterpret_cast<const char*>(roles.in + nrow * p.n_c) + ((size_t)head << 7), nlines - head, t);
-        stage_wait(bar, parity);
-        parity ^= 1u;
-        const auto m = fast::ModelOf<2>::make_staged(fast::StagedRow{roles.in + row * p.n_c, stg, nst}, roles.out + row * p.n_c,
-                                                     p.kx, p.model_p0, N, true);
-        const StageNext next{stg, roles.in + (nlines ? nrow : row) * p.n_c, nst * 16u, bar, nlines != 0 && t == 0};
-        nl_fast_row_x2<PT>(sm, t, ti, tf, m, next);
-    }
-}
 
 // ---------------------------------------------------------------------------------------
 // EXPERIMENT, opt-in (RKS_RFFT_HALF=1), not measured yet: K4 for the real-field models (1 = u u_x, 3 = cubic) with the

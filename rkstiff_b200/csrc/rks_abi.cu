@@ -131,8 +131,7 @@ struct rks_plan {
     bool nl_small;                  // n in {64, 128, 256}: the same pipeline on slabs of packed rows
     bool no_fuse;                   // default: K1 and K4 as separate kernels (north_star decomposition); RKS_FUSE=1 fuses
     bool pretransform;              // intermediate NLS stages: K1 applies the first inverse FFT pass (RKS_PT=0 disables)
-    bool rfft_half;                 // EXPERIMENT (RKS_RFFT_HALF=1): half-length forward transform for the real-field models
-    bool k4_x2;                     // EXPERIMENT (RKS_K4_X2=1): n = 8192 pre-transformed NLS evaluation with 8 warps x 255 registers
+    bool rfft_half;                 // real-field models: half-length forward transform (default for n <= 1024)
     size_t nl_smem;
     // N-D grid model (rks_set_model_nd): strided-axis handles, the fused last-axis kernel, spectral grid dims
     struct rks_axis* nd_axes[2] = {nullptr, nullptr};
@@ -574,12 +573,10 @@ static int prepare_nl_launch(rks_plan* p, int model, long long n, cplx* twf_dev,
     DevPlan& d = p->d;
     p->nl_fast = (n >= 512 && n <= 8192) && !getenv("RKS_NL_GENERIC");
     p->no_fuse = getenv("RKS_FUSE") == nullptr;       // fused K1+K4 is opt-in (RKS_FUSE=1): see DESIGN.md 4
-    p->k4_x2 = getenv("RKS_K4_X2") != nullptr && p->nl_fast && n == 8192 && model == RKS_MODEL_NLS_FFT;
-    if (p->k4_x2) {
-        const int sm = (int)nl_fast_smem<16>(RKS_MODEL_NLS_FFT, 0);
-        CUDA_TRY(cudaFuncSetAttribute(nl_fast_x2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-    }
-    p->rfft_half = getenv("RKS_RFFT_HALF") != nullptr && p->nl_fast && n <= 4096
+    // real-field models: half-length forward transform (fft_real.cuh).  Measured (profiles/r02_k4_ab.md): 7 % faster
+    // than the full-length pair for n = 512 and 1024, slower for n >= 2048 (three more row barriers per row)
+    const char* rh = getenv("RKS_RFFT_HALF");
+    p->rfft_half = p->nl_fast && (rh ? (rh[0] != '0' && n <= 4096) : n <= 1024)
                    && (model == RKS_MODEL_UUX_RFFT || model == RKS_MODEL_CUBIC_RFFT);
     if (p->rfft_half) {
         const auto a = cudaFuncAttributeMaxDynamicSharedMemorySize;
@@ -903,12 +900,6 @@ static void launch_nl_fast_pre_t(rks_plan* p, int j, int force, cudaStream_t str
     nl_fast_pre_kernel<W><<<grid, THREADS, nl_fast_smem<W>(RKS_MODEL_NLS_FFT, 0), stream>>>(p->d, j, force, none);
 }
 static void dispatch_nl_fast_pre(rks_plan* p, int j, int force, cudaStream_t stream) {
-    if (p->k4_x2) {
-        const unsigned grid = (unsigned)(p->d.batch < p->sm_count ? p->d.batch : p->sm_count);
-        nl_fast_x2_kernel<true><<<grid, 256, nl_fast_smem<16>(RKS_MODEL_NLS_FFT, 0), stream>>>(p->d, j, force);
-        p->launches += 1;
-        return;
-    }
     switch (p->d.n) {
         case 1024: launch_nl_fast_pre_t<2>(p, j, force, stream); break;
         case 2048: launch_nl_fast_pre_t<4>(p, j, force, stream); break;
@@ -1612,7 +1603,7 @@ extern "C" int rks_set_model_nd(rks_plan* p, int model, int nd, const int64_t* g
     for (int k = 0; k < 3; ++k) p->nd_spec[k] = spec[k];
     p->d.model = model; p->d.model_p0 = p0; p->d.n = grid[nd - 1];
     p->nl_fast = false; p->nl_small = false; p->no_fuse = true; p->pretransform = false;
-    p->rfft_half = false; p->k4_x2 = false;
+    p->rfft_half = false;
     CUDA_TRY(cudaGetLastError());
     (void)stream;
     return RKS_OK;

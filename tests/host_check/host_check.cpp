@@ -16,7 +16,6 @@
 #include "../../rkstiff_b200/csrc/fft.cuh"
 #include "../../rkstiff_b200/csrc/fft_fast.cuh"
 #include "../../rkstiff_b200/csrc/fft_real.cuh"
-#include "../../rkstiff_b200/csrc/fft_fast_x2.cuh"
 #include "../../rkstiff_b200/csrc/fft_axis.cuh"
 #include "../../rkstiff_b200/csrc/fuse.cuh"
 
@@ -74,41 +73,6 @@ static void pre_row(const cplx* k, cplx* out, double gamma, const fast::Twiddles
     for (int T = 0; T < TR; ++T) fast::phase_last<N>(sm.data(), T, tw, m);
 }
 
-// serial emulation of the two-logical-threads-per-thread passes (fft_fast_x2.cuh): TR / 2 physical threads per row;
-// pre = the row is pre-transformed (K1 applied the first inverse pass) and the first pass is phase_pre_x2
-template <int N, class Model>
-static void fast_row_x2(const Model& m, const fast::Twiddles& tw, bool pre) {
-    constexpr int TP = 16 * fast::Plan<N>::W;
-    std::vector<cplx> sm(N);
-    if (pre) {
-        for (int t = 0; t < TP; ++t) fast::phase_pre_x2<N>(sm.data(), t, tw, m);
-    } else {
-        for (int t = 0; t < TP; ++t) fast::phase_first_x2<N>(sm.data(), t, tw, m);
-        for (int t = 0; t < TP; ++t) fast::phase_middle_x2<N, 2, true>(sm.data(), t, tw, m);
-    }
-    if (fast::middle_passes<N>() == 2)
-        for (int t = 0; t < TP; ++t) fast::phase_middle_x2<N, 3, true>(sm.data(), t, tw, m);
-    for (int t = 0; t < TP; ++t) fast::phase_core_x2<N>(sm.data(), t, m);
-    if (fast::middle_passes<N>() == 2)
-        for (int t = 0; t < TP; ++t) fast::phase_middle_x2<N, 3, false>(sm.data(), t, tw, m);
-    for (int t = 0; t < TP; ++t) fast::phase_middle_x2<N, 2, false>(sm.data(), t, tw, m);
-    for (int t = 0; t < TP; ++t) fast::phase_last_x2<N>(sm.data(), t, tw, m);
-}
-template <int N>
-static void x2_nls_row(const cplx* k, cplx* out, double gamma, const fast::Twiddles& tw, bool pre) {
-    using P = fast::Plan<N>;
-    constexpr int R1 = P::R1, Q1 = N / R1;
-    std::vector<cplx> kt(k, k + N);
-    if (pre) {
-        for (int col = 0; col < Q1; ++col) {                // stage_pre_kernel's butterflies
-            cplx a[R1];
-            for (int s = 0; s < R1; ++s) a[s] = k[col + s * Q1];
-            fast::pre_butterfly<R1>(a, tw.t1, col);
-            for (int r = 0; r < R1; ++r) kt[col + r * Q1] = a[fast::perm<R1>(r)];
-        }
-    }
-    fast_row_x2<N>(fast::ModelOf<2>::make(kt.data(), out, nullptr, gamma, N, true), tw, pre);
-}
 
 // serial emulation of the real-field variant (fft_real.cuh): inverse passes as in fast_row, then the paired core
 // pass, the forward middle pass on the even blocks and the half-length last pass with its exchange
@@ -243,22 +207,6 @@ int hc_nl_fast(int model, int n, const double* in, const double* kx, double p0, 
     if (model == 2) return fast_dispatch(n, fast::ModelOf<2>::make(cin, co, kx, p0, n, true), tw);
     if (model == 3) return fast_dispatch(n, fast::ModelOf<3>::make(cin, co, kx, p0, n, true), tw);
     return fast_dispatch(n, fast::ModelOf<4>::make(cin, co, kx, p0, n, true), tw);
-}
-
-// NLS evaluation of one row through the two-logical-threads-per-thread passes, plain or pre-transformed input
-int hc_nl_x2(int n, const double* in, double gamma, double* out, int pre) {
-    std::vector<cplx> tab(fast::TW_TOTAL);
-    for (int j = 0; j < fast::TW_TOTAL; ++j) tab[j] = fast::twiddle_table_entry(j, n);
-    const fast::Twiddles tw{tab.data() + fast::TW_T1, tab.data() + fast::TW_T2, tab.data() + fast::TW_T3};
-    const cplx* cin = reinterpret_cast<const cplx*>(in);
-    cplx* co = reinterpret_cast<cplx*>(out);
-    switch (n) {
-        case 1024: x2_nls_row<1024>(cin, co, gamma, tw, pre != 0); return 0;
-        case 2048: x2_nls_row<2048>(cin, co, gamma, tw, pre != 0); return 0;
-        case 4096: x2_nls_row<4096>(cin, co, gamma, tw, pre != 0); return 0;
-        case 8192: x2_nls_row<8192>(cin, co, gamma, tw, pre != 0); return 0;
-    }
-    return -1;
 }
 
 // real-field models (1 = u u_x, 3 = cubic) through the half-length forward transform of fft_real.cuh

@@ -435,22 +435,6 @@ def test_real_field_half_length_forward_matches_numpy(hc, n):
     assert hc.hc_nl_fast_real(2, n, ptr(uf), None, ctypes.c_double(1.0), ptr(out)) != 0     # complex-field model: not applicable
 
 
-@pytest.mark.parametrize("n", [1024, 2048, 4096, 8192])
-def test_two_logical_threads_per_thread_passes_are_bit_identical(hc, n):
-    """fft_fast_x2.cuh (opt-in kernel): 'all loads, all butterflies, all stores' over the butterflies of two logical
-    threads performs the same operations on the same data as the one-butterfly-at-a-time passes."""
-    p = problems.nls(n, batch=2, half_width=20.0, seed=n + 7)
-    rng = np.random.default_rng(n)
-    for row in p.u0:
-        row = np.ascontiguousarray(row + 1e-3 * (rng.standard_normal(n) + 1j * rng.standard_normal(n)))
-        plain, out = np.empty_like(row), np.empty_like(row)
-        assert hc.hc_nl_fast(2, n, ptr(row), None, ctypes.c_double(2.0), ptr(plain)) == 0
-        for pre in (0, 1):
-            out[:] = 0
-            assert hc.hc_nl_x2(n, ptr(row), ctypes.c_double(2.0), ptr(out), pre) == 0
-            np.testing.assert_array_equal(out, plain)
-
-
 # ------------------------------------------------------------------------------------------------
 # coefficient storage of large grids (DESIGN.md 4): per-axis exponential tables, grouped records
 # ------------------------------------------------------------------------------------------------
