@@ -172,6 +172,10 @@ class Engine:
         #: error controller (rks_norm_override); None for diagonal operators
         self.norm_map: Optional[Callable] = None
         self._norm_keep = None
+        self._group_graphs = {}                       # sharded shared-dt trial captured with its NCCL all-reduces
+        self._group_graph_ok = True
+        self._group_graph_launches = 0
+        self._replayed_launches = 0
 
     def _coef_strategy(self, lin: torch.Tensor, want: str):
         """How the coefficient arrays of this plan are stored: None = one entry per mode (1-D rows:
@@ -233,8 +237,12 @@ class Engine:
         check(lib.rks_set_config(self.plan, byref(cfg), self.st))
         self._h_host = None
 
-    def launches(self) -> int:
+    def launches_raw(self) -> int:
         return int(lib.rks_kernel_launches(self.plan))
+
+    def launches(self) -> int:
+        """Kernel launches of this plan, including those replayed from the captured sharded-trial graph."""
+        return self.launches_raw() + self._replayed_launches
 
     # -- state ----------------------------------------------------------------------------
     def begin(self, t0: float, tf: float, h: float, store_freq: int, step_mode: bool, keep_fsal: bool = False):
@@ -370,8 +378,39 @@ class Engine:
                                      c_void_p(ring_t.data_ptr()) if ring is not None else None,
                                      ring.shape[0] if ring is not None else 0, self.st))
         else:
+            self._run_trials_group(k, ring, ring_t)
+
+    def _run_trials_group(self, k: int, ring, ring_t) -> None:
+        """Sharded shared-dt ensemble: one trial = ~17 launches plus two NCCL all-reduces of the error scalars.
+        The first trial runs eagerly (it creates the communicator and every lazily initialised kernel attribute);
+        the trial is then captured ONCE into a CUDA graph -- NCCL collectives included -- and replayed, so the
+        per-trial host cost is one graph launch, as on the single-GPU path (rks_run_trials).  RKS_GROUP_GRAPH=0
+        or a failed capture keeps the eager loop."""
+        import os
+        key = (ring.data_ptr(), ring_t.data_ptr(), ring.shape[0]) if ring is not None else None
+        graph = self._group_graphs.get(key)
+        if graph is None and self._group_graph_ok and os.environ.get("RKS_GROUP_GRAPH", "1")[:1] != "0" and k > 1:
+            self.enqueue_trial(None, ring, ring_t)
+            k -= 1
+            try:
+                torch.cuda.synchronize(self.device)
+                before = self.launches_raw()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.enqueue_trial(None, ring, ring_t)
+                self._group_graph_launches = self.launches_raw() - before
+                self._replayed_launches -= self._group_graph_launches      # the capture itself launched nothing
+                self._group_graphs[key] = graph = (g, ring, ring_t)         # keeps the ring alive with the graph
+            except Exception:                                               # noqa: BLE001
+                self._group_graph_ok = False
+                torch.cuda.synchronize(self.device)
+        if graph is not None:
             for _ in range(k):
-                self.enqueue_trial(None, ring, ring_t)
+                graph[0].replay()
+            self._replayed_launches += k * self._group_graph_launches
+            return
+        for _ in range(k):
+            self.enqueue_trial(None, ring, ring_t)
 
     # -- fixed step -----------------------------------------------------------------------
     def ensure_fixed_coeffs(self, h: float) -> None:

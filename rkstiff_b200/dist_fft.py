@@ -54,6 +54,22 @@ class SlabFFT:
         dist.all_to_all_single(out, a, group=self.group)
         return out
 
+    def _exchange_lists(self, outs, ins):
+        """Asynchronous all-to-all of per-peer CONTIGUOUS blocks (``ins[g]`` goes to rank g, ``outs[g]`` arrives from
+        rank g); returns a list of work handles.  NCCL: one grouped send/recv launch on the communicator's stream, so
+        the exchange of one chunk runs beside the transforms of another; other backends (gloo in the CPU tests):
+        point-to-point operations."""
+        if dist.get_backend(self.group) == "nccl":
+            return [dist.all_to_all(outs, ins, group=self.group, async_op=True)]
+        outs[self.rank].copy_(ins[self.rank])
+        ops = []
+        for g in range(self.world):
+            if g != self.rank:
+                peer = dist.get_global_rank(self.group, g) if self.group is not None else g
+                ops.append(dist.P2POp(dist.isend, ins[g], peer, group=self.group))
+                ops.append(dist.P2POp(dist.irecv, outs[g], peer, group=self.group))
+        return dist.batch_isend_irecv(ops) if ops else []
+
     # -- transforms -------------------------------------------------------------------------
     def forward(self, f: torch.Tensor, skip_last: bool = False) -> torch.Tensor:
         """real-space slab ``(n0/G, n1, ...)`` -> spectral block ``(n0, n1/G, ...)`` (unnormalised).
@@ -81,6 +97,9 @@ class SlabFFT:
         """``F{ N( F^-1{ s } ) }`` with the engine's kernels only: ``axes[d]`` is the ``AxisFFT`` of grid axis d
         (d < nd-1), ``rows`` the fused last-axis kernel (inverse, pointwise N, forward).  Two all-to-alls."""
         G, (n0, n1), nd = self.world, self.shape[:2], len(self.shape)
+        chunks = self._pipeline_chunks()
+        if chunks > 1:
+            return self._fused_nl_pipelined(s, rows, axes, out, chunks)
         work = torch.empty_like(s)
         axes[0].inverse_(s, 0, out=work)                                   # s itself must stay intact
         a = self._exchange(work.reshape((G, n0 // G, n1 // G) + self.rest))
@@ -102,6 +121,62 @@ class SlabFFT:
             rows(a, out=a)
             a = a.reshape((n0 // G, G, n1 // G)).permute((1, 0, 2)).contiguous()
         b = self._exchange(a).reshape(self.spec_shape)
+        return axes[0].forward_(b, 0, out=out)
+
+
+    # -- overlapped exchange ------------------------------------------------------------------
+    #: x-plane groups the exchange of a 3-D (or higher) evaluation is split into (RKS_SLAB_CHUNKS overrides; 1 = off)
+    PIPELINE_CHUNKS = 4
+
+    def _pipeline_chunks(self) -> int:
+        """How many x-plane groups to pipeline: needs >= 3 dimensions, more than one rank and a divisor of the local
+        plane count; the largest divisor <= the requested number is used."""
+        import os
+        want = int(os.environ.get("RKS_SLAB_CHUNKS", self.PIPELINE_CHUNKS))
+        m = self.shape[0] // self.world
+        if self.world == 1 or len(self.shape) < 3 or want <= 1:
+            return 1
+        c = min(want, m)
+        while m % c:
+            c -= 1
+        return c
+
+    def _fused_nl_pipelined(self, s: torch.Tensor, rows, axes, out: Optional[torch.Tensor], C: int) -> torch.Tensor:
+        """``fused_nl`` with the two all-to-alls split into C groups of this rank's x planes ("chunk along
+        the local axis to overlap with FFT passes").  After the axis-0 inverse, group c of every destination's planes
+        is one contiguous block, so group c's exchange (NCCL stream) runs while group c-1 goes through the axis-1
+        transform, the fused last-axis kernel and the axis-1 forward transform (stepping stream), and group c-2
+        travels back.  Only the two axis-0 passes are outside the overlap.  Same kernels on the same values as the
+        unchunked route: results are bit-identical."""
+        G, (n0, n1), nd = self.world, self.shape[:2], len(self.shape)
+        m = n0 // G
+        mc = m // C
+        work = torch.empty_like(s)
+        axes[0].inverse_(s, 0, out=work)                                   # s itself must stay intact
+        wv = work.reshape((G, m, n1 // G) + self.rest)                     # [destination g][its x plane][my y chunk]
+        a = torch.empty((C, G, mc, n1 // G) + self.rest, dtype=s.dtype, device=s.device)
+        b = torch.empty_like(s)
+        bv = b.reshape((G, m, n1 // G) + self.rest)                        # [source g = x block][x plane][my y chunk]
+        arriving = [self._exchange_lists([a[c, g] for g in range(G)], [wv[g, c * mc:(c + 1) * mc] for g in range(G)])
+                    for c in range(C)]
+        leaving = []
+        for c in range(C):
+            for w in arriving[c]:
+                w.wait()
+            ac = a[c]                                                      # (G, my planes of group c, g's y chunk, rest)
+            if nd == 3:
+                ac = ac.reshape((G, mc, n1 // G, self.rest[0]))
+            axes[1].chunked_(ac, True)
+            for d in range(2, nd - 1):
+                axes[d].inverse_(ac, d + 1)
+            rows(ac, out=ac)
+            for d in range(nd - 2, 1, -1):
+                axes[d].forward_(ac, d + 1)
+            axes[1].chunked_(ac, False)
+            leaving.append(self._exchange_lists([bv[g, c * mc:(c + 1) * mc] for g in range(G)], [a[c, g] for g in range(G)]))
+        for ws in leaving:
+            for w in ws:
+                w.wait()
         return axes[0].forward_(b, 0, out=out)
 
 

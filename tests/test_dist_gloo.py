@@ -107,3 +107,81 @@ def test_slab_fft_matches_fftn_and_round_trips():
         assert pr.exitcode == 0
     for _, e_fwd, e_back in res:
         assert e_fwd < 1e-12 and e_back < 1e-13
+
+
+class _TorchAxis:
+    """CPU stand-in for models.AxisFFT (natural order instead of digit-reversed: invisible to a pointwise N)."""
+
+    def inverse_(self, x, dim, out=None):
+        res = torch.fft.ifft(x, dim=dim)
+        if out is None:
+            x.copy_(res)
+            return x
+        out.copy_(res)
+        return out
+
+    def forward_(self, x, dim, out=None):
+        res = torch.fft.fft(x, dim=dim)
+        if out is None:
+            x.copy_(res)
+            return x
+        out.copy_(res)
+        return out
+
+    def chunked_(self, x, inverse):
+        # x: (G, outer, n/G, inner...) block-major along the transformed axis
+        G, outer, nb = x.shape[:3]
+        y = x.permute((1, 0, 2) + tuple(range(3, x.dim()))).reshape((outer, G * nb) + tuple(x.shape[3:]))
+        y = torch.fft.ifft(y, dim=1) if inverse else torch.fft.fft(y, dim=1)
+        x.copy_(y.reshape((outer, G, nb) + tuple(x.shape[3:])).permute((1, 0, 2) + tuple(range(3, x.dim()))))
+        return x
+
+
+def _rows_nls(a, out=None):
+    f = torch.fft.ifft(a, dim=-1)
+    res = 2j * torch.fft.fft((f.real ** 2 + f.imag ** 2) * f, dim=-1)
+    out.copy_(res)
+    return out
+
+
+def _pipeline_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from rkstiff_b200.dist_fft import SlabFFT
+    shape = (8, 4, 6)
+    g = torch.Generator().manual_seed(1)
+    full = torch.randn(shape, dtype=torch.float64, generator=g) + 1j * torch.randn(shape, dtype=torch.float64, generator=g)
+    f = torch.fft.ifftn(full)
+    want_full = 2j * torch.fft.fftn((f.real ** 2 + f.imag ** 2) * f)
+    fft = SlabFFT(shape)
+    s = fft.spec_slice(full)
+    axes = [_TorchAxis(), _TorchAxis()]
+    errs = []
+    for chunks in ("1", "2", "4"):
+        os.environ["RKS_SLAB_CHUNKS"] = chunks
+        keep = s.clone()
+        got = fft.fused_nl(s, _rows_nls, axes)
+        errs.append((chunks, fft._pipeline_chunks(), float((got - fft.spec_slice(want_full)).abs().max()),
+                     float((s - keep).abs().max())))
+    q.put((rank, errs))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pipelined_slab_exchange_equals_single_exchange():
+    """The x-plane-chunked all-to-all pipeline of SlabFFT.fused_nl (dist_fft.py) against fftn of the whole grid."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pipeline_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    for _, errs in res:
+        assert [e[1] for e in errs] == [1, 2, 4]          # 8 / 2 = 4 local planes: 1, 2 and 4 groups
+        for _, _, err, touched in errs:
+            assert err < 1e-10 and touched == 0.0           # the input spectrum stays intact

@@ -1,0 +1,30 @@
+#!/bin/bash
+# round 2, call 3 (1 GPU): full suite incl. the size-class parity tests, the new default bench line (cfg2 + secondary cfg3/4/5),
+# the reference arm, smoke, and the ncu --set full inventory of every kernel family at the bench geometry
+mkdir -p gpurun_out; O=gpurun_out; T=r02c
+echo "== size-class parity tests"; timeout 900 python -m pytest tests/test_gpu_size_classes.py -x -q > $O/${T}_size_classes.log 2>&1; echo "rc=$?"; tail -5 $O/${T}_size_classes.log
+echo "== full GPU suite"; timeout 1500 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_size_classes.py > $O/${T}_gpu_suite.log 2>&1; echo "rc=$?"; tail -4 $O/${T}_gpu_suite.log
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${T}_smoke.log 2>&1; echo "rc=$?"; tail -3 $O/${T}_smoke.log
+echo "== default bench line"; /usr/bin/time -v timeout 900 python bench.py > $O/${T}_bench_default.json 2> $O/${T}_bench_default.err; echo "rc=$?"; grep -E "Elapsed|Maximum resident" $O/${T}_bench_default.err
+python - <<'PY'
+import json
+d = json.load(open("gpurun_out/r02c_bench_default.json"))
+def show(tag, x):
+    if "error" in x:
+        print(tag, "ERROR", x["error"]); return
+    r = x.get("roofline", {})
+    print(tag, "ms/step %.3f value %.3e e2e %.3e frac %s whole %s cpu %s" % (x["ms_per_step"], x["value"], x["e2e"]["value"], r.get("frac"),
+          (r.get("whole_step") or {}).get("frac"), (x.get("cpu_baseline") or {}).get("value")))
+    print("   parity:", (x.get("cpu_baseline") or {}).get("parity"), "clocks:", x.get("clocks"))
+show("cfg2", d)
+for k, v in d.get("secondary", {}).items():
+    show(k, v)
+PY
+echo "== reference arm"; timeout 600 python bench.py --impl reference > $O/${T}_bench_reference.json 2> $O/${T}_bench_reference.err; echo "rc=$?"; cut -c1-300 $O/${T}_bench_reference.json
+echo "== ncu inventory"
+for w in cfg2 cfg3 cfg4 cfg5 cfg2b; do
+  timeout 900 ncu --set full --clock-control none --profile-from-start off -k regex:rks -f -o /tmp/${T}_inv_$w python tools/prof_all.py $w > $O/${T}_inv_$w.log 2>&1; echo "$w rc=$?"
+  ncu -i /tmp/${T}_inv_$w.ncu-rep --page raw --csv > $O/${T}_inv_${w}_raw.csv 2>/dev/null
+done
+python tools/ncu_summary.py cfg2=$O/${T}_inv_cfg2_raw.csv cfg3=$O/${T}_inv_cfg3_raw.csv cfg4=$O/${T}_inv_cfg4_raw.csv cfg5=$O/${T}_inv_cfg5_raw.csv cfg2b=$O/${T}_inv_cfg2b_raw.csv > $O/${T}_ncu_all_kernels.csv
+wc -l $O/${T}_ncu_all_kernels.csv; cut -d, -f1,2,7,8,9,10,11,12,13 $O/${T}_ncu_all_kernels.csv | cut -c1-220
