@@ -205,9 +205,7 @@ RKS_HD void row_st(cplx* p, cplx v) {
 #endif
 }
 
-// Where a row's input comes from: an existing array (plain evaluation) or the stage combine
-// evaluated on the fly (fuse.cuh).  `sink` optionally stores the value as the new state u+ and
-// tracks max |u+|^2 for the error controller.
+// Where a row's input comes from: a plain array, or partly the TMA staging buffer (StagedRow).
 struct ArraySource {
     const cplx* in;
     RKS_HD cplx value(long long p) const { return row_ld(in + p); }
@@ -221,32 +219,10 @@ struct StagedRow {
     RKS_HD cplx value(long long p) const { return p < nst ? stg[p] : row_ld(in + p); }
     RKS_HD cplx get(int k) const { return k < nst ? stg[k] : row_ld(in + k); }
 };
-struct StateSink {
-    cplx* kout;                     // nullptr: the stage value is not a state
-    unsigned long long* mx;         // nullptr: no max tracking; else running max of the bit pattern of |k|^2
-    RKS_HD void operator()(long long p, cplx v) const {
-        if (kout) row_st(kout + p, v);
-        if (mx) {
-            const double a = v.x * v.x + v.y * v.y;
-            unsigned long long bits;
-#if defined(__CUDA_ARCH__)
-            bits = (a != a) ? 0x7ff8000000000000ull : (unsigned long long)__double_as_longlong(a);
-#else
-            bits = 0; (void)a;
-#endif
-            if (bits > *mx) *mx = bits;
-        }
-    }
-};
-
 template <class Src>
 struct NlsModelT {          // N = i gamma fft(|f|^2 f), f = ifft(u^)      (demos/nls.ipynb)
-    Src src; StateSink sink; cplx* out; double gamma; int n; bool on;
-    RKS_HD cplx load(int p) const {
-        const cplx v = src.value(p);
-        if (on) sink(p, v);
-        return v;
-    }
+    Src src; cplx* out; double gamma; int n; bool on;
+    RKS_HD cplx load(int p) const { return src.value(p); }
     RKS_HD cplx pointwise(cplx z) const {
         const double sc = 1.0 / (double)n;
         const cplx f = mk(z.x * sc, z.y * sc);
@@ -258,14 +234,10 @@ struct NlsModelT {          // N = i gamma fft(|f|^2 f), f = ifft(u^)      (demo
 using NlsModel = NlsModelT<ArraySource>;
 
 // N = -c rfft(irfft(u^) irfft(i kx u^))  (models.py:140-143).  `Half` yields the half spectrum value at
-// index k <= n/2: a global array (plain evaluation) or the smem staging row of the fused kernel.
+// index k <= n/2: a global array or the TMA staging row.
 struct GlobalHalf {
     const cplx* in;
     RKS_HD cplx get(int k) const { return row_ld(in + k); }
-};
-struct SmemHalf {
-    const cplx* stage;
-    RKS_HD cplx get(int k) const { return stage[k]; }
 };
 template <class Half>
 struct UuxModelT {
@@ -348,10 +320,10 @@ template <> struct ModelOf<1> {
 template <> struct ModelOf<2> {
     using type = NlsModel;
     RKS_HD static type make(const cplx* in, cplx* out, const double*, double p0, int n, bool on) {
-        return type{ArraySource{in}, StateSink{nullptr, nullptr}, out, p0, n, on};
+        return type{ArraySource{in}, out, p0, n, on};
     }
     RKS_HD static NlsModelT<StagedRow> make_staged(StagedRow s, cplx* out, const double*, double p0, int n, bool on) {
-        return NlsModelT<StagedRow>{s, StateSink{nullptr, nullptr}, out, p0, n, on};
+        return NlsModelT<StagedRow>{s, out, p0, n, on};
     }
 };
 template <> struct ModelOf<3> {

@@ -9,7 +9,6 @@
 #include "fft_fast.cuh"
 #include "fft_real.cuh"
 #include "fft_axis.cuh"
-#include "fuse.cuh"
 
 namespace rks {
 
@@ -812,19 +811,15 @@ struct StageNext {          // after the first pass: start copying the head of t
     RKS_D void operator()() const { if (go) stage_issue(stg, src, bytes, bar); }
 };
 
-// FK = 0: N_j = N(existing array).  FK = 1 / 2: the stage combine (fuse.cuh, complex / real
-// coefficient arrays) is evaluated in the load prologue, so the stage value k never goes to HBM
-// unless it is a state (fd.write_k: final stage of fixed-step and FSAL methods).
-// PT: the input row is a pre-transformed stage value (stage_pre_kernel below; complex-field models, FK = 0).
-template <int W, int MODEL, int FK, bool PT = false>
-RKS_D void nl_fast_kernel_body(const DevPlan& p, int j, int force, FuseDesc fd) {
-    static_assert(!PT || (FK == 0 && MODEL == 2), "pre-transformed rows: plain evaluation of the NLS model only");
-    using CT = typename std::conditional<FK == 2, double, cplx>::type;
+// N_j = N(existing array) for rows of n = 512 W points.
+// PT: the input row is a pre-transformed stage value (stage_pre_kernel above; complex-field models).
+template <int W, int MODEL, bool PT = false>
+RKS_D void nl_fast_kernel_body(const DevPlan& p, int j, int force) {
+    static_assert(!PT || MODEL == 2, "pre-transformed rows: the NLS model only");
     constexpr int N = 512 * W;
     constexpr int TR = 32 * W;                       // threads per row
     constexpr int THREADS = W == 16 ? 512 : 256;
     constexpr int RPC = THREADS / TR;                // rows per CTA
-    constexpr int STAGE_LD = N / 2 + 8;              // staging row of the fused u u_x models (half spectrum)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const NlRoles roles = nl_roles(p, j, force);
     if (!roles.run) return;
@@ -832,37 +827,14 @@ RKS_D void nl_fast_kernel_body(const DevPlan& p, int j, int force, FuseDesc fd) 
 
     const int lrow = threadIdx.x / TR, T = threadIdx.x - lrow * TR;
     cplx* sm = reinterpret_cast<cplx*>(smem_raw) + (size_t)lrow * N;
-    cplx* stage = reinterpret_cast<cplx*>(smem_raw) + (size_t)RPC * N + (size_t)lrow * STAGE_LD;
     const fast::Twiddles ti{p.twf + fast::TW_T1, p.twf + fast::TW_T2, p.twf + fast::TW_T3};
     const cplx* twf2 = p.twf + fast::TW_TOTAL;
     const fast::Twiddles tf{twf2 + fast::TW_T1, twf2 + fast::TW_T2, twf2 + fast::TW_T3};
     const int lines = (int)((p.n_c * 16 + 127) >> 7);
     const long long groups = (p.batch + RPC - 1) / RPC;
 
-    // fused mode: resolve the term list once (roles and h are fixed for the whole launch)
-    const cplx* xbase[FUSE_MAX_TERMS];
-    const CT* cbase[FUSE_MAX_TERMS];
-    double sc[FUSE_MAX_TERMS];
-    cplx* kbase = nullptr;
-    unsigned long long mx = 0ull;
-    if (FK > 0) {
-        const Ctrl* c = p.ctrl;
-        const bool adapt = method_adaptive(p.method);
-        const int u_sel = adapt ? c->u_sel : 0, n_sel = adapt ? c->n_sel : 0;
-        const double h = c->h;
-#pragma unroll
-        for (int t = 0; t < FUSE_MAX_TERMS; ++t) {
-            if (t < fd.nterms) {
-                xbase[t] = fd.src[t] == 0 ? p.U[u_sel] : p.NL[nl_phys(p.method, fd.src[t], n_sel)];
-                cbase[t] = fd.slot[t] < 0 ? nullptr : (const CT*)p.coef + (size_t)fd.slot[t] * p.lin_elems;
-                sc[t] = fd.c0[t] + fd.c1[t] * h;
-            }
-        }
-        if (fd.write_k) kbase = adapt ? p.U[1 - u_sel] : p.U[0];
-    }
-
-    // n = 8192, plain evaluation: input rows arrive through the TMA staging buffer
-    constexpr bool STAGED = W == 16 && FK == 0 && MODEL >= 1 && MODEL <= 3;
+    // n = 8192: input rows arrive through the TMA staging buffer
+    constexpr bool STAGED = W == 16 && MODEL >= 1 && MODEL <= 3;
     cplx* stg = reinterpret_cast<cplx*>(smem_raw) + (size_t)RPC * N;
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(stg + NL_STAGE_ELEMS);
     int* arrived = reinterpret_cast<int*>(bar + 1);          // PT: warps that have consumed the staging buffer
@@ -896,74 +868,21 @@ RKS_D void nl_fast_kernel_body(const DevPlan& p, int j, int force, FuseDesc fd) 
             // !PT: thread 0 issues the copy after the row barrier; PT: the lane the counter elects
             const StageNext next{stg, roles.in + (nlines ? nrow : rr) * p.n_c, nst * 16u, bar, nlines != 0 && (PT || threadIdx.x == 0)};
             nl_fast_row<N, PT>(sm, T, lrow, RPC, ti, tf, m, next, arrived);
-        } else if (FK == 0) {
+        } else {
             prefetch_row_l2<TR>(roles.in + (nlines ? nrow : rr) * p.n_c, nlines, T);
             const auto m = fast::ModelOf<MODEL>::make(roles.in + rr * p.n_c, out, p.kx, p.model_p0, N, on);
             nl_fast_row<N, PT>(sm, T, lrow, RPC, ti, tf, m);
-        } else {
-            FuseSource<CT> src;
-            src.nterms = fd.nterms;
-#pragma unroll
-            for (int t = 0; t < FUSE_MAX_TERMS; ++t) {
-                if (t < fd.nterms) {
-                    src.x[t] = xbase[t] + rr * p.n_c;
-                    src.c[t] = cbase[t];
-                    src.sc[t] = sc[t];
-                    prefetch_row_l2<TR>(xbase[t] + (nlines ? nrow : rr) * p.n_c, nlines, T);
-                }
-            }
-            const fast::StateSink sink{kbase ? kbase + rr * p.n_c : nullptr, fd.track_max ? &mx : nullptr};
-            if (MODEL != 1 && MODEL != 2) {
-                // fused combine is only instantiated for the u u_x and NLS models
-            } else if (MODEL == 1) {
-                // half spectrum of the stage value: computed once per mode, staged in smem (the
-                // inverse transform needs every mode twice: k and its Hermitian partner n - k)
-                constexpr int HALF = N / 2 + 1;
-                for (int q0 = T; q0 < HALF; q0 += 2 * TR) {      // two modes per iteration: more loads in flight
-                    const int q1 = q0 + TR;
-                    const cplx v0 = src.value(q0);
-                    const cplx v1 = src.value(q1 < HALF ? q1 : q0);
-                    if (on) sink(q0, v0);
-                    stage[q0] = v0;
-                    if (q1 < HALF) {
-                        if (on) sink(q1, v1);
-                        stage[q1] = v1;
-                    }
-                }
-                row_barrier<TR>(lrow, RPC);
-                const fast::UuxModelT<fast::SmemHalf> m{fast::SmemHalf{stage}, out, p.kx, p.model_p0, N, on};
-                nl_fast_row<N>(sm, T, lrow, RPC, ti, tf, m);
-            } else {
-                const fast::NlsModelT<FuseSource<CT>> m{src, sink, out, p.model_p0, N, on};
-                nl_fast_row<N>(sm, T, lrow, RPC, ti, tf, m);
-            }
-        }
-    }
-    if (FK > 0 && fd.track_max) {
-        // block max of |u+|^2 -> one atomicMax per block (solveras.py:451: magu.max())
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long t = __shfl_xor_sync(0xffffffffu, mx, o);
-            mx = t > mx ? t : mx;
-        }
-        __shared__ unsigned long long smx[THREADS / 32];
-        if ((threadIdx.x & 31) == 0) smx[threadIdx.x >> 5] = mx;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long m = smx[0];
-            for (int i = 1; i < THREADS / 32; ++i) m = smx[i] > m ? smx[i] : m;
-            if (m) atomicMax((unsigned long long*)&p.ctrl->red[0], m);
         }
     }
 }
-template <int W, int MODEL, int FK>
-__global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_fast_kernel(const __grid_constant__ DevPlan p, int j, int force, FuseDesc fd) { nl_fast_kernel_body<W, MODEL, FK>(p, j, force, fd); }
+template <int W, int MODEL>
+__global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_fast_kernel(const __grid_constant__ DevPlan p, int j, int force) { nl_fast_kernel_body<W, MODEL>(p, j, force); }
 // the same evaluation of a row K1 has pre-transformed (NLS model)
 template <int W>
-__global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_fast_pre_kernel(const __grid_constant__ DevPlan p, int j, int force, FuseDesc fd) { nl_fast_kernel_body<W, 2, 0, true>(p, j, force, fd); }
+__global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_fast_pre_kernel(const __grid_constant__ DevPlan p, int j, int force) { nl_fast_kernel_body<W, 2, true>(p, j, force); }
 // one plan per blockIdx.z: ensembles whose trajectories keep their own dt (rks_multi_*)
-template <int W, int MODEL, int FK>
-__global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_fast_kernel_multi(const DevPlan* plans, int j, int force, FuseDesc fd) { nl_fast_kernel_body<W, MODEL, FK>(plans[blockIdx.z], j, force, fd); }
+template <int W, int MODEL>
+__global__ void __launch_bounds__((W == 16 ? 512 : 256), (W == 16 ? 1 : 2)) nl_fast_kernel_multi(const DevPlan* plans, int j, int force) { nl_fast_kernel_body<W, MODEL>(plans[blockIdx.z], j, force); }
 
 
 // ---------------------------------------------------------------------------------------

@@ -129,7 +129,6 @@ struct rks_plan {
     int nl_rows_per_cta, nl_threads;
     bool nl_fast;                   // n in {512..8192}: register-resident FFT kernel (fft_fast.cuh)
     bool nl_small;                  // n in {64, 128, 256}: the same pipeline on slabs of packed rows
-    bool no_fuse;                   // default: K1 and K4 as separate kernels (north_star decomposition); RKS_FUSE=1 fuses
     bool pretransform;              // intermediate NLS stages: K1 applies the first inverse FFT pass (RKS_PT=0 disables)
     bool rfft_half;                 // real-field models: half-length forward transform (default for n <= 1024)
     size_t nl_smem;
@@ -140,71 +139,60 @@ struct rks_plan {
     long long nd_spec[3] = {0, 0, 0};
 };
 
-// smem of a fast NL launch: the row slabs plus, for the fused u u_x models, one staging row each
+// smem of a fast NL launch: the row slabs
 template <int W>
-static size_t nl_fast_smem(int model, int fk) {
+static size_t nl_fast_smem(int model) {
     constexpr int THREADS = W == 16 ? 512 : 256;
     constexpr int RPC = THREADS / (32 * W);
-    size_t elems = (size_t)RPC * 512 * W;
-    if (fk > 0 && model == RKS_MODEL_UUX_RFFT) elems += (size_t)RPC * (512 * W / 2 + 8);
-    size_t bytes = elems * sizeof(cplx);
-    // n = 8192 plain evaluation: TMA staging buffer for the next row + its mbarrier (kernels.cuh)
-    if (W == 16 && fk == 0 && model >= RKS_MODEL_UUX_RFFT && model <= RKS_MODEL_CUBIC_RFFT) bytes += NL_STAGE_BYTES;
+    size_t bytes = (size_t)RPC * 512 * W * sizeof(cplx);
+    // n = 8192: TMA staging buffer for the next row + its mbarrier (kernels.cuh)
+    if (W == 16 && model >= RKS_MODEL_UUX_RFFT && model <= RKS_MODEL_CUBIC_RFFT) bytes += NL_STAGE_BYTES;
     return bytes;
 }
 
-template <int W, int MODEL, int FK>
-static void launch_nl_fast_t(rks_plan* p, int j, int force, const FuseDesc& fd, cudaStream_t stream) {
+template <int W, int MODEL>
+static void launch_nl_fast_t(rks_plan* p, int j, int force, cudaStream_t stream) {
     const DevPlan& d = p->d;
     constexpr int THREADS = W == 16 ? 512 : 256;
     constexpr int RPC = THREADS / (32 * W);
-    const size_t smem = nl_fast_smem<W>(MODEL, FK);
+    const size_t smem = nl_fast_smem<W>(MODEL);
     if (p->multi_n) {
-        if constexpr (FK == 0)
-            nl_fast_kernel_multi<W, MODEL, 0><<<dim3(1, 1, (unsigned)p->multi_n), THREADS, smem, stream>>>(p->multi_dev, j, force, fd);
+        nl_fast_kernel_multi<W, MODEL><<<dim3(1, 1, (unsigned)p->multi_n), THREADS, smem, stream>>>(p->multi_dev, j, force);
         return;
     }
     const long long groups = (d.batch + RPC - 1) / RPC;
     const long long resident = (long long)p->sm_count * (W == 16 ? 1 : 2);
     const unsigned grid = (unsigned)(groups < resident ? groups : resident);
-    nl_fast_kernel<W, MODEL, FK><<<grid, THREADS, smem, stream>>>(d, j, force, fd);
+    nl_fast_kernel<W, MODEL><<<grid, THREADS, smem, stream>>>(d, j, force);
 }
 
-// fk: 0 plain, 1 fused with complex coefficient arrays, 2 fused with real ones (models 1 and 2 only)
 template <int W>
-static void launch_nl_fast(rks_plan* p, int j, int force, const FuseDesc& fd, int fk, cudaStream_t stream) {
-    const int model = p->d.model;
-    if (model == RKS_MODEL_CUBIC_RFFT) { launch_nl_fast_t<W, 3, 0>(p, j, force, fd, stream); return; }
-    if (model == RKS_MODEL_SINE_GORDON) { launch_nl_fast_t<W, 4, 0>(p, j, force, fd, stream); return; }
-    const bool uux = model == RKS_MODEL_UUX_RFFT;
-    if (fk == 0) uux ? launch_nl_fast_t<W, 1, 0>(p, j, force, fd, stream) : launch_nl_fast_t<W, 2, 0>(p, j, force, fd, stream);
-    else if (fk == 1) uux ? launch_nl_fast_t<W, 1, 1>(p, j, force, fd, stream) : launch_nl_fast_t<W, 2, 1>(p, j, force, fd, stream);
-    else uux ? launch_nl_fast_t<W, 1, 2>(p, j, force, fd, stream) : launch_nl_fast_t<W, 2, 2>(p, j, force, fd, stream);
+static void launch_nl_fast(rks_plan* p, int j, int force, cudaStream_t stream) {
+    switch (p->d.model) {
+        case RKS_MODEL_UUX_RFFT: launch_nl_fast_t<W, 1>(p, j, force, stream); break;
+        case RKS_MODEL_NLS_FFT: launch_nl_fast_t<W, 2>(p, j, force, stream); break;
+        case RKS_MODEL_CUBIC_RFFT: launch_nl_fast_t<W, 3>(p, j, force, stream); break;
+        default: launch_nl_fast_t<W, 4>(p, j, force, stream); break;
+    }
 }
 
+template <int W, int MODEL>
+static cudaError_t prepare_nl_fast_t() {
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    cudaError_t e = cudaFuncSetAttribute(nl_fast_kernel<W, MODEL>, attr, (int)nl_fast_smem<W>(MODEL));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel_multi<W, MODEL>, attr, (int)nl_fast_smem<W>(MODEL));
+    if (MODEL == 2 && W > 1 && e == cudaSuccess)
+        e = cudaFuncSetAttribute(nl_fast_pre_kernel<(W > 1 ? W : 2)>, attr, (int)nl_fast_smem<W>(MODEL));
+    return e;
+}
 template <int W>
 static cudaError_t prepare_nl_fast(int model) {
-    cudaError_t e = cudaSuccess;
-    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    if (model == RKS_MODEL_UUX_RFFT) {
-        e = cudaFuncSetAttribute(nl_fast_kernel<W, 1, 0>, attr, (int)nl_fast_smem<W>(model, 0));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel_multi<W, 1, 0>, attr, (int)nl_fast_smem<W>(model, 0));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 1, 1>, attr, (int)nl_fast_smem<W>(model, 1));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 1, 2>, attr, (int)nl_fast_smem<W>(model, 2));
-    } else if (model == RKS_MODEL_NLS_FFT) {
-        e = cudaFuncSetAttribute(nl_fast_kernel<W, 2, 0>, attr, (int)nl_fast_smem<W>(model, 0));
-        if (W > 1 && e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_pre_kernel<(W > 1 ? W : 2)>, attr, (int)nl_fast_smem<W>(model, 0));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel_multi<W, 2, 0>, attr, (int)nl_fast_smem<W>(model, 0));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 2, 1>, attr, (int)nl_fast_smem<W>(model, 1));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel<W, 2, 2>, attr, (int)nl_fast_smem<W>(model, 2));
-    } else if (model == RKS_MODEL_CUBIC_RFFT) {
-        e = cudaFuncSetAttribute(nl_fast_kernel<W, 3, 0>, attr, (int)nl_fast_smem<W>(model, 0));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel_multi<W, 3, 0>, attr, (int)nl_fast_smem<W>(model, 0));
-    } else {
-        e = cudaFuncSetAttribute(nl_fast_kernel<W, 4, 0>, attr, (int)nl_fast_smem<W>(model, 0));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel_multi<W, 4, 0>, attr, (int)nl_fast_smem<W>(model, 0));
+    switch (model) {
+        case RKS_MODEL_UUX_RFFT: return prepare_nl_fast_t<W, 1>();
+        case RKS_MODEL_NLS_FFT: return prepare_nl_fast_t<W, 2>();
+        case RKS_MODEL_CUBIC_RFFT: return prepare_nl_fast_t<W, 3>();
+        default: return prepare_nl_fast_t<W, 4>();
     }
-    return e;
 }
 
 template <int N>
@@ -480,7 +468,6 @@ extern "C" int rks_plan_create_independent(rks_plan** out, int method, int64_t b
     p->have_h_coeff_host = false;
     p->roles_u_sel = p->roles_n_sel = 0;
     p->use_graph = getenv("RKS_NO_GRAPH") == nullptr;
-    p->no_fuse = true;
     p->nl_fast = false;
     p->nl_small = false;
     CUDA_TRY(cudaGetDevice(&p->device));
@@ -572,7 +559,6 @@ extern "C" int rks_set_config(rks_plan* p, const rks_config* cfg, void* stream) 
 static int prepare_nl_launch(rks_plan* p, int model, long long n, cplx* twf_dev, cudaStream_t stream) {
     DevPlan& d = p->d;
     p->nl_fast = (n >= 512 && n <= 8192) && !getenv("RKS_NL_GENERIC");
-    p->no_fuse = getenv("RKS_FUSE") == nullptr;       // fused K1+K4 is opt-in (RKS_FUSE=1): see DESIGN.md 4
     // real-field models: half-length forward transform (fft_real.cuh).  Measured (profiles/r02_k4_ab.md): 7 % faster
     // than the full-length pair for n = 512 and 1024, slower for n >= 2048 (three more row barriers per row)
     const char* rh = getenv("RKS_RFFT_HALF");
@@ -876,13 +862,13 @@ extern "C" int rks_stage(rks_plan* p, int s, void* stream_v) {
 // ---------------------------------------------------------------------------------------
 // K4 dispatch
 // ---------------------------------------------------------------------------------------
-static void dispatch_nl_fast(rks_plan* p, int j, int force, const FuseDesc& fd, int fk, cudaStream_t stream) {
+static void dispatch_nl_fast(rks_plan* p, int j, int force, cudaStream_t stream) {
     switch (p->d.n) {
-        case 512: launch_nl_fast<1>(p, j, force, fd, fk, stream); break;
-        case 1024: launch_nl_fast<2>(p, j, force, fd, fk, stream); break;
-        case 2048: launch_nl_fast<4>(p, j, force, fd, fk, stream); break;
-        case 4096: launch_nl_fast<8>(p, j, force, fd, fk, stream); break;
-        default: launch_nl_fast<16>(p, j, force, fd, fk, stream); break;
+        case 512: launch_nl_fast<1>(p, j, force, stream); break;
+        case 1024: launch_nl_fast<2>(p, j, force, stream); break;
+        case 2048: launch_nl_fast<4>(p, j, force, stream); break;
+        case 4096: launch_nl_fast<8>(p, j, force, stream); break;
+        default: launch_nl_fast<16>(p, j, force, stream); break;
     }
     p->launches += 1;
 }
@@ -892,12 +878,10 @@ template <int W>
 static void launch_nl_fast_pre_t(rks_plan* p, int j, int force, cudaStream_t stream) {
     constexpr int THREADS = W == 16 ? 512 : 256;
     constexpr int RPC = THREADS / (32 * W);
-    FuseDesc none;
-    memset(&none, 0, sizeof(none));
     const long long groups = (p->d.batch + RPC - 1) / RPC;
     const long long resident = (long long)p->sm_count * (W == 16 ? 1 : 2);
     const unsigned grid = (unsigned)(groups < resident ? groups : resident);
-    nl_fast_pre_kernel<W><<<grid, THREADS, nl_fast_smem<W>(RKS_MODEL_NLS_FFT, 0), stream>>>(p->d, j, force, none);
+    nl_fast_pre_kernel<W><<<grid, THREADS, nl_fast_smem<W>(RKS_MODEL_NLS_FFT), stream>>>(p->d, j, force);
 }
 static void dispatch_nl_fast_pre(rks_plan* p, int j, int force, cudaStream_t stream) {
     switch (p->d.n) {
@@ -962,9 +946,7 @@ static int launch_nl(rks_plan* p, int j, int force, cudaStream_t stream) {
     }
 
     if (p->nl_fast) {
-        FuseDesc none;
-        memset(&none, 0, sizeof(none));
-        dispatch_nl_fast(p, j, force, none, 0, stream);
+        dispatch_nl_fast(p, j, force, stream);
         return RKS_OK;
     }
     if (p->multi_n) {
@@ -997,17 +979,8 @@ extern "C" int rks_nl(rks_plan* p, int j, void* stream) {
     return RKS_OK;
 }
 
-// Stage s followed by the nonlinear evaluation it feeds.  With a fast fused model the combine is
-// evaluated in the load prologue of the NL kernel (one launch, the stage value never goes to HBM
-// unless it is a state); otherwise this is rks_stage + rks_nl.
-static bool can_fuse_stage(const rks_plan* p, int s) {
-    const int m = p->method, S = method_stages(m);
-    if (!p->nl_fast || p->no_fuse || p->multi_n || p->nd_rows || p->d.lin_elems != p->d.n_c) return false;
-    if (p->d.model != RKS_MODEL_UUX_RFFT && p->d.model != RKS_MODEL_NLS_FFT) return false;
-    if (s == S && m == M_ETD35) return false;              // last ETD35 stage emits err and feeds no N
-    return true;
-}
-
+// Stage s followed by the nonlinear evaluation it feeds: K1 then K4 as separate kernels (the north_star
+// decomposition; folding the combine into K4's load prologue was measured slower and removed).
 // Intermediate stage of a fast NLS-type plan: its value only feeds N(.), so K1 may hand it over pre-transformed
 // (stage_pre_kernel -> nl_fast_pre_kernel).  The last stage is a state and keeps the natural layout.
 static bool can_pretransform(const rks_plan* p, int s) {
@@ -1028,24 +1001,15 @@ static int stage_nl_parts(rks_plan* p, int s, int part, void* stream_v) {
     // etd4.py:174) or N_last (FSAL methods, if34.py:129); none for ETD35
     const int j = s < S ? s + 1 : (adapt ? (method_fsal(m) ? S + 1 : 0) : 1);
     cudaStream_t stream = (cudaStream_t)stream_v;
-    if (can_pretransform(p, s) && (part != 0 || !can_fuse_stage(p, s))) {
+    if (can_pretransform(p, s)) {
         if (part != 2) launch_stage_pre(p, s, stream);
         if (part != 1) dispatch_nl_fast_pre(p, j, adapt ? 0 : 1, stream);
         CUDA_TRY(cudaGetLastError());
         return RKS_OK;
     }
-    if (part != 0 || !can_fuse_stage(p, s)) {
-        if (part != 2)
-            if (int rc = rks_stage(p, s, stream_v)) return rc;
-        return (j && part != 1) ? rks_nl(p, j, stream_v) : RKS_OK;
-    }
-    FuseDesc fd = fuse_desc(m, s);
-    fd.write_k = (s == S) ? 1 : 0;
-    fd.track_max = (s == S && adapt) ? 1 : 0;
-    const int fk = (method_is_if(m) && !p->d.lin_complex) ? 2 : 1;
-    dispatch_nl_fast(p, j, adapt ? 0 : 1, fd, fk, stream);
-    CUDA_TRY(cudaGetLastError());
-    return RKS_OK;
+    if (part != 2)
+        if (int rc = rks_stage(p, s, stream_v)) return rc;
+    return (j && part != 1) ? rks_nl(p, j, stream_v) : RKS_OK;
 }
 extern "C" int rks_stage_nl(rks_plan* p, int s, void* stream) { return stage_nl_parts(p, s, 0, stream); }
 extern "C" int rks_stage_nl_part(rks_plan* p, int s, int part, void* stream) {
@@ -1349,7 +1313,7 @@ extern "C" int rks_rows_create(rks_rows** out, int model, int64_t n, const doubl
     HandleGuard<rks_rows, rks_rows_destroy> guard{r};
     rks_plan* p = &r->plan;
     memset(&p->d, 0, sizeof(DevPlan));
-    p->launches = 0; p->no_fuse = true; p->use_graph = false; p->pinned_raw = nullptr; p->pinned_log = nullptr;
+    p->launches = 0; p->use_graph = false; p->pinned_raw = nullptr; p->pinned_log = nullptr;
     const bool half = model == RKS_MODEL_UUX_RFFT || model == RKS_MODEL_CUBIC_RFFT;
     const long long n_c = half ? n / 2 + 1 : n;
     const size_t tw_b = align_up(sizeof(cplx) * (size_t)n), twf_b = align_up(sizeof(cplx) * 2 * fast::TW_TOTAL);
@@ -1602,7 +1566,7 @@ extern "C" int rks_set_model_nd(rks_plan* p, int model, int nd, const int64_t* g
     p->nd = nd;
     for (int k = 0; k < 3; ++k) p->nd_spec[k] = spec[k];
     p->d.model = model; p->d.model_p0 = p0; p->d.n = grid[nd - 1];
-    p->nl_fast = false; p->nl_small = false; p->no_fuse = true; p->pretransform = false;
+    p->nl_fast = false; p->nl_small = false; p->pretransform = false;
     p->rfft_half = false;
     CUDA_TRY(cudaGetLastError());
     (void)stream;

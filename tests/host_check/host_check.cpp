@@ -17,7 +17,6 @@
 #include "../../rkstiff_b200/csrc/fft_fast.cuh"
 #include "../../rkstiff_b200/csrc/fft_real.cuh"
 #include "../../rkstiff_b200/csrc/fft_axis.cuh"
-#include "../../rkstiff_b200/csrc/fuse.cuh"
 
 using namespace rks;
 
@@ -427,24 +426,6 @@ int hc_embedded_err(int method, int n, const double* const* N, const double* coe
         else return -1;
     }
     return 0;
-}
-
-// the run-time term list of fuse.cuh evaluated for one stage (complex coefficients): must agree
-// with stage_combine of stages.cuh
-int hc_fused_stage(int method, int stage, int n, const double* u, const double* const* N, const double* coef, double h,
-                   double* out) {
-    const FuseDesc d = fuse_desc(method, stage);
-    FuseSource<cplx> src;
-    src.nterms = d.nterms;
-    for (int t = 0; t < d.nterms; ++t) {
-        src.x[t] = reinterpret_cast<const cplx*>(d.src[t] == 0 ? u : N[d.src[t]]);
-        src.c[t] = d.slot[t] < 0 ? nullptr : reinterpret_cast<const cplx*>(coef) + (size_t)d.slot[t] * n;
-        src.sc[t] = d.c0[t] + d.c1[t] * h;
-        if (!src.x[t]) return -1;
-    }
-    cplx* co = reinterpret_cast<cplx*>(out);
-    for (int i = 0; i < n; ++i) co[i] = src.value(i);
-    return d.nterms;
 }
 
 // controller: feed (sum_u2, sum_e2) of one trial; state is a caller-held opaque Ctrl blob

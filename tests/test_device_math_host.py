@@ -33,7 +33,7 @@ def hc():
     src = os.path.join(HERE, "host_check", "host_check.cpp")
     lib = os.path.join(HERE, "host_check", "libhostcheck.so")
     deps = [src] + [os.path.join(HERE, "..", "rkstiff_b200", "csrc", f)
-                    for f in ("common.cuh", "coeffs.cuh", "stages.cuh", "errctl.cuh", "fft.cuh", "fft_fast.cuh", "fft_axis.cuh", "fuse.cuh")]
+                    for f in ("common.cuh", "coeffs.cuh", "stages.cuh", "errctl.cuh", "fft.cuh", "fft_fast.cuh", "fft_axis.cuh")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", lib, src])
     return ctypes.CDLL(lib)
@@ -214,27 +214,6 @@ def test_one_trial_state_matches_oracle(hc, prob, h, method):
         assert np.linalg.norm(err - ref[1]) < 1e-14 * np.linalg.norm(k)
     else:
         assert rel(k, ref) < 1e-13
-
-
-@pytest.mark.parametrize("method", METHODS)
-def test_fused_term_list_matches_stage_formulas(hc, method):
-    """fuse.cuh: the run-time term list the fused stage+NL kernel evaluates == stages.cuh formulas."""
-    p = problems.kdv(128)
-    h = 0.02
-    _, coef = device_coeffs(hc, method, p.lin_op, h)
-    n = p.u0.shape[0]
-    rng = np.random.default_rng(3)
-    N = {j: rng.standard_normal(n) + 1j * rng.standard_normal(n) for j in range(1, 8)}
-    arr = (ctypes.c_void_p * 8)()
-    for j in range(1, 8):
-        arr[j] = ptr(N[j])
-    err = np.zeros(n, dtype=np.complex128)
-    for s in range(1, STAGES[method] + 1):
-        ref = np.empty(n, dtype=np.complex128)
-        got = np.empty(n, dtype=np.complex128)
-        assert hc.hc_stage(MID[method], s, n, ptr(p.u0), arr, ptr(coef), ctypes.c_double(h), ptr(ref), ptr(err)) == 0
-        assert hc.hc_fused_stage(MID[method], s, n, ptr(p.u0), arr, ptr(coef), ctypes.c_double(h), ptr(got)) > 0
-        assert rel(got, ref) < 1e-15
 
 
 class _Canned(OracleSolver):
