@@ -487,17 +487,21 @@ def time_kernel(torch, fn, reps):
 
 
 def timed_evolve(ctx, fn):
-    """Device time of fn() (one evolve call), max over ranks, with the clocks sampled during it on rank 0."""
+    """Device time of fn() (one evolve call), max over ranks.  Returns (result, seconds, clock sampler): the caller
+    stops the sampler after the e2e repetitions of the same call, so that a timed region shorter than the 100 ms
+    sampling period (cfg 4: 28 trials x 3 ms) still gets clock samples taken under the same load."""
     torch = ctx.torch
     ctx.barrier()
     sampler = ClockSampler(ctx.local) if ctx.rank == 0 else None
+    time.sleep(0.15 if sampler else 0.0)               # nvidia-smi is up before the timed region starts
+    ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     out = fn()
     e1.record()
     ctx.barrier()
     secs = ctx.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
-    return out, secs, (sampler.stop() if sampler else None)
+    return out, secs, sampler
 
 
 def e2e_evolve(ctx, sol, u0, call, reps=2):
@@ -553,7 +557,7 @@ def run_cfg5(ctx, args, cpu=True):
     sol = rk.ETD35(lin, nl, config=rk.SolverConfig(epsilon=1e-5), group=ctx.group)
     sol.evolve(u0, 0.0, 0.02, store_data=False)              # warm-up (plans, NCCL, graph capture)
     l0 = sol._engine.launches()
-    _, secs, clocks = timed_evolve(ctx, lambda: sol.evolve(u0, 0.0, 0.2, store_data=False))
+    _, secs, sampler = timed_evolve(ctx, lambda: sol.evolve(u0, 0.0, 0.2, store_data=False))
     trials = len(sol.trial_log)
     launches = sol._engine.launches() - l0
     accepted = sum(1 for r in sol.trial_log if r[2])
@@ -563,6 +567,7 @@ def run_cfg5(ctx, args, cpu=True):
     p_survey = 25 + 7 + 2 + 6 * survey
     alg = 16.0 * p_survey * local_elems * trials
     e_secs, e_trials, e_bytes = e2e_evolve(ctx, sol, u0, lambda ud: sol.evolve(ud, 0.0, 0.2, store_data=False), reps=1)
+    clocks = sampler.stop() if sampler else None
     out = {"metric": METRIC, "value": n ** 3 * trials / secs, "unit": UNIT, "n_gpus": world, "steps": trials, "warmup": 0,
            "ms_per_step": 1e3 * secs / trials, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
@@ -606,7 +611,7 @@ def run_cfg4(ctx, args, cpu=True):
     sol = rk.IF45DP(lin, nl, config=rk.SolverConfig(epsilon=1e-4))
     sol.evolve(uf0, 0.0, 0.01, store_data=False)          # warm-up
     l0 = sol._engine.launches()
-    _, secs, clocks = timed_evolve(ctx, lambda: sol.evolve(uf0, 0.0, 0.2, store_data=False))
+    _, secs, sampler = timed_evolve(ctx, lambda: sol.evolve(uf0, 0.0, 0.2, store_data=False))
     trials = len(sol.trial_log)
     launches = sol._engine.launches() - l0
     n_c = n * (n // 2 + 1)
@@ -616,6 +621,7 @@ def run_cfg4(ctx, args, cpu=True):
     coef_storage = sol._engine.coef_storage
     alg = (16.0 * p_survey + (8 * 29 if coef_storage == "arrays" else 0)) * n_c * trials
     e_secs, e_trials, e_bytes = e2e_evolve(ctx, sol, uf0, lambda ud: sol.evolve(ud, 0.0, 0.2, store_data=False))
+    clocks = sampler.stop() if sampler else None
     out = {"metric": METRIC, "value": ctx.world * n * n * trials / secs, "unit": UNIT, "n_gpus": ctx.world, "steps": trials,
            "warmup": 0, "ms_per_step": 1e3 * secs / trials, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -655,7 +661,8 @@ def run_cfg2b(ctx, args):
     lin, nl = rk.models.nls_ops(kx, 2.0)
     sol = rk.ETD35(lin, nl, config=rk.SolverConfig(epsilon=1e-6))
     sol.evolve_independent(u0, 0.0, 0.02, keep_log=False)          # warm-up: plan, graph capture
-    _, secs_max, clocks = timed_evolve(ctx, lambda: sol.evolve_independent(u0, 0.0, 1.0, keep_log=False))
+    _, secs_max, sampler = timed_evolve(ctx, lambda: sol.evolve_independent(u0, 0.0, 1.0, keep_log=False))
+    clocks = sampler.stop() if sampler else None
     rows = sol._engine.read_rows()
     local_trials = sum(int(r.trial_count) for r in rows)
     steps_max = int(ctx.max_over_ranks(float(max(int(r.trial_count) for r in rows))))

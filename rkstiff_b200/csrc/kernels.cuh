@@ -8,6 +8,7 @@
 #include "fft.cuh"
 #include "fft_fast.cuh"
 #include "fft_real.cuh"
+#include "fft_pair.cuh"
 #include "fft_axis.cuh"
 
 namespace rks {
@@ -935,6 +936,65 @@ __global__ void __launch_bounds__(256, 2) nl_fast_real_kernel(const __grid_const
         const auto m = fast::ModelOf<MODEL>::make(roles.in + rr * p.n_c, roles.out + rr * p.n_c, p.kx, p.model_p0, N, on);
         nl_fast_row_real<N>(sm, T, lrow, RPC, ti, tf, m);
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// K4 for the single-real-field cubic model, two rows per complex transform (fft_pair.cuh): n = 512 ... 4096.
+// A slab holds a row PAIR; 256 threads = 256 / (32 W) pairs per CTA, two CTAs per SM, persistent over pair groups.
+// ---------------------------------------------------------------------------------------
+template <int N, class Model>
+RKS_D void nl_fast_row_pair(cplx* sm, int T, int lrow, int rpc, const fast::Twiddles& ti, const fast::Twiddles& tf,
+                            const Model& m) {
+    using P = fast::Plan<N>;
+    constexpr int TR = 32 * P::W, NB = (N / P::R1) / TR;
+    fast::phase_first<N>(sm, T, ti, m);
+    row_barrier<TR>(lrow, rpc);
+    fast::phase_middle<N, 2, true>(sm, T, ti, m);   __syncwarp();
+    fast::phase_core<N>(sm, T, m);                  __syncwarp();
+    fast::phase_middle<N, 2, false>(sm, T, tf, m);
+    row_barrier<TR>(lrow, rpc);
+    cplx a[NB * P::R1];
+    fast::phase_pair_load<N>(sm, T, a);
+    row_barrier<TR>(lrow, rpc);                      // every thread holds its butterflies: the slab may take W
+    fast::phase_pair_publish<N>(sm, T, tf, a);
+    row_barrier<TR>(lrow, rpc);
+    fast::phase_pair_store<N>(sm, T, a, m);
+    row_barrier<TR>(lrow, rpc);                      // partners are read before the next pair's first pass overwrites them
+}
+template <int W>
+RKS_D void nl_fast_pair_kernel_body(const DevPlan& p, int j, int force) {
+    static_assert(W <= 8, "row pairs of 512 ... 4096 points");
+    constexpr int N = 512 * W, TR = 32 * W, THREADS = 256, RPC = THREADS / TR;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const NlRoles roles = nl_roles(p, j, force);
+    if (!roles.run) return;
+    if (p.ctrl && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&p.ctrl->nl_evals, 1ull);
+    const int lrow = threadIdx.x / TR, T = threadIdx.x - lrow * TR;
+    cplx* sm = reinterpret_cast<cplx*>(smem_raw) + (size_t)lrow * N;
+    const fast::Twiddles ti{p.twf + fast::TW_T1, p.twf + fast::TW_T2, p.twf + fast::TW_T3};
+    const cplx* twf2 = p.twf + fast::TW_TOTAL;
+    const fast::Twiddles tf{twf2 + fast::TW_T1, twf2 + fast::TW_T2, twf2 + fast::TW_T3};
+    const int lines = (int)((2 * p.n_c * 16 + 127) >> 7);           // a pair is two consecutive rows
+    const long long pairs = (p.batch + 1) / 2;
+    const long long groups = (pairs + RPC - 1) / RPC;
+    for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
+        const long long pair = g * RPC + lrow;
+        const long long ra = 2 * pair, rb = ra + 1;
+        const bool on_a = ra < p.batch, on_b = rb < p.batch;
+        const long long sa = on_a ? ra : p.batch - 1, sb = on_b ? rb : p.batch - 1;
+        const long long npair = pair + (long long)gridDim.x * RPC;
+        if (2 * npair < p.batch) {
+            const int nl = 2 * npair + 1 < p.batch ? lines : (lines + 1) / 2;
+            prefetch_row_l2<TR>(roles.in + 2 * npair * p.n_c, nl, T);
+        }
+        const fast::PairedCubicModel m{roles.in + sa * p.n_c, roles.in + sb * p.n_c, roles.out + sa * p.n_c,
+                                       roles.out + sb * p.n_c, p.model_p0, N, on_a, on_b};
+        nl_fast_row_pair<N>(sm, T, lrow, RPC, ti, tf, m);
+    }
+}
+template <int W>
+__global__ void __launch_bounds__(256, 2) nl_fast_pair_kernel(const __grid_constant__ DevPlan p, int j, int force) {
+    nl_fast_pair_kernel_body<W>(p, j, force);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -131,6 +131,7 @@ struct rks_plan {
     bool nl_small;                  // n in {64, 128, 256}: the same pipeline on slabs of packed rows
     bool pretransform;              // intermediate NLS stages: K1 applies the first inverse FFT pass (RKS_PT=0 disables)
     bool rfft_half;                 // real-field models: half-length forward transform (default for n <= 1024)
+    bool pair_rows;                 // cubic model, n = 512 ... 4096: two rows per complex transform (fft_pair.cuh)
     size_t nl_smem;
     // N-D grid model (rks_set_model_nd): strided-axis handles, the fused last-axis kernel, spectral grid dims
     struct rks_axis* nd_axes[2] = {nullptr, nullptr};
@@ -564,6 +565,15 @@ static int prepare_nl_launch(rks_plan* p, int model, long long n, cplx* twf_dev,
     const char* rh = getenv("RKS_RFFT_HALF");
     p->rfft_half = p->nl_fast && (rh ? (rh[0] != '0' && n <= 4096) : n <= 1024)
                    && (model == RKS_MODEL_UUX_RFFT || model == RKS_MODEL_CUBIC_RFFT);
+    // single-real-field cubic model: two rows share one complex transform pair (RKS_PAIR_ROWS=0: off)
+    const char* pr = getenv("RKS_PAIR_ROWS");
+    p->pair_rows = p->nl_fast && n <= 4096 && model == RKS_MODEL_CUBIC_RFFT && !(pr && pr[0] == '0');
+    if (p->pair_rows) {
+        const auto a = cudaFuncAttributeMaxDynamicSharedMemorySize;
+        const int sm = 256 / 32 * 512 * (int)sizeof(cplx);          // pairs per CTA x n x 16 B = 64 KB for every n
+        CUDA_TRY(n == 512 ? cudaFuncSetAttribute(nl_fast_pair_kernel<1>, a, sm) : n == 1024 ? cudaFuncSetAttribute(nl_fast_pair_kernel<2>, a, sm)
+                 : n == 2048 ? cudaFuncSetAttribute(nl_fast_pair_kernel<4>, a, sm) : cudaFuncSetAttribute(nl_fast_pair_kernel<8>, a, sm));
+    }
     if (p->rfft_half) {
         const auto a = cudaFuncAttributeMaxDynamicSharedMemorySize;
         const int sm = 256 / 32 * 512 * (int)sizeof(cplx);          // rows per CTA x n x 16 B = 64 KB for every n
@@ -928,6 +938,25 @@ static void launch_nl_fast_real(rks_plan* p, int j, int force, cudaStream_t stre
     p->launches += 1;
 }
 
+// cubic model: row pairs (fft_pair.cuh)
+template <int W>
+static void launch_nl_fast_pair_t(rks_plan* p, int j, int force, cudaStream_t stream) {
+    constexpr int RPC = 256 / (32 * W);
+    const long long pairs = (p->d.batch + 1) / 2;
+    const long long groups = (pairs + RPC - 1) / RPC, resident = (long long)p->sm_count * 2;
+    const unsigned grid = (unsigned)(groups < resident ? groups : resident);
+    nl_fast_pair_kernel<W><<<grid, 256, (size_t)RPC * 512 * W * sizeof(cplx), stream>>>(p->d, j, force);
+}
+static void launch_nl_fast_pair(rks_plan* p, int j, int force, cudaStream_t stream) {
+    switch (p->d.n) {
+        case 512: launch_nl_fast_pair_t<1>(p, j, force, stream); break;
+        case 1024: launch_nl_fast_pair_t<2>(p, j, force, stream); break;
+        case 2048: launch_nl_fast_pair_t<4>(p, j, force, stream); break;
+        default: launch_nl_fast_pair_t<8>(p, j, force, stream); break;
+    }
+    p->launches += 1;
+}
+
 static int launch_nl_nd(rks_plan* p, int j, int force, cudaStream_t stream);
 
 static int launch_nl(rks_plan* p, int j, int force, cudaStream_t stream) {
@@ -938,6 +967,10 @@ static int launch_nl(rks_plan* p, int j, int force, cudaStream_t stream) {
         else if (d.n == 128) launch_nl_small<128>(p, j, force, stream);
         else launch_nl_small<256>(p, j, force, stream);
         p->launches += 1;
+        return RKS_OK;
+    }
+    if (p->nl_fast && p->pair_rows && !p->multi_n) {
+        launch_nl_fast_pair(p, j, force, stream);
         return RKS_OK;
     }
     if (p->nl_fast && p->rfft_half && !p->multi_n) {
@@ -1568,6 +1601,7 @@ extern "C" int rks_set_model_nd(rks_plan* p, int model, int nd, const int64_t* g
     p->d.model = model; p->d.model_p0 = p0; p->d.n = grid[nd - 1];
     p->nl_fast = false; p->nl_small = false; p->pretransform = false;
     p->rfft_half = false;
+    p->pair_rows = false;
     CUDA_TRY(cudaGetLastError());
     (void)stream;
     return RKS_OK;

@@ -16,6 +16,7 @@
 #include "../../rkstiff_b200/csrc/fft.cuh"
 #include "../../rkstiff_b200/csrc/fft_fast.cuh"
 #include "../../rkstiff_b200/csrc/fft_real.cuh"
+#include "../../rkstiff_b200/csrc/fft_pair.cuh"
 #include "../../rkstiff_b200/csrc/fft_axis.cuh"
 
 using namespace rks;
@@ -98,6 +99,22 @@ static int fast_real_dispatch(int n, const Model& m, const fast::Twiddles& tw) {
         case 4096: fast_row_real<4096>(m, tw); return 0;
     }
     return -1;
+}
+
+// serial emulation of the paired-row kernel (fft_pair.cuh): the unchanged passes on the packed row, then the three
+// steps of the last pass (load / publish / store), each run for every thread before the next (the row barriers)
+template <int N, class Model>
+static void fast_row_pair(const Model& m, const fast::Twiddles& tw) {
+    using P = fast::Plan<N>;
+    constexpr int TR = 32 * P::W, NB = (N / P::R1) / TR, PER = NB * P::R1;
+    std::vector<cplx> sm(N), regs((size_t)TR * PER);
+    for (int T = 0; T < TR; ++T) fast::phase_first<N>(sm.data(), T, tw, m);
+    for (int T = 0; T < TR; ++T) fast::phase_middle<N, 2, true>(sm.data(), T, tw, m);
+    for (int T = 0; T < TR; ++T) fast::phase_core<N>(sm.data(), T, m);
+    for (int T = 0; T < TR; ++T) fast::phase_middle<N, 2, false>(sm.data(), T, tw, m);
+    for (int T = 0; T < TR; ++T) fast::phase_pair_load<N>(sm.data(), T, regs.data() + (size_t)T * PER);
+    for (int T = 0; T < TR; ++T) fast::phase_pair_publish<N>(sm.data(), T, tw, regs.data() + (size_t)T * PER);
+    for (int T = 0; T < TR; ++T) fast::phase_pair_store<N>(sm.data(), T, regs.data() + (size_t)T * PER, m);
 }
 
 template <class Model>
@@ -217,6 +234,22 @@ int hc_nl_fast_real(int model, int n, const double* in, const double* kx, double
     cplx* co = reinterpret_cast<cplx*>(out);
     if (model == 1) return fast_real_dispatch(n, fast::ModelOf<1>::make(cin, co, kx, p0, n, true), tw);
     if (model == 3) return fast_real_dispatch(n, fast::ModelOf<3>::make(cin, co, kx, p0, n, true), tw);
+    return -1;
+}
+
+// cubic model on a row pair (in_b may be null: odd tail, the second row is zeros and nothing is stored for it)
+int hc_nl_fast_pair(int n, const double* in_a, const double* in_b, double c, double* out_a, double* out_b) {
+    std::vector<cplx> tab(fast::TW_TOTAL);
+    for (int j = 0; j < fast::TW_TOTAL; ++j) tab[j] = fast::twiddle_table_entry(j, n);
+    const fast::Twiddles tw{tab.data() + fast::TW_T1, tab.data() + fast::TW_T2, tab.data() + fast::TW_T3};
+    const fast::PairedCubicModel m{reinterpret_cast<const cplx*>(in_a), reinterpret_cast<const cplx*>(in_b ? in_b : in_a),
+                                   reinterpret_cast<cplx*>(out_a), reinterpret_cast<cplx*>(out_b), c, n, true, in_b != nullptr};
+    switch (n) {
+        case 512: fast_row_pair<512>(m, tw); return 0;
+        case 1024: fast_row_pair<1024>(m, tw); return 0;
+        case 2048: fast_row_pair<2048>(m, tw); return 0;
+        case 4096: fast_row_pair<4096>(m, tw); return 0;
+    }
     return -1;
 }
 

@@ -414,6 +414,38 @@ def test_real_field_half_length_forward_matches_numpy(hc, n):
     assert hc.hc_nl_fast_real(2, n, ptr(uf), None, ctypes.c_double(1.0), ptr(out)) != 0     # complex-field model: not applicable
 
 
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096])
+def test_paired_rows_cubic_model_matches_numpy(hc, n):
+    """fft_pair.cuh: two real rows through ONE complex transform pair == -rfft(irfft(u)^3) of each row; rows of very
+    different size (the rounding cross-talk is relative to the larger row) and the odd tail (second row absent)."""
+    rng = np.random.default_rng(n + 1)
+    nc = n // 2 + 1
+    decay = np.exp(-0.02 * np.arange(nc))
+
+    def row(scale):
+        v = scale * decay * (rng.standard_normal(nc) + 1j * rng.standard_normal(nc))
+        v[0] += 0.7j * scale                     # c2r drops the imaginary parts of DC and Nyquist
+        v[-1] -= 0.4j * scale
+        return np.ascontiguousarray(v)
+
+    a, b = row(1.0), row(3.0)
+    oa, ob = np.empty_like(a), np.empty_like(b)
+    assert hc.hc_nl_fast_pair(n, ptr(a), ptr(b), ctypes.c_double(-1.0), ptr(oa), ptr(ob)) == 0
+    ra = -np.fft.rfft(np.fft.irfft(a, n) ** 3)
+    rb = -np.fft.rfft(np.fft.irfft(b, n) ** 3)
+    tol = 1e-14 * np.log2(n)
+    assert rel(oa, ra) < tol * (np.linalg.norm(rb) / np.linalg.norm(ra)) and rel(ob, rb) < tol
+    assert oa[0].imag == 0.0 and oa[-1].imag == 0.0
+    # odd tail: one row alone, nothing written for the absent partner
+    oa2, sentinel = np.empty_like(a), np.full_like(b, 123.0)
+    assert hc.hc_nl_fast_pair(n, ptr(a), None, ctypes.c_double(-1.0), ptr(oa2), ptr(sentinel)) == 0
+    assert rel(oa2, ra) < tol and np.all(sentinel == 123.0)
+    # the full-length single-row pipeline computes the same thing
+    full = np.empty_like(a)
+    assert hc.hc_nl_fast(3, n, ptr(a), None, ctypes.c_double(-1.0), ptr(full)) == 0
+    assert rel(oa2, full) < tol
+
+
 # ------------------------------------------------------------------------------------------------
 # coefficient storage of large grids (DESIGN.md 4): per-axis exponential tables, grouped records
 # ------------------------------------------------------------------------------------------------

@@ -366,6 +366,30 @@ def test_fused_new_models_match_numpy(rk, name, n):
     assert rel(host(f(u)), p.nl_func(p.u0)) < 1e-13          # the torch.fft restatement of the same model
 
 
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096])
+@pytest.mark.parametrize("batch", [1, 2, 7, 300])
+def test_paired_rows_cubic_model(rk, n, batch):
+    """fft_pair.cuh: the cubic model runs two rows per complex transform (n = 512 ... 4096): even / odd batches, a
+    single row, several pair groups per persistent CTA, and the in-place evaluation the N-D grids use (RowNL)."""
+    p = problems.allen_cahn_1d(n, batch=batch, seed=n + batch)
+    u0 = p.u0.reshape(batch, -1) * (1.0 + np.arange(batch))[:, None]       # rows of different size share a transform
+    ref = p.nl_func(u0)
+    sol = rk.ETD4(dev(p.lin_op), fused_for(rk, p))
+    u = dev(u0)
+    eng = sol._get_engine(u)
+    eng.set_u(u)
+    eng.nl(1)
+    got = host(eng.state_view("N1"))
+    scale = np.linalg.norm(ref, axis=1).max()
+    for b in range(batch):                      # per row: the cross-talk is relative to the larger row of a pair
+        assert np.linalg.norm(got[b] - ref[b]) < 2e-14 * np.log2(n) * scale
+    assert rel(got, ref) < 2e-14 * np.log2(n)
+    rows = rk.models.RowNL(3, n, None, -1.0, "cuda")
+    work = u.clone()
+    rows(work, out=work)
+    np.testing.assert_array_equal(host(work), got)
+
+
 @pytest.mark.parametrize("path", ["fused", "callable"])
 @pytest.mark.parametrize("name,method,tf,eps", [("allen_cahn_1d", "IF45DP", 0.5, 1e-4), ("allen_cahn_1d", "ETD35", 3.0, 1e-5),
                                                 ("sine_gordon", "ETD35", 2.0, 1e-6), ("sine_gordon", "IF34", 2.0, 1e-5)])

@@ -13,13 +13,15 @@ import rkstiff_b200 as rk  # noqa: E402
 tot = 1 << (int(sys.argv[1]) if len(sys.argv) > 1 else 25)
 dev = torch.device("cuda", 0)
 out = []
-for model in ("nls", "uux"):
+for model in ("nls", "uux", "cubic"):
     for n in (512, 1024, 2048, 4096, 8192):
         n_c = n if model == "nls" else n // 2 + 1
         batch = tot // n
         kx = torch.linspace(0, 10, n_c, dtype=torch.float64, device=dev)
         if model == "nls":
             lin, nl = rk.models.nls_ops(kx, 2.0)
+        elif model == "cubic":
+            lin, nl = rk.models.allen_cahn_1d_ops(kx)
         else:
             lin, nl = rk.models.ks_ops(kx)
         sol = rk.ETD4(lin, nl)
@@ -40,5 +42,5 @@ for model in ("nls", "uux"):
         out.append(f"{model} n={n:5d} B={batch:6d}  {t*1e6:8.1f} us  {gbs:7.0f} GB/s  {batch*n/t/1e9:6.2f} Ggp/s")
         del sol, eng, u
         torch.cuda.empty_cache()
-print(os.environ.get("RKS_LIB", "default"))
+print(os.environ.get("RKS_LIB", "default"), {k: v for k, v in os.environ.items() if k.startswith("RKS_") and k != "RKS_LIB"})
 print("\n".join(out))
