@@ -91,17 +91,9 @@ struct Twiddles {
     const cplx* t2;     // pass 2
     const cplx* t3;     // pass 3 (n = 8192 only)
 };
-// Pass 1 (large stride: every lane its own twiddle) holds the powers 1, 2, 4, 8 as four rows of TW_S1 entries.
-// Passes 2 and 3 hold ALL powers r = 1 .. 15 as rows of TW_S2 / TW_S3 entries: a pass with a short stride
-// (Q <= RKS_TW_TABLE_MAXQ) has only Q distinct twiddle indices, the 32 lanes of a load share 8 or 16 table words
-// (one or two wavefronts), so reading w^(r j) costs next to nothing on the LSU pipe while generating the powers
-// from w^1 costs 6 (radix 8) or 14 (radix 16) complex products per butterfly on the FP64 pipe that bounds K4.
+// each pass table holds the powers k = 1, 2, 4, 8 as four rows of TW_S{1,2,3} entries
 constexpr int TW_S1 = 512, TW_S2 = 64, TW_S3 = 16;
-constexpr int TW_ROWS1 = 4, TW_ROWS23 = 15;
-constexpr int TW_T1 = 0, TW_T2 = TW_ROWS1 * TW_S1, TW_T3 = TW_T2 + TW_ROWS23 * TW_S2, TW_TOTAL = TW_T3 + TW_ROWS23 * TW_S3;
-#ifndef RKS_TW_TABLE_MAXQ
-#define RKS_TW_TABLE_MAXQ 16
-#endif
+constexpr int TW_T1 = 0, TW_T2 = 4 * TW_S1, TW_T3 = TW_T2 + 4 * TW_S2, TW_TOTAL = TW_T3 + 4 * TW_S3;
 
 // static plan of an n-point row
 template <int N> struct Plan;
@@ -134,12 +126,11 @@ RKS_HD cplx twiddle_table_entry_n(int idx) {
     using P = Plan<N>;
     constexpr int Q1 = N / P::R1, Q2 = Q1 / P::R2, Q3 = Q2 / P::R3;
     int j, m, k, q;
-    long long power;
-    if (idx < TW_T2) { k = idx / TW_S1; j = idx % TW_S1; m = N; q = Q1; power = 1ll << k; }
-    else if (idx < TW_T3) { k = (idx - TW_T2) / TW_S2; j = (idx - TW_T2) % TW_S2; m = Q1; q = Q2; power = k + 1; }
-    else { k = (idx - TW_T3) / TW_S3; j = (idx - TW_T3) % TW_S3; m = Q2; q = Q3; power = k + 1; }
+    if (idx < TW_T2) { k = idx / TW_S1; j = idx % TW_S1; m = N; q = Q1; }
+    else if (idx < TW_T3) { k = (idx - TW_T2) / TW_S2; j = (idx - TW_T2) % TW_S2; m = Q1; q = Q2; }
+    else { k = (idx - TW_T3) / TW_S3; j = (idx - TW_T3) % TW_S3; m = Q2; q = Q3; }
     if (j >= q) j = 0;
-    j = (int)(((long long)j * power) % m);           // w^(power j)
+    j = (int)(((long long)j << k) % m);              // w^(2^k j)
     double s, c;
 #if defined(__CUDA_ARCH__)
     sincospi(-2.0 * (double)j / (double)m, &s, &c);
@@ -165,26 +156,24 @@ RKS_HD cplx twiddle_table_entry(int idx, int n) {
 // squarings (error <= ~8 ulp on the twiddle); otherwise the four powers are read from the table
 // rows.  The remaining powers are products of at most three of them.  Twiddle loads compete with
 // the shared-memory passes for the LSU pipe.
-// POW2: `tab` has the rows 1, 2, 4, 8 (pass 1), which RKS_TW_SQUARE=0 reads instead of squaring.
-template <int R, bool INV, class Slot, bool POW2 = false>
+template <int R, bool INV, class Slot>
 RKS_HD void twiddle_scale(cplx* v, const cplx* tab, int stride, int i, Slot slot) {
-    constexpr bool SQ = RKS_TW_SQUARE || !POW2;
     if (R == 1) return;
     const cplx w1 = cj<INV>(tw_ld(tab + i));
     v[slot(1)] = v[slot(1)] * w1;
     if (R == 2) return;
-    const cplx w2 = SQ ? w1 * w1 : cj<INV>(tw_ld(tab + stride + i));
+    const cplx w2 = RKS_TW_SQUARE ? w1 * w1 : cj<INV>(tw_ld(tab + stride + i));
     const cplx w3 = w1 * w2;
     v[slot(2)] = v[slot(2)] * w2;
     v[slot(3)] = v[slot(3)] * w3;
     if (R == 4) return;
-    const cplx w4 = SQ ? w2 * w2 : cj<INV>(tw_ld(tab + 2 * stride + i));
+    const cplx w4 = RKS_TW_SQUARE ? w2 * w2 : cj<INV>(tw_ld(tab + 2 * stride + i));
     v[slot(4)] = v[slot(4)] * w4;
     v[slot(5)] = v[slot(5)] * (w4 * w1);
     v[slot(6)] = v[slot(6)] * (w4 * w2);
     v[slot(7)] = v[slot(7)] * (w4 * w3);
     if (R == 8) return;
-    const cplx w8 = SQ ? w4 * w4 : cj<INV>(tw_ld(tab + 3 * stride + i));
+    const cplx w8 = RKS_TW_SQUARE ? w4 * w4 : cj<INV>(tw_ld(tab + 3 * stride + i));
     v[slot(8)] = v[slot(8)] * w8;
     v[slot(9)] = v[slot(9)] * (w8 * w1);
     v[slot(10)] = v[slot(10)] * (w8 * w2);
@@ -194,20 +183,6 @@ RKS_HD void twiddle_scale(cplx* v, const cplx* tab, int stride, int i, Slot slot
     v[slot(13)] = v[slot(13)] * (w12 * w1);
     v[slot(14)] = v[slot(14)] * (w12 * w2);
     v[slot(15)] = v[slot(15)] * (w12 * w3);
-}
-
-// v[slot(r)] *= w^r with every power read from the full table of a short-stride pass (rows r = 1 .. R-1)
-template <int R, bool INV, class Slot>
-RKS_HD void twiddle_scale_table(cplx* v, const cplx* tab, int stride, int i, Slot slot) {
-#pragma unroll
-    for (int r = 1; r < R; ++r) v[slot(r)] = v[slot(r)] * cj<INV>(tw_ld(tab + (r - 1) * stride + i));
-}
-// twiddles of a pass with stride Q whose table has rows of TS entries
-template <int R, int Q, int TS, bool INV, class Slot>
-RKS_HD void pass_twiddles(cplx* v, const cplx* tab, int j, Slot slot) {
-    if (Q <= 1) return;
-    if (TS != TW_S1 && Q <= RKS_TW_TABLE_MAXQ) twiddle_scale_table<R, INV>(v, tab, TS, j, slot);
-    else twiddle_scale<R, INV, Slot, TS == TW_S1>(v, tab, TS, j, slot);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -419,11 +394,11 @@ RKS_HD void bf_store_global(const Model& m, int p0, const cplx* a) {
 template <int R, int Q, int TS>
 RKS_HD void bf_dif(cplx* a, const cplx* tab, int j) {          // inverse butterfly, then twiddles on the outputs
     dftR<R, true>(a);
-    pass_twiddles<R, Q, TS, true>(a, tab, j, SlotPerm<R>());
+    if (Q > 1) twiddle_scale<R, true>(a, tab, TS, j, SlotPerm<R>());
 }
 template <int R, int Q, int TS>
 RKS_HD void bf_dit(cplx* a, const cplx* tab, int j) {          // twiddles on the inputs, then forward butterfly
-    pass_twiddles<R, Q, TS, false>(a, tab, j, SlotId());
+    if (Q > 1) twiddle_scale<R, false>(a, tab, TS, j, SlotId());
     dftR<R, false>(a);
 }
 template <int R, class Model>
@@ -530,7 +505,7 @@ RKS_HD void phase_middle(cplx* sm, int T, const Twiddles& tw, const Model& m) {
 template <int R1>
 RKS_HD void pre_butterfly(cplx* a, const cplx* t1, int j) {     // a[s] = k[j + Q1 s] -> a[perm(r)] = row[j + Q1 r]
     dftR<R1, true>(a);
-    twiddle_scale<R1, true, SlotPerm<R1>, true>(a, t1, TW_S1, j, SlotPerm<R1>());
+    twiddle_scale<R1, true>(a, t1, TW_S1, j, SlotPerm<R1>());
 }
 // first pass of K4 on a pre-transformed row: middle pass 2 of the inverse transform, input from the model
 template <int N, class Model>
