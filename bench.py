@@ -401,10 +401,20 @@ class Ctx:
         gc.collect()
         self.torch.cuda.empty_cache()
 
-    def close(self):
+    def close(self, rc=0):
         if self.world > 1:
+            import threading
             import torch.distributed as dist
+            self.release()
+            # the JSON line is out; a communicator that refuses to shut down must not hold the job hostage
+            sys.stdout.flush()
+            sys.stderr.flush()
+            threading.Timer(60.0, lambda: os._exit(rc)).start()
+            self.torch.cuda.synchronize()
             dist.destroy_process_group()
+            os._exit(rc)
+        if rc:
+            raise SystemExit(rc)
 
 
 def parity_sample(torch, rk, workload, method, device):
@@ -954,6 +964,7 @@ def guarded(ctx, name, fn):
 
 def run_ours(args):
     ctx = Ctx()
+    rc = 1
     try:
         if args.workload == "cfg2b":
             line = run_cfg2b(ctx, args)
@@ -979,9 +990,13 @@ def run_ours(args):
                     line["parity"] = guarded(ctx, "parity", lambda: parity_multi(ctx))
                 line["secondary"] = sec
         if ctx.rank == 0:
-            print(json.dumps(line))
+            print(json.dumps(line), flush=True)
+        rc = 0
+    except Exception:                                           # noqa: BLE001
+        import traceback
+        traceback.print_exc()
     finally:
-        ctx.close()
+        ctx.close(rc)
 
 
 def main():

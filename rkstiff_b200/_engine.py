@@ -200,8 +200,15 @@ class Engine:
             return None                                   # too few repeats to pay for the gather
         return ("indexed", values, index)
 
+    def close(self) -> None:
+        """Release the captured sharded-trial graphs (they hold NCCL kernels: call this, or drop the solver, before
+        ``torch.distributed.destroy_process_group()``)."""
+        self._group_graphs = {}
+        self._group_graph_ok = False
+
     def __del__(self):
         try:
+            self._group_graphs = {}
             if getattr(self, "plan", None):
                 lib.rks_plan_destroy(self.plan)
                 self.plan = None
@@ -396,7 +403,8 @@ class Engine:
                 torch.cuda.synchronize(self.device)
                 before = self.launches_raw()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                # thread_local: the NCCL watchdog thread keeps polling its events while this thread captures
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     self.enqueue_trial(None, ring, ring_t)
                 self._group_graph_launches = self.launches_raw() - before
                 self._replayed_launches -= self._group_graph_launches      # the capture itself launched nothing

@@ -101,6 +101,33 @@ RKS_HD void dit_level(cplx* tile, const cplx* tw, const Col& c, int bt, int nbt)
     }
 }
 
+// Long axes (N >= 2048) in TWO kernels.  A whole column of N rows is 64 KB, so the one-kernel tile above can only be two
+// columns wide: 32-byte row segments, a quarter of a DRAM page burst each, 0.33-0.40 of the HBM roofline measured
+// for N = 4096 (profiles/r01_v7_launches_cfg4_4096.csv).  Level 1 -- the radix-16 butterflies over stride N/16 --
+// needs no exchange at all: its 16 inputs are 16 rows of ONE column, so it runs as a streaming pass with the lanes
+// of a warp on 32 adjacent columns (512-byte row segments, no shared memory).  What remains are 16 independent
+// transforms of length N/16 per column, i.e. the one-kernel transform of [16 outer][N/16][inner] with its 8-column
+// tiles.  Same butterflies, twiddles and order as levels 1 | 2, 3 of the one-kernel plan: bit-identical results.
+// The intermediate array travels through the L2 (126 MB): the second kernel walks the column blocks in the opposite
+// direction, so it starts on the lines the first one wrote last.
+template <int N, bool INV>
+RKS_HD void outer_butterfly(const cplx* gin, cplx* gout, long long rstride, int j, const cplx* tw) {
+    constexpr int R = 16, Q = N / R;
+    cplx a[R];
+#pragma unroll
+    for (int s = 0; s < R; ++s) a[s] = fast::row_ld(gin + (long long)(j + Q * s) * rstride);
+    if (INV) {
+        fast::dftR<R, true>(a);
+        fast::twiddle_scale<R, true>(a, tw, 0, j, fast::SlotPerm<R>());
+    } else {
+        fast::twiddle_scale<R, false>(a, tw, 0, j, fast::SlotId());
+        fast::dftR<R, false>(a);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) fast::row_st(gout + (long long)(j + Q * r) * rstride, a[fast::perm<R>(r)]);
+}
+RKS_HD constexpr bool axis_split(int n) { return n >= 2048; }
+
 // level LEVEL of one tile.  The caller separates the levels: __syncthreads on the device; the serial host
 // emulation runs a level for every thread before the next one
 template <int N, bool INV, int LEVEL>

@@ -115,6 +115,12 @@ class BaseSolver(ABC):
         self._engine = eng
         return eng
 
+    def close(self) -> None:
+        """Release device-side resources tied to a process group: the sharded shared-dt trial is a captured CUDA
+        graph that holds NCCL kernels and must be gone before ``torch.distributed.destroy_process_group()``."""
+        for eng in self._engines.values():
+            eng.close()
+
     def _config_signature(self):
         c = self._rks_config()
         return tuple(getattr(c, f) for f, _ in c._fields_)

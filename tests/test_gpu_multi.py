@@ -21,6 +21,15 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _teardown(sol):
+    """The sharded trial is a captured CUDA graph holding NCCL kernels: release it before the communicator goes."""
+    import torch.distributed as dist
+    sol.close()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def _worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -37,8 +46,7 @@ def _worker(rank, world, port, q):
     uf = sol.evolve(torch.from_numpy(p.u0[lo:hi].copy()).cuda(), 0.0, 0.2, store_freq=3)
     q.put((rank, lo, hi, [r[0] for r in sol.trial_log], [r[2] for r in sol.trial_log], list(sol.t),
            uf.cpu().numpy()))
-    dist.barrier()
-    dist.destroy_process_group()
+    _teardown(sol)
 
 
 def test_sharded_shared_dt_ensemble_matches_whole_batch():
@@ -82,8 +90,7 @@ def _slab_worker(rank, world, port, q):
     sol = rk.ETD35(lin, nl, config=rk.SolverConfig(epsilon=1e-5), group=dist.group.WORLD)
     uf = sol.evolve(u0, 0.0, 0.2)
     q.put((rank, [r[0] for r in sol.trial_log], [r[2] for r in sol.trial_log], uf.cpu().numpy()))
-    dist.barrier()
-    dist.destroy_process_group()
+    _teardown(sol)
 
 
 def test_cfg5_slab_decomposed_nls3d_matches_flattened_oracle():
