@@ -31,7 +31,11 @@ template <> struct APlan<4096> { static constexpr int R1 = 16, R2 = 16, R3 = 16;
 
 // tile geometry: 64 KB tiles (128 KB for N = 4096 so that a row segment is still a full 32-byte sector)
 template <int N> RKS_HD constexpr int tile_cols() { return N <= 512 ? 8 : N == 1024 ? 4 : 2; }
-template <int N> RKS_HD constexpr int tile_threads() { return N == 4096 ? 512 : 256; }
+// threads: one first-level butterfly per thread where the tile has that many (N / R1 butterflies x C columns), so no
+// thread idles through a level; resident CTAs per SM: as many as the 227 KB of shared memory and 64 K registers
+// allow -- short axes (the second kernel of the two-kernel route, 256^3 grids) need several small tiles in flight
+template <int N> RKS_HD constexpr int tile_threads() { return N == 4096 ? 512 : N >= 512 ? 256 : N == 256 ? 128 : 64; }
+template <int N> RKS_HD constexpr int tile_blocks() { return N == 4096 ? 1 : N >= 1024 ? 2 : N == 512 ? 3 : N == 256 ? 5 : 8; }
 template <int N> RKS_HD constexpr int last_radix() {
     return APlan<N>::R3 > 1 ? APlan<N>::R3 : APlan<N>::R2 > 1 ? APlan<N>::R2 : APlan<N>::R1;
 }
@@ -100,33 +104,6 @@ RKS_HD void dit_level(cplx* tile, const cplx* tw, const Col& c, int bt, int nbt)
         }
     }
 }
-
-// Long axes (N >= 2048) in TWO kernels.  A whole column of N rows is 64 KB, so the one-kernel tile above can only be two
-// columns wide: 32-byte row segments, a quarter of a DRAM page burst each, 0.33-0.40 of the HBM roofline measured
-// for N = 4096 (profiles/r01_v7_launches_cfg4_4096.csv).  Level 1 -- the radix-16 butterflies over stride N/16 --
-// needs no exchange at all: its 16 inputs are 16 rows of ONE column, so it runs as a streaming pass with the lanes
-// of a warp on 32 adjacent columns (512-byte row segments, no shared memory).  What remains are 16 independent
-// transforms of length N/16 per column, i.e. the one-kernel transform of [16 outer][N/16][inner] with its 8-column
-// tiles.  Same butterflies, twiddles and order as levels 1 | 2, 3 of the one-kernel plan: bit-identical results.
-// The intermediate array travels through the L2 (126 MB): the second kernel walks the column blocks in the opposite
-// direction, so it starts on the lines the first one wrote last.
-template <int N, bool INV>
-RKS_HD void outer_butterfly(const cplx* gin, cplx* gout, long long rstride, int j, const cplx* tw) {
-    constexpr int R = 16, Q = N / R;
-    cplx a[R];
-#pragma unroll
-    for (int s = 0; s < R; ++s) a[s] = fast::row_ld(gin + (long long)(j + Q * s) * rstride);
-    if (INV) {
-        fast::dftR<R, true>(a);
-        fast::twiddle_scale<R, true>(a, tw, 0, j, fast::SlotPerm<R>());
-    } else {
-        fast::twiddle_scale<R, false>(a, tw, 0, j, fast::SlotId());
-        fast::dftR<R, false>(a);
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) fast::row_st(gout + (long long)(j + Q * r) * rstride, a[fast::perm<R>(r)]);
-}
-RKS_HD constexpr bool axis_split(int n) { return n >= 2048; }
 
 // level LEVEL of one tile.  The caller separates the levels: __syncthreads on the device; the serial host
 // emulation runs a level for every thread before the next one

@@ -1278,21 +1278,16 @@ __global__ void __launch_bounds__(256) copy_u_multi_kernel(const DevPlan* plans,
 // CTAs loop over (outer, column tile) pairs.  in == out is allowed: a CTA reads its whole tile
 // before it writes any of it.
 // ---------------------------------------------------------------------------------------
-// order: 0 = tiles outer-major, ascending; 1 = column-tile-major, DESCENDING; 2 = column-tile-major, ascending (the
-// two-kernel transform of a long axis walks the column blocks in opposite directions in its two kernels, fft_axis.cuh)
 template <int N, bool INV>
 RKS_D void axis_fft_body(const cplx* in, cplx* out, long long outer, long long inner, const cplx* tw, double scale,
-                         long long ostride, long long bstride, int rb_shift, int order = 0) {
+                         long long ostride, long long bstride, int rb_shift) {
     constexpr int C = axis::tile_cols<N>(), NBT = axis::tile_threads<N>() / C;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     cplx* tile = reinterpret_cast<cplx*>(smem_raw);
     const int col = threadIdx.x % C, bt = threadIdx.x / C;
     const long long tpo = (inner + C - 1) / C, tiles = outer * tpo;
     for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-        long long o, ct;
-        if (order == 0) { o = t / tpo; ct = t - o * tpo; }
-        else { const long long tt = order == 1 ? tiles - 1 - t : t; ct = tt / outer; o = tt - ct * outer; }
-        const long long c0 = ct * C;
+        const long long o = t / tpo, c0 = (t - o * tpo) * C;
         const long long off = o * ostride + c0 + col;
         const axis::Col c{in + off, out + off, inner, bstride, rb_shift, col, c0 + col < inner};
         axis::tile_level<N, INV, 0>(tile, tw, c, bt, NBT, scale);
@@ -1304,55 +1299,21 @@ RKS_D void axis_fft_body(const cplx* in, cplx* out, long long outer, long long i
     }
 }
 template <int N, bool INV>
-__global__ void __launch_bounds__(axis::tile_threads<N>(), (N == 4096 ? 1 : N == 512 ? 3 : 2))
+__global__ void __launch_bounds__(axis::tile_threads<N>(), axis::tile_blocks<N>())
 axis_fft_kernel(const cplx* in, cplx* out, long long outer, long long inner, const cplx* tw, double scale,
-                long long ostride, long long bstride, int rb_shift, int order) {
-    axis_fft_body<N, INV>(in, out, outer, inner, tw, scale, ostride, bstride, rb_shift, order);
+                long long ostride, long long bstride, int rb_shift) {
+    axis_fft_body<N, INV>(in, out, outer, inner, tw, scale, ostride, bstride, rb_shift);
 }
 // the same transform as one step of the nonlinear term N_j of an N-D grid model (rks_set_model_nd): arrays and
 // the run predicate come from the control block (no host sync, graph replay); the first step of an evaluation
 // reads the stage value and writes N_j, the others work on N_j in place
 template <int N, bool INV>
-__global__ void __launch_bounds__(axis::tile_threads<N>(), (N == 4096 ? 1 : N == 512 ? 3 : 2))
+__global__ void __launch_bounds__(axis::tile_threads<N>(), axis::tile_blocks<N>())
 axis_fft_plan_kernel(const __grid_constant__ DevPlan p, int j, int force, int first, long long outer, long long inner,
-                     const cplx* tw, double scale, int order) {
+                     const cplx* tw, double scale) {
     const NlRoles r = nl_roles(p, j, force);
     if (!r.run) return;
-    axis_fft_body<N, INV>(first ? r.in : r.out, r.out, outer, inner, tw, scale, (long long)N * inner, 0, 31, order);
-}
-
-// level 1 of a long axis as a streaming pass (fft_axis.cuh outer_butterfly): block = 32 columns x 8 butterflies;
-// blocks run over the butterflies of a column block first, then over the column blocks (descending if `reverse`)
-constexpr int AXO_COLS = 32, AXO_ROWS = 8;
-template <int N, bool INV>
-RKS_D void axis_outer_body(const cplx* in, cplx* out, long long outer, long long inner, const cplx* tw, int reverse) {
-    constexpr int Q = N / 16, JB = Q / AXO_ROWS;
-    const long long cbs = (inner + AXO_COLS - 1) / AXO_COLS;
-    const long long per_o = cbs * JB, blocks = outer * per_o;
-    for (long long b = blockIdx.x; b < blocks; b += gridDim.x) {
-        const long long bb = reverse ? blocks - 1 - b : b;
-        const long long o = bb / per_o, rem = bb - o * per_o;
-        const long long cb = rem / JB;
-        const int j = (int)(rem - cb * JB) * AXO_ROWS + (int)(threadIdx.x / AXO_COLS);
-        const long long col = cb * AXO_COLS + (threadIdx.x % AXO_COLS);
-        if (col < inner) {
-            const long long off = o * (long long)N * inner + col;
-            axis::outer_butterfly<N, INV>(in + off, out + off, inner, j, tw);
-        }
-    }
-}
-template <int N, bool INV>
-__global__ void __launch_bounds__(AXO_COLS * AXO_ROWS, 2)
-axis_outer_kernel(const cplx* in, cplx* out, long long outer, long long inner, const cplx* tw, int reverse) {
-    axis_outer_body<N, INV>(in, out, outer, inner, tw, reverse);
-}
-template <int N, bool INV>
-__global__ void __launch_bounds__(AXO_COLS * AXO_ROWS, 2)
-axis_outer_plan_kernel(const __grid_constant__ DevPlan p, int j, int force, int first, long long outer, long long inner,
-                       const cplx* tw, int reverse) {
-    const NlRoles r = nl_roles(p, j, force);
-    if (!r.run) return;
-    axis_outer_body<N, INV>(first ? r.in : r.out, r.out, outer, inner, tw, reverse);
+    axis_fft_body<N, INV>(first ? r.in : r.out, r.out, outer, inner, tw, scale, (long long)N * inner, 0, 31);
 }
 
 }  // namespace rks

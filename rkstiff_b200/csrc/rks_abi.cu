@@ -1419,7 +1419,6 @@ struct rks_axis {
     cplx* tw = nullptr;
     long long n = 0;
     int sm_count = 0;
-    rks_axis* sub = nullptr;        // n >= 2048: the n/16-point transform of the two-kernel route (fft_axis.cuh)
 };
 
 template <int N>
@@ -1430,39 +1429,16 @@ static cudaError_t axis_prepare() {
     return e;
 }
 
-// `total`: length of the whole axis (= N, or 16 N when this is the second kernel of the two-kernel route): the inverse
-// transform scales by 1 / total at its last level
 template <int N>
 static void axis_launch(const rks_axis* a, const cplx* in, cplx* out, long long outer, long long inner, int inverse,
-                        long long ostride, long long bstride, int rb_shift, cudaStream_t stream, long long total = N,
-                        int order = 0) {
+                        long long ostride, long long bstride, int rb_shift, cudaStream_t stream) {
     constexpr int C = axis::tile_cols<N>();
     const size_t smem = (size_t)N * C * sizeof(cplx);
     const long long tiles = outer * ((inner + C - 1) / C);
-    const long long cap = (long long)a->sm_count * (N == 4096 ? 1 : N == 512 ? 3 : 2) * 4;      // persistent CTAs, a few per slot
+    const long long cap = (long long)a->sm_count * axis::tile_blocks<N>() * 4;      // persistent CTAs, a few per slot
     const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
-    if (inverse) axis_fft_kernel<N, true><<<grid, axis::tile_threads<N>(), smem, stream>>>(in, out, outer, inner, a->tw, 1.0 / (double)total, ostride, bstride, rb_shift, order);
-    else axis_fft_kernel<N, false><<<grid, axis::tile_threads<N>(), smem, stream>>>(in, out, outer, inner, a->tw, 1.0, ostride, bstride, rb_shift, order);
-}
-// grid of the streaming level-1 pass: persistent, a few blocks per resident slot
-static unsigned axis_outer_grid(const rks_axis* a, long long outer, long long inner) {
-    const long long blocks = outer * ((inner + AXO_COLS - 1) / AXO_COLS) * ((a->n / 16) / AXO_ROWS);
-    const long long cap = (long long)a->sm_count * 2 * 8;
-    return (unsigned)(blocks < cap ? blocks : cap);
-}
-// plain strided axis of length n >= 2048 in two kernels (fft_axis.cuh): level 1 streaming, then [16 outer][n/16][inner]
-template <int N>
-static void axis_launch_split(const rks_axis* a, const cplx* in, cplx* out, long long outer, long long inner, int inverse,
-                              cudaStream_t stream) {
-    constexpr int S = N / 16;
-    const unsigned grid = axis_outer_grid(a, outer, inner);
-    if (inverse) {
-        axis_outer_kernel<N, true><<<grid, AXO_COLS * AXO_ROWS, 0, stream>>>(in, out, outer, inner, a->tw, 0);
-        axis_launch<S>(a->sub, out, out, outer * 16, inner, 1, (long long)S * inner, 0, 31, stream, N, 1);
-    } else {
-        axis_launch<S>(a->sub, in, out, outer * 16, inner, 0, (long long)S * inner, 0, 31, stream, N, 2);
-        axis_outer_kernel<N, false><<<grid, AXO_COLS * AXO_ROWS, 0, stream>>>(out, out, outer, inner, a->tw, 1);
-    }
+    if (inverse) axis_fft_kernel<N, true><<<grid, axis::tile_threads<N>(), smem, stream>>>(in, out, outer, inner, a->tw, 1.0 / (double)N, ostride, bstride, rb_shift);
+    else axis_fft_kernel<N, false><<<grid, axis::tile_threads<N>(), smem, stream>>>(in, out, outer, inner, a->tw, 1.0, ostride, bstride, rb_shift);
 }
 
 extern "C" int rks_axis_create(rks_axis** out, int64_t n, void* stream_v) {
@@ -1492,9 +1468,6 @@ extern "C" int rks_axis_create(rks_axis** out, int64_t n, void* stream_v) {
     }
     if (e != cudaSuccess) return fail(RKS_ERR_CUDA, "axis kernel attributes: %s", cudaGetErrorString(e));
     CUDA_TRY(cudaGetLastError());
-    const char* sp = getenv("RKS_AXIS_SPLIT");
-    if (axis::axis_split((int)n) && !(sp && sp[0] == '0'))
-        if (int rc = rks_axis_create(&a->sub, n / 16, stream_v)) return rc;
     guard.release();
     *out = a;
     return RKS_OK;
@@ -1536,14 +1509,8 @@ static int axis_apply(rks_axis* a, const void* in, void* out, int64_t outer, int
         case 256: axis_launch<256>(a, i, o, outer, inner, inverse, ostride, bstride, rb_shift, stream); break;
         case 512: axis_launch<512>(a, i, o, outer, inner, inverse, ostride, bstride, rb_shift, stream); break;
         case 1024: axis_launch<1024>(a, i, o, outer, inner, inverse, ostride, bstride, rb_shift, stream); break;
-        case 2048:
-            if (a->sub && rb_shift == 31) axis_launch_split<2048>(a, i, o, outer, inner, inverse, stream);
-            else axis_launch<2048>(a, i, o, outer, inner, inverse, ostride, bstride, rb_shift, stream);
-            break;
-        default:
-            if (a->sub && rb_shift == 31) axis_launch_split<4096>(a, i, o, outer, inner, inverse, stream);
-            else axis_launch<4096>(a, i, o, outer, inner, inverse, ostride, bstride, rb_shift, stream);
-            break;
+        case 2048: axis_launch<2048>(a, i, o, outer, inner, inverse, ostride, bstride, rb_shift, stream); break;
+        default: axis_launch<4096>(a, i, o, outer, inner, inverse, ostride, bstride, rb_shift, stream); break;
     }
     CUDA_TRY(cudaGetLastError());
     return RKS_OK;
@@ -1558,38 +1525,14 @@ static int axis_apply(rks_axis* a, const void* in, void* out, int64_t outer, int
 // ---------------------------------------------------------------------------------------
 template <int N>
 static void axis_launch_plan(const rks_axis* a, const DevPlan& d, int j, int force, int first, long long outer, long long inner,
-                             int inverse, cudaStream_t stream, long long total = N, int order = 0) {
+                             int inverse, cudaStream_t stream) {
     constexpr int C = axis::tile_cols<N>();
     const size_t smem = (size_t)N * C * sizeof(cplx);
     const long long tiles = outer * ((inner + C - 1) / C);
-    const long long cap = (long long)a->sm_count * (N == 4096 ? 1 : N == 512 ? 3 : 2) * 4;
+    const long long cap = (long long)a->sm_count * axis::tile_blocks<N>() * 4;
     const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
-    if (inverse) axis_fft_plan_kernel<N, true><<<grid, axis::tile_threads<N>(), smem, stream>>>(d, j, force, first, outer, inner, a->tw, 1.0 / (double)total, order);
-    else axis_fft_plan_kernel<N, false><<<grid, axis::tile_threads<N>(), smem, stream>>>(d, j, force, first, outer, inner, a->tw, 1.0, order);
-}
-// two-kernel route of a long axis inside an engine model; returns the number of launches
-template <int N>
-static int axis_launch_plan_split(const rks_axis* a, const DevPlan& d, int j, int force, int first, long long outer,
-                                  long long inner, int inverse, cudaStream_t stream) {
-    if constexpr (N < 2048) {
-        axis_launch_plan<N>(a, d, j, force, first, outer, inner, inverse, stream);
-        return 1;
-    } else {
-        if (!a->sub) {
-            axis_launch_plan<N>(a, d, j, force, first, outer, inner, inverse, stream);
-            return 1;
-        }
-        constexpr int S = N / 16;
-        const unsigned grid = axis_outer_grid(a, outer, inner);
-        if (inverse) {
-            axis_outer_plan_kernel<N, true><<<grid, AXO_COLS * AXO_ROWS, 0, stream>>>(d, j, force, first, outer, inner, a->tw, 0);
-            axis_launch_plan<S>(a->sub, d, j, force, 0, outer * 16, inner, 1, stream, N, 1);
-        } else {
-            axis_launch_plan<S>(a->sub, d, j, force, first, outer * 16, inner, 0, stream, N, 2);
-            axis_outer_plan_kernel<N, false><<<grid, AXO_COLS * AXO_ROWS, 0, stream>>>(d, j, force, 0, outer, inner, a->tw, 1);
-        }
-        return 2;
-    }
+    if (inverse) axis_fft_plan_kernel<N, true><<<grid, axis::tile_threads<N>(), smem, stream>>>(d, j, force, first, outer, inner, a->tw, 1.0 / (double)N);
+    else axis_fft_plan_kernel<N, false><<<grid, axis::tile_threads<N>(), smem, stream>>>(d, j, force, first, outer, inner, a->tw, 1.0);
 }
 template <int N>
 static cudaError_t axis_plan_prepare() {
@@ -1607,11 +1550,10 @@ static cudaError_t axis_plan_prepare() {
 static void axis_step(rks_plan* p, int which, int j, int force, int first, long long outer, long long inner, int inverse,
                       cudaStream_t stream) {
     const rks_axis* a = p->nd_axes[which];
-    int launched = 1;
-#define RKS_CALL(N) launched = axis_launch_plan_split<N>(a, p->d, j, force, first, outer, inner, inverse, stream)
+#define RKS_CALL(N) axis_launch_plan<N>(a, p->d, j, force, first, outer, inner, inverse, stream)
     RKS_AXIS_SWITCH(a->n, RKS_CALL)
 #undef RKS_CALL
-    p->launches += launched;
+    p->launches += 1;
 }
 
 static int launch_nl_nd(rks_plan* p, int j, int force, cudaStream_t stream) {
@@ -1664,7 +1606,6 @@ extern "C" int rks_set_model_nd(rks_plan* p, int model, int nd, const int64_t* g
         cudaError_t e = cudaSuccess;
 #define RKS_CALL(N) e = axis_plan_prepare<N>()
         RKS_AXIS_SWITCH(grid[k], RKS_CALL)
-        if (e == cudaSuccess && axis::axis_split((int)grid[k])) { RKS_AXIS_SWITCH(grid[k] / 16, RKS_CALL) }
 #undef RKS_CALL
         if (e != cudaSuccess) return fail(RKS_ERR_CUDA, "axis kernel attributes: %s", cudaGetErrorString(e));
     }
@@ -1682,7 +1623,6 @@ extern "C" int rks_set_model_nd(rks_plan* p, int model, int nd, const int64_t* g
 
 extern "C" void rks_axis_destroy(rks_axis* a) {
     if (!a) return;
-    if (a->sub) rks_axis_destroy(a->sub);
     cudaFree(a->tw);
     delete a;
 }

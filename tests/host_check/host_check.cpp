@@ -195,40 +195,6 @@ static void axis_all(const cplx* in, cplx* out, long long inner) {
         axis_level_all<N, INV, 2>(tile.data(), tw.data(), in, out, inner, c0);
     }
 }
-// two-kernel route of a long axis (fft_axis.cuh outer_butterfly + the N/16-point transform of the 16 row blocks)
-template <int N, bool INV>
-static void axis_split_all(const cplx* in, cplx* out, long long inner) {
-    constexpr int S = N / 16, C = axis::tile_cols<S>();
-    std::vector<cplx> tw(N), tws(S), tile((size_t)S * C);
-    for (int j = 0; j < N; ++j) tw[j] = mk(cos(-2.0 * M_PI * j / N), sin(-2.0 * M_PI * j / N));
-    for (int j = 0; j < S; ++j) tws[j] = mk(cos(-2.0 * M_PI * j / S), sin(-2.0 * M_PI * j / S));
-    auto sub = [&](const cplx* src) {
-        for (int blk = 0; blk < 16; ++blk) {
-            const cplx* bi = src + (long long)blk * S * inner;
-            cplx* bo = out + (long long)blk * S * inner;
-            for (long long c0 = 0; c0 < inner; c0 += C)
-                for (int level = 0; level < 3; ++level)
-                    for (int tid = 0; tid < axis::tile_threads<S>(); ++tid) {
-                        const int col = tid % C, bt = tid / C, nbt = axis::tile_threads<S>() / C;
-                        const axis::Col c{bi + c0 + col, bo + c0 + col, inner, 0, 31, col, c0 + col < inner};
-                        const double scale = INV ? 1.0 / (double)N : 1.0;
-                        if (level == 0) axis::tile_level<S, INV, 0>(tile.data(), tws.data(), c, bt, nbt, scale);
-                        else if (level == 1) axis::tile_level<S, INV, 1>(tile.data(), tws.data(), c, bt, nbt, scale);
-                        else axis::tile_level<S, INV, 2>(tile.data(), tws.data(), c, bt, nbt, scale);
-                    }
-        }
-    };
-    if (INV) {
-        for (long long col = 0; col < inner; ++col)
-            for (int j = 0; j < S; ++j) axis::outer_butterfly<N, true>(in + col, out + col, inner, j, tw.data());
-        sub(out);
-    } else {
-        sub(in);
-        for (long long col = 0; col < inner; ++col)
-            for (int j = 0; j < S; ++j) axis::outer_butterfly<N, false>(out + col, out + col, inner, j, tw.data());
-    }
-}
-
 template <bool INV>
 static int axis_dispatch(int n, const cplx* in, cplx* out, long long inner) {
     switch (n) {
@@ -497,15 +463,6 @@ int hc_embedded_err(int method, int n, const double* const* N, const double* coe
 
 // controller: feed (sum_u2, sum_e2) of one trial; state is a caller-held opaque Ctrl blob
 // in / out: [n][inner] complex128 (one `outer` slice); inverse: natural -> digit-reversed rows
-// the two-kernel route of a long axis (n = 2048, 4096)
-int hc_axis_fft_split(int n, int inverse, const double* in, double* out, long long inner) {
-    const cplx* i = (const cplx*)in;
-    cplx* o = (cplx*)out;
-    if (n == 2048) { inverse ? axis_split_all<2048, true>(i, o, inner) : axis_split_all<2048, false>(i, o, inner); return 0; }
-    if (n == 4096) { inverse ? axis_split_all<4096, true>(i, o, inner) : axis_split_all<4096, false>(i, o, inner); return 0; }
-    return -1;
-}
-
 int hc_axis_fft(int n, int inverse, const double* in, double* out, long long inner) {
     return inverse ? axis_dispatch<true>(n, (const cplx*)in, (cplx*)out, inner)
                    : axis_dispatch<false>(n, (const cplx*)in, (cplx*)out, inner);

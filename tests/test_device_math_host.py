@@ -339,21 +339,6 @@ def test_axis_fft_levels_match_numpy(hc, n):
     np.testing.assert_allclose(w, reff, rtol=0, atol=1e-13 * np.abs(reff).max() * np.log2(n))
 
 
-@pytest.mark.parametrize("n", [2048, 4096])
-def test_two_kernel_long_axis_is_bit_identical_to_the_tile_kernel(hc, n):
-    """fft_axis.cuh: level 1 of a long axis as a streaming pass + the n/16-point tile transform of the 16 row blocks
-    does the same operations in the same order as the one-kernel plan: same bits, both directions."""
-    rng = np.random.default_rng(n)
-    inner = 5
-    x = np.ascontiguousarray(rng.standard_normal((n, inner)) + 1j * rng.standard_normal((n, inner)))
-    for inverse in (1, 0):
-        one, two = np.empty_like(x), np.empty_like(x)
-        assert hc.hc_axis_fft(n, inverse, ptr(x), ptr(one), ctypes.c_longlong(inner)) == 0
-        assert hc.hc_axis_fft_split(n, inverse, ptr(x), ptr(two), ctypes.c_longlong(inner)) == 0
-        np.testing.assert_array_equal(one, two)
-    assert hc.hc_axis_fft_split(1024, 1, ptr(x), ptr(two), ctypes.c_longlong(inner)) != 0
-
-
 @pytest.mark.parametrize("n", [64, 128, 256])
 @pytest.mark.parametrize("model", [1, 2, 3, 4])
 def test_packed_short_row_pipeline_matches_generic_rows(hc, n, model):
