@@ -48,18 +48,33 @@ class SlabFFT:
         return a[:, self.rank * m:(self.rank + 1) * m].contiguous()
 
     def _exchange(self, a: torch.Tensor) -> torch.Tensor:
+        """All-to-all of the leading-axis blocks of ``a`` (block g goes to rank g)."""
         if self.world == 1:
             return a
         out = torch.empty_like(a)
+        if self._nccl() and a.shape[0] == self.world:
+            # this rank's own block never leaves the GPU: a plain device copy instead of a self-send through the
+            # communicator's channels (the block is 1/G of the data: half of it on two GPUs)
+            for w in self._exchange_lists([out[g] for g in range(self.world)], [a[g] for g in range(self.world)]):
+                w.wait()
+            return out
         dist.all_to_all_single(out, a, group=self.group)
         return out
+
+    def _nccl(self) -> bool:
+        return dist.get_backend(self.group) == "nccl"
 
     def _exchange_lists(self, outs, ins):
         """Asynchronous all-to-all of per-peer CONTIGUOUS blocks (``ins[g]`` goes to rank g, ``outs[g]`` arrives from
         rank g); returns a list of work handles.  NCCL: one grouped send/recv launch on the communicator's stream, so
         the exchange of one chunk runs beside the transforms of another; other backends (gloo in the CPU tests):
         point-to-point operations."""
-        if dist.get_backend(self.group) == "nccl":
+        if self._nccl():
+            me = self.rank
+            outs[me].copy_(ins[me])                              # own block: device copy on the stepping stream
+            nothing = ins[me].new_empty(0)
+            ins = [nothing if g == me else t for g, t in enumerate(ins)]
+            outs = [nothing if g == me else t for g, t in enumerate(outs)]
             return [dist.all_to_all(outs, ins, group=self.group, async_op=True)]
         outs[self.rank].copy_(ins[self.rank])
         ops = []
@@ -125,8 +140,11 @@ class SlabFFT:
 
 
     # -- overlapped exchange ------------------------------------------------------------------
-    #: x-plane groups the exchange of a 3-D (or higher) evaluation is split into (RKS_SLAB_CHUNKS overrides; 1 = off)
-    PIPELINE_CHUNKS = 4
+    #: x-plane groups the exchange of a 3-D (or higher) evaluation is split into (RKS_SLAB_CHUNKS overrides; 1 = off).
+    #: Measured on 2 B200s, 512^3 (profiles/r02f_cfg5_chunks*.json, r02i_cfg5_*.json): 35.8 ms per trial unchunked,
+    #: 36.0-38.7 ms with 2-8 groups, whatever the SM margin left to NCCL or its stream priority -- the NCCL
+    #: send/recv kernels and the transforms do not overlap in practice, so the pipeline is off by default.
+    PIPELINE_CHUNKS = 1
 
     def _pipeline_chunks(self) -> int:
         """How many x-plane groups to pipeline: needs >= 3 dimensions, more than one rank and a divisor of the local
