@@ -267,6 +267,15 @@ int rks_axis_apply(rks_axis* axis, const void* in, void* out, int64_t outer, int
  * transposes either side of the exchange never have to be materialised */
 int rks_axis_apply_chunked(rks_axis* axis, const void* in, void* out, int64_t outer, int64_t inner, int64_t chunks,
                            int inverse, void* stream);
+/* same transform with the OUTPUT rows scattered over the ranks of a slab decomposition (single large N-D grids,
+ * the distributed transpose of `fftn` -- demos/nls.ipynb:496-511 on a sharded grid): the n output rows
+ * are split into `out_chunks` equal blocks, block g laid out [outer][n/out_chunks][inner] at the device address
+ * out_bases[g] (an int64 array in device memory).  The addresses may be PEER mappings of other GPUs' buffers
+ * (NVLink): the stores of the transform's last level then are the all-to-all exchange, and no collective runs.
+ * Input: plain [outer][n][inner] (in_chunks = 1) or chunk-major [in_chunks][outer][n/in_chunks][inner].
+ * The caller orders the ranks (a barrier before the destination buffers are read or rewritten). */
+int rks_axis_apply_scatter(rks_axis* axis, const void* in, const int64_t* out_bases, int64_t outer, int64_t inner,
+                           int64_t in_chunks, int64_t out_chunks, int inverse, void* stream);
 void rks_axis_destroy(rks_axis* axis);
 
 /* the only syncing calls */

@@ -98,6 +98,7 @@ def _load():
         "rks_axis_create": (c_int, [POINTER(P), c_int64, P]),
         "rks_axis_apply": (c_int, [P, P, P, c_int64, c_int64, c_int, P]),
         "rks_axis_apply_chunked": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int, P]),
+        "rks_axis_apply_scatter": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, P]),
         "rks_axis_destroy": (None, [P]),
         "rks_read_ctrl": (c_int, [P, POINTER(RksCtrl), P]),
         "rks_read_log": (c_int, [P, POINTER(RksTrialRec), c_int, c_int, P]),

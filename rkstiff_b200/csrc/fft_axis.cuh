@@ -50,10 +50,21 @@ struct Col {                 // one thread's column of the tile and of the globa
     int rb_shift;            // rows per block = 1 << rb_shift (31: a single block, plain strided axis)
     int col;                 // column within the tile
     bool ok;                 // column exists (inner need not be a multiple of C)
+    // Scattered output (slab-decomposed grids, dist_fft.py): the rows of the transformed axis belong to different
+    // ranks, 1 << o_shift consecutive rows each; otab[g] is the address of rank g's block IN RANK g's MEMORY (peer
+    // mapping over NVLink), so the last level's stores ARE the exchange.  nullptr: plain output through gout.
+    const long long* otab = nullptr;
+    int o_shift = 31;
+    long long ooff = 0;      // offset inside a destination block: outer index x block stride + column
     // Row p of the axis.  Blocked rows: the axis is split over G chunks that sit G-major in memory, as an
     // all-to-all delivers them (dist_fft.py) -- row p = chunk p >> rb_shift, offset p & mask.
     RKS_HD long long row(int p) const {
         return (long long)(p >> rb_shift) * bstride + (long long)(p & (int)((1u << rb_shift) - 1u)) * gstride;
+    }
+    RKS_HD cplx* out_row(int p) const {
+        if (otab)
+            return reinterpret_cast<cplx*>(otab[p >> o_shift]) + ooff + (long long)(p & (int)((1u << o_shift) - 1u)) * gstride;
+        return gout + row(p);
     }
 };
 
@@ -75,7 +86,7 @@ RKS_HD void dif_level(cplx* tile, const cplx* tw, const Col& c, int bt, int nbt,
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const cplx v = a[fast::perm<R>(r)];
-            if (LAST) { if (c.ok) fast::row_st(c.gout + c.row(p0 + Q * r), mk(v.x * scale, v.y * scale)); }
+            if (LAST) { if (c.ok) fast::row_st(c.out_row(p0 + Q * r), mk(v.x * scale, v.y * scale)); }
             else tile[fast::swz<SH>(p0 + Q * r) * C + c.col] = v;
         }
     }
@@ -99,7 +110,7 @@ RKS_HD void dit_level(cplx* tile, const cplx* tw, const Col& c, int bt, int nbt)
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const cplx v = a[fast::perm<R>(r)];
-            if (LAST) { if (c.ok) fast::row_st(c.gout + c.row(p0 + Q * r), v); }
+            if (LAST) { if (c.ok) fast::row_st(c.out_row(p0 + Q * r), v); }
             else tile[fast::swz<SH>(p0 + Q * r) * C + c.col] = v;
         }
     }

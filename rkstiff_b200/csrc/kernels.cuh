@@ -1278,9 +1278,11 @@ __global__ void __launch_bounds__(256) copy_u_multi_kernel(const DevPlan* plans,
 // CTAs loop over (outer, column tile) pairs.  in == out is allowed: a CTA reads its whole tile
 // before it writes any of it.
 // ---------------------------------------------------------------------------------------
+// otab / o_shift: scattered output (fft_axis.cuh Col): destination blocks are laid out [outer][1 << o_shift][inner]
 template <int N, bool INV>
 RKS_D void axis_fft_body(const cplx* in, cplx* out, long long outer, long long inner, const cplx* tw, double scale,
-                         long long ostride, long long bstride, int rb_shift) {
+                         long long ostride, long long bstride, int rb_shift, const long long* otab = nullptr,
+                         int o_shift = 31) {
     constexpr int C = axis::tile_cols<N>(), NBT = axis::tile_threads<N>() / C;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     cplx* tile = reinterpret_cast<cplx*>(smem_raw);
@@ -1289,7 +1291,8 @@ RKS_D void axis_fft_body(const cplx* in, cplx* out, long long outer, long long i
     for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
         const long long o = t / tpo, c0 = (t - o * tpo) * C;
         const long long off = o * ostride + c0 + col;
-        const axis::Col c{in + off, out + off, inner, bstride, rb_shift, col, c0 + col < inner};
+        const axis::Col c{in + off, out + off, inner, bstride, rb_shift, col, c0 + col < inner,
+                          otab, o_shift, otab ? o * ((long long)inner << o_shift) + c0 + col : 0};
         axis::tile_level<N, INV, 0>(tile, tw, c, bt, NBT, scale);
         __syncthreads();
         axis::tile_level<N, INV, 1>(tile, tw, c, bt, NBT, scale);
@@ -1303,6 +1306,13 @@ __global__ void __launch_bounds__(axis::tile_threads<N>(), axis::tile_blocks<N>(
 axis_fft_kernel(const cplx* in, cplx* out, long long outer, long long inner, const cplx* tw, double scale,
                 long long ostride, long long bstride, int rb_shift) {
     axis_fft_body<N, INV>(in, out, outer, inner, tw, scale, ostride, bstride, rb_shift);
+}
+// the same transform with its output rows scattered over the ranks of a slab decomposition (peer memory)
+template <int N, bool INV>
+__global__ void __launch_bounds__(axis::tile_threads<N>(), axis::tile_blocks<N>())
+axis_fft_scatter_kernel(const cplx* in, long long outer, long long inner, const cplx* tw, double scale,
+                        long long ostride, long long bstride, int rb_shift, const long long* otab, int o_shift) {
+    axis_fft_body<N, INV>(in, nullptr, outer, inner, tw, scale, ostride, bstride, rb_shift, otab, o_shift);
 }
 // the same transform as one step of the nonlinear term N_j of an N-D grid model (rks_set_model_nd): arrays and
 // the run predicate come from the control block (no host sync, graph replay); the first step of an evaluation

@@ -1516,6 +1516,48 @@ static int axis_apply(rks_axis* a, const void* in, void* out, int64_t outer, int
     return RKS_OK;
 }
 
+template <int N>
+static void axis_launch_scatter(const rks_axis* a, const cplx* in, const long long* otab, long long outer, long long inner,
+                                int inverse, long long ostride, long long bstride, int rb_shift, int o_shift, cudaStream_t stream) {
+    constexpr int C = axis::tile_cols<N>();
+    const size_t smem = (size_t)N * C * sizeof(cplx);
+    const long long tiles = outer * ((inner + C - 1) / C);
+    const long long cap = (long long)a->sm_count * axis::tile_blocks<N>() * 4;
+    const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
+    // (per device and cheap: set on every launch rather than cached)
+    if (inverse) cudaFuncSetAttribute(axis_fft_scatter_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else cudaFuncSetAttribute(axis_fft_scatter_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (inverse) axis_fft_scatter_kernel<N, true><<<grid, axis::tile_threads<N>(), smem, stream>>>(in, outer, inner, a->tw, 1.0 / (double)N, ostride, bstride, rb_shift, otab, o_shift);
+    else axis_fft_scatter_kernel<N, false><<<grid, axis::tile_threads<N>(), smem, stream>>>(in, outer, inner, a->tw, 1.0, ostride, bstride, rb_shift, otab, o_shift);
+}
+
+extern "C" int rks_axis_apply_scatter(rks_axis* a, const void* in, const int64_t* out_bases, int64_t outer, int64_t inner,
+                                      int64_t in_chunks, int64_t out_chunks, int inverse, void* stream_v) {
+    if (!a) return fail(RKS_ERR_ARG, "axis handle is null");
+    if (!in || !out_bases || outer <= 0 || inner <= 0) return fail(RKS_ERR_ARG, "bad axis-transform arguments");
+    if ((uintptr_t)in & 15) return fail(RKS_ERR_ARG, "axis arrays must be 16-byte aligned");
+    if (in_chunks < 1 || (in_chunks & (in_chunks - 1)) || in_chunks > a->n) return fail(RKS_ERR_ARG, "in_chunks must be a power of two <= n");
+    if (out_chunks < 1 || (out_chunks & (out_chunks - 1)) || out_chunks > a->n) return fail(RKS_ERR_ARG, "out_chunks must be a power of two <= n");
+    auto log2i = [](long long v) { int s = 0; while ((1ll << s) < v) ++s; return s; };
+    const long long rb = a->n / in_chunks;
+    const int rb_shift = in_chunks == 1 ? 31 : log2i(rb);
+    const long long ostride = in_chunks == 1 ? a->n * inner : rb * inner;
+    const long long bstride = in_chunks == 1 ? 0 : outer * rb * inner;
+    const int o_shift = log2i(a->n / out_chunks);
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    const cplx* i = (const cplx*)in;
+    const long long* tab = (const long long*)out_bases;
+#define RKS_CALL(N) axis_launch_scatter<N>(a, i, tab, outer, inner, inverse, ostride, bstride, rb_shift, o_shift, stream)
+    switch (a->n) {
+        case 16: RKS_CALL(16); break; case 32: RKS_CALL(32); break; case 64: RKS_CALL(64); break; case 128: RKS_CALL(128); break;
+        case 256: RKS_CALL(256); break; case 512: RKS_CALL(512); break; case 1024: RKS_CALL(1024); break;
+        case 2048: RKS_CALL(2048); break; default: RKS_CALL(4096); break;
+    }
+#undef RKS_CALL
+    CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // N-D grid models as engine models: N_j of a 2-D / 3-D spectral grid = inverse transforms over the strided axes
 // (stage value -> N_j, then in place), the fused last-axis kernel on the rows of N_j, forward transforms over the

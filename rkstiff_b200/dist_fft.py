@@ -35,6 +35,7 @@ class SlabFFT:
         self.rest = self.shape[2:]
         self.real_shape = (n0 // self.world, n1) + self.rest          # this rank's real-space slab
         self.spec_shape = (n0, n1 // self.world) + self.rest          # this rank's spectral pencil block
+        self._peer = None                                             # symmetric buffers of the peer-memory exchange
 
     # -- layout helpers ---------------------------------------------------------------------
     def real_slice(self, a: torch.Tensor) -> torch.Tensor:
@@ -108,10 +109,71 @@ class SlabFFT:
         return torch.fft.ifftn(a, dim=tuple(range(1, nd - 1 if skip_last and nd > 2 else nd)))
 
 
+    # -- exchange through peer memory ----------------------------------------------------------
+    def _peer_setup(self, like: torch.Tensor) -> bool:
+        """Symmetric buffers for the two exchanges of a 3-D evaluation (torch symmetric memory: every rank maps every
+        rank's buffer over NVLink) and the address tables the scattering transforms take.  False -- and the NCCL
+        route stays in use -- when RKS_SLAB_P2P=0, off CUDA/NCCL, for other ranks than 3-D power-of-two worlds, or
+        when the rendezvous fails on this system."""
+        if self._peer is not None:
+            return self._peer is not False
+        import os
+        self._peer = False
+        G, nd = self.world, len(self.shape)
+        ok = (G > 1 and nd == 3 and like.is_cuda and self._nccl() and G & (G - 1) == 0
+              and os.environ.get("RKS_SLAB_P2P", "1")[:1] != "0")
+        try:
+            if ok:
+                import torch.distributed._symmetric_memory as symm_mem
+                n0, n1, n2 = self.shape
+                m, q = n0 // G, n1 // G
+                numel = G * m * q * n2                                   # = the local block of the grid
+                bufs = [symm_mem.empty(numel, dtype=torch.complex128, device=like.device) for _ in range(2)]
+                group = self.group if self.group is not None else dist.group.WORLD
+                hdls = [symm_mem.rendezvous(b, group) for b in bufs]
+                block = m * q * n2 * 16                                  # bytes of one (source, destination) block
+                tabs = [torch.tensor([int(h.buffer_ptrs[g]) + self.rank * block for g in range(G)], dtype=torch.int64,
+                                     device=like.device) for h in hdls]
+                self._peer = {"bufs": bufs, "hdls": hdls, "tabs": tabs}
+        except Exception as exc:                                          # noqa: BLE001
+            import warnings
+            warnings.warn(f"slab exchange through peer memory unavailable ({exc!r}): using NCCL all-to-all")
+            ok = False
+        # every rank must take the same route
+        flag = torch.tensor([1 if self._peer else 0], dtype=torch.int32, device=like.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            self._peer = False
+        return self._peer is not False
+
+    def _fused_nl_peer(self, s: torch.Tensor, rows, axes, out: Optional[torch.Tensor]) -> torch.Tensor:
+        """3-D ``fused_nl`` without a collective: the inverse transform over axis 0 stores its output rows straight
+        into the x-plane owners' buffers, and the forward transform over axis 1 stores its rows straight into the
+        y-chunk owners' buffers (``AxisFFT.scatter_``: the last level's stores go over NVLink), so each exchange is
+        fused into the kernel that produces its data -- no extra pass over HBM, no NCCL kernel.  One barrier after
+        each scattering kernel orders the ranks (a buffer is rewritten only after the barrier that follows its last
+        read).  Same kernels and values as the NCCL route: bit-identical results."""
+        G, (n0, n1, n2) = self.world, self.shape
+        m, q = n0 // G, n1 // G
+        bufs, hdls, tabs = self._peer["bufs"], self._peer["hdls"], self._peer["tabs"]
+        # [inverse over x | exchange]: row p of the x axis belongs to rank p // m; lands as a[my rank][p % m][ky][z]
+        axes[0].scatter_(s, tabs[0], 1, q * n2, 1, True)
+        hdls[0].barrier()
+        a = bufs[0].view(G, m, q, n2)                                     # [source rank = ky chunk][my x planes][ky][z]
+        axes[1].chunked_(a, True)
+        rows(a, out=a)
+        # [forward over y | exchange]: row p of the ky axis belongs to rank p // q; lands as b[my rank][x][p % q][z]
+        axes[1].scatter_(a, tabs[1], m, n2, G, False)
+        hdls[1].barrier()
+        return axes[0].forward_(bufs[1].view(self.spec_shape), 0, out=out)
+
     def fused_nl(self, s: torch.Tensor, rows, axes, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``F{ N( F^-1{ s } ) }`` with the engine's kernels only: ``axes[d]`` is the ``AxisFFT`` of grid axis d
-        (d < nd-1), ``rows`` the fused last-axis kernel (inverse, pointwise N, forward).  Two all-to-alls."""
+        (d < nd-1), ``rows`` the fused last-axis kernel (inverse, pointwise N, forward).  Two exchanges: through peer
+        memory, fused into the transforms (3-D grids on NVLink-connected GPUs), else two all-to-alls."""
         G, (n0, n1), nd = self.world, self.shape[:2], len(self.shape)
+        if G > 1 and nd == 3 and self._peer_setup(s):
+            return self._fused_nl_peer(s, rows, axes, out)
         chunks = self._pipeline_chunks()
         if chunks > 1:
             return self._fused_nl_pipelined(s, rows, axes, out, chunks)

@@ -261,6 +261,20 @@ class AxisFFT:
                                                    inner, int(x.shape[0]), int(bool(inverse)), st))
         return x
 
+    def scatter_(self, x: torch.Tensor, out_bases: torch.Tensor, outer: int, inner: int, in_chunks: int, inverse: bool) -> None:
+        """Transform whose output rows go to ``out_bases.numel()`` destination blocks (``rks_axis_apply_scatter``):
+        ``out_bases`` is an int64 device tensor of block addresses, peer mappings included -- the stores of the last
+        level are the exchange of a slab-decomposed grid (dist_fft.py).  ``x``: ``[outer][n][inner]`` (in_chunks = 1)
+        or chunk-major ``[in_chunks][outer][n / in_chunks][inner]``."""
+        from ctypes import c_void_p
+        if x.dtype != torch.complex128 or not x.is_contiguous() or x.numel() != outer * self.n * inner:
+            raise ValueError("AxisFFT.scatter_ needs a contiguous complex128 array of outer * n * inner elements")
+        if out_bases.dtype != torch.int64 or not out_bases.is_cuda or not out_bases.is_contiguous():
+            raise ValueError("AxisFFT.scatter_: out_bases must be a contiguous int64 CUDA tensor")
+        st = c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        _abi.check(_abi.lib.rks_axis_apply_scatter(self._h, c_void_p(x.data_ptr()), c_void_p(out_bases.data_ptr()), int(outer),
+                                                   int(inner), int(in_chunks), int(out_bases.numel()), int(bool(inverse)), st))
+
     def inverse_(self, x: torch.Tensor, dim: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """ifft along ``dim`` (scaled 1/n), rows left in digit-reversed order; in place unless ``out`` is given."""
         return self._apply(x, dim, 1, out)

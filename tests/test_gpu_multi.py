@@ -21,13 +21,18 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _teardown(sol):
-    """The sharded trial is a captured CUDA graph holding NCCL kernels: release it before the communicator goes."""
+def _teardown(sol, q):
+    """The sharded trial is a captured CUDA graph holding NCCL kernels: release it before the communicator goes.
+    The worker then leaves without running interpreter shutdown (symmetric-memory mappings of the slab exchange
+    and NCCL's own threads make that order-dependent): results are flushed to the queue first."""
     import torch.distributed as dist
     sol.close()
     torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()
+    q.close()
+    q.join_thread()
+    os._exit(0)
 
 
 def _worker(rank, world, port, q):
@@ -46,7 +51,7 @@ def _worker(rank, world, port, q):
     uf = sol.evolve(torch.from_numpy(p.u0[lo:hi].copy()).cuda(), 0.0, 0.2, store_freq=3)
     q.put((rank, lo, hi, [r[0] for r in sol.trial_log], [r[2] for r in sol.trial_log], list(sol.t),
            uf.cpu().numpy()))
-    _teardown(sol)
+    _teardown(sol, q)
 
 
 def test_sharded_shared_dt_ensemble_matches_whole_batch():
@@ -90,7 +95,7 @@ def _slab_worker(rank, world, port, q):
     sol = rk.ETD35(lin, nl, config=rk.SolverConfig(epsilon=1e-5), group=dist.group.WORLD)
     uf = sol.evolve(u0, 0.0, 0.2)
     q.put((rank, [r[0] for r in sol.trial_log], [r[2] for r in sol.trial_log], uf.cpu().numpy()))
-    _teardown(sol)
+    _teardown(sol, q)
 
 
 def test_cfg5_slab_decomposed_nls3d_matches_flattened_oracle():
