@@ -13,9 +13,9 @@ Workloads (BASELINE.json configs):
   cfg2b: cfg2 with an independent dt per trajectory.
 Metric: real-space grid points x RK (trial) steps per second, whole job over all GPUs.
 
-Without --workload the ONE JSON line is the cfg2 line plus `secondary` (the same measurement of cfg3, cfg4 and
-cfg5 at N = 1; of cfg3 and the slab-decomposed cfg5 at N > 1, each with roofline / e2e / clocks and, at N = 1,
-cpu_baseline) and, at N > 1, `parity` (a small sharded shared-dt ensemble and a 16^3 slab run against the oracle:
+Without --workload the ONE JSON line is the cfg2 line plus `secondary` (the same measurement of cfg3, cfg2b, cfg4
+and cfg5 at N = 1; of cfg3, cfg2b and the slab-decomposed cfg5 at N > 1, each with roofline / clocks and -- except
+cfg2b -- e2e and, at N = 1, cpu_baseline) and, at N > 1, `parity` (a small sharded shared-dt ensemble and a 16^3 slab run against the oracle:
 the GPU test lease has one GPU, so this is where multi-GPU parity is checked on hardware).
 
 N > 1: one process per GPU under torchrun; the batch is sharded by rank (weak scaling, 4096 or
@@ -694,6 +694,13 @@ def run_cfg2b(ctx, args):
             "gpu_launches": sol._engine.launches(), "clocks": clocks}
 
 
+def _release_after(ctx, fn):
+    try:
+        return fn()
+    finally:
+        ctx.release()
+
+
 def run_1d(ctx, args, workload, cpu=True):
     """cfg2 / cfg3: device-resident K timed steps, the per-kernel roofline, e2e through evolve(), CPU baseline."""
     torch = ctx.torch
@@ -981,7 +988,8 @@ def run_ours(args):
                 cpu = not args.no_cpu_baseline
                 sub = argparse.Namespace(**vars(args))
                 sub.method, sub.size = None, None
-                sec = {"cfg3": guarded(ctx, "cfg3", lambda: run_1d(ctx, sub, "cfg3", cpu=cpu))}
+                sec = {"cfg3": guarded(ctx, "cfg3", lambda: run_1d(ctx, sub, "cfg3", cpu=cpu)),
+                       "cfg2b": guarded(ctx, "cfg2b", lambda: _release_after(ctx, lambda: run_cfg2b(ctx, sub)))}
                 if ctx.world == 1:
                     sec["cfg4"] = guarded(ctx, "cfg4", lambda: run_cfg4(ctx, sub, cpu=cpu))
                     sec["cfg5"] = guarded(ctx, "cfg5", lambda: run_cfg5(ctx, sub, cpu=cpu))
