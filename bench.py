@@ -958,8 +958,29 @@ def parity_multi(ctx):
     return out
 
 
-def guarded(ctx, name, fn):
-    """A secondary workload must never take the primary line down with it."""
+#: seconds a secondary workload may take before the line is emitted without it
+SECONDARY_LIMIT = 150.0
+
+
+def guarded(ctx, name, fn, line=None, slot=None):
+    """A secondary workload must never take the primary line down with it: an exception becomes an `error` entry, and
+    a workload that does not come back within SECONDARY_LIMIT (a rank stuck in a collective cannot be interrupted)
+    makes every rank leave -- rank 0 prints the line with what has been measured so far first."""
+    import threading
+
+    def bail():
+        if line is not None and ctx.rank == 0:
+            if slot is not None:
+                slot[name] = {"error": f"{name}: no result within {SECONDARY_LIMIT:.0f} s"}
+            print(json.dumps(line), flush=True)
+        sys.stderr.write(f"bench.py: secondary workload {name} timed out on rank {ctx.rank}\n")
+        sys.stderr.flush()
+        os._exit(0)
+
+    timer = threading.Timer(SECONDARY_LIMIT, bail) if line is not None else None
+    if timer:
+        timer.daemon = True
+        timer.start()
     try:
         return fn()
     except Exception as exc:                                    # noqa: BLE001
@@ -967,6 +988,9 @@ def guarded(ctx, name, fn):
         traceback.print_exc(file=sys.stderr)
         ctx.release()
         return {"error": f"{name}: {type(exc).__name__}: {exc}"}
+    finally:
+        if timer:
+            timer.cancel()
 
 
 def run_ours(args):
@@ -988,15 +1012,16 @@ def run_ours(args):
                 cpu = not args.no_cpu_baseline
                 sub = argparse.Namespace(**vars(args))
                 sub.method, sub.size = None, None
-                sec = {"cfg3": guarded(ctx, "cfg3", lambda: run_1d(ctx, sub, "cfg3", cpu=cpu)),
-                       "cfg2b": guarded(ctx, "cfg2b", lambda: _release_after(ctx, lambda: run_cfg2b(ctx, sub)))}
-                if ctx.world == 1:
-                    sec["cfg4"] = guarded(ctx, "cfg4", lambda: run_cfg4(ctx, sub, cpu=cpu))
-                    sec["cfg5"] = guarded(ctx, "cfg5", lambda: run_cfg5(ctx, sub, cpu=cpu))
-                else:
-                    sec["cfg5"] = guarded(ctx, "cfg5", lambda: run_cfg5(ctx, sub, cpu=False))
-                    line["parity"] = guarded(ctx, "parity", lambda: parity_multi(ctx))
+                sec = {}
                 line["secondary"] = sec
+                sec["cfg3"] = guarded(ctx, "cfg3", lambda: run_1d(ctx, sub, "cfg3", cpu=cpu), line, sec)
+                sec["cfg2b"] = guarded(ctx, "cfg2b", lambda: _release_after(ctx, lambda: run_cfg2b(ctx, sub)), line, sec)
+                if ctx.world == 1:
+                    sec["cfg4"] = guarded(ctx, "cfg4", lambda: run_cfg4(ctx, sub, cpu=cpu), line, sec)
+                    sec["cfg5"] = guarded(ctx, "cfg5", lambda: run_cfg5(ctx, sub, cpu=cpu), line, sec)
+                else:
+                    line["parity"] = guarded(ctx, "parity", lambda: parity_multi(ctx), line, line)
+                    sec["cfg5"] = guarded(ctx, "cfg5", lambda: run_cfg5(ctx, sub, cpu=False), line, sec)
         if ctx.rank == 0:
             print(json.dumps(line), flush=True)
         rc = 0

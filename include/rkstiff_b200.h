@@ -277,6 +277,12 @@ int rks_axis_apply_chunked(rks_axis* axis, const void* in, void* out, int64_t ou
 int rks_axis_apply_scatter(rks_axis* axis, const void* in, const int64_t* out_bases, int64_t outer, int64_t inner,
                            int64_t in_chunks, int64_t out_chunks, int inverse, void* stream);
 void rks_axis_destroy(rks_axis* axis);
+/* Barrier between the ranks that share peer-mapped buffers (the order points of rks_axis_apply_scatter), enqueued on
+ * `stream`: flag_bases[g] (int64 array in device memory) is the address, in rank g's memory, of `world` uint64 flags
+ * that start at zero; `epoch` must grow by one per call on every rank.  Rank r stores epoch into flag r of every rank
+ * (system-scope release: everything this stream did before is visible to whoever sees the flag) and waits until its
+ * own flags all reach epoch.  One 32-thread block, one NVLink round trip. */
+int rks_peer_barrier(const int64_t* flag_bases, int world, int rank, uint64_t epoch, void* stream);
 
 /* the only syncing calls */
 int rks_read_ctrl(rks_plan* plan, rks_ctrl_host* out, void* stream);

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import (POINTER, Structure, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_void_p)
+from ctypes import (POINTER, Structure, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p)
 
 from . import _build
 
@@ -100,6 +100,7 @@ def _load():
         "rks_axis_apply_chunked": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int, P]),
         "rks_axis_apply_scatter": (c_int, [P, P, P, c_int64, c_int64, c_int64, c_int64, c_int, P]),
         "rks_axis_destroy": (None, [P]),
+        "rks_peer_barrier": (c_int, [P, c_int, c_int, c_uint64, P]),
         "rks_read_ctrl": (c_int, [P, POINTER(RksCtrl), P]),
         "rks_read_log": (c_int, [P, POINTER(RksTrialRec), c_int, c_int, P]),
         "rks_read_rows": (c_int, [P, POINTER(RksCtrl), c_int64, P]),

@@ -1314,6 +1314,21 @@ axis_fft_scatter_kernel(const cplx* in, long long outer, long long inner, const 
                         long long ostride, long long bstride, int rb_shift, const long long* otab, int o_shift) {
     axis_fft_body<N, INV>(in, nullptr, outer, inner, tw, scale, ostride, bstride, rb_shift, otab, o_shift);
 }
+// barrier between ranks that write into each other's memory (rks_peer_barrier): thread g signals rank g, then waits
+// for rank g's signal.  Stream order makes the earlier kernels' stores happen-before the release.
+__global__ void peer_barrier_kernel(const long long* flag_bases, int world, int rank, unsigned long long epoch) {
+    const int g = threadIdx.x;
+    if (g >= world) return;
+    unsigned long long* theirs = reinterpret_cast<unsigned long long*>(flag_bases[g]) + rank;
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(flag_bases[rank]) + g;
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+    unsigned long long seen;
+    do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+    } while (seen < epoch);
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+}
 // the same transform as one step of the nonlinear term N_j of an N-D grid model (rks_set_model_nd): arrays and
 // the run predicate come from the control block (no host sync, graph replay); the first step of an evaluation
 // reads the stage value and writes N_j, the others work on N_j in place

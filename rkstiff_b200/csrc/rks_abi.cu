@@ -1558,6 +1558,13 @@ extern "C" int rks_axis_apply_scatter(rks_axis* a, const void* in, const int64_t
     return RKS_OK;
 }
 
+extern "C" int rks_peer_barrier(const int64_t* flag_bases, int world, int rank, uint64_t epoch, void* stream_v) {
+    if (!flag_bases || world < 1 || world > 32 || rank < 0 || rank >= world) return fail(RKS_ERR_ARG, "bad peer-barrier arguments");
+    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream_v>>>((const long long*)flag_bases, world, rank, (unsigned long long)epoch);
+    CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // N-D grid models as engine models: N_j of a 2-D / 3-D spectral grid = inverse transforms over the strided axes
 // (stage value -> N_j, then in place), the fused last-axis kernel on the rows of N_j, forward transforms over the

@@ -134,7 +134,15 @@ class SlabFFT:
                 block = m * q * n2 * 16                                  # bytes of one (source, destination) block
                 tabs = [torch.tensor([int(h.buffer_ptrs[g]) + self.rank * block for g in range(G)], dtype=torch.int64,
                                      device=like.device) for h in hdls]
-                self._peer = {"bufs": bufs, "hdls": hdls, "tabs": tabs}
+                # flags of the engine's own barrier kernel (rks_peer_barrier): G uint64 per rank, zero before first use
+                flags = symm_mem.empty(32, dtype=torch.int64, device=like.device)
+                flags.zero_()
+                fh = symm_mem.rendezvous(flags, group)
+                ftab = torch.tensor([int(fh.buffer_ptrs[g]) for g in range(G)], dtype=torch.int64, device=like.device)
+                torch.cuda.synchronize(like.device)
+                fh.barrier()                                             # every rank's flags are zero before anyone signals
+                self._peer = {"bufs": bufs, "hdls": hdls, "tabs": tabs, "flags": flags, "fh": fh, "ftab": ftab, "epoch": 0,
+                              "own_barrier": os.environ.get("RKS_PEER_BARRIER", "1")[:1] != "0"}
         except Exception as exc:                                          # noqa: BLE001
             import warnings
             warnings.warn(f"slab exchange through peer memory unavailable ({exc!r}): using NCCL all-to-all")
@@ -145,6 +153,20 @@ class SlabFFT:
         if int(flag.item()) == 0:
             self._peer = False
         return self._peer is not False
+
+    def _peer_barrier(self, which: int) -> None:
+        """Order point between the ranks: the engine's one-block flag kernel (one NVLink round trip) or, with
+        RKS_PEER_BARRIER=0, the symmetric-memory handle's own barrier."""
+        pr = self._peer
+        if not pr["own_barrier"]:
+            pr["hdls"][which].barrier()
+            return
+        from ctypes import c_void_p
+        from . import _abi
+        pr["epoch"] += 1
+        dev = pr["flags"].device
+        _abi.check(_abi.lib.rks_peer_barrier(c_void_p(pr["ftab"].data_ptr()), self.world, self.rank, pr["epoch"],
+                                             c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
 
     def _fused_nl_peer(self, s: torch.Tensor, rows, axes, out: Optional[torch.Tensor]) -> torch.Tensor:
         """3-D ``fused_nl`` without a collective: the inverse transform over axis 0 stores its output rows straight
@@ -158,13 +180,13 @@ class SlabFFT:
         bufs, hdls, tabs = self._peer["bufs"], self._peer["hdls"], self._peer["tabs"]
         # [inverse over x | exchange]: row p of the x axis belongs to rank p // m; lands as a[my rank][p % m][ky][z]
         axes[0].scatter_(s, tabs[0], 1, q * n2, 1, True)
-        hdls[0].barrier()
+        self._peer_barrier(0)
         a = bufs[0].view(G, m, q, n2)                                     # [source rank = ky chunk][my x planes][ky][z]
         axes[1].chunked_(a, True)
         rows(a, out=a)
         # [forward over y | exchange]: row p of the ky axis belongs to rank p // q; lands as b[my rank][x][p % q][z]
         axes[1].scatter_(a, tabs[1], m, n2, G, False)
-        hdls[1].barrier()
+        self._peer_barrier(1)
         return axes[0].forward_(bufs[1].view(self.spec_shape), 0, out=out)
 
     def fused_nl(self, s: torch.Tensor, rows, axes, out: Optional[torch.Tensor] = None) -> torch.Tensor:
