@@ -29,13 +29,26 @@ template <> struct APlan<1024> { static constexpr int R1 = 16, R2 = 8,  R3 = 8; 
 template <> struct APlan<2048> { static constexpr int R1 = 16, R2 = 16, R3 = 8;  };
 template <> struct APlan<4096> { static constexpr int R1 = 16, R2 = 16, R3 = 16; };
 
+// tuning knobs of the 512-point tile (tools/build_variant.sh -DRKS_AX512_C=... ; defaults = measured best)
+#ifndef RKS_AX512_C
+#define RKS_AX512_C 8
+#endif
+#ifndef RKS_AX512_T
+#define RKS_AX512_T 256
+#endif
+#ifndef RKS_AX512_B
+#define RKS_AX512_B 3
+#endif
+#ifndef RKS_AX_UNROLL
+#define RKS_AX_UNROLL 1
+#endif
 // tile geometry: 64 KB tiles (128 KB for N = 4096 so that a row segment is still a full 32-byte sector)
-template <int N> RKS_HD constexpr int tile_cols() { return N <= 512 ? 8 : N == 1024 ? 4 : 2; }
+template <int N> RKS_HD constexpr int tile_cols() { return N == 512 ? RKS_AX512_C : N < 512 ? 8 : N == 1024 ? 4 : 2; }
 // threads: one first-level butterfly per thread where the tile has that many (N / R1 butterflies x C columns), so no
 // thread idles through a level; resident CTAs per SM: as many as the 227 KB of shared memory and 64 K registers
 // allow -- short axes (the second kernel of the two-kernel route, 256^3 grids) need several small tiles in flight
-template <int N> RKS_HD constexpr int tile_threads() { return N == 4096 ? 512 : N >= 512 ? 256 : N == 256 ? 128 : 64; }
-template <int N> RKS_HD constexpr int tile_blocks() { return N == 4096 ? 1 : N >= 1024 ? 2 : N == 512 ? 3 : N == 256 ? 5 : 8; }
+template <int N> RKS_HD constexpr int tile_threads() { return N == 4096 ? 512 : N == 512 ? RKS_AX512_T : N > 512 ? 256 : N == 256 ? 128 : 64; }
+template <int N> RKS_HD constexpr int tile_blocks() { return N == 4096 ? 1 : N >= 1024 ? 2 : N == 512 ? RKS_AX512_B : N == 256 ? 5 : 8; }
 template <int N> RKS_HD constexpr int last_radix() {
     return APlan<N>::R3 > 1 ? APlan<N>::R3 : APlan<N>::R2 > 1 ? APlan<N>::R2 : APlan<N>::R1;
 }
@@ -72,7 +85,8 @@ struct Col {                 // one thread's column of the tile and of the globa
 template <int N, int R, int Q, bool FIRST, bool LAST>
 RKS_HD void dif_level(cplx* tile, const cplx* tw, const Col& c, int bt, int nbt, double scale) {
     constexpr int C = tile_cols<N>(), SH = tile_shift<N>();
-#pragma unroll 1
+    constexpr int UNR = RKS_AX_UNROLL;
+#pragma unroll UNR
     for (int u = bt; u < N / R; u += nbt) {
         const int j = u % Q, p0 = (u / Q) * (R * Q) + j;
         cplx a[R];
@@ -96,7 +110,8 @@ RKS_HD void dif_level(cplx* tile, const cplx* tw, const Col& c, int bt, int nbt,
 template <int N, int R, int Q, bool FIRST, bool LAST>
 RKS_HD void dit_level(cplx* tile, const cplx* tw, const Col& c, int bt, int nbt) {
     constexpr int C = tile_cols<N>(), SH = tile_shift<N>();
-#pragma unroll 1
+    constexpr int UNR = RKS_AX_UNROLL;
+#pragma unroll UNR
     for (int u = bt; u < N / R; u += nbt) {
         const int j = u % Q, p0 = (u / Q) * (R * Q) + j;
         cplx a[R];
