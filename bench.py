@@ -368,6 +368,19 @@ class Ctx:
         torch.cuda.set_device(self.local)
         self.device = torch.device("cuda", self.local)
         self.group = None
+        self.cpu_affinity = None
+        if self.world > 1 and os.environ.get("RKS_BENCH_NUMA", "1")[:1] != "0":
+            # one process per GPU: run on the CPUs next to this rank's GPU, so that the pinned host buffers of the e2e
+            # leg are NUMA-local and eight ranks do not pull their shards through one socket's memory
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                handle = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda._parse_visible_devices()[self.local]
+                                                           if hasattr(torch.cuda, "_parse_visible_devices") else self.local)
+                pynvml.nvmlDeviceSetCpuAffinity(handle)
+                self.cpu_affinity = len(os.sched_getaffinity(0))
+            except Exception:                                    # noqa: BLE001
+                self.cpu_affinity = None
         if self.world > 1:
             import torch.distributed as dist
             dist.init_process_group("nccl", device_id=self.device)
@@ -851,7 +864,8 @@ def run_1d(ctx, args, workload, cpu=True):
            "h2d_bytes_per_step": state_bytes * reps_e2e / steps_e2e, "d2h_bytes_per_step": state_bytes * reps_e2e / steps_e2e,
            "call": f"{method}.evolve(u0, ...) of the workload's horizon with u0 copied from pinned host memory and the "
                    "final state copied back, per call",
-           "steps_per_call": steps_e2e / reps_e2e, "h2d_bytes_per_call": state_bytes, "d2h_bytes_per_call": state_bytes}
+           "steps_per_call": steps_e2e / reps_e2e, "h2d_bytes_per_call": state_bytes, "d2h_bytes_per_call": state_bytes,
+           "cpus_bound_to_this_gpu": ctx.cpu_affinity}
     del sol, eng, u0, u_host, out_host, lin, nl
     ctx.release()
 

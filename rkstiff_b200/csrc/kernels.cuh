@@ -450,8 +450,15 @@ RKS_D void stage_kernel_body(const DevPlan& p) {
 // Coefficients shared by the batch: three CTAs per SM (<= 85 registers; the six-stage methods' last stages otherwise
 // sit at 86-90 registers = two CTAs, where the IF45DP one ran at 0.90 of the roofline: 638 -> 563 us with three).
 // Per-element coefficients (full-size arrays, gathered records, separable tables) need the registers.
+// resident CTAs the separable / indexed coefficient variants are compiled for (tuning knobs; 1 = no register cap)
+#ifndef RKS_STAGE_SEP_BLOCKS
+#define RKS_STAGE_SEP_BLOCKS 3      // measured: cfg 4 trial 2.926 -> 2.844 ms (profiles/r02s_cfg4_*.json)
+#endif
+#ifndef RKS_STAGE_IDX_BLOCKS
+#define RKS_STAGE_IDX_BLOCKS 1      // measured: 3 or 4 are slower (cfg 5: 44.1 -> 45.5 / 47.1 ms)
+#endif
 template <int M, int S, typename CT, int CM>
-__global__ void __launch_bounds__(256, (CM == CM_COLUMN ? 3 : 1)) stage_kernel(const __grid_constant__ DevPlan p) { stage_kernel_body<M, S, CT, CM>(p); }
+__global__ void __launch_bounds__(256, (CM == CM_COLUMN ? 3 : CM == CM_SEPARABLE ? RKS_STAGE_SEP_BLOCKS : CM == CM_INDEXED ? RKS_STAGE_IDX_BLOCKS : 1)) stage_kernel(const __grid_constant__ DevPlan p) { stage_kernel_body<M, S, CT, CM>(p); }
 // one plan per blockIdx.z: ensembles whose trajectories keep their own dt (rks_multi_*)
 template <int M, int S, typename CT, int CM>
 __global__ void __launch_bounds__(256) stage_kernel_multi(const DevPlan* plans) { stage_kernel_body<M, S, CT, CM>(plans[blockIdx.z]); }
