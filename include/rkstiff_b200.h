@@ -58,8 +58,15 @@ enum rks_model {
     RKS_MODEL_NLS_FFT = 2,  /* N = i*gamma * fft(|ifft u^|^2 ifft u^); demos/nls.ipynb. n_c = n, params[0]=gamma */
     RKS_MODEL_CUBIC_RFFT = 3,   /* N = c * rfft(irfft(u^)^3): Fourier-diagonal Allen-Cahn (c = -1, L = 1 - eps k^2, the
                                    split of models.py:240-244). n_c = n/2+1, params[0]=c, kx unused */
-    RKS_MODEL_SINE_GORDON = 4   /* psi = phi_t + i Omega phi: N = fft(phi - sin phi), phi^ = (psi^(k) - conj psi^(-k))/(2 i Omega);
+    RKS_MODEL_SINE_GORDON = 4,  /* psi = phi_t + i Omega phi: N = fft(phi - sin phi), phi^ = (psi^(k) - conj psi^(-k))/(2 i Omega);
                                    n_c = n, kx = Omega(k) = sqrt(1 + k^2) */
+    /* Row transforms only (rks_rows_*; not stepping models): spectral derivatives with the K4 transform pair run the
+     * other way round -- forward transform, multiplier, inverse transform (rkstiff/derivatives.py:47-179).  `kx` of
+     * rks_rows_create points at n complex128 multipliers mult[k] = conj((i kx[k])^m) / n in FFT order. */
+    RKS_MODEL_DERIV_FFT = 5,        /* dx_fft, derivatives.py:126-179: complex rows of n points, out = ifft(M fft(in)) */
+    RKS_MODEL_DERIV_RFFT_PAIR = 6   /* dx_rfft, derivatives.py:47-123: real rows, two per complex transform: `in`/`out`
+                                       are float64 arrays, row pair q = rows 2q, 2q+1 (batch counts PAIRS); the
+                                       multiplier table must be Hermitian (mult[n-k] = conj mult[k], real at k = n/2) */
 };
 
 enum rks_status {
@@ -243,6 +250,11 @@ int rks_snapshot(rks_plan* plan, void* snap_ring, double* snap_t, int snap_cap, 
  * the engine's kernels: RKS_MODEL_NLS_FFT: out = i*p0*|in|^2 in (count complex128);
  * RKS_MODEL_CUBIC_RFFT: out = p0*in^3 (count float64).  in == out is allowed.  No plan needed. */
 int rks_pointwise(int model, const void* in, void* out, int64_t count, double p0, void* stream);
+
+/* y[b] = A x[b], A a dense n x n complex128 matrix (row-major), x and y `batch` vectors of n complex128: the two
+ * basis changes per nonlinear evaluation of diagonalize=True, N'(k) = S^-1 N(S k) (rkstiff/etd35.py:463,
+ * etd34.py:286, if34.py:209), and the physical |S u+| the controller looks at (etd35.py:495).  x != y. */
+int rks_gemv(const void* a, const void* x, void* y, int64_t n, int64_t batch, void* stream);
 
 /* Standalone fused row transform: out_row = F{ N( F^-1{ in_row } ) } along the contiguous axis of any
  * (batch, n_c) complex128 array -- the innermost-axis part of an N-D nonlinear term (the caller

@@ -15,6 +15,7 @@ RKS_ABI_VERSION = 1
 
 METHOD_IDS = {"IF4": 0, "ETD4": 1, "ETD5": 2, "IF34": 3, "ETD34": 4, "ETD35": 5, "IF45DP": 6}
 MODEL_NONE, MODEL_UUX_RFFT, MODEL_NLS_FFT, MODEL_CUBIC_RFFT, MODEL_SINE_GORDON = 0, 1, 2, 3, 4
+MODEL_DERIV_FFT, MODEL_DERIV_RFFT_PAIR = 5, 6      # row transforms only (derivatives.py)
 CTRL_RUNNING, CTRL_DONE, CTRL_MAX_LOOPS, CTRL_MIN_STEP = 0, 1, 2, 3
 LOG_CAP = 4096
 ROW_LOG_CAP = 64
@@ -92,6 +93,7 @@ def _load():
         "rks_run_fixed": (c_int, [P, c_int, P]),
         "rks_snapshot": (c_int, [P, P, P, c_int, P]),
         "rks_pointwise": (c_int, [c_int, P, P, c_int64, c_double, P]),
+        "rks_gemv": (c_int, [P, P, P, c_int64, c_int64, P]),
         "rks_rows_create": (c_int, [POINTER(P), c_int, c_int64, P, c_double, P]),
         "rks_rows_apply": (c_int, [P, P, P, c_int64, P]),
         "rks_rows_destroy": (None, [P]),

@@ -17,6 +17,8 @@
 // conflict free.  All functions are __host__ __device__: tests/host_check runs the same phase
 // sequence serially on the CPU.
 #pragma once
+#include <type_traits>
+#include <utility>
 #include "common.cuh"
 
 namespace rks {
@@ -305,6 +307,73 @@ struct SineGordonModel {
     RKS_HD void store(int p, cplx v) const { if (on) row_st(out + p, v); }
 };
 
+// ---- spectral derivative rows (rkstiff/derivatives.py:47-179): forward transform, (i kx)^m, inverse transform ----
+// The K4 pipeline is inverse-DIF, pointwise, forward-DIT.  On conjugated data it computes the mirrored pair,
+// fft(x) = conj(ifft_unnormalised(conj x)): the row is loaded conjugated, the "inverse" passes leave conj(X) in
+// digit-reversed order, the pointwise step multiplies position p by mult[k(p)] = conj((i kx[k])^m) / n where k(p) is
+// the frequency the position holds (DigitMap), the "forward" passes return conj(ifft(M X)), and the store conjugates
+// again.  A model that needs the position offers pointwise_at(z, p) next to pointwise(z).
+struct DigitMap {
+    // in-place DIF with radices R1, R2, R3 (, R4): position digits d1 (top bits), d2, d3, d4 hold frequency
+    // k = d1 + R1 (d2 + R2 (d3 + R3 d4)).  l1 < 0: the generic kernel's chain of radix-4 passes (+ one radix-2).
+    int L, l1, l2, l3;
+    RKS_HD int freq(int pos) const {
+        if (l1 < 0) {
+            int k = 0, sh = 0, rem = L;
+            while (rem >= 2) { k |= ((pos >> (rem - 2)) & 3) << sh; sh += 2; rem -= 2; }
+            if (rem) k |= (pos & 1) << sh;
+            return k;
+        }
+        const int s1 = L - l1, s2 = s1 - l2, s3 = s2 - l3;
+        const int d1 = pos >> s1, d2 = (pos >> s2) & ((1 << l2) - 1), d3 = (pos >> s3) & ((1 << l3) - 1);
+        const int d4 = pos & ((1 << s3) - 1);
+        return d1 | (d2 << l1) | (d3 << (l1 + l2)) | (d4 << (l1 + l2 + l3));
+    }
+};
+RKS_HD constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v >> 1); }
+template <int N> RKS_HD DigitMap digit_map_n() {
+    using P = Plan<N>;
+    // packed rows (N < 512): radix N / 64 over stride 64 inside the row, then 8, 8
+    return DigitMap{ilog2(N), N < 512 ? ilog2(N / 64) : ilog2(P::R1), ilog2(P::R2), ilog2(P::R3)};
+}
+RKS_HD DigitMap digit_map(int n, bool generic) {
+    if (generic) return DigitMap{ilog2(n), -1, 0, 0};
+    switch (n) {
+        case 64: return digit_map_n<64>();
+        case 128: return digit_map_n<128>();
+        case 256: return digit_map_n<256>();
+        case 512: return digit_map_n<512>();
+        case 1024: return digit_map_n<1024>();
+        case 2048: return digit_map_n<2048>();
+        case 4096: return digit_map_n<4096>();
+        default: return digit_map_n<8192>();
+    }
+}
+template <class M, class = void> struct has_pos : std::false_type {};
+template <class M>
+struct has_pos<M, std::void_t<decltype(std::declval<const M&>().pointwise_at(std::declval<cplx>(), 0))>> : std::true_type {};
+template <class M> RKS_HD cplx pointwise_of(const M& m, cplx z, int pos) {
+    if constexpr (has_pos<M>::value) return m.pointwise_at(z, pos);
+    else return m.pointwise(z);
+}
+struct DerivModel {          // complex rows (dx_fft, derivatives.py:126-179): out = ifft((i kx)^m fft(in))
+    const cplx* in; cplx* out; const cplx* mult; DigitMap map; bool on;
+    RKS_HD cplx load(int p) const { return conj(row_ld(in + p)); }
+    RKS_HD cplx pointwise(cplx z) const { return z; }
+    RKS_HD cplx pointwise_at(cplx z, int pos) const { return z * tw_ld(mult + map.freq(pos)); }
+    RKS_HD void store(int p, cplx v) const { if (on) row_st(out + p, conj(v)); }
+};
+// real rows (dx_rfft, derivatives.py:47-123), two per complex transform: z = a + i b, and since the multiplier is
+// Hermitian (M[n-k] = conj M[k], real at the Nyquist frequency: what irfft keeps) the result is a' + i b'.
+// `in` / `out` are float64 arrays of n-point rows; row pair q = rows 2q, 2q+1 = 2n consecutive doubles.
+struct DerivPairModel {
+    const double* in; double* out; const cplx* mult; DigitMap map; int n; bool on;
+    RKS_HD cplx load(int p) const { return mk(in[p], -in[n + p]); }
+    RKS_HD cplx pointwise(cplx z) const { return z; }
+    RKS_HD cplx pointwise_at(cplx z, int pos) const { return z * tw_ld(mult + map.freq(pos)); }
+    RKS_HD void store(int p, cplx v) const { if (on) { out[p] = v.x; out[n + p] = -v.y; } }
+};
+
 // model ids of include/rkstiff_b200.h -> model objects reading/writing plain arrays
 // (make_staged: input row partly staged in shared memory, models 1-3)
 template <int MODEL> struct ModelOf;
@@ -341,6 +410,20 @@ template <> struct ModelOf<4> {
         return type{in, out, kx, n, on};
     }
 };
+// 5, 6: spectral derivatives; `kx` points at the complex multiplier table, p0 != 0 selects the generic kernel's digit order
+template <> struct ModelOf<5> {
+    using type = DerivModel;
+    RKS_HD static type make(const cplx* in, cplx* out, const double* kx, double p0, int n, bool on) {
+        return type{in, out, reinterpret_cast<const cplx*>(kx), digit_map(n, p0 != 0.0), on};
+    }
+};
+template <> struct ModelOf<6> {
+    using type = DerivPairModel;
+    RKS_HD static type make(const cplx* in, cplx* out, const double* kx, double p0, int n, bool on) {
+        return type{reinterpret_cast<const double*>(in), reinterpret_cast<double*>(out), reinterpret_cast<const cplx*>(kx),
+                    digit_map(n, p0 != 0.0), n, on};
+    }
+};
 
 // 512 / N consecutive rows of an N-point model packed into one 512-point slab (N = 64, 128, 256):
 // slab position p belongs to row p / N.  Rows past the end of the batch read zeros and store nothing.
@@ -355,6 +438,8 @@ struct PackedModel {
         return sub < nvalid ? row(sub).load(p % N) : mk(0.0, 0.0);
     }
     RKS_HD cplx pointwise(cplx z) const { return row(0).pointwise(z); }
+    template <class M = typename ModelOf<MODEL>::type, class = std::enable_if_t<has_pos<M>::value>>
+    RKS_HD cplx pointwise_at(cplx z, int p) const { return row(0).pointwise_at(z, p % N); }
     RKS_HD void store(int p, cplx v) const {
         const int sub = p / N;
         if (sub < nvalid) row(sub).store(p % N, v);
@@ -402,11 +487,11 @@ RKS_HD void bf_dit(cplx* a, const cplx* tab, int j) {          // twiddles on th
     dftR<R, false>(a);
 }
 template <int R, class Model>
-RKS_HD void bf_core(cplx* a, const Model& m) {                  // innermost inverse bf, N(.), innermost forward bf
+RKS_HD void bf_core(cplx* a, const Model& m, int p0) {          // innermost inverse bf, N(.), innermost forward bf
     cplx c[R];
     dftR<R, true>(a);
 #pragma unroll
-    for (int r = 0; r < R; ++r) c[r] = m.pointwise(a[perm<R>(r)]);
+    for (int r = 0; r < R; ++r) c[r] = pointwise_of(m, a[perm<R>(r)], p0 + r);
     dftR<R, false>(c);
 #pragma unroll
     for (int r = 0; r < R; ++r) a[r] = c[r];
@@ -442,7 +527,7 @@ RKS_HD void core_pass(cplx* sm, const int (&p0)[NB], const Model& m) {
     for (int b = 0; b < NB; ++b) {
         cplx a[R];
         bf_load<R, 1, SH>(sm, p0[b], a);
-        bf_core<R>(a, m);
+        bf_core<R>(a, m, p0[b]);
         bf_store<R, 1, SH>(sm, p0[b], a);
     }
 }

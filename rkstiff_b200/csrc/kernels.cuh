@@ -690,7 +690,7 @@ RKS_D void nl_kernel_body(const DevPlan& p, int j, int force, int rows_per_cta) 
         __syncthreads();
     }
     if (active)
-        for (int q = tid; q < n; q += tpr) x[q] = m.pointwise(x[q]);
+        for (int q = tid; q < n; q += tpr) x[q] = fast::pointwise_of(m, x[q], q);
     __syncthreads();
     for (int q = 0; q < np; ++q) {
         if (active) fft_dit_pass(x, log2n, q, p.tw, tid, tpr);
@@ -719,6 +719,31 @@ RKS_D void row_barrier(int lrow, int rpc) {
 }
 
 struct NoHook { RKS_D void operator()() const {} };
+
+// n = 8192 (one row per CTA, 16 warps): the warps leave every row barrier in step, so the four warps of a
+// scheduler load together, compute together and store together and the LSU and the FP64 pipe are busy in turn
+// instead of at the same time.  Before the last-pass butterflies of a row (the first FP64-heavy phase after the
+// barrier) the warps of a scheduler (slot = warp / 4) are therefore put one phase apart: one computes while the
+// previous one already stores and loads the next row, and the offsets survive the barrier-free part of that row.
+// Measured in round 2 (profiles/r02t_*, r02u_*, r02v_*; same box, interleaved runs): pre-transformed rows
+// 312-314 -> 285-288 us per evaluation, plain rows 338 -> 316 us; no effect at n = 4096 (two CTAs per SM are out
+// of step anyway), so n = 8192 only.
+//   RKS_ROW_STAGGER_MODE 1 (default): slot s spins s * RKS_ROW_STAGGER_CYC (default 1100) cycles;
+//   2: slot s starts its butterfly when slot s - 1 has finished (named barriers 1..3, self-timed: 290-293 us);
+//   0: off.  RKS_ROW_STAGGER_NP=0 switches the spin of the rows that are not pre-transformed off.
+__constant__ int c_row_stagger_mode;
+__constant__ int c_row_stagger_cyc;
+__constant__ int c_row_stagger_np;
+RKS_D void spin_cycles(long long c) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < c) {}
+}
+template <int W>
+RKS_D void row_stagger_spin(int T) {
+    if (W != 16) return;
+    const int slot = T >> 7;
+    if (slot) spin_cycles((long long)slot * c_row_stagger_cyc);
+}
 
 // `after_first` runs once the first pass has consumed the row's input (staging buffer free again).
 // PT: the row is pre-transformed (fft_fast.cuh pre_butterfly: K1 already applied the first inverse pass), so
@@ -757,6 +782,7 @@ RKS_D void nl_fast_row(cplx* sm, int T, int lrow, int rpc, const fast::Twiddles&
     fast::phase_middle<N, 2, false>(sm, T, tf, m);
     row_barrier<TR>(lrow, rpc);
     if constexpr (!PT) {
+        if (W == 16 && c_row_stagger_np) row_stagger_spin<W>(T);
         fast::phase_last<N>(sm, T, tf, m);
         // no barrier here -- the last pass reads exactly the slab positions (T + 32 W c + Q1 s) that the same
         // thread overwrites in the first pass of its next row, so warps run on into the next row's loads.
@@ -769,7 +795,12 @@ RKS_D void nl_fast_row(cplx* sm, int T, int lrow, int rpc, const fast::Twiddles&
         cplx a[R1];
         fast::bf_load<R1, Q1, P::SH>(sm, T, a);
         row_barrier<TR>(lrow, rpc);
+        const int mode = W == 16 ? c_row_stagger_mode : 0;
+        const int slot = T >> 7;
+        if (mode == 1) row_stagger_spin<W>(T);
+        if (mode == 2 && slot > 0) asm volatile("bar.sync %0, 256;" ::"r"(slot) : "memory");
         fast::bf_dit<R1, Q1, fast::TW_S1>(a, tf.t1, T);
+        if (mode == 2 && slot < W / 4 - 1) asm volatile("bar.arrive %0, 256;" ::"r"(slot + 1) : "memory");
         fast::bf_store_global<R1, Q1>(m, T, a);
     }
 }
@@ -1226,6 +1257,29 @@ __global__ void controller_kernel(DevPlan p) {
 
 // pointwise nonlinearity of the N-D models, applied between two library transforms (one read + one
 // write instead of the half-dozen elementwise passes a torch expression costs)
+// Dense complex matrix times vector(s), y[b] = A x[b]: the basis changes of diagonalize=True (etd35.py:463, 495:
+// N'(k) = S^-1 N(S k), |S u+| for the controller).  One warp per matrix row, lanes stride the row (512-byte coalesced
+// segments of A, x from L1/L2), shuffle reduction; grid (ceil(n / 4), batch).  Bound by the read of A (n^2 x 16 B).
+__global__ void __launch_bounds__(128) gemv_kernel(const cplx* __restrict__ a, const cplx* __restrict__ x, cplx* __restrict__ y,
+                                                   int n) {
+    const int lane = threadIdx.x & 31, i = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const cplx* row = a + (size_t)i * n;
+    const cplx* xb = x + (size_t)blockIdx.y * n;
+    double sr = 0.0, si = 0.0;
+    for (int j = lane; j < n; j += 32) {
+        const cplx av = ldg(row + j), xv = ldg(xb + j);
+        sr += av.x * xv.x - av.y * xv.y;
+        si += av.x * xv.y + av.y * xv.x;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sr += __shfl_xor_sync(0xffffffffu, sr, o);
+        si += __shfl_xor_sync(0xffffffffu, si, o);
+    }
+    if (lane == 0) y[(size_t)blockIdx.y * n + i] = mk(sr, si);
+}
+
 __global__ void __launch_bounds__(256) pointwise_nls_kernel(const cplx* in, cplx* out, long long count, double gamma) {
     for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < count; e += (long long)gridDim.x * 256) {
         const cplx f = ldcs(in + e);

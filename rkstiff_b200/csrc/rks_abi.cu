@@ -169,9 +169,11 @@ static void launch_nl_fast_t(rks_plan* p, int j, int force, cudaStream_t stream)
     constexpr int THREADS = W == 16 ? 512 : 256;
     constexpr int RPC = THREADS / (32 * W);
     const size_t smem = nl_fast_smem<W>(MODEL);
-    if (p->multi_n) {
-        nl_fast_kernel_multi<W, MODEL><<<dim3(1, 1, (unsigned)p->multi_n), THREADS, smem, stream>>>(p->multi_dev, j, force);
-        return;
+    if constexpr (MODEL <= 4) {      // independent-dt plans step the stepping models only
+        if (p->multi_n) {
+            nl_fast_kernel_multi<W, MODEL><<<dim3(1, 1, (unsigned)p->multi_n), THREADS, smem, stream>>>(p->multi_dev, j, force);
+            return;
+        }
     }
     const long long groups = (d.batch + RPC - 1) / RPC;
     const long long resident = (long long)p->sm_count * (W == 16 ? 1 : 2);
@@ -185,6 +187,8 @@ static void launch_nl_fast(rks_plan* p, int j, int force, cudaStream_t stream) {
         case RKS_MODEL_UUX_RFFT: launch_nl_fast_t<W, 1>(p, j, force, stream); break;
         case RKS_MODEL_NLS_FFT: launch_nl_fast_t<W, 2>(p, j, force, stream); break;
         case RKS_MODEL_CUBIC_RFFT: launch_nl_fast_t<W, 3>(p, j, force, stream); break;
+        case RKS_MODEL_DERIV_FFT: launch_nl_fast_t<W, 5>(p, j, force, stream); break;
+        case RKS_MODEL_DERIV_RFFT_PAIR: launch_nl_fast_t<W, 6>(p, j, force, stream); break;
         default: launch_nl_fast_t<W, 4>(p, j, force, stream); break;
     }
 }
@@ -193,7 +197,8 @@ template <int W, int MODEL>
 static cudaError_t prepare_nl_fast_t() {
     const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
     cudaError_t e = cudaFuncSetAttribute(nl_fast_kernel<W, MODEL>, attr, (int)nl_fast_smem<W>(MODEL));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel_multi<W, MODEL>, attr, (int)nl_fast_smem<W>(MODEL));
+    if constexpr (MODEL <= 4)
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nl_fast_kernel_multi<W, MODEL>, attr, (int)nl_fast_smem<W>(MODEL));
     if (MODEL == 2 && W > 1 && e == cudaSuccess)
         e = cudaFuncSetAttribute(nl_fast_pre_kernel<(W > 1 ? W : 2)>, attr, (int)nl_fast_smem<W>(MODEL));
     return e;
@@ -204,6 +209,8 @@ static cudaError_t prepare_nl_fast(int model) {
         case RKS_MODEL_UUX_RFFT: return prepare_nl_fast_t<W, 1>();
         case RKS_MODEL_NLS_FFT: return prepare_nl_fast_t<W, 2>();
         case RKS_MODEL_CUBIC_RFFT: return prepare_nl_fast_t<W, 3>();
+        case RKS_MODEL_DERIV_FFT: return prepare_nl_fast_t<W, 5>();
+        case RKS_MODEL_DERIV_RFFT_PAIR: return prepare_nl_fast_t<W, 6>();
         default: return prepare_nl_fast_t<W, 4>();
     }
 }
@@ -216,6 +223,8 @@ static cudaError_t prepare_nl_small(int model) {
         case RKS_MODEL_UUX_RFFT: return cudaFuncSetAttribute(nl_small_kernel<N, 1>, attr, smem);
         case RKS_MODEL_NLS_FFT: return cudaFuncSetAttribute(nl_small_kernel<N, 2>, attr, smem);
         case RKS_MODEL_CUBIC_RFFT: return cudaFuncSetAttribute(nl_small_kernel<N, 3>, attr, smem);
+        case RKS_MODEL_DERIV_FFT: return cudaFuncSetAttribute(nl_small_kernel<N, 5>, attr, smem);
+        case RKS_MODEL_DERIV_RFFT_PAIR: return cudaFuncSetAttribute(nl_small_kernel<N, 6>, attr, smem);
         default: return cudaFuncSetAttribute(nl_small_kernel<N, 4>, attr, smem);
     }
 }
@@ -596,6 +605,15 @@ static int prepare_nl_launch(rks_plan* p, int model, long long n, cplx* twf_dev,
                                   : (uux ? cudaFuncSetAttribute(nl_fast_real_kernel<8, 1>, a, sm) : cudaFuncSetAttribute(nl_fast_real_kernel<8, 3>, a, sm));
         CUDA_TRY(e);
     }
+    {   // per-row offsets between the warps of a scheduler in barrier-synchronised rows (kernels.cuh row_stagger_spin)
+        const char* sm = getenv("RKS_ROW_STAGGER_MODE");
+        const char* sg = getenv("RKS_ROW_STAGGER_CYC");
+        const char* np = getenv("RKS_ROW_STAGGER_NP");
+        const int mode = sm ? atoi(sm) : 1, v = sg ? atoi(sg) : 1100, vnp = np ? atoi(np) : 1;
+        CUDA_TRY(cudaMemcpyToSymbol(c_row_stagger_mode, &mode, sizeof(int)));
+        CUDA_TRY(cudaMemcpyToSymbol(c_row_stagger_cyc, &v, sizeof(int)));
+        CUDA_TRY(cudaMemcpyToSymbol(c_row_stagger_np, &vnp, sizeof(int)));
+    }
     const char* pt = getenv("RKS_PT");
     p->pretransform = !(pt && pt[0] == '0');           // pre-transformed intermediate stages
     p->nl_small = (n == 64 || n == 128 || n == 256) && !getenv("RKS_NL_GENERIC");
@@ -626,7 +644,10 @@ static int prepare_nl_launch(rks_plan* p, int model, long long n, cplx* twf_dev,
     if (model == RKS_MODEL_UUX_RFFT) CUDA_TRY(cudaFuncSetAttribute(nl_kernel<1>, attr, (int)p->nl_smem));
     else if (model == RKS_MODEL_NLS_FFT) CUDA_TRY(cudaFuncSetAttribute(nl_kernel<2>, attr, (int)p->nl_smem));
     else if (model == RKS_MODEL_CUBIC_RFFT) CUDA_TRY(cudaFuncSetAttribute(nl_kernel<3>, attr, (int)p->nl_smem));
+    else if (model == RKS_MODEL_DERIV_FFT) CUDA_TRY(cudaFuncSetAttribute(nl_kernel<5>, attr, (int)p->nl_smem));
+    else if (model == RKS_MODEL_DERIV_RFFT_PAIR) CUDA_TRY(cudaFuncSetAttribute(nl_kernel<6>, attr, (int)p->nl_smem));
     else CUDA_TRY(cudaFuncSetAttribute(nl_kernel<4>, attr, (int)p->nl_smem));
+    if (model > RKS_MODEL_SINE_GORDON) return RKS_OK;          // no independent-dt variant of the derivative rows
     if (model == RKS_MODEL_UUX_RFFT) CUDA_TRY(cudaFuncSetAttribute(nl_kernel_multi<1>, attr, (int)p->nl_smem));
     else if (model == RKS_MODEL_NLS_FFT) CUDA_TRY(cudaFuncSetAttribute(nl_kernel_multi<2>, attr, (int)p->nl_smem));
     else if (model == RKS_MODEL_CUBIC_RFFT) CUDA_TRY(cudaFuncSetAttribute(nl_kernel_multi<3>, attr, (int)p->nl_smem));
@@ -928,6 +949,8 @@ static void launch_nl_small(rks_plan* p, int j, int force, cudaStream_t stream) 
         case RKS_MODEL_UUX_RFFT: launch_nl_small_t<N, 1>(p, j, force, stream); break;
         case RKS_MODEL_NLS_FFT: launch_nl_small_t<N, 2>(p, j, force, stream); break;
         case RKS_MODEL_CUBIC_RFFT: launch_nl_small_t<N, 3>(p, j, force, stream); break;
+        case RKS_MODEL_DERIV_FFT: launch_nl_small_t<N, 5>(p, j, force, stream); break;
+        case RKS_MODEL_DERIV_RFFT_PAIR: launch_nl_small_t<N, 6>(p, j, force, stream); break;
         default: launch_nl_small_t<N, 4>(p, j, force, stream); break;
     }
 }
@@ -1007,6 +1030,8 @@ static int launch_nl(rks_plan* p, int j, int force, cudaStream_t stream) {
     if (d.model == RKS_MODEL_UUX_RFFT) nl_kernel<1><<<grid, p->nl_threads, p->nl_smem, stream>>>(d, j, force, p->nl_rows_per_cta);
     else if (d.model == RKS_MODEL_NLS_FFT) nl_kernel<2><<<grid, p->nl_threads, p->nl_smem, stream>>>(d, j, force, p->nl_rows_per_cta);
     else if (d.model == RKS_MODEL_CUBIC_RFFT) nl_kernel<3><<<grid, p->nl_threads, p->nl_smem, stream>>>(d, j, force, p->nl_rows_per_cta);
+    else if (d.model == RKS_MODEL_DERIV_FFT) nl_kernel<5><<<grid, p->nl_threads, p->nl_smem, stream>>>(d, j, force, p->nl_rows_per_cta);
+    else if (d.model == RKS_MODEL_DERIV_RFFT_PAIR) nl_kernel<6><<<grid, p->nl_threads, p->nl_smem, stream>>>(d, j, force, p->nl_rows_per_cta);
     else nl_kernel<4><<<grid, p->nl_threads, p->nl_smem, stream>>>(d, j, force, p->nl_rows_per_cta);
     p->launches += 1;
     return RKS_OK;
@@ -1351,9 +1376,10 @@ struct rks_rows {
 extern "C" int rks_rows_create(rks_rows** out, int model, int64_t n, const double* kx, double p0, void* stream_v) {
     if (!out) return fail(RKS_ERR_ARG, "out is null");
     *out = nullptr;
-    if (model < RKS_MODEL_UUX_RFFT || model > RKS_MODEL_SINE_GORDON) return fail(RKS_ERR_ARG, "unknown model id");
+    if (model < RKS_MODEL_UUX_RFFT || model > RKS_MODEL_DERIV_RFFT_PAIR) return fail(RKS_ERR_ARG, "unknown model id");
+    const bool deriv = model == RKS_MODEL_DERIV_FFT || model == RKS_MODEL_DERIV_RFFT_PAIR;
     if (n < 16 || n > MODEL_MAX_N || (n & (n - 1))) return fail(RKS_ERR_UNSUPPORTED, "n must be a power of two in [16, 16384]");
-    if ((model == RKS_MODEL_UUX_RFFT || model == RKS_MODEL_SINE_GORDON) && !kx) return fail(RKS_ERR_ARG, "kx is null");
+    if ((model == RKS_MODEL_UUX_RFFT || model == RKS_MODEL_SINE_GORDON || deriv) && !kx) return fail(RKS_ERR_ARG, "kx is null");
     cudaStream_t stream = (cudaStream_t)stream_v;
     rks_rows* r = new (std::nothrow) rks_rows();
     if (!r) return fail(RKS_ERR_ARG, "out of host memory");
@@ -1364,7 +1390,8 @@ extern "C" int rks_rows_create(rks_rows** out, int model, int64_t n, const doubl
     const bool half = model == RKS_MODEL_UUX_RFFT || model == RKS_MODEL_CUBIC_RFFT;
     const long long n_c = half ? n / 2 + 1 : n;
     const size_t tw_b = align_up(sizeof(cplx) * (size_t)n), twf_b = align_up(sizeof(cplx) * 2 * fast::TW_TOTAL);
-    const size_t kx_b = align_up(sizeof(double) * (size_t)n_c);
+    const size_t kx_elems = deriv ? 2 * (size_t)n : (size_t)n_c;      // derivative rows: n complex multipliers
+    const size_t kx_b = align_up(sizeof(double) * kx_elems);
     CUDA_TRY(cudaGetDevice(&p->device));
     CUDA_TRY(usable_sm_count(&p->sm_count, p->device));
     CUDA_TRY(cudaMalloc(&r->dev_mem, tw_b + twf_b + kx_b));
@@ -1378,8 +1405,10 @@ extern "C" int rks_rows_create(rks_rows** out, int model, int64_t n, const doubl
     while ((1ll << log2n) < n) ++log2n;
     d.log2n = log2n;
     twiddle_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((cplx*)w, (int)n);
-    if (kx) CUDA_TRY(cudaMemcpyAsync(w + tw_b + twf_b, kx, sizeof(double) * (size_t)n_c, cudaMemcpyDeviceToDevice, stream));
+    if (kx) CUDA_TRY(cudaMemcpyAsync(w + tw_b + twf_b, kx, sizeof(double) * kx_elems, cudaMemcpyDeviceToDevice, stream));
     if (int rc = prepare_nl_launch(p, model, n, (cplx*)(w + tw_b), stream)) return rc;
+    // derivative rows: the frequency a position holds depends on the kernel family (fft_fast.cuh DigitMap)
+    if (deriv) d.model_p0 = (p->nl_fast || p->nl_small) ? 0.0 : 1.0;
     CUDA_TRY(cudaGetLastError());
     guard.release();
     *out = r;
@@ -1691,6 +1720,17 @@ extern "C" int rks_pointwise(int model, const void* in, void* out, int64_t count
     if (model == RKS_MODEL_NLS_FFT) pointwise_nls_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const cplx*)in, (cplx*)out, count, p0);
     else if (model == RKS_MODEL_CUBIC_RFFT) pointwise_cubic_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const double*)in, (double*)out, count, p0);
     else return fail(RKS_ERR_UNSUPPORTED, "no pointwise kernel for this model");
+    CUDA_TRY(cudaGetLastError());
+    return RKS_OK;
+}
+
+// dense basis change of diagonalize=True (etd35.py:463, 495)
+extern "C" int rks_gemv(const void* a, const void* x, void* y, int64_t n, int64_t batch, void* stream_v) {
+    if (!a || !x || !y || n <= 0 || batch <= 0 || n > (1 << 20) || batch > 65535) return fail(RKS_ERR_ARG, "bad gemv arguments");
+    if (x == y) return fail(RKS_ERR_ARG, "gemv: x and y must not alias");
+    if (((uintptr_t)a | (uintptr_t)x | (uintptr_t)y) & 15) return fail(RKS_ERR_ARG, "gemv arrays must be 16-byte aligned");
+    gemv_kernel<<<dim3((unsigned)((n + 3) / 4), (unsigned)batch), 128, 0, (cudaStream_t)stream_v>>>((const cplx*)a, (const cplx*)x,
+                                                                                              (cplx*)y, (int)n);
     CUDA_TRY(cudaGetLastError());
     return RKS_OK;
 }

@@ -81,15 +81,30 @@ class BaseSolver(ABC):
         if self._S is not None:
             if self._nl_eig is None:
                 # N'(k) = S^-1 N(S k)  (etd35.py:463): two dense matrix-vector products around the user's callable
-                self._nl_eig = lambda k: torch.matmul(self._Sinv, self.nl_func(torch.matmul(self._S, k)).to(torch.complex128))
+                self._nl_eig = lambda k: self._gemv(self._Sinv, self.nl_func(self._gemv(self._S, k)))
             return self._nl_eig
         return None if self._fused() is not None else self.nl_func
 
+    @staticmethod
+    def _gemv(mat: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+        """mat @ x for a dense complex128 matrix and a vector (or a batch of row vectors) on the engine's own kernel
+        (rks_gemv: one warp per matrix row), on the current stream."""
+        from ctypes import c_void_p
+        n = mat.shape[0]
+        xv = x.to(torch.complex128).contiguous()
+        if xv.shape[-1] != n:
+            raise ValueError(f"state of {xv.shape[-1]} points does not match the {n} x {n} operator")
+        y = torch.empty_like(xv)
+        st = c_void_p(torch.cuda.current_stream(mat.device).cuda_stream)
+        _abi.check(_abi.lib.rks_gemv(c_void_p(mat.data_ptr()), c_void_p(xv.data_ptr()), c_void_p(y.data_ptr()), n,
+                                     xv.numel() // n, st))
+        return y
+
     def _to_eig(self, u: torch.Tensor) -> torch.Tensor:
-        return u if self._S is None else torch.matmul(self._Sinv, u.to(torch.complex128))
+        return u if self._S is None else self._gemv(self._Sinv, u)
 
     def _to_phys(self, v: torch.Tensor) -> torch.Tensor:
-        return v if self._S is None else torch.matmul(self._S, v)
+        return v if self._S is None else self._gemv(self._S, v)
 
     def _get_engine(self, u: torch.Tensor) -> Engine:
         key = tuple(u.shape)

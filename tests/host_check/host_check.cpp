@@ -168,7 +168,7 @@ static void generic_row(const Model& m, int n, int nthreads) {
     const int np = fft_num_passes(log2n);
     for (int q = 0; q < np; ++q)
         for (int t = 0; t < nthreads; ++t) ifft_dif_pass(x.data(), log2n, q, tw.data(), t, nthreads);
-    for (int q = 0; q < n; ++q) x[q] = m.pointwise(x[q]);
+    for (int q = 0; q < n; ++q) x[q] = fast::pointwise_of(m, x[q], q);
     for (int q = 0; q < np; ++q)
         for (int t = 0; t < nthreads; ++t) fft_dit_pass(x.data(), log2n, q, tw.data(), t, nthreads);
     for (int q = 0; q < n; ++q) m.store(q, x[q]);
@@ -222,6 +222,8 @@ int hc_nl_fast(int model, int n, const double* in, const double* kx, double p0, 
     if (model == 1) return fast_dispatch(n, fast::ModelOf<1>::make(cin, co, kx, p0, n, true), tw);
     if (model == 2) return fast_dispatch(n, fast::ModelOf<2>::make(cin, co, kx, p0, n, true), tw);
     if (model == 3) return fast_dispatch(n, fast::ModelOf<3>::make(cin, co, kx, p0, n, true), tw);
+    if (model == 5) return fast_dispatch(n, fast::ModelOf<5>::make(cin, co, kx, 0.0, n, true), tw);    // derivative rows
+    if (model == 6) return fast_dispatch(n, fast::ModelOf<6>::make(cin, co, kx, 0.0, n, true), tw);
     return fast_dispatch(n, fast::ModelOf<4>::make(cin, co, kx, p0, n, true), tw);
 }
 
@@ -296,6 +298,8 @@ int hc_nl_packed(int model, int n, int rows, const double* in, const double* kx,
     if (model == 1) return packed_dispatch<1>(n, rows, n_c, cin, co, kx, p0, tw);
     if (model == 2) return packed_dispatch<2>(n, rows, n_c, cin, co, kx, p0, tw);
     if (model == 3) return packed_dispatch<3>(n, rows, n_c, cin, co, kx, p0, tw);
+    if (model == 5) return packed_dispatch<5>(n, rows, n_c, cin, co, kx, 0.0, tw);
+    if (model == 6) return packed_dispatch<6>(n, rows, n_c, cin, co, kx, 0.0, tw);      // rows = row PAIRS
     return packed_dispatch<4>(n, rows, n_c, cin, co, kx, p0, tw);
 }
 
@@ -305,6 +309,8 @@ void hc_nl(int model, int n, const double* in, const double* kx, double p0, doub
     if (model == 1) generic_row(fast::ModelOf<1>::make(cin, co, kx, p0, n, true), n, nthreads);
     else if (model == 2) generic_row(fast::ModelOf<2>::make(cin, co, kx, p0, n, true), n, nthreads);
     else if (model == 3) generic_row(fast::ModelOf<3>::make(cin, co, kx, p0, n, true), n, nthreads);
+    else if (model == 5) generic_row(fast::ModelOf<5>::make(cin, co, kx, 1.0, n, true), n, nthreads);   // p0 != 0: generic digit order
+    else if (model == 6) generic_row(fast::ModelOf<6>::make(cin, co, kx, 1.0, n, true), n, nthreads);
     else generic_row(fast::ModelOf<4>::make(cin, co, kx, p0, n, true), n, nthreads);
 }
 

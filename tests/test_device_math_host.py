@@ -488,3 +488,60 @@ def test_grouped_record_layout(hc, method, real):
         assert out[g] * elem % 32 == 0 and out[g] >= end
         end = out[g] + bin(masks[g]).count("1")
     assert out[0] >= end and out[0] * elem % 32 == 0
+
+
+# ---- spectral derivative rows (fft_fast.cuh DerivModel / DerivPairModel, rkstiff/derivatives.py:47-179) ----
+def _deriv_table(kx_full, order, n):
+    """what rkstiff_b200/derivatives.py hands to rks_rows_create: conj((i kx)^order) / n in FFT order"""
+    return np.ascontiguousarray(np.conj((1j * kx_full) ** order) / n)
+
+
+def _hc_deriv(hc, model, n, x, table):
+    """one row (model 5: complex; model 6: a row PAIR of reals) through the kernel family the engine uses for n"""
+    out = np.empty_like(x)
+    if n >= 512:
+        assert hc.hc_nl_fast(model, n, ptr(x), ptr(table), ctypes.c_double(0.0), ptr(out)) == 0
+    elif n >= 64:
+        assert hc.hc_nl_packed(model, n, 1, ptr(x), ptr(table), ctypes.c_double(0.0), ptr(out)) == 0
+    else:
+        hc.hc_nl(model, n, ptr(x), ptr(table), ctypes.c_double(0.0), ptr(out), 8)
+    return out
+
+
+@pytest.mark.parametrize("n", [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_derivative_rows_complex_match_numpy(hc, n, order):
+    rng = np.random.default_rng(100 * n + order)
+    kx = 2 * np.pi * np.fft.fftfreq(n, d=0.37)
+    z = np.ascontiguousarray(rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    got = _hc_deriv(hc, 5, n, z, _deriv_table(kx, order, n))
+    ref = np.fft.ifft((1j * kx) ** order * np.fft.fft(z))
+    assert rel(got, ref) < 4e-16 * np.log2(n) * 4
+
+
+@pytest.mark.parametrize("n", [16, 64, 256, 512, 1024, 8192])
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+def test_derivative_rows_real_pairs_match_numpy(hc, n, order):
+    """two real rows per complex transform; the Nyquist multiplier keeps its real part only (what irfft does)"""
+    rng = np.random.default_rng(7 * n + order)
+    kr = 2 * np.pi * np.fft.rfftfreq(n, d=0.11)
+    half = (1j * kr) ** order
+    half[-1] = half[-1].real
+    full = np.concatenate([half, np.conj(half[1:-1][::-1])])
+    table = np.ascontiguousarray(np.conj(full) / n)
+    pair = np.ascontiguousarray(rng.standard_normal((2, n)))
+    got = _hc_deriv(hc, 6, n, pair, table)
+    ref = np.fft.irfft((1j * kr) ** order * np.fft.rfft(pair, axis=-1), n=n, axis=-1)
+    assert rel(got, ref) < 4e-16 * np.log2(n) * 4
+
+
+def test_packed_derivative_rows_keep_rows_apart(hc):
+    """n = 64: eight rows share one 512-point slab; positions map to frequencies row by row (PackedModel::pointwise_at)"""
+    n, rows, order = 64, 11, 1
+    rng = np.random.default_rng(5)
+    kx = 2 * np.pi * np.fft.fftfreq(n, d=0.5)
+    z = np.ascontiguousarray(rng.standard_normal((rows, n)) + 1j * rng.standard_normal((rows, n)))
+    out = np.empty_like(z)
+    assert hc.hc_nl_packed(5, n, rows, ptr(z), ptr(_deriv_table(kx, order, n)), ctypes.c_double(0.0), ptr(out)) == 0
+    ref = np.fft.ifft((1j * kx) ** order * np.fft.fft(z, axis=-1), axis=-1)
+    assert rel(out, ref) < 2e-14

@@ -134,21 +134,36 @@ def test_host_snapshot_pipeline_matches_device_snapshots(rk):
 
 
 def test_device_derivatives_on_the_gpu():
-    """derivatives.dx_rfft / dx_fft on CUDA tensors against NumPy (reference derivatives.py:47-179), batched."""
+    """derivatives.dx_rfft / dx_fft on CUDA tensors against NumPy (reference derivatives.py:47-179), batched: every
+    kernel family behind rks_rows_* (generic 16 / 32, packed 64 ... 256, register path 512 ... 8192), odd row
+    counts (real rows go in pairs), and lengths the engine does not transform (16384, 96: torch.fft on the device)."""
     import numpy as np
     import torch
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
+    from rkstiff_b200 import _abi
     from rkstiff_b200 import derivatives as d
-    n = 256
-    x = np.arange(n) * (2 * np.pi / n)
-    kr = 2 * np.pi * np.fft.rfftfreq(n, d=2 * np.pi / n)
-    kc = 2 * np.pi * np.fft.fftfreq(n, d=2 * np.pi / n)
-    u = np.stack([np.sin(3 * x) + 0.5 * np.cos(5 * x), np.cos(x) ** 3])
-    for order in (1, 2, 3):
-        got = d.dx_rfft(torch.from_numpy(kr).cuda(), torch.from_numpy(u).cuda(), order).cpu().numpy()
-        ref = np.fft.irfft((1j * kr) ** order * np.fft.rfft(u, axis=-1), n=n, axis=-1)
-        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-11 * np.abs(ref).max())
-    z = u[0] + 1j * u[1]
-    got = d.dx_fft(torch.from_numpy(kc).cuda(), torch.from_numpy(z).cuda(), 2).cpu().numpy()
-    np.testing.assert_allclose(got, np.fft.ifft((1j * kc) ** 2 * np.fft.fft(z)), rtol=0, atol=1e-11 * np.abs(z).max() * 25)
+    assert _abi.lib is not None
+    rng = np.random.default_rng(11)
+    for n in (16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 96):
+        x = np.arange(n) * (2 * np.pi / n)
+        kr = 2 * np.pi * np.fft.rfftfreq(n, d=2 * np.pi / n)
+        kc = 2 * np.pi * np.fft.fftfreq(n, d=2 * np.pi / n)
+        u = np.stack([np.sin(3 * x) + 0.5 * np.cos(5 * x), np.cos(x) ** 3, rng.standard_normal(n)])      # 3 rows: odd
+        for order in (1, 2, 3):
+            got = d.dx_rfft(torch.from_numpy(kr).cuda(), torch.from_numpy(u).cuda(), order).cpu().numpy()
+            ref = np.fft.irfft((1j * kr) ** order * np.fft.rfft(u, axis=-1), n=n, axis=-1)
+            assert got.shape == ref.shape
+            np.testing.assert_allclose(got, ref, rtol=0, atol=1e-12 * np.abs(ref).max())
+        z = np.stack([u[0] + 1j * u[1], u[2] - 0.5j * u[0]]).reshape(2, 1, n)
+        got = d.dx_fft(torch.from_numpy(kc).cuda(), torch.from_numpy(z).cuda(), 2).cpu().numpy()
+        ref = np.fft.ifft((1j * kc) ** 2 * np.fft.fft(z, axis=-1), axis=-1)
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-12 * np.abs(ref).max())
+    # a reusable handle on a larger batch, single row included
+    n = 1024
+    kr = torch.from_numpy(2 * np.pi * np.fft.rfftfreq(n, d=0.05)).cuda()
+    dd = d.SpectralDerivative(kr, n, 1, real=True)
+    big = torch.from_numpy(rng.standard_normal((257, n))).cuda()
+    ref = np.fft.irfft((1j * kr.cpu().numpy()) * np.fft.rfft(big.cpu().numpy(), axis=-1), n=n, axis=-1)
+    np.testing.assert_allclose(dd(big).cpu().numpy(), ref, rtol=0, atol=1e-12 * np.abs(ref).max())
+    np.testing.assert_allclose(dd(big[0]).cpu().numpy(), ref[0], rtol=0, atol=1e-12 * np.abs(ref).max())

@@ -14,7 +14,7 @@ tot = 1 << (int(sys.argv[1]) if len(sys.argv) > 1 else 25)
 dev = torch.device("cuda", 0)
 out = []
 for model in ("nls", "uux", "cubic"):
-    for n in (512, 1024, 2048, 4096, 8192):
+    for n in [int(v) for v in os.environ.get("BENCH_NL_N", "512,1024,2048,4096,8192").split(",")]:
         n_c = n if model == "nls" else n // 2 + 1
         batch = tot // n
         kx = torch.linspace(0, 10, n_c, dtype=torch.float64, device=dev)

@@ -14,7 +14,7 @@ method = sys.argv[1] if len(sys.argv) > 1 else "ETD35"
 trials = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 dev = torch.device("cuda", 0)
 adaptive = method in ("IF34", "ETD34", "ETD35", "IF45DP")
-for n in (512, 1024, 2048, 4096, 8192):
+for n in [int(v) for v in os.environ.get("PT_SWEEP_N", "512,1024,2048,4096,8192").split(",")]:
     batch = (1 << 25) // n
     w = 40.0 * math.pi
     dx = 2 * w / n
