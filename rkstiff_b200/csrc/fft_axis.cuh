@@ -39,16 +39,26 @@ template <> struct APlan<4096> { static constexpr int R1 = 16, R2 = 16, R3 = 16;
 #ifndef RKS_AX512_B
 #define RKS_AX512_B 3
 #endif
+// the same for the 4096-point tile (128 KB at C = 2: one CTA per SM, load / levels / store of a tile do not overlap)
+#ifndef RKS_AX4096_C
+#define RKS_AX4096_C 2
+#endif
+#ifndef RKS_AX4096_T
+#define RKS_AX4096_T 512
+#endif
+#ifndef RKS_AX4096_B
+#define RKS_AX4096_B 1
+#endif
 #ifndef RKS_AX_UNROLL
 #define RKS_AX_UNROLL 1
 #endif
 // tile geometry: 64 KB tiles (128 KB for N = 4096 so that a row segment is still a full 32-byte sector)
-template <int N> RKS_HD constexpr int tile_cols() { return N == 512 ? RKS_AX512_C : N < 512 ? 8 : N == 1024 ? 4 : 2; }
+template <int N> RKS_HD constexpr int tile_cols() { return N == 512 ? RKS_AX512_C : N < 512 ? 8 : N == 1024 ? 4 : N == 4096 ? RKS_AX4096_C : 2; }
 // threads: one first-level butterfly per thread where the tile has that many (N / R1 butterflies x C columns), so no
 // thread idles through a level; resident CTAs per SM: as many as the 227 KB of shared memory and 64 K registers
 // allow -- short axes (the second kernel of the two-kernel route, 256^3 grids) need several small tiles in flight
-template <int N> RKS_HD constexpr int tile_threads() { return N == 4096 ? 512 : N == 512 ? RKS_AX512_T : N > 512 ? 256 : N == 256 ? 128 : 64; }
-template <int N> RKS_HD constexpr int tile_blocks() { return N == 4096 ? 1 : N >= 1024 ? 2 : N == 512 ? RKS_AX512_B : N == 256 ? 5 : 8; }
+template <int N> RKS_HD constexpr int tile_threads() { return N == 4096 ? RKS_AX4096_T : N == 512 ? RKS_AX512_T : N > 512 ? 256 : N == 256 ? 128 : 64; }
+template <int N> RKS_HD constexpr int tile_blocks() { return N == 4096 ? RKS_AX4096_B : N >= 1024 ? 2 : N == 512 ? RKS_AX512_B : N == 256 ? 5 : 8; }
 template <int N> RKS_HD constexpr int last_radix() {
     return APlan<N>::R3 > 1 ? APlan<N>::R3 : APlan<N>::R2 > 1 ? APlan<N>::R2 : APlan<N>::R1;
 }

@@ -728,7 +728,8 @@ struct NoHook { RKS_D void operator()() const {} };
 // Measured in round 2 (profiles/r02t_*, r02u_*, r02v_*; same box, interleaved runs): pre-transformed rows
 // 312-314 -> 285-288 us per evaluation, plain rows 338 -> 316 us; no effect at n = 4096 (two CTAs per SM are out
 // of step anyway), so n = 8192 only.
-//   RKS_ROW_STAGGER_MODE 1 (default): slot s spins s * RKS_ROW_STAGGER_CYC (default 1100) cycles;
+//   RKS_ROW_STAGGER_MODE 1 (default): slot s spins s * RKS_ROW_STAGGER_CYC (default 1000; 800 ... 1200 measured alike,
+//      1300 and more lose the gain) cycles;
 //   2: slot s starts its butterfly when slot s - 1 has finished (named barriers 1..3, self-timed: 290-293 us);
 //   0: off.  RKS_ROW_STAGGER_NP=0 switches the spin of the rows that are not pre-transformed off.
 __constant__ int c_row_stagger_mode;

@@ -609,7 +609,7 @@ static int prepare_nl_launch(rks_plan* p, int model, long long n, cplx* twf_dev,
         const char* sm = getenv("RKS_ROW_STAGGER_MODE");
         const char* sg = getenv("RKS_ROW_STAGGER_CYC");
         const char* np = getenv("RKS_ROW_STAGGER_NP");
-        const int mode = sm ? atoi(sm) : 1, v = sg ? atoi(sg) : 1100, vnp = np ? atoi(np) : 1;
+        const int mode = sm ? atoi(sm) : 1, v = sg ? atoi(sg) : 1000, vnp = np ? atoi(np) : 1;
         CUDA_TRY(cudaMemcpyToSymbol(c_row_stagger_mode, &mode, sizeof(int)));
         CUDA_TRY(cudaMemcpyToSymbol(c_row_stagger_cyc, &v, sizeof(int)));
         CUDA_TRY(cudaMemcpyToSymbol(c_row_stagger_np, &vnp, sizeof(int)));
