@@ -49,6 +49,11 @@ template <> struct APlan<4096> { static constexpr int R1 = 16, R2 = 16, R3 = 16;
 #ifndef RKS_AX4096_B
 #define RKS_AX4096_B 1
 #endif
+// rows of the NEXT tile that cp.async copies into the spare shared memory while the current tile is transformed
+// (0 = off): with one 128 KB tile per SM nothing else overlaps the tile's load with its levels and stores
+#ifndef RKS_AX4096_STAGE_ROWS
+#define RKS_AX4096_STAGE_ROWS 3072
+#endif
 #ifndef RKS_AX_UNROLL
 #define RKS_AX_UNROLL 1
 #endif
@@ -59,6 +64,10 @@ template <int N> RKS_HD constexpr int tile_cols() { return N == 512 ? RKS_AX512_
 // allow -- short axes (the second kernel of the two-kernel route, 256^3 grids) need several small tiles in flight
 template <int N> RKS_HD constexpr int tile_threads() { return N == 4096 ? RKS_AX4096_T : N == 512 ? RKS_AX512_T : N > 512 ? 256 : N == 256 ? 128 : 64; }
 template <int N> RKS_HD constexpr int tile_blocks() { return N == 4096 ? RKS_AX4096_B : N >= 1024 ? 2 : N == 512 ? RKS_AX512_B : N == 256 ? 5 : 8; }
+template <int N> RKS_HD constexpr int stage_rows() { return N == 4096 ? RKS_AX4096_STAGE_ROWS : 0; }
+template <int N> RKS_HD constexpr int tile_smem() { return (N + stage_rows<N>()) * tile_cols<N>() * 16; }
+// persistent CTAs per resident slot: one when the next tile is staged (a CTA's first tile cannot be), else a few
+template <int N> RKS_HD constexpr int tile_waves() { return stage_rows<N>() > 0 ? 1 : 4; }
 template <int N> RKS_HD constexpr int last_radix() {
     return APlan<N>::R3 > 1 ? APlan<N>::R3 : APlan<N>::R2 > 1 ? APlan<N>::R2 : APlan<N>::R1;
 }
@@ -79,6 +88,7 @@ struct Col {                 // one thread's column of the tile and of the globa
     const long long* otab = nullptr;
     int o_shift = 31;
     long long ooff = 0;      // offset inside a destination block: outer index x block stride + column
+    const cplx* stg = nullptr;   // staged copy of the tile's first stage_rows<N>() input rows ([swz(row)][C]), or nullptr
     // Row p of the axis.  Blocked rows: the axis is split over G chunks that sit G-major in memory, as an
     // all-to-all delivers them (dist_fft.py) -- row p = chunk p >> rb_shift, offset p & mask.
     RKS_HD long long row(int p) const {
@@ -91,6 +101,14 @@ struct Col {                 // one thread's column of the tile and of the globa
     }
 };
 
+// input row p of the tile's column: from the staged copy when the row was prefetched, else from global memory
+template <int N>
+RKS_HD cplx first_ld(const Col& c, int p) {
+    if (!c.ok) return mk(0.0, 0.0);
+    if (stage_rows<N>() > 0 && c.stg && p < stage_rows<N>()) return c.stg[fast::swz<tile_shift<N>()>(p) * tile_cols<N>() + c.col];
+    return fast::row_ld(c.gin + c.row(p));
+}
+
 // one decimation-in-frequency level of the inverse transform: rows p0 + Q s, twiddles on the outputs
 template <int N, int R, int Q, bool FIRST, bool LAST>
 RKS_HD void dif_level(cplx* tile, const cplx* tw, const Col& c, int bt, int nbt, double scale) {
@@ -102,7 +120,7 @@ RKS_HD void dif_level(cplx* tile, const cplx* tw, const Col& c, int bt, int nbt,
         cplx a[R];
 #pragma unroll
         for (int s = 0; s < R; ++s) {
-            if (FIRST) a[s] = c.ok ? fast::row_ld(c.gin + c.row(p0 + Q * s)) : mk(0.0, 0.0);
+            if (FIRST) a[s] = first_ld<N>(c, p0 + Q * s);
             else a[s] = tile[fast::swz<SH>(p0 + Q * s) * C + c.col];
         }
         fast::dftR<R, true>(a);
@@ -127,7 +145,7 @@ RKS_HD void dit_level(cplx* tile, const cplx* tw, const Col& c, int bt, int nbt)
         cplx a[R];
 #pragma unroll
         for (int s = 0; s < R; ++s) {
-            if (FIRST) a[s] = c.ok ? fast::row_ld(c.gin + c.row(p0 + Q * s)) : mk(0.0, 0.0);
+            if (FIRST) a[s] = first_ld<N>(c, p0 + Q * s);
             else a[s] = tile[fast::swz<SH>(p0 + Q * s) * C + c.col];
         }
         if (Q > 1) fast::twiddle_scale<R, false>(a, tw, 0, j * (N / (R * Q)), fast::SlotId());

@@ -1452,7 +1452,7 @@ struct rks_axis {
 
 template <int N>
 static cudaError_t axis_prepare() {
-    const int smem = N * axis::tile_cols<N>() * (int)sizeof(cplx);
+    const int smem = axis::tile_smem<N>();
     cudaError_t e = cudaFuncSetAttribute(axis_fft_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(axis_fft_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     return e;
@@ -1462,9 +1462,9 @@ template <int N>
 static void axis_launch(const rks_axis* a, const cplx* in, cplx* out, long long outer, long long inner, int inverse,
                         long long ostride, long long bstride, int rb_shift, cudaStream_t stream) {
     constexpr int C = axis::tile_cols<N>();
-    const size_t smem = (size_t)N * C * sizeof(cplx);
+    const size_t smem = (size_t)axis::tile_smem<N>();
     const long long tiles = outer * ((inner + C - 1) / C);
-    const long long cap = (long long)a->sm_count * axis::tile_blocks<N>() * 4;      // persistent CTAs, a few per slot
+    const long long cap = (long long)a->sm_count * axis::tile_blocks<N>() * axis::tile_waves<N>();      // persistent CTAs, a few per slot
     const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
     if (inverse) axis_fft_kernel<N, true><<<grid, axis::tile_threads<N>(), smem, stream>>>(in, out, outer, inner, a->tw, 1.0 / (double)N, ostride, bstride, rb_shift);
     else axis_fft_kernel<N, false><<<grid, axis::tile_threads<N>(), smem, stream>>>(in, out, outer, inner, a->tw, 1.0, ostride, bstride, rb_shift);
@@ -1549,9 +1549,9 @@ template <int N>
 static void axis_launch_scatter(const rks_axis* a, const cplx* in, const long long* otab, long long outer, long long inner,
                                 int inverse, long long ostride, long long bstride, int rb_shift, int o_shift, cudaStream_t stream) {
     constexpr int C = axis::tile_cols<N>();
-    const size_t smem = (size_t)N * C * sizeof(cplx);
+    const size_t smem = (size_t)axis::tile_smem<N>();
     const long long tiles = outer * ((inner + C - 1) / C);
-    const long long cap = (long long)a->sm_count * axis::tile_blocks<N>() * 4;
+    const long long cap = (long long)a->sm_count * axis::tile_blocks<N>() * axis::tile_waves<N>();
     const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
     // (per device and cheap: set on every launch rather than cached)
     if (inverse) cudaFuncSetAttribute(axis_fft_scatter_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1605,16 +1605,16 @@ template <int N>
 static void axis_launch_plan(const rks_axis* a, const DevPlan& d, int j, int force, int first, long long outer, long long inner,
                              int inverse, cudaStream_t stream) {
     constexpr int C = axis::tile_cols<N>();
-    const size_t smem = (size_t)N * C * sizeof(cplx);
+    const size_t smem = (size_t)axis::tile_smem<N>();
     const long long tiles = outer * ((inner + C - 1) / C);
-    const long long cap = (long long)a->sm_count * axis::tile_blocks<N>() * 4;
+    const long long cap = (long long)a->sm_count * axis::tile_blocks<N>() * axis::tile_waves<N>();
     const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
     if (inverse) axis_fft_plan_kernel<N, true><<<grid, axis::tile_threads<N>(), smem, stream>>>(d, j, force, first, outer, inner, a->tw, 1.0 / (double)N);
     else axis_fft_plan_kernel<N, false><<<grid, axis::tile_threads<N>(), smem, stream>>>(d, j, force, first, outer, inner, a->tw, 1.0);
 }
 template <int N>
 static cudaError_t axis_plan_prepare() {
-    const int smem = N * axis::tile_cols<N>() * (int)sizeof(cplx);
+    const int smem = axis::tile_smem<N>();
     cudaError_t e = cudaFuncSetAttribute(axis_fft_plan_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(axis_fft_plan_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     return e;
