@@ -719,9 +719,6 @@ RKS_D void row_barrier(int lrow, int rpc) {
 }
 
 struct NoHook { RKS_D void operator()() const {} };
-RKS_D unsigned smem_u32(const void* p);
-RKS_D void stage_wait(unsigned long long* bar, unsigned parity);
-RKS_D void mbar_arrive(unsigned long long* bar);
 
 // n = 8192 (one row per CTA, 16 warps): the warps leave every row barrier in step, so the four warps of a
 // scheduler load together, compute together and store together and the LSU and the FP64 pipe are busy in turn
@@ -755,8 +752,7 @@ RKS_D void row_stagger_spin(int T) {
 // (PT with a staging buffer): shared counter of the warps that have consumed the buffer.
 template <int N, bool PT = false, class Model, class Hook = NoHook>
 RKS_D void nl_fast_row(cplx* sm, int T, int lrow, int rpc, const fast::Twiddles& ti, const fast::Twiddles& tf,
-                       const Model& m, const Hook& after_first = Hook(), int* arrived = nullptr,
-                       unsigned long long* rowbar = nullptr, unsigned rowpar = 0) {
+                       const Model& m, const Hook& after_first = Hook(), int* arrived = nullptr) {
     using P = fast::Plan<N>;
     constexpr int W = P::W, TR = 32 * W;
     if (PT) {
@@ -799,10 +795,7 @@ RKS_D void nl_fast_row(cplx* sm, int T, int lrow, int rpc, const fast::Twiddles&
         static_assert(Q1 == 32 * W, "pre-transformed rows: one last-pass butterfly per thread");
         cplx a[R1];
         fast::bf_load<R1, Q1, P::SH>(sm, T, a);
-        // rowbar (n = 8192): the barrier is split -- arrive here, wait only before this thread's next write into the
-        // slab (end of this function), so no warp waits for the slowest warp's slab loads before its butterfly
-        if (rowbar) mbar_arrive(rowbar);
-        else row_barrier<TR>(lrow, rpc);
+        row_barrier<TR>(lrow, rpc);
         const int mode = W == 16 ? c_row_stagger_mode : 0;
         const int slot = T >> 7;
         if (mode == 1) row_stagger_spin<W>(T);
@@ -810,7 +803,6 @@ RKS_D void nl_fast_row(cplx* sm, int T, int lrow, int rpc, const fast::Twiddles&
         fast::bf_dit<R1, Q1, fast::TW_S1>(a, tf.t1, T);
         if (mode == 2 && slot < W / 4 - 1) asm volatile("bar.arrive %0, 256;" ::"r"(slot + 1) : "memory");
         fast::bf_store_global<R1, Q1>(m, T, a);
-        if (rowbar) stage_wait(rowbar, rowpar);
     }
 }
 
@@ -825,10 +817,7 @@ RKS_D void prefetch_row_l2(const void* row, int lines, int T) {
 // mbarrier, one elected thread: arm it with the byte count, issue the bulk copies; every thread
 // waits on the phase parity before the first pass reads the staging buffer.
 constexpr int NL_STAGE_ELEMS = 6144;                 // 96 KB next to the 128 KB row slab
-constexpr int NL_STAGE_BYTES = NL_STAGE_ELEMS * 16 + 32;     // + TMA mbarrier, consumed-warps counter, split row barrier
-#ifndef RKS_ROW_SPLITBAR
-#define RKS_ROW_SPLITBAR 1
-#endif
+constexpr int NL_STAGE_BYTES = NL_STAGE_ELEMS * 16 + 16;
 RKS_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 RKS_D void stage_init(unsigned long long* bar) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
@@ -845,9 +834,6 @@ RKS_D void stage_issue(cplx* stg, const cplx* src, unsigned bytes, unsigned long
                      ::"r"(smem_u32(stg) + off), "l"(reinterpret_cast<const char*>(src) + off), "r"(sz), "r"(b)
                      : "memory");
     }
-}
-RKS_D void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 RKS_D void stage_wait(unsigned long long* bar, unsigned parity) {
     asm volatile(
@@ -892,19 +878,12 @@ RKS_D void nl_fast_kernel_body(const DevPlan& p, int j, int force) {
     cplx* stg = reinterpret_cast<cplx*>(smem_raw) + (size_t)RPC * N;
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(stg + NL_STAGE_ELEMS);
     int* arrived = reinterpret_cast<int*>(bar + 1);          // PT: warps that have consumed the staging buffer
-    unsigned long long* rowbar = bar + 2;                     // PT: split barrier after the last-pass slab loads
-    constexpr bool SPLIT = STAGED && PT && RKS_ROW_SPLITBAR;
-    unsigned rowpar = 0;
     const int nst = p.n_c < NL_STAGE_ELEMS ? (int)p.n_c : NL_STAGE_ELEMS;
     unsigned parity = 0;
     if (STAGED) {
         if (threadIdx.x == 0) {
             *arrived = 0;
             stage_init(bar);
-            if (SPLIT) {
-                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(rowbar)), "r"(TR) : "memory");
-                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            }
             if ((long long)blockIdx.x < groups) stage_issue(stg, roles.in + (long long)blockIdx.x * p.n_c, nst * 16u, bar);
         }
         __syncthreads();
@@ -928,8 +907,7 @@ RKS_D void nl_fast_kernel_body(const DevPlan& p, int j, int force) {
                                                              p.model_p0, N, on);
             // !PT: thread 0 issues the copy after the row barrier; PT: the lane the counter elects
             const StageNext next{stg, roles.in + (nlines ? nrow : rr) * p.n_c, nst * 16u, bar, nlines != 0 && (PT || threadIdx.x == 0)};
-            nl_fast_row<N, PT>(sm, T, lrow, RPC, ti, tf, m, next, arrived, SPLIT ? rowbar : nullptr, rowpar);
-            rowpar ^= 1u;
+            nl_fast_row<N, PT>(sm, T, lrow, RPC, ti, tf, m, next, arrived);
         } else {
             prefetch_row_l2<TR>(roles.in + (nlines ? nrow : rr) * p.n_c, nlines, T);
             const auto m = fast::ModelOf<MODEL>::make(roles.in + rr * p.n_c, out, p.kx, p.model_p0, N, on);
