@@ -167,3 +167,29 @@ def test_device_derivatives_on_the_gpu():
     ref = np.fft.irfft((1j * kr.cpu().numpy()) * np.fft.rfft(big.cpu().numpy(), axis=-1), n=n, axis=-1)
     np.testing.assert_allclose(dd(big).cpu().numpy(), ref, rtol=0, atol=1e-12 * np.abs(ref).max())
     np.testing.assert_allclose(dd(big[0]).cpu().numpy(), ref[0], rtol=0, atol=1e-12 * np.abs(ref).max())
+
+
+def test_gemv_kernel_matches_numpy():
+    """rks_gemv (the S / S^-1 products of diagonalize=True, etd35.py:463, 495) against NumPy: vector and batch of
+    row vectors, sizes that are not multiples of the warp or of the rows-per-CTA."""
+    import numpy as np
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from rkstiff_b200.solver import BaseSolver
+    rng = np.random.default_rng(3)
+    for n, batch in ((1, 1), (5, 1), (33, 3), (130, 1), (257, 4)):
+        a = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        x = rng.standard_normal((batch, n)) + 1j * rng.standard_normal((batch, n))
+        xs = x[0] if batch == 1 else x
+        got = BaseSolver._gemv(torch.from_numpy(a).cuda(), torch.from_numpy(np.ascontiguousarray(xs)).cuda()).cpu().numpy()
+        ref = xs @ a.T
+        assert got.shape == ref.shape
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-13 * np.abs(ref).max() * n)
+    # a real state vector is widened (the reference's nl_func may return float arrays)
+    a = rng.standard_normal((7, 7)) + 0j
+    v = rng.standard_normal(7)
+    got = BaseSolver._gemv(torch.from_numpy(a).cuda(), torch.from_numpy(v).cuda()).cpu().numpy()
+    np.testing.assert_allclose(got, a @ v, rtol=0, atol=1e-13)
+    with pytest.raises(ValueError):
+        BaseSolver._gemv(torch.from_numpy(a).cuda(), torch.zeros(6, dtype=torch.complex128, device="cuda"))
