@@ -221,6 +221,16 @@ struct StagedRow {
     RKS_HD cplx value(long long p) const { return p < nst ? stg[p] : row_ld(in + p); }
     RKS_HD cplx get(int k) const { return k < nst ? stg[k] : row_ld(in + k); }
 };
+// pre-transformed rows: the first SL points of every warp's 512-point slice are staged (kernels.cuh stage_issue_sliced)
+struct SlicedStagedRow {
+    static constexpr int SL = 384;         // 16 x 384 = the 6144 points of the staging buffer (uneven shares -- more for the
+                                           // warps that start later, or earlier -- measured slower: profiles/r02ac_*)
+    const cplx* in; const cplx* stg;
+    RKS_HD cplx value(long long p) const {
+        const int o = (int)p & 511;
+        return o < SL ? stg[((int)p >> 9) * SL + o] : row_ld(in + p);
+    }
+};
 template <class Src>
 struct NlsModelT {          // N = i gamma fft(|f|^2 f), f = ifft(u^)      (demos/nls.ipynb)
     Src src; cplx* out; double gamma; int n; bool on;

@@ -846,6 +846,26 @@ RKS_D void stage_wait(unsigned long long* bar, unsigned parity) {
         "RKS_STAGE_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Pre-transformed rows read their input slice by slice (warp w owns points 512 w ... 512 w + 511), so staging the HEAD
+// of the row would leave the last warps -- the ones the stagger starts last -- reading global memory only.  Instead the
+// first PT_SLICE_STAGED points of EVERY slice are staged: 16 bulk copies of 6 KB on the same mbarrier.
+#ifndef RKS_PT_SLICED
+#define RKS_PT_SLICED 1
+#endif
+constexpr int PT_SLICE_STAGED = fast::SlicedStagedRow::SL;
+RKS_D void stage_issue_sliced(cplx* stg, const cplx* src, unsigned long long* bar) {
+    const unsigned b = smem_u32(bar);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(16u * PT_SLICE_STAGED * 16u) : "memory");
+    for (int w = 0; w < 16; ++w)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(stg + w * PT_SLICE_STAGED)), "l"(src + w * 512), "r"(PT_SLICE_STAGED * 16u), "r"(b)
+                     : "memory");
+}
+struct SlicedStageNext {
+    cplx* stg; const cplx* src; unsigned long long* bar; bool go;
+    RKS_D void operator()() const { if (go) stage_issue_sliced(stg, src, bar); }
+};
 struct StageNext {          // after the first pass: start copying the head of the next row
     cplx* stg; const cplx* src; unsigned bytes; unsigned long long* bar; bool go;
     RKS_D void operator()() const { if (go) stage_issue(stg, src, bytes, bar); }
@@ -884,7 +904,10 @@ RKS_D void nl_fast_kernel_body(const DevPlan& p, int j, int force) {
         if (threadIdx.x == 0) {
             *arrived = 0;
             stage_init(bar);
-            if ((long long)blockIdx.x < groups) stage_issue(stg, roles.in + (long long)blockIdx.x * p.n_c, nst * 16u, bar);
+            if ((long long)blockIdx.x < groups) {
+                if (PT && RKS_PT_SLICED) stage_issue_sliced(stg, roles.in + (long long)blockIdx.x * p.n_c, bar);
+                else stage_issue(stg, roles.in + (long long)blockIdx.x * p.n_c, nst * 16u, bar);
+            }
         }
         __syncthreads();
     }
@@ -896,7 +919,19 @@ RKS_D void nl_fast_kernel_body(const DevPlan& p, int j, int force) {
         const long long nrow = row + (long long)gridDim.x * RPC;     // the row this slot handles next
         const int nlines = nrow < p.batch ? lines : 0;
         cplx* out = roles.out + rr * p.n_c;
-        if constexpr (STAGED) {
+        if constexpr (STAGED && PT && RKS_PT_SLICED) {
+            // L2-prefetch the unstaged tail of every slice of the next row: 16 lines of 128 bytes per slice
+            if (nlines && T < 256) {
+                const char* base = reinterpret_cast<const char*>(roles.in + nrow * p.n_c);
+                const int w = T >> 4, l = T & 15;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ((size_t)(512 * w + PT_SLICE_STAGED) << 4) + ((size_t)l << 7)));
+            }
+            stage_wait(bar, parity);
+            parity ^= 1u;
+            const fast::NlsModelT<fast::SlicedStagedRow> m{fast::SlicedStagedRow{roles.in + rr * p.n_c, stg}, out, p.model_p0, N, on};
+            const SlicedStageNext next{stg, roles.in + (nlines ? nrow : rr) * p.n_c, bar, nlines != 0};
+            nl_fast_row<N, PT>(sm, T, lrow, RPC, ti, tf, m, next, arrived);
+        } else if constexpr (STAGED) {
             // L2-prefetch only the tail of the next row that does not fit the staging buffer
             const int head = (nst * 16) >> 7;
             if (nlines > head)
