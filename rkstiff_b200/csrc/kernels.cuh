@@ -725,7 +725,7 @@ struct NoHook { RKS_D void operator()() const {} };
 // instead of at the same time.  Before the last-pass butterflies of a row (the first FP64-heavy phase after the
 // barrier) the warps of a scheduler (slot = warp / 4) are therefore put one phase apart: one computes while the
 // previous one already stores and loads the next row, and the offsets survive the barrier-free part of that row.
-// Measured in round 2 (profiles/r02t_*, r02u_*, r02v_*; same box, interleaved runs): pre-transformed rows
+// Measured in round 2 (profiles/r02t_row_stagger.md; same box, interleaved runs): pre-transformed rows
 // 312-314 -> 285-288 us per evaluation, plain rows 338 -> 316 us; no effect at n = 4096 (two CTAs per SM are out
 // of step anyway), so n = 8192 only.
 //   RKS_ROW_STAGGER_MODE 1 (default): slot s spins s * RKS_ROW_STAGGER_CYC (default 1000; 800 ... 1200 measured alike,
@@ -1291,8 +1291,6 @@ __global__ void controller_kernel(DevPlan p) {
     *c = local;
 }
 
-// pointwise nonlinearity of the N-D models, applied between two library transforms (one read + one
-// write instead of the half-dozen elementwise passes a torch expression costs)
 // Dense complex matrix times vector(s), y[b] = A x[b]: the basis changes of diagonalize=True (etd35.py:463, 495:
 // N'(k) = S^-1 N(S k), |S u+| for the controller).  One warp per matrix row, lanes stride the row (512-byte coalesced
 // segments of A, x from L1/L2), shuffle reduction; grid (ceil(n / 4), batch).  Bound by the read of A (n^2 x 16 B).
@@ -1316,6 +1314,8 @@ __global__ void __launch_bounds__(128) gemv_kernel(const cplx* __restrict__ a, c
     if (lane == 0) y[(size_t)blockIdx.y * n + i] = mk(sr, si);
 }
 
+// pointwise nonlinearity of the N-D models, applied between two library transforms (one read + one
+// write instead of the half-dozen elementwise passes a torch expression costs)
 __global__ void __launch_bounds__(256) pointwise_nls_kernel(const cplx* in, cplx* out, long long count, double gamma) {
     for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < count; e += (long long)gridDim.x * 256) {
         const cplx f = ldcs(in + e);
