@@ -154,3 +154,18 @@ def test_chebyshev_grid_and_dense_allen_cahn_operator():
     with pytest.raises(TypeError):
         grids.construct_x_cheb(4.0, device="cpu")
 
+
+
+def test_derivative_multiplier_matches_numpy_powers():
+    """derivatives._ik_power: (i kx)^n with exact zeros in the vanishing part, as NumPy's repeated complex products
+    give (rkstiff/derivatives.py:119,176); magnitudes within one rounding of NumPy's."""
+    import numpy as np
+    import torch
+    from rkstiff_b200.derivatives import _engine_length, _ik_power
+    kx = 2 * np.pi * np.fft.fftfreq(64, d=0.3)
+    for order in range(0, 9):
+        got = _ik_power(torch.from_numpy(kx), order).numpy()
+        ref = (1j * kx) ** order
+        assert np.array_equal(got.real == 0, ref.real == 0) and np.array_equal(got.imag == 0, ref.imag == 0)
+        np.testing.assert_allclose(got, ref, rtol=4e-16, atol=0)
+    assert [n for n in (8, 16, 96, 512, 8192, 16384) if _engine_length(n)] == [16, 512, 8192]
