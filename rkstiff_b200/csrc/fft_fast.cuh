@@ -56,47 +56,9 @@ template <bool INV> RKS_HD void dft4(cplx& x0, cplx& x1, cplx& x2, cplx& x3) {
     const cplx t0 = x0 + x2, t1 = x0 - x2, t2 = x1 + x3, t3 = rot<INV>(x1 - x3);
     x0 = t0 + t2; x1 = t1 + t3; x2 = t0 - t2; x3 = t1 - t3;
 }
-// Rotations by odd multiples of pi/4 are sqrt(1/2) times a sum / difference of the parts; the factor sqrt(1/2) is
-// folded into the additions of the butterfly that follows (a +- SQH u as two FMAs): 2 + 4 instead of 4 + 4 FP64
-// instructions per rotated value (RKS_SQH_FOLD=0: multiply first, as in round 1).
-#ifndef RKS_SQH_FOLD
-#define RKS_SQH_FOLD 1
-#endif
-template <bool INV> RKS_HD cplx unit8(cplx a) {         // a * w8^1 / SQH   (mulw(a, SQH, SQH))
-    return INV ? mk(a.x - a.y, a.x + a.y) : mk(a.x + a.y, a.y - a.x);
-}
-template <bool INV> RKS_HD cplx unit8c(cplx a) {        // a * w8^3 / SQH   (mulw(a, -SQH, SQH))
-    return INV ? mk(-a.x - a.y, a.x - a.y) : mk(a.y - a.x, -a.x - a.y);
-}
-RKS_HD void dft2_scaled(cplx& a, cplx& u, double k) {   // (a, k u) -> (a + k u, a - k u)
-    const cplx t = a;
-    a = mk(fma(k, u.x, t.x), fma(k, u.y, t.y));
-    u = mk(fma(-k, u.x, t.x), fma(-k, u.y, t.y));
-}
-// dft4 whose input x2 is SQH * u2
-template <bool INV> RKS_HD void dft4_s2(cplx& x0, cplx& x1, cplx& u2, cplx& x3) {
-    const cplx t0 = mk(fma(SQH, u2.x, x0.x), fma(SQH, u2.y, x0.y)), t1 = mk(fma(-SQH, u2.x, x0.x), fma(-SQH, u2.y, x0.y));
-    const cplx t2 = x1 + x3, t3 = rot<INV>(x1 - x3);
-    x0 = t0 + t2; x1 = t1 + t3; u2 = t0 - t2; x3 = t1 - t3;
-}
-// dft4 whose inputs x1, x3 are SQH * u1, SQH * u3
-template <bool INV> RKS_HD void dft4_s13(cplx& x0, cplx& u1, cplx& x2, cplx& u3) {
-    const cplx t0 = x0 + x2, t1 = x0 - x2, s = u1 + u3, d = rot<INV>(u1 - u3);
-    x0 = mk(fma(SQH, s.x, t0.x), fma(SQH, s.y, t0.y));
-    u1 = mk(fma(SQH, d.x, t1.x), fma(SQH, d.y, t1.y));
-    x2 = mk(fma(-SQH, s.x, t0.x), fma(-SQH, s.y, t0.y));
-    u3 = mk(fma(-SQH, d.x, t1.x), fma(-SQH, d.y, t1.y));
-}
 template <bool INV> RKS_HD void dft8(cplx* v) {
     dft4<INV>(v[0], v[2], v[4], v[6]);                  // E[k1] -> slot 2 k1
     dft4<INV>(v[1], v[3], v[5], v[7]);                  // O[k1] -> slot 2 k1 + 1
-    if (RKS_SQH_FOLD) {
-        v[3] = unit8<INV>(v[3]);                        // * w8^1 / SQH
-        v[5] = rot<INV>(v[5]);                          // * w8^2
-        v[7] = unit8c<INV>(v[7]);                       // * w8^3 / SQH
-        dft2<INV>(v[0], v[1]); dft2_scaled(v[2], v[3], SQH); dft2<INV>(v[4], v[5]); dft2_scaled(v[6], v[7], SQH);
-        return;
-    }
     v[3] = mulw<INV>(v[3], SQH, SQH);                   // * w8^1
     v[5] = rot<INV>(v[5]);                              // * w8^2
     v[7] = mulw<INV>(v[7], -SQH, SQH);                  // * w8^3
@@ -108,16 +70,6 @@ template <bool INV> RKS_HD void dft16(cplx* v) {
     dft4<INV>(v[2], v[6], v[10], v[14]);
     dft4<INV>(v[3], v[7], v[11], v[15]);
     // * w16^(b k1)
-    if (RKS_SQH_FOLD) {
-        v[5] = mulw<INV>(v[5], C8, S8);      v[6] = unit8<INV>(v[6]);      v[7] = mulw<INV>(v[7], S8, C8);
-        v[9] = unit8<INV>(v[9]);             v[10] = rot<INV>(v[10]);      v[11] = unit8c<INV>(v[11]);
-        v[13] = mulw<INV>(v[13], S8, C8);    v[14] = unit8c<INV>(v[14]);   v[15] = mulw<INV>(v[15], -C8, -S8);
-        dft4<INV>(v[0], v[1], v[2], v[3]);              // y[k1 + 4 k2] -> slot 4 k1 + k2
-        dft4_s2<INV>(v[4], v[5], v[6], v[7]);
-        dft4_s13<INV>(v[8], v[9], v[10], v[11]);
-        dft4_s2<INV>(v[12], v[13], v[14], v[15]);
-        return;
-    }
     v[5] = mulw<INV>(v[5], C8, S8);      v[6] = mulw<INV>(v[6], SQH, SQH);     v[7] = mulw<INV>(v[7], S8, C8);
     v[9] = mulw<INV>(v[9], SQH, SQH);    v[10] = rot<INV>(v[10]);              v[11] = mulw<INV>(v[11], -SQH, SQH);
     v[13] = mulw<INV>(v[13], S8, C8);    v[14] = mulw<INV>(v[14], -SQH, SQH);  v[15] = mulw<INV>(v[15], -C8, -S8);
